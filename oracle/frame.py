@@ -1,0 +1,325 @@
+"""oracle/frame.py -- functional torch restatement of the reference graph ABOVE the MSDA op.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Plain fp32/fp64 PyTorch ops on whatever device the
+tensors live on (CPU for the checker and the cpu_baseline); no nn.Module, no autograd state: every function
+takes the reference's own ``state_dict`` (same key names and shapes) plus explicit tensors.
+
+Restated reference code (paths relative to /root/reference/):
+  msda_core            models/ops/functions/ms_deform_attn_func.py:44-64   (grid_sample formulation)
+  msda_module          models/ops/modules/ms_deform_attn.py:88-130
+  mha                  torch.nn.functional.multi_head_attention_forward math path (torch/nn/functional.py),
+                       reached from models/deformable_decoder.py:245-252 and models/query_updater.py:125
+  encoder              models/deformable_encoder.py:29-60, 97-131
+  decoder              models/deformable_decoder.py:56-171, 245-319   (USE_DAB=True branch)
+  transformer          models/deformable_transformer.py:175-259
+  heads                models/memotr.py:147-195
+  update_tracks        models/query_updater.py:82-166                  (USE_DAB=True branch)
+  pos_to_pos_embed     models/utils.py:78-85 ; inverse_sigmoid utils/utils.py:61-74
+
+Parity status: the reference ships no test for anything in this file ("parity unpinned" by the reference's
+own tests); it is pinned instead against the reference modules themselves, imported and run in the
+authoring container by oracle/make_golden.py -> tests/golden/frame_small.npz (tests/test_oracle_cpu.py).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+LN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- small pieces
+def linear(sd, key, x):
+    return F.linear(x, sd[key + ".weight"], sd[key + ".bias"])
+
+
+def layer_norm(sd, key, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], LN_EPS)
+
+
+def mlp(sd, key, x, n_layers):
+    """models/mlp.py:13-25 -- ReLU between layers, none after the last."""
+    for i in range(n_layers):
+        x = linear(sd, f"{key}.layers.{i}", x)
+        if i < n_layers - 1:
+            x = torch.relu(x)
+    return x
+
+
+def ffn_block(sd, key, x, norm_key=None):
+    """models/ffn.py:15-25: LN(x + W2 relu(W1 x)).  norm_key defaults to '<key>.norm'."""
+    y = linear(sd, key + ".linear2", torch.relu(linear(sd, key + ".linear1", x)))
+    return layer_norm(sd, norm_key or key + ".norm", x + y)
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def pos_to_pos_embed(pos, num_pos_feats=64, temperature=10000, scale=2 * math.pi):
+    """models/utils.py:78-85: interleaved sin/cos, coordinate-major."""
+    pos = pos * scale
+    i = torch.arange(num_pos_feats, dtype=torch.float32, device=pos.device)
+    dim_i = temperature ** (2 * torch.div(i, 2, rounding_mode="trunc") / num_pos_feats)
+    e = pos[..., None] / dim_i
+    e = torch.stack((e[..., 0::2].sin(), e[..., 1::2].cos()), dim=-1)
+    return torch.flatten(e, start_dim=-3)
+
+
+def mha(sd, key, q, k, v, n_heads, key_padding_mask=None):
+    """nn.MultiheadAttention(batch_first=True), need_weights path: separate q/k/v in-projections from the
+    chunks of in_proj_weight, q scaled by 1/sqrt(d) before QK^T, additive -inf key padding mask, softmax, PV,
+    out_proj.  q,k,v: (B, N, C)."""
+    B, Nq, C = q.shape
+    Nk = k.shape[1]
+    d = C // n_heads
+    w, b = sd[key + ".in_proj_weight"], sd[key + ".in_proj_bias"]
+    qp = F.linear(q, w[:C], b[:C])
+    kp = F.linear(k, w[C:2 * C], b[C:2 * C])
+    vp = F.linear(v, w[2 * C:], b[2 * C:])
+    qp = qp.view(B, Nq, n_heads, d).transpose(1, 2) * math.sqrt(1.0 / d)
+    kp = kp.view(B, Nk, n_heads, d).transpose(1, 2)
+    vp = vp.view(B, Nk, n_heads, d).transpose(1, 2)
+    logits = qp @ kp.transpose(-1, -2)
+    if key_padding_mask is not None:
+        logits = logits.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    att = torch.softmax(logits, dim=-1)
+    out = (att @ vp).transpose(1, 2).reshape(B, Nq, C)
+    return linear(sd, key + ".out_proj", out)
+
+
+# ----------------------------------------------------------------------------------------------- MSDA
+def msda_core(value, shapes, loc, attn):
+    """ms_deform_attn_core_pytorch (func.py:44-64): per level grid_sample(bilinear, zeros,
+    align_corners=False) on 2*loc-1, weighted by attn and summed over levels*points."""
+    B, S, H, D = value.shape
+    _, Lq, _, L, K, _ = loc.shape
+    sizes = [int(h) * int(w) for h, w in shapes]
+    grids = 2 * loc - 1
+    sampled = []
+    for lvl, (h, w) in enumerate(shapes):
+        h, w = int(h), int(w)
+        start = sum(sizes[:lvl])
+        v = value[:, start:start + h * w].flatten(2).transpose(1, 2).reshape(B * H, D, h, w)
+        g = grids[:, :, :, lvl].transpose(1, 2).flatten(0, 1)
+        sampled.append(F.grid_sample(v, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+    a = attn.transpose(1, 2).reshape(B * H, 1, Lq, L * K)
+    out = (torch.stack(sampled, dim=-2).flatten(-2) * a).sum(-1).view(B, H * D, Lq)
+    return out.transpose(1, 2).contiguous()
+
+
+def msda_module(sd, key, query, ref, src, shapes, lsi, padding_mask, n_heads, n_levels, n_points, core=None):
+    """MSDeformAttn.forward (modules/ms_deform_attn.py:88-130).  `core(value, shapes, lsi, loc, attn)` may
+    replace the grid_sample formulation (e.g. with the C oracle or the CUDA op under test)."""
+    B, Lq, C = query.shape
+    S = src.shape[1]
+    value = linear(sd, key + ".value_proj", src)
+    if padding_mask is not None:
+        value = value.masked_fill(padding_mask[..., None], 0.0)
+    value = value.view(B, S, n_heads, C // n_heads)
+    off = linear(sd, key + ".sampling_offsets", query).view(B, Lq, n_heads, n_levels, n_points, 2)
+    aw = linear(sd, key + ".attention_weights", query).view(B, Lq, n_heads, n_levels * n_points)
+    aw = torch.softmax(aw, -1).view(B, Lq, n_heads, n_levels, n_points)
+    shapes_t = torch.as_tensor([[int(h), int(w)] for h, w in shapes], dtype=torch.long, device=query.device)
+    if ref.shape[-1] == 2:
+        norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1)        # (W_l, H_l), ms_deform_attn.py:117
+        loc = ref[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + off / n_points * ref[:, :, None, :, None, 2:] * 0.5
+    if core is None:
+        out = msda_core(value, shapes, loc, aw)
+    else:
+        out = core(value, shapes_t, lsi, loc, aw)
+    return linear(sd, key + ".output_proj", out)
+
+
+# ----------------------------------------------------------------------------------------------- encoder
+def encoder_reference_points(shapes, valid_ratios, device):
+    """DeformableEncoder.get_reference_points (deformable_encoder.py:29-40)."""
+    refs = []
+    for lvl, (h, w) in enumerate(shapes):
+        h, w = int(h), int(w)
+        ry, rx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device),
+                                torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device), indexing="ij")
+        ry = ry.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * h)
+        rx = rx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * w)
+        refs.append(torch.stack((rx, ry), -1))
+    refs = torch.cat(refs, 1)
+    return refs[:, :, None] * valid_ratios[:, None]
+
+
+def encoder_layer(sd, key, src, pos, ref, shapes, lsi, padding_mask, cfg, core=None):
+    a = msda_module(sd, key + ".self_attn", src + pos, ref, src, shapes, lsi, padding_mask,
+                    cfg["n_heads"], cfg["n_levels"], cfg["n_enc_points"], core)
+    src = layer_norm(sd, key + ".norm1", src + a)
+    return ffn_block(sd, key, src, norm_key=key + ".norm2")
+
+
+def encoder(sd, key, src, pos, shapes, lsi, valid_ratios, padding_mask, cfg, core=None):
+    ref = encoder_reference_points(shapes, valid_ratios, src.device)
+    for i in range(cfg["n_enc_layers"]):
+        src = encoder_layer(sd, f"{key}.layers.{i}", src, pos, ref, shapes, lsi, padding_mask, cfg, core)
+    return src
+
+
+# ----------------------------------------------------------------------------------------------- decoder
+def decoder_layer(sd, key, tgt, query_pos, ref_in, memory, shapes, lsi, query_mask, mem_mask, cfg, merge, core=None):
+    """DeformableDecoderLayer.forward (deformable_decoder.py:275-319)."""
+    nd = cfg["n_det_queries"]
+    track_tgt = None
+    if not merge:
+        track_tgt, tgt = tgt[:, nd:], tgt[:, :nd]
+        query_pos, ref_in, query_mask = query_pos[:, :nd], ref_in[:, :nd], query_mask[:, :nd]
+    qk = tgt + query_pos
+    tgt = layer_norm(sd, key + ".norm2", tgt + mha(sd, key + ".self_attn", qk, qk, tgt, cfg["n_heads"], query_mask))
+    a = msda_module(sd, key + ".cross_attn", tgt + query_pos, ref_in, memory, shapes, lsi, mem_mask,
+                    cfg["n_heads"], cfg["n_levels"], cfg["n_dec_points"], core)
+    tgt = layer_norm(sd, key + ".norm1", tgt + a)
+    tgt = ffn_block(sd, key, tgt, norm_key=key + ".norm3")
+    if not merge:
+        tgt = torch.cat((tgt, track_tgt), dim=1)
+    return tgt
+
+
+def decoder(sd, key, bbox_key, tgt, ref, memory, shapes, lsi, valid_ratios, query_mask, mem_mask, cfg, core=None):
+    """DeformableDecoder.forward, USE_DAB branch with iterative box refinement
+    (deformable_decoder.py:56-171).  Returns (outputs[n,B,Nq,C], refs[n,B,Nq,4], queries[n,B,Nq,C])."""
+    C = tgt.shape[-1]
+    nd, merge_layer = cfg["n_det_queries"], cfg["merge_det_track_layer"]
+    outs, refs, queries = [], [], []
+    out = tgt
+    for lid in range(cfg["n_dec_layers"]):
+        ref_in = ref[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
+        anchor = pos_to_pos_embed(ref_in[:, :, 0, :], num_pos_feats=C // 2)
+        raw_pos = mlp(sd, key + ".ref_point_head", anchor, 2)
+        scale = mlp(sd, key + ".query_scale", out, 2) if lid != 0 else 1
+        query_pos = scale * raw_pos
+        queries.append(out)
+        out = decoder_layer(sd, f"{key}.layers.{lid}", out, query_pos, ref_in, memory, shapes, lsi, query_mask,
+                            mem_mask, cfg, merge=(lid >= merge_layer), core=core)
+        new_ref = (mlp(sd, f"{bbox_key}.{lid}", out, 3) + inverse_sigmoid(ref)).sigmoid()
+        if lid < merge_layer:
+            ref = torch.cat((new_ref[:, :nd], ref[:, nd:]), dim=1)
+        else:
+            ref = new_ref
+        outs.append(out)
+        refs.append(ref)
+    return torch.stack(outs), torch.stack(refs), torch.stack(queries)
+
+
+# ----------------------------------------------------------------------------------------------- transformer
+def valid_ratio(mask):
+    """DeformableTransformer.get_valid_ratio (deformable_transformer.py:175-190) -> (B, 2) as (w, h)."""
+    _, H, W = mask.shape
+    vh = torch.sum(~mask[:, :, 0], 1).float() / H
+    vw = torch.sum(~mask[:, 0, :], 1).float() / W
+    return torch.stack([vw, vh], -1)
+
+
+def flatten_levels(sd, key, srcs, masks, pos_embeds):
+    """deformable_transformer.py:196-220."""
+    src_f, mask_f, pos_f, shapes = [], [], [], []
+    for lvl, (s, m, p) in enumerate(zip(srcs, masks, pos_embeds)):
+        shapes.append((s.shape[2], s.shape[3]))
+        src_f.append(s.flatten(2).transpose(1, 2))
+        mask_f.append(m.flatten(1))
+        pos_f.append(p.flatten(2).transpose(1, 2) + sd[key + ".level_embed"][lvl].view(1, 1, -1))
+    sizes = [h * w for h, w in shapes]
+    lsi = torch.as_tensor([sum(sizes[:i]) for i in range(len(sizes))], dtype=torch.long, device=srcs[0].device)
+    vr = torch.stack([valid_ratio(m) for m in masks], 1)
+    return torch.cat(src_f, 1), torch.cat(mask_f, 1), torch.cat(pos_f, 1), shapes, lsi, vr
+
+
+def transformer(sd, srcs, masks, pos_embeds, query_embed, ref_pts, query_mask, cfg, core=None, key="transformer",
+                bbox_key="bbox_embed"):
+    """DeformableTransformer.forward (deformable_transformer.py:192-259), DAB branch.
+    -> outputs (n,B,Nq,C), init_ref (B,Nq,4), inter_refs (n,B,Nq,4), inter_queries (n,B,Nq,C), memory."""
+    src, mask, pos, shapes, lsi, vr = flatten_levels(sd, key, srcs, masks, pos_embeds)
+    memory = encoder(sd, key + ".encoder", src, pos, shapes, lsi, vr, mask, cfg, core)
+    init_ref = ref_pts.sigmoid()
+    outs, refs, queries = decoder(sd, key + ".decoder", bbox_key, query_embed, init_ref, memory, shapes, lsi, vr,
+                                  query_mask, mask, cfg, core)
+    return outs, init_ref, refs, queries, memory
+
+
+def heads(sd, outs, init_ref, refs):
+    """models/memotr.py:147-162: per-level class / box heads with inverse-sigmoid reference."""
+    logits, boxes = [], []
+    for lvl in range(outs.shape[0]):
+        r = inverse_sigmoid(init_ref if lvl == 0 else refs[lvl - 1])
+        logits.append(linear(sd, f"class_embed.{lvl}", outs[lvl]))
+        boxes.append((mlp(sd, f"bbox_embed.{lvl}", outs[lvl], 3) + r).sigmoid())
+    return torch.stack(logits), torch.stack(boxes)
+
+
+def frame_forward(sd, srcs, masks, pos_embeds, track_ref_pts, track_query_embed, cfg, core=None):
+    """MeMOTR.forward minus the backbone / input projections (models/memotr.py:128-195), batch 1.
+    track_ref_pts (Nt,4) and track_query_embed (Nt,C) are TrackInstances.ref_pts / .query_embed."""
+    ref_pts = torch.cat((sd["det_anchor"], track_ref_pts), 0)[None]
+    query_embed = torch.cat((sd["det_query_embed"], track_query_embed), 0)[None]
+    query_mask = torch.zeros((1, ref_pts.shape[1]), dtype=torch.bool, device=ref_pts.device)
+    outs, init_ref, refs, queries, memory = transformer(sd, srcs, masks, pos_embeds, query_embed, ref_pts,
+                                                        query_mask, cfg, core)
+    logits, boxes = heads(sd, outs, init_ref, refs)
+    return {
+        "pred_logits": logits[-1], "pred_bboxes": boxes[-1],
+        "last_ref_pts": inverse_sigmoid(refs[-2]), "init_ref_pts": inverse_sigmoid(init_ref),
+        "query_mask": query_mask, "outputs": outs[-1],
+        "aux_logits": logits[:-1], "aux_bboxes": boxes[:-1], "aux_queries": queries[1:],
+        "memory": memory,
+    }
+
+
+# ----------------------------------------------------------------------------------------------- query updater
+def update_tracks(sd, t, cfg, key="query_updater"):
+    """QueryUpdater.update_tracks_embedding for one batch item (query_updater.py:82-166, DAB branch).
+    `t` is a dict with ref_pts, query_embed, output_embed, last_output, long_memory, logits, boxes.
+    Returns a new dict with the five updated fields (+ is_pos)."""
+    C = t["output_embed"].shape[-1]
+    lam, thr = cfg["long_memory_lambda"], cfg["update_thresh"]
+    scores = t["logits"].sigmoid().max(dim=1).values
+    is_pos = scores > thr
+    ref_pts = t["ref_pts"].clone()
+    ref_pts[is_pos] = inverse_sigmoid(t["boxes"][is_pos])
+    query_pos = pos_to_pos_embed(ref_pts.sigmoid(), num_pos_feats=C // 2)
+    out_e, last_e, long_m = t["output_embed"], t["last_output"], t["long_memory"]
+    conf = torch.sigmoid(mlp(sd, key + ".confidence_weight_net.0", out_e, 2))
+    short = mlp(sd, key + ".short_memory_fusion", torch.cat((conf * out_e, last_e), -1), 2)
+    query_pos = mlp(sd, key + ".query_pos_head", query_pos, 2)
+    q, k = short + query_pos, long_m + query_pos
+    tgt = out_e + mha(sd, key + ".memory_attn", q[None], k[None], out_e[None], 8)[0]
+    tgt = ffn_block(sd, key + ".memory_ffn", layer_norm(sd, key + ".memory_norm", tgt))
+    feat = ffn_block(sd, key + ".query_feat_ffn", layer_norm(sd, key + ".query_feat_norm", long_m + tgt))
+    m = is_pos[:, None]
+    new_long = (1 - lam) * long_m + lam * out_e
+    query_embed = t["query_embed"].clone()
+    query_embed[is_pos] = feat[is_pos]
+    return {
+        "ref_pts": ref_pts, "query_embed": query_embed,
+        "long_memory": long_m * ~m + new_long * m,
+        "last_output": last_e * ~m + out_e * m,
+        "is_pos": is_pos,
+    }
+
+
+# ----------------------------------------------------------------------------------------------- configs
+def dancetrack_cfg():
+    """Hot-path hyper-parameters of configs/train_dancetrack.yaml:60-75,89-90."""
+    return dict(d_model=256, d_ffn=2048, n_levels=4, n_heads=8, n_enc_points=4, n_dec_points=4, n_enc_layers=6,
+                n_dec_layers=6, merge_det_track_layer=1, n_det_queries=300, update_thresh=0.5,
+                long_memory_lambda=0.01, num_classes=1)
+
+
+def to_reference_config(cfg):
+    """The same numbers as the flat upper-case dict the reference build() functions read."""
+    return {
+        "HIDDEN_DIM": cfg["d_model"], "FFN_DIM": cfg["d_ffn"], "NUM_FEATURE_LEVELS": cfg["n_levels"],
+        "NUM_HEADS": cfg["n_heads"], "NUM_ENC_POINTS": cfg["n_enc_points"], "NUM_DEC_POINTS": cfg["n_dec_points"],
+        "NUM_ENC_LAYERS": cfg["n_enc_layers"], "NUM_DEC_LAYERS": cfg["n_dec_layers"],
+        "MERGE_DET_TRACK_LAYER": cfg["merge_det_track_layer"], "DROPOUT": 0.0, "ACTIVATION": "ReLU",
+        "RETURN_INTER_DEC": True, "NUM_DET_QUERIES": cfg["n_det_queries"], "EXTRA_TRACK_ATTN": False,
+        "USE_CHECKPOINT": False, "CHECKPOINT_LEVEL": 2, "USE_DAB": True, "VISUALIZE": False,
+        "UPDATE_THRESH": cfg["update_thresh"], "LONG_MEMORY_LAMBDA": cfg["long_memory_lambda"],
+        "TP_DROP_RATE": 0.0, "FP_INSERT_RATE": 0.0,
+    }

@@ -1,0 +1,194 @@
+#!/usr/bin/env python
+"""oracle/make_golden.py -- run the REFERENCE's own Python in the authoring container and store its outputs.
+
+TEST INFRASTRUCTURE.  Needs /root/reference (read-only mount); it does not exist on the GPU box, so this
+script is only ever run here and its products are committed under tests/golden/:
+
+  msda_core.npz     ms_deform_attn_core_pytorch (models/ops/functions/ms_deform_attn_func.py:44-64) forward in
+                    fp64/fp32 and its autograd gradients, on the shapes and seed of models/ops/test.py:21-36,
+                    plus BASELINE.json config #1 (B=1, 4 DanceTrack levels, H=8, D=32, K=4, Lq=100) and a border
+                    variant (loc = rand*1.2-0.1).
+  frame_small.npz   MeMOTR.forward (models/memotr.py:97-195, backbone and input projections bypassed) and
+                    QueryUpdater.update_tracks_embedding (models/query_updater.py:82-166) of the reference
+                    nn.Modules on oracle.synth's small configuration (weights/inputs regenerated from seeds, only
+                    outputs stored).
+  frame_full.npz    the same at the DanceTrack 1333x800 configuration (S=22323, 300+100 queries, 6+6 layers).
+
+The compiled reference op cannot run on a CPU ("Not implemented on the CPU", src/ms_deform_attn.h:38), so --
+exactly as BASELINE.md section 3 prescribes -- MSDeformAttnFunction.apply is routed to the reference's own
+ms_deform_attn_core_pytorch, and a stub satisfies `import MultiScaleDeformableAttention` (func.py:21).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import synth  # noqa: E402
+from oracle import frame as oframe  # noqa: E402
+
+
+def import_reference():
+    assert os.path.isdir(REF), "the reference is only mounted in the authoring container"
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    sys.path.insert(0, REF)
+    import models.ops.functions.ms_deform_attn_func as func
+    import models.ops.modules.ms_deform_attn as mod
+
+    class _CpuFunction:
+        @staticmethod
+        def apply(value, shapes, lsi, loc, attn, im2col_step):
+            return func.ms_deform_attn_core_pytorch(value, shapes, loc, attn)
+
+    mod.MSDeformAttnFunction = _CpuFunction
+    return func
+
+
+def golden_msda(func):
+    out = {}
+    # --- models/ops/test.py shapes -------------------------------------------------------------------
+    for name, (shapes, kw) in {
+        "tiny": (((6, 4), (3, 2)), dict(B=1, H=2, D=2, K=2, Lq=2, seed=3)),
+        "tiny_d32": (((6, 4), (3, 2)), dict(B=2, H=2, D=32, K=2, Lq=3, seed=4)),
+        "tiny_d30": (((6, 4), (3, 2)), dict(B=1, H=2, D=30, K=2, Lq=2, seed=5)),
+        "tiny_border": (((6, 4), (3, 2)), dict(B=2, H=3, D=8, K=3, Lq=5, seed=6, border=True)),
+        "cfg1": (synth.DANCETRACK_SHAPES, dict(B=1, H=8, D=32, K=4, Lq=100, seed=3)),
+        "cfg1_border": (synth.DANCETRACK_SHAPES, dict(B=1, H=8, D=32, K=4, Lq=100, seed=7, border=True)),
+    }.items():
+        value, shp, lsi, loc, attn = synth.msda_inputs(shapes, **kw)
+        with torch.no_grad():
+            out[f"{name}.fwd32"] = func.ms_deform_attn_core_pytorch(value, shp, loc, attn).numpy()
+            out[f"{name}.fwd64"] = func.ms_deform_attn_core_pytorch(value.double(), shp, loc.double(), attn.double()).numpy()
+        v, l, a = (t.double().requires_grad_(True) for t in (value, loc, attn))
+        y = func.ms_deform_attn_core_pytorch(v, shp, l, a)
+        g = torch.Generator().manual_seed(11)
+        go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        gv, gl, ga = torch.autograd.grad(y, (v, l, a), go)
+        out[f"{name}.grad_out"] = go.numpy()
+        if name.startswith("cfg1"):          # 22323x8x32 fp64 is too big to commit: keep two projections over D
+            r = torch.randn(kw["D"], generator=torch.Generator().manual_seed(12), dtype=torch.float64)
+            out[f"{name}.grad_value_sumD"] = gv.sum(-1).float().numpy()
+            out[f"{name}.grad_value_dotD"] = (gv * r).sum(-1).float().numpy()
+        else:
+            out[f"{name}.grad_value"] = gv.numpy()
+        out[f"{name}.grad_loc"] = gl.numpy()
+        out[f"{name}.grad_attn"] = ga.numpy()
+        out[f"{name}.meta"] = np.asarray([kw.get("B", 1), kw["H"], kw["D"], kw["K"], kw["Lq"], kw["seed"],
+                                          int(kw.get("border", False))], dtype=np.int64)
+        out[f"{name}.shapes"] = np.asarray(shapes, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "msda_core.npz"), **out)
+    print("msda_core.npz:", len(out), "arrays")
+
+
+class _FakeBackbone:
+    """Stands in for BackboneWithPE (models/backbone.py:101-125): hands MeMOTR.forward the synthetic pyramid."""
+
+    def __init__(self, srcs, masks, pos):
+        from utils.nested_tensor import NestedTensor
+        self._feats = [NestedTensor(s, m) for s, m in zip(srcs[:3], masks[:3])]
+        self._pos = pos
+        self.position_embedding = lambda nt: self._pos[3]
+
+    def n_inter_layers(self):
+        return 3
+
+    def n_inter_channels(self):
+        return [8, 8, 8]
+
+    def __call__(self, frame):
+        return self._feats, list(self._pos[:3])
+
+
+class _Const(nn.Module):
+    def __init__(self, t):
+        super().__init__()
+        self.t = t
+
+    def forward(self, _):
+        return self.t
+
+
+def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
+    import models.memotr as memotr
+    from models.deformable_transformer import build as build_tr
+    from models.query_updater import build as build_qu
+    from structures.track_instances import TrackInstances
+    from utils.nested_tensor import NestedTensor
+
+    rc = oframe.to_reference_config(cfg)
+    x = synth.frame_inputs(cfg, shapes, n_tracks, seed=seed_x, padded=padded)
+    torch.manual_seed(0)
+    model = memotr.MeMOTR(backbone=_FakeBackbone(x["srcs"], x["masks"], x["pos"]), transformer=build_tr(rc),
+                          query_updater=build_qu(rc), num_classes=cfg["num_classes"],
+                          n_det_queries=cfg["n_det_queries"], n_feature_levels=cfg["n_levels"],
+                          hidden_dim=cfg["d_model"], ffn_dim=cfg["d_ffn"], dropout=0.0, aux_loss=True,
+                          with_box_refine=True, use_checkpoint=False, use_dab=True)
+    model.feature_projs = nn.ModuleList([nn.Identity(), nn.Identity(), nn.Identity(), _Const(x["srcs"][3])])
+    model.eval()
+
+    # the hot-path parameter table must match the reference's state_dict exactly (names and shapes)
+    want = synth.hot_path_param_shapes(cfg)
+    # (transformer.decoder.bbox_embed.* are aliases of bbox_embed.* -- the same tensors registered twice by
+    #  set_refine_bbox_embed, deformable_transformer.py:272-274 -- and feature_projs is outside the hot path)
+    have = {k: tuple(v.shape) for k, v in model.state_dict().items()
+            if not k.startswith(("feature_projs", "transformer.decoder.bbox_embed"))}
+    assert have == want, (set(have) ^ set(want), [k for k in have if k in want and have[k] != want[k]])
+    sd = synth.hot_path_state_dict(cfg, seed=seed_w)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("feature_projs", "transformer.decoder.bbox_embed"))
+                                  for k in missing), (missing, unexpected)
+    for i in range(cfg["n_dec_layers"]):     # aliases really are the same storage
+        assert model.transformer.decoder.bbox_embed[i].layers[0].weight.data_ptr() == \
+            model.bbox_embed[i].layers[0].weight.data_ptr()
+
+    h3, w3 = shapes[3]
+    frame_mask = x["masks"][3].repeat_interleave(8, 1).repeat_interleave(8, 2)
+    frame = NestedTensor(torch.zeros(1, 3, h3 * 8, w3 * 8), frame_mask)
+    tr = TrackInstances(hidden_dim=cfg["d_model"], num_classes=cfg["num_classes"], use_dab=True)
+    tr.ref_pts = x["tracks"]["ref_pts"].clone()
+    tr.query_embed = x["tracks"]["query_embed"].clone()
+    with torch.no_grad():
+        res = model(frame=frame, tracks=[tr])
+    out = {
+        "pred_logits": res["pred_logits"], "pred_bboxes": res["pred_bboxes"], "last_ref_pts": res["last_ref_pts"],
+        "init_ref_pts": res["init_ref_pts"], "outputs": res["outputs"],
+        "aux_logits": torch.stack([a["pred_logits"] for a in res["aux_outputs"]]),
+        "aux_bboxes": torch.stack([a["pred_bboxes"] for a in res["aux_outputs"]]),
+        "aux_queries": torch.stack([a["queries"] for a in res["aux_outputs"]]),
+    }
+
+    # QueryUpdater.update_tracks_embedding on the synthetic track state
+    t2 = TrackInstances(hidden_dim=cfg["d_model"], num_classes=cfg["num_classes"], use_dab=True)
+    for k, v in x["tracks"].items():
+        setattr(t2, k, v.clone())
+    t2.ids = torch.arange(n_tracks)
+    with torch.no_grad():
+        upd = model.query_updater.update_tracks_embedding([t2])[0]
+    for k in ("ref_pts", "query_embed", "long_memory", "last_output"):
+        out["upd_" + k] = getattr(upd, k)
+
+    arrays = {k: v.detach().numpy() for k, v in out.items()}
+    arrays["meta"] = np.asarray([n_tracks, seed_w, seed_x, int(padded)], dtype=np.int64)
+    arrays["shapes"] = np.asarray(shapes, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, f"frame_{tag}.npz"), **arrays)
+    print(f"frame_{tag}.npz:", {k: v.shape for k, v in arrays.items()})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    func = import_reference()
+    golden_msda(func)
+    golden_frame(synth.small_cfg(), synth.SMALL_SHAPES, n_tracks=5, seed_w=0, seed_x=1, padded=False, tag="small")
+    golden_frame(synth.small_cfg(), synth.SMALL_SHAPES, n_tracks=5, seed_w=2, seed_x=3, padded=True, tag="small_padded")
+    if "--full" in sys.argv:
+        cfg = oframe.dancetrack_cfg()
+        golden_frame(cfg, synth.DANCETRACK_SHAPES, n_tracks=100, seed_w=0, seed_x=1, padded=False, tag="full")
