@@ -1,0 +1,79 @@
+"""memotr_b200/_lib.py -- ctypes binding of the C ABI (include/memotr_b200.h -> csrc/libmemotr_b200.so).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing or a call fails, a
+RuntimeError is raised (the reference raises the same exception type from AT_ASSERTM/AT_ERROR,
+/root/reference/models/ops/src/cuda/ms_deform_attn_cuda.cu:28-52, src/ms_deform_attn.h:35-38).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmemotr_b200.so")
+ABI_VERSION = 1
+
+F32, F64, BF16 = 0, 1, 2
+_DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
+
+_lib = None
+
+_vp, _i = ctypes.c_void_p, ctypes.c_int
+_SIGNATURES = {
+    "memotr_abi_version": ([], _i),
+    "memotr_last_error": ([], ctypes.c_char_p),
+    "memotr_msda_forward": ([_vp] * 6 + [_i] * 8 + [_vp], _i),
+    "memotr_msda_backward": ([_vp] * 9 + [_i] * 8 + [_vp], _i),
+}
+
+
+def exported_symbols():
+    """Every symbol include/memotr_b200.h declares (checked by tests/test_abi_cpu.py against the header)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"memotr_b200: CUDA library {LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (or `python memotr_b200/build.py`).  There is no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(l, name)           # AttributeError here = header/library mismatch: fail loudly
+            fn.argtypes, fn.restype = argtypes, restype
+        if l.memotr_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"memotr_b200: ABI version {l.memotr_abi_version()} != expected {ABI_VERSION}")
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().memotr_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"memotr_b200: unsupported dtype {t.dtype}") from None
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(**tensors):
+    """The reference's argument checks (ms_deform_attn_cuda.cu:28-38, ms_deform_attn.h:35-38)."""
+    for name, t in tensors.items():
+        if not t.is_cuda:
+            raise RuntimeError("Not implemented on the CPU" if name == "value" else f"{name} must be a CUDA tensor")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")

@@ -1,0 +1,64 @@
+// common.cuh -- shared helpers for the sm_100a kernels behind the C ABI (include/memotr_b200.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/memotr_b200.h"
+
+namespace memotr {
+
+// ---- error plumbing: thread-local message, integer return codes across the C ABI ---------------------------
+inline char *err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  return MEMOTR_OK;
+}
+
+#define MEMOTR_REQUIRE(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) return ::memotr::fail(MEMOTR_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- small device helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// 8 bf16 (16 bytes) -> 8 floats
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 &u, float (&f)[8]) {
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f32x8_to_bf16(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+}  // namespace memotr

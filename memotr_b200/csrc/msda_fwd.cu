@@ -1,0 +1,284 @@
+// msda_fwd.cu -- multi-scale deformable attention, forward, for sm_100a.
+//
+// Replaces ms_deformable_im2col_gpu_kernel + ms_deform_attn_im2col_bilinear
+// (/root/reference/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299 and :33-84) and the host wrapper
+// ms_deform_attn_cuda_forward (src/cuda/ms_deform_attn_cuda.cu:20-80).
+//
+// Layout (unchanged from the reference): value (B,S,H,D) pixel-major; sampling_loc
+// (B,Lq,H,L,K,2) with (x,y) last; attn_weight (B,Lq,H,L,K); output (B,Lq,H*D).
+//
+// Kernels
+//   msda_fwd_vec<...>   D == 32.  A group of G lanes owns one (b,q,head): fp32 -> 8 lanes x float4, bf16 -> 4 lanes
+//                       x 8 channels (one 16-byte load per lane per corner, i.e. one full 128 B / 64 B row of the
+//                       head per corner).  All K points of a level are decoded first, then their 4K corner loads
+//                       are issued back to back (memory-level parallelism), then the blend runs in the reference's
+//                       order.  No shared memory, no atomics, every output element written exactly once.
+//   msda_fwd_generic<T> any D, float or double: one thread per output scalar (the reference's mapping); used for
+//                       odd channel counts and for the fp64 gradcheck path.
+//
+// fp32 rounding: the operation sequence below is the one the reference kernel executes after nvcc's FMA
+// contraction (read from its sm_100a SASS):  h = fma(loc_y, H, -0.5);  val = fma(w4,v4, fma(w3,v3, fma(w1,v1, w2*v2)));
+// col = fma(weight, val, col), levels outer / points inner.  Explicit __f*_rn intrinsics pin it, so the fp32
+// output is bit-identical to the reference op (tests/test_msda_gpu.py checks this against oracle/_ref).
+#include "common.cuh"
+
+namespace memotr {
+
+template <typename T>
+struct LocIO;
+template <>
+struct LocIO<float> {
+  static __device__ __forceinline__ float2 xy(const float *loc, long i) {
+    return __ldg(reinterpret_cast<const float2 *>(loc) + i);
+  }
+  static __device__ __forceinline__ float w(const float *a, long i) { return __ldg(a + i); }
+};
+template <>
+struct LocIO<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 xy(const __nv_bfloat16 *loc, long i) {
+    const unsigned int raw = __ldg(reinterpret_cast<const unsigned int *>(loc) + i);
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw));
+  }
+  static __device__ __forceinline__ float w(const __nv_bfloat16 *a, long i) {
+    const unsigned short raw = __ldg(reinterpret_cast<const unsigned short *>(a) + i);
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(&raw));
+  }
+};
+
+// One lane's slice of a head row: CH channels held as floats.
+template <typename T>
+struct Row;
+template <>
+struct Row<float> {
+  static constexpr int CH = 4;  // float4
+  static __device__ __forceinline__ void load(const float *p, bool ok, float (&v)[4]) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) t = ldg_f4(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Row<__nv_bfloat16> {
+  static constexpr int CH = 8;  // 8 x bf16 = 16 bytes
+  static __device__ __forceinline__ void load(const __nv_bfloat16 *p, bool ok, float (&v)[8]) {
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) t = __ldg(reinterpret_cast<const uint4 *>(p));
+    bf16x8_to_f32(t, v);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[8]) {
+    *reinterpret_cast<uint4 *>(p) = f32x8_to_bf16(v);
+  }
+};
+
+// KT > 0: points per level known at compile time (fully unrolled, loads batched per level); KT == 0: runtime K.
+template <typename T, int KT>
+__global__ void __launch_bounds__(256)
+msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+             const T *__restrict__ loc, const T *__restrict__ attn, T *__restrict__ out, int S, int H, int L, int Lq,
+             int Kr, long n_qh) {
+  constexpr int D = 32;
+  constexpr int CH = Row<T>::CH;
+  constexpr int G = D / CH;  // lanes per (b,q,head)
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long qh = tid / G;
+  if (qh >= n_qh) return;
+  const int sub = (int)(tid % G);
+  const int m = (int)(qh % H);
+  const int b = (int)((qh / H) / Lq);
+  const int K = KT ? KT : Kr;
+  const int xs = H * D;  // elements between x-neighbours
+  const long pbase = qh * L * K;
+
+  float acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+
+  for (int l = 0; l < L; ++l) {
+    const int Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
+    const float Hf = (float)Hh, Wf = (float)Ww;
+    const int ys = Ww * xs;
+    const T *lvl = value + ((long)b * S + __ldg(lsi + l)) * xs + m * D + sub * CH;
+
+    if constexpr (KT > 0) {
+      float w1[KT], w2[KT], w3[KT], w4[KT], aw[KT];
+      int o00[KT];
+      unsigned okm[KT];  // bit0..3: corner valid, bit4: point contributes
+#pragma unroll
+      for (int p = 0; p < KT; ++p) {
+        const float2 xy = LocIO<T>::xy(loc, pbase + l * KT + p);
+        aw[p] = LocIO<T>::w(attn, pbase + l * KT + p);
+        const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
+        const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
+        const float hfl = floorf(h_im), wfl = floorf(w_im);
+        const int y0 = (int)hfl, x0 = (int)wfl;
+        const float lh = __fsub_rn(h_im, hfl), lw = __fsub_rn(w_im, wfl);
+        const float hh = __fsub_rn(1.f, lh), hw = __fsub_rn(1.f, lw);
+        w1[p] = __fmul_rn(hh, hw), w2[p] = __fmul_rn(hh, lw), w3[p] = __fmul_rn(lh, hw), w4[p] = __fmul_rn(lh, lw);
+        const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
+        okm[p] = inside ? (16u | (y0ok && x0ok ? 1u : 0u) | (y0ok && x1ok ? 2u : 0u) | (y1ok && x0ok ? 4u : 0u) |
+                           (y1ok && x1ok ? 8u : 0u))
+                        : 0u;
+        o00[p] = inside ? y0 * ys + x0 * xs : 0;
+      }
+      float v1[KT][CH], v2[KT][CH], v3[KT][CH], v4[KT][CH];
+#pragma unroll
+      for (int p = 0; p < KT; ++p) {
+        const T *p00 = lvl + o00[p];
+        Row<T>::load(p00, okm[p] & 1u, v1[p]);
+        Row<T>::load(p00 + xs, okm[p] & 2u, v2[p]);
+        Row<T>::load(p00 + ys, okm[p] & 4u, v3[p]);
+        Row<T>::load(p00 + ys + xs, okm[p] & 8u, v4[p]);
+      }
+#pragma unroll
+      for (int p = 0; p < KT; ++p) {
+        const bool contributes = okm[p] & 16u;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const float val = __fmaf_rn(w4[p], v4[p][c],
+                                      __fmaf_rn(w3[p], v3[p][c], __fmaf_rn(w1[p], v1[p][c], __fmul_rn(w2[p], v2[p][c]))));
+          const float nxt = __fmaf_rn(aw[p], val, acc[c]);
+          acc[c] = contributes ? nxt : acc[c];
+        }
+      }
+    } else {
+      for (int p = 0; p < K; ++p) {
+        const float2 xy = LocIO<T>::xy(loc, pbase + l * K + p);
+        const float aw = LocIO<T>::w(attn, pbase + l * K + p);
+        const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
+        if (h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf) {
+          const float hfl = floorf(h_im), wfl = floorf(w_im);
+          const int y0 = (int)hfl, x0 = (int)wfl;
+          const float lh = __fsub_rn(h_im, hfl), lw = __fsub_rn(w_im, wfl);
+          const float hh = __fsub_rn(1.f, lh), hw = __fsub_rn(1.f, lw);
+          const float w1 = __fmul_rn(hh, hw), w2 = __fmul_rn(hh, lw), w3 = __fmul_rn(lh, hw), w4 = __fmul_rn(lh, lw);
+          const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
+          const T *p00 = lvl + (y0 * ys + x0 * xs);
+          float v1[CH], v2[CH], v3[CH], v4[CH];
+          Row<T>::load(p00, y0ok && x0ok, v1);
+          Row<T>::load(p00 + xs, y0ok && x1ok, v2);
+          Row<T>::load(p00 + ys, y1ok && x0ok, v3);
+          Row<T>::load(p00 + ys + xs, y1ok && x1ok, v4);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const float val =
+                __fmaf_rn(w4, v4[c], __fmaf_rn(w3, v3[c], __fmaf_rn(w1, v1[c], __fmul_rn(w2, v2[c]))));
+            acc[c] = __fmaf_rn(aw, val, acc[c]);
+          }
+        }
+      }
+    }
+  }
+  Row<T>::store(out + qh * D + sub * CH, acc);
+}
+
+// ---- generic: any D, float / double; one thread per output scalar ------------------------------------------
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c);
+template <>
+__device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <>
+__device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+                 const T *__restrict__ loc, const T *__restrict__ attn, T *__restrict__ out, int S, int H, int D,
+                 int L, int Lq, int K, long n_out) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_out; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    const long qh = idx / D;
+    const int m = (int)(qh % H);
+    const int b = (int)((qh / H) / Lq);
+    const long xs = (long)H * D;
+    const long pbase = qh * L * K;
+    T col = 0;
+    for (int l = 0; l < L; ++l) {
+      const int Hh = (int)shapes[2 * l], Ww = (int)shapes[2 * l + 1];
+      const long ys = Ww * xs;
+      const T *lvl = value + ((long)b * S + lsi[l]) * xs + m * D + c;
+      for (int p = 0; p < K; ++p) {
+        const T lx = loc[(pbase + l * K + p) * 2], ly = loc[(pbase + l * K + p) * 2 + 1];
+        const T aw = attn[pbase + l * K + p];
+        const T h_im = fma_t<T>(ly, (T)Hh, (T)-0.5), w_im = fma_t<T>(lx, (T)Ww, (T)-0.5);
+        if (h_im > -1 && w_im > -1 && h_im < Hh && w_im < Ww) {
+          const T hfl = floor(h_im), wfl = floor(w_im);
+          const int y0 = (int)hfl, x0 = (int)wfl;
+          const T lh = h_im - hfl, lw = w_im - wfl, hh = (T)1 - lh, hw = (T)1 - lw;
+          const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
+          const T *p00 = lvl + (y0 * ys + x0 * xs);
+          const T v1 = (y0ok && x0ok) ? p00[0] : (T)0;
+          const T v2 = (y0ok && x1ok) ? p00[xs] : (T)0;
+          const T v3 = (y1ok && x0ok) ? p00[ys] : (T)0;
+          const T v4 = (y1ok && x1ok) ? p00[ys + xs] : (T)0;
+          const T w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+          const T val = fma_t<T>(w4, v4, fma_t<T>(w3, v3, fma_t<T>(w1, v1, w2 * v2)));
+          col = fma_t<T>(aw, val, col);
+        }
+      }
+    }
+    out[idx] = col;
+  }
+}
+
+template <typename T>
+static int launch_vec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+                      void *out, int B, int S, int H, int L, int Lq, int K, cudaStream_t st) {
+  constexpr int G = 32 / Row<T>::CH;
+  const long n_qh = (long)B * Lq * H;
+  const long threads = n_qh * G;
+  const int grid = (int)((threads + 255) / 256);
+  auto a = [&](auto kern) {
+    kern<<<grid, 256, 0, st>>>((const T *)value, shapes, lsi, (const T *)loc, (const T *)attn, (T *)out, S, H, L, Lq,
+                               K, n_qh);
+  };
+  switch (K) {
+    case 1: a(msda_fwd_vec<T, 1>); break;
+    case 2: a(msda_fwd_vec<T, 2>); break;
+    case 4: a(msda_fwd_vec<T, 4>); break;
+    case 8: a(msda_fwd_vec<T, 8>); break;
+    default: a(msda_fwd_vec<T, 0>); break;
+  }
+  return check_launch("msda_fwd_vec");
+}
+
+}  // namespace memotr
+
+using namespace memotr;
+
+extern "C" int memotr_msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_idx,
+                                   const void *sampling_loc, const void *attn_weight, void *output, int B, int S,
+                                   int H, int D, int L, int Lq, int K, int dtype, void *stream) {
+  MEMOTR_REQUIRE(B >= 0 && S > 0 && H > 0 && D > 0 && L > 0 && Lq >= 0 && K > 0, "msda_forward: bad sizes");
+  MEMOTR_REQUIRE((long)B * S * H * D < (1L << 31), "msda_forward: value has >= 2^31 elements");
+  if ((long)B * Lq == 0) return MEMOTR_OK;
+  MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && sampling_loc && attn_weight && output,
+                 "msda_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = (D == 32) && aligned16(value) && aligned16(output) &&
+                      ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0);
+  if (dtype == MEMOTR_F32 && vec_ok)
+    return launch_vec<float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L, Lq,
+                             K, st);
+  if (dtype == MEMOTR_BF16) {
+    MEMOTR_REQUIRE(vec_ok, "msda_forward: bf16 requires D == 32 and 16-byte aligned buffers");
+    return launch_vec<__nv_bfloat16>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S,
+                                     H, L, Lq, K, st);
+  }
+  const long n_out = (long)B * Lq * H * D;
+  const int grid = (int)((n_out + 255) / 256 > (1L << 30) ? (1L << 30) : (n_out + 255) / 256);
+  if (dtype == MEMOTR_F32) {
+    msda_fwd_generic<float><<<grid, 256, 0, st>>>((const float *)value, spatial_shapes, level_start_idx,
+                                                  (const float *)sampling_loc, (const float *)attn_weight,
+                                                  (float *)output, S, H, D, L, Lq, K, n_out);
+  } else if (dtype == MEMOTR_F64) {
+    msda_fwd_generic<double><<<grid, 256, 0, st>>>((const double *)value, spatial_shapes, level_start_idx,
+                                                   (const double *)sampling_loc, (const double *)attn_weight,
+                                                   (double *)output, S, H, D, L, Lq, K, n_out);
+  } else {
+    return fail(MEMOTR_EINVAL, "msda_forward: unknown dtype %d", dtype);
+  }
+  return check_launch("msda_fwd_generic");
+}
