@@ -78,6 +78,105 @@ MEMOTR_API int memotr_msda_backward(const void *value, const int64_t *spatial_sh
                          void *grad_value, void *grad_sampling_loc, void *grad_attn_weight, int B, int S, int H,
                          int D, int L, int Lq, int K, int dtype, void *stream);
 
+
+/*
+ * Engine variant of the forward op: value/output in `dtype` (F32 or BF16), sampling locations and attention
+ * weights always fp32 (the outputs of memotr_msda_prep), D == 32, and an explicit pixel stride (elements between
+ * consecutive pixels of `value`, >= H*32) so that the value maps of all decoder layers can live interleaved in one
+ * (S, n_layers*256) buffer written by a single GEMM.  Same arithmetic as memotr_msda_forward.
+ */
+MEMOTR_API int memotr_msda_forward_ex(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                      const int64_t *level_start_idx, const float *sampling_loc,
+                                      const float *attn_weight, void *output, int B, int S, int H, int L, int Lq,
+                                      int K, int dtype, void *stream);
+
+/*
+ * Sampling locations + attention weights from the raw projections -- models/ops/modules/ms_deform_attn.py:108-120.
+ *   ol            (Lq, ldol) fp32: per row [ offsets (H,L,K,2) | logits (H,L*K) ]  (one GEMM with the stacked
+ *                 sampling_offsets / attention_weights weights)
+ *   valid_ratios  (L,2) fp32 (w,h) per level -- models/deformable_transformer.py:175-190
+ *   mode 0 (encoder self-attention): query q is the q-th pixel of the pyramid; its 2-d reference point is rebuilt from
+ *          spatial_shapes / level_start_idx / valid_ratios  (models/deformable_encoder.py:29-40);  ref4 unused
+ *   mode 1 (decoder cross-attention): ref4 (Lq,4) sigmoid-space boxes, scaled per level by valid_ratios
+ *          (models/deformable_decoder.py:82-84)
+ *   -> sampling_loc (Lq,H,L,K,2) fp32, attn_weight (Lq,H,L,K) fp32 (softmax over the joint L*K axis)
+ */
+MEMOTR_API int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatial_shapes,
+                                const int64_t *level_start_idx, const float *valid_ratios, const float *ref4, int mode,
+                                float *sampling_loc, float *attn_weight, int Lq, int H, int L, int K, void *stream);
+
+/*
+ * C = epilogue(A . W^T):  v = acc + bias;  act (0 none, 1 ReLU, 2 sigmoid);  v *= mul;  v += add;  rows with
+ * rowzero[m] != 0 are written as zeros.  A (M,K) lda, W (N,K) ldw, both `ab_dtype` (F32 or BF16); C (M,N) ldc in
+ * `c_dtype` (F32, or BF16 when ab_dtype is BF16); mul/add (M,N) in ab_dtype; bias fp32; fp32 accumulation.
+ * path 0 = auto (bf16 with N % 64 == 0, K % 64 == 0 -> tcgen05/TMA tensor-core kernel, otherwise CUDA-core kernel),
+ * 1 = force CUDA cores, 2 = force tensor cores (MEMOTR_ENOSYS if the shape is unsupported).
+ * Replaces torch.nn.functional.linear at every call site of the hot path: models/ops/modules/ms_deform_attn.py:104-129,
+ * models/deformable_encoder.py:97-107, models/deformable_decoder.py:245-273, models/mlp.py:22-25, models/ffn.py:15-25,
+ * models/query_updater.py:109-132, models/memotr.py:153-154 (and the padding-mask fill of ms_deform_attn.py:106).
+ */
+MEMOTR_API int memotr_linear(const void *A, int lda, const void *W, int ldw, const float *bias, const void *mul,
+                             int ldmul, const void *add, int ldadd, const unsigned char *rowzero, void *C, int ldc,
+                             int M, int N, int K, int ab_dtype, int c_dtype, int act, int path, void *stream);
+
+/*
+ * y = LayerNorm(x [+ x2]) (C == 256, eps as given, affine fp32); optional ypos = y + pos and fp32 copy y32.
+ * models/deformable_encoder.py:124-130, models/deformable_decoder.py:251-252,313-318, models/ffn.py:23-24,
+ * models/query_updater.py:126-133.
+ */
+MEMOTR_API int memotr_layernorm(const void *x, int x_dtype, int ldx, const void *x2, int ldx2, const float *gamma,
+                                const float *beta, float eps, void *y, int y_dtype, int ldy, const void *pos,
+                                int ldpos, void *ypos, int ldypos, float *y32, int ldy32, int M, int C, void *stream);
+
+/*
+ * Multi-head attention core (head_dim 32): O = softmax(Q K^T / sqrt(32) + key_padding_mask) V per head.
+ * Q (Nq, n_heads*32) ldq, K/V (Nk, n_heads*32); key_padding_mask (Nk) uint8 or NULL (1 = ignore key).
+ * nn.MultiheadAttention math path at models/deformable_decoder.py:245-252 and models/query_updater.py:125.
+ */
+MEMOTR_API int memotr_mha(const void *Q, int ldq, const void *K, int ldk, const void *V, int ldv,
+                          const unsigned char *key_padding_mask, void *O, int ldo, int Nq, int Nk, int n_heads,
+                          int head_dim, int dtype, void *stream);
+
+/* One pyramid level, (C,HW) fp32 maps -> token rows [row0,row0+HW): src^T, pos^T+level_embed, and their sum.
+ * models/deformable_transformer.py:200-216 (+ with_pos_embed, models/deformable_encoder.py:124). */
+MEMOTR_API int memotr_tokens_from_nchw(const float *src, const float *pos, const float *level_embed, void *src_tok,
+                                       void *pos_tok, void *q_tok, int C, int HW, int row0, int ld, int dtype,
+                                       void *stream);
+
+/* valid ratio (w,h) of one level's (H,W) uint8 padding mask -- models/deformable_transformer.py:175-190 */
+MEMOTR_API int memotr_valid_ratio(const unsigned char *mask, int H, int W, float *out2, void *stream);
+
+/* sine embedding of (N,4) boxes -> (N,512): models/utils.py:78-85; optional sigmoid first (query_updater.py:102) and
+ * per-coordinate scale (deformable_decoder.py:82-91); dim_t = the 128 divisors 10000^(2*(i//2)/128). */
+MEMOTR_API int memotr_sine_embed(const float *pts, int ldp, const float *scale4, int apply_sigmoid, const float *dim_t,
+                                 void *out, int ldo, int N, int out_dtype, void *stream);
+
+/* out = a + b, (M,N) with leading dimensions -- with_pos_embed (deformable_decoder.py:246,304), query_updater.py:121-122 */
+MEMOTR_API int memotr_add(const void *a, int lda, const void *b, int ldb, void *out, int ldo, int M, int N, int dtype,
+                          void *stream);
+
+/* strided copy with dtype conversion (torch.cat / slicing / .to(dtype) on the hot path) */
+MEMOTR_API int memotr_convert(const void *src, int src_dtype, int lds, void *dst, int dst_dtype, int ldd, int M, int N,
+                              void *stream);
+
+/* new = sigmoid(delta + inverse_sigmoid(ref)); ref_next rows [0,n_take) = new, others = ref
+ * (models/deformable_decoder.py:139-159; the same expression yields pred_bboxes, models/memotr.py:147-160) */
+MEMOTR_API int memotr_box_refine(const float *delta, const float *ref, float *new_ref, float *ref_next, int N,
+                                 int n_take, void *stream);
+
+/* op 0: sigmoid, op 1: inverse_sigmoid (utils/utils.py:61-74) */
+MEMOTR_API int memotr_unary(const float *in, float *out, long n, int op, void *stream);
+
+/* QueryUpdater first step: is_pos = max_c sigmoid(logits) > thr; ref_new = is_pos ? inverse_sigmoid(boxes) : ref_pts
+ * (models/query_updater.py:84-85,99-102) */
+MEMOTR_API int memotr_upd_prepare(const float *logits, int ncls, const float *boxes, const float *ref_pts, float thr,
+                                  unsigned char *is_pos, float *ref_new, int Nt, void *stream);
+
+/* QueryUpdater last step, in place on the fp32 track state (models/query_updater.py:135-147) */
+MEMOTR_API int memotr_upd_finalize(const unsigned char *is_pos, const void *feat, int feat_dtype, int ldf,
+                                   const float *out_e, float *query_embed, float *long_memory, float *last_output,
+                                   float lam, int Nt, int C, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,12 +18,26 @@ _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 
 _lib = None
 
-_vp, _i = ctypes.c_void_p, ctypes.c_int
+_vp, _i, _f, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_long
 _SIGNATURES = {
     "memotr_abi_version": ([], _i),
     "memotr_last_error": ([], ctypes.c_char_p),
     "memotr_msda_forward": ([_vp] * 6 + [_i] * 8 + [_vp], _i),
     "memotr_msda_backward": ([_vp] * 9 + [_i] * 8 + [_vp], _i),
+    "memotr_msda_forward_ex": ([_vp, _i] + [_vp] * 5 + [_i] * 7 + [_vp], _i),
+    "memotr_msda_prep": ([_vp, _i] + [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 4 + [_vp], _i),
+    "memotr_linear": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 7 + [_vp], _i),
+    "memotr_layernorm": ([_vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp], _i),
+    "memotr_mha": ([_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 5 + [_vp], _i),
+    "memotr_tokens_from_nchw": ([_vp] * 6 + [_i] * 5 + [_vp], _i),
+    "memotr_valid_ratio": ([_vp, _i, _i, _vp, _vp], _i),
+    "memotr_sine_embed": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp], _i),
+    "memotr_add": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
+    "memotr_convert": ([_vp, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
+    "memotr_box_refine": ([_vp] * 4 + [_i, _i, _vp], _i),
+    "memotr_unary": ([_vp, _vp, _l, _i, _vp], _i),
+    "memotr_upd_prepare": ([_vp, _i, _vp, _vp, _f, _vp, _vp, _i, _vp], _i),
+    "memotr_upd_finalize": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp], _i),
 }
 
 

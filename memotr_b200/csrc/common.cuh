@@ -61,4 +61,28 @@ __device__ __forceinline__ uint4 f32x8_to_bf16(const float (&f)[8]) {
   return u;
 }
 
+// ---- dtype conversion + the GEMM epilogue description shared by gemm_simt.cu and gemm_tc.cu -------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+
+struct Epilogue {
+  const float *bias;             // (N) or null
+  const void *mul;               // (M,N) activation dtype or null: result *= mul
+  const void *add;               // (M,N) activation dtype or null: result += add  (residual)
+  const unsigned char *rowzero;  // (M) or null: rows with rowzero[m] != 0 are written as 0 (padding mask)
+  int ldmul, ldadd, act;
+};
+
 }  // namespace memotr

@@ -1,0 +1,320 @@
+// gemm_tc.cu -- bf16 tensor-core GEMM for sm_100a:  C = epilogue(A . W^T + bias),  A (M,K) and W (N,K) both K-major.
+//
+// Stands in for the dense layers the reference runs as fp32 cuBLAS SGEMM:
+// the MSDeformAttn projections (models/ops/modules/ms_deform_attn.py:104-129), the encoder/decoder FFNs
+// (models/deformable_encoder.py:97-107, models/deformable_decoder.py:263-273), the MLPs and the MHA in/out
+// projections (models/deformable_decoder.py:245-252, models/query_updater.py:109-132).
+//
+// Blackwell design (one CTA = one 128 x BN output tile, 6 warps, warp-specialised):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d of a 128x64 A box and a BNx64 W box per k-block into a 3-stage
+//            shared-memory ring (SWIZZLE_128B), completion counted on an mbarrier (expect_tx).
+//   warp 1   allocates TMEM, then one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16,
+//            bf16 x bf16 -> fp32 accumulator in TMEM), 4 per k-block; tcgen05.commit frees the smem stage and, after the
+//            last k-block, signals the epilogue.
+//   warps 2-5 epilogue: tcgen05.ld 32x32b (one accumulator row per thread, 32 columns at a time) -> bias / ReLU /
+//            sigmoid / multiplier / residual / padding-mask -> 16-byte stores.
+// Rows beyond M are zero-filled by TMA on load and masked on store.  96 KB (BN=128) or 72 KB (BN=64) of shared memory
+// and BN TMEM columns per CTA, so 2-3 CTAs are resident per SM and one tile's epilogue overlaps another's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace memotr {
+
+namespace tc {
+
+constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t umma_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;  // + barriers/tmem slot + slack for 1024 B alignment
+};
+
+template <int BN, typename TC>
+__global__ void __launch_bounds__(192)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TC *__restrict__ C,
+               int ldc, int M, int N, int K, Epilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  using SM = Smem<BN>;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::BAR_OFFSET);
+  uint64_t *empty = full + STAGES;
+  uint64_t *tmem_full = empty + STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.y, n_blk = blockIdx.x;
+  const int num_k = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate BN TMEM columns, publish the base address through shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, SM::STAGE_BYTES);
+        uint8_t *sa = smem + s * SM::STAGE_BYTES;
+        tma_load_2d(sa, &tmA, full + s, kb * BK, m_blk * BM);
+        tma_load_2d(sa + A_BYTES, &tmW, full + s, kb * BK, n_blk * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full + s, ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // advance 16 bf16 = 32 B = 2 x 16-byte units inside the swizzle atom
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(empty + s);  // implicit fence::before_thread_sync; frees the stage when the MMAs have read it
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) ----
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int quarter = warp & 3;
+    const int row = m_blk * BM + quarter * 32 + lane;
+    const bool row_ok = row < M;
+    const bool zero_row = row_ok && ep.rowzero && ep.rowzero[row];
+    const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
+    const __nv_bfloat16 *addp = (const __nv_bfloat16 *)ep.add + (long)row * ep.ldadd;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      const int col0 = n_blk * BN + c0;
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.bias + col0 + j));
+          v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+        }
+      }
+      if (ep.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (ep.act == ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      }
+      if (ep.mul) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float t[8];
+          bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(mulp + col0 + j)), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j + i] *= t[i];
+        }
+      }
+      if (ep.add) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float t[8];
+          bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(addp + col0 + j)), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j + i] += t[i];
+        }
+      }
+      if (zero_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      TC *dst = C + (long)row * ldc + col0;
+      if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = v[j + i];
+          *reinterpret_cast<uint4 *>(dst + j) = f32x8_to_bf16(t);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ---- host side: TMA descriptors through the driver entry point (no link-time libcuda dependency) -------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// 2-D bf16 row-major (rows, cols) with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle
+static bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, typename TC>
+static int launch(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
+                  const Epilogue &ep, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN))
+    return fail(MEMOTR_ECUDA, "linear(tc): cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
+  auto kern = gemm_tc_kernel<BN, TC>;
+  static bool attr_set = false;  // idempotent attribute; benign if two threads race to set the same value
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "linear(tc): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(N / BN, ceil_div(M, BM));
+  kern<<<grid, 192, Smem<BN>::TOTAL, st>>>(tmA, tmW, (TC *)C, ldc, M, N, K, ep);
+  return check_launch("gemm_tc");
+}
+
+}  // namespace tc
+
+bool linear_tc_supported(int lda, int ldw, int ldc, int c_dtype, int M, int N, int K, const void *A, const void *W,
+                         const void *C) {
+  (void)M;
+  const int cal = c_dtype == MEMOTR_F32 ? 4 : 8;  // 16-byte row segments on store
+  return N % 64 == 0 && K % tc::BK == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % cal == 0 && aligned16(A) &&
+         aligned16(W) && aligned16(C) && tc::encode_fn() != nullptr;
+}
+
+int linear_tc_bf16(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int c_dtype, int M, int N, int K,
+                   const Epilogue &ep, cudaStream_t st) {
+  if (ep.mul && (ep.ldmul % 8 != 0 || !aligned16(ep.mul))) return fail(MEMOTR_EINVAL, "linear(tc): mul misaligned");
+  if (ep.add && (ep.ldadd % 8 != 0 || !aligned16(ep.add))) return fail(MEMOTR_EINVAL, "linear(tc): add misaligned");
+  if (ep.bias && !aligned16(ep.bias)) return fail(MEMOTR_EINVAL, "linear(tc): bias misaligned");
+  const bool wide = N % 128 == 0;
+  if (c_dtype == MEMOTR_F32)
+    return wide ? tc::launch<128, float>(A, lda, W, ldw, C, ldc, M, N, K, ep, st)
+                : tc::launch<64, float>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);
+  return wide ? tc::launch<128, __nv_bfloat16>(A, lda, W, ldw, C, ldc, M, N, K, ep, st)
+              : tc::launch<64, __nv_bfloat16>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);
+}
+
+}  // namespace memotr

@@ -20,6 +20,8 @@
 // contraction (read from its sm_100a SASS):  h = fma(loc_y, H, -0.5);  val = fma(w4,v4, fma(w3,v3, fma(w1,v1, w2*v2)));
 // col = fma(weight, val, col), levels outer / points inner.  Explicit __f*_rn intrinsics pin it, so the fp32
 // output is bit-identical to the reference op (tests/test_msda_gpu.py checks this against oracle/_ref).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace memotr {
@@ -73,23 +75,20 @@ struct Row<__nv_bfloat16> {
   }
 };
 
+// One (b,q,head) group's work: `sub` is this lane's slice of the 32 channels.
 // KT > 0: points per level known at compile time (fully unrolled, loads batched per level); KT == 0: runtime K.
-template <typename T, int KT>
-__global__ void __launch_bounds__(256)
-msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
-             const T *__restrict__ loc, const T *__restrict__ attn, T *__restrict__ out, int S, int H, int L, int Lq,
-             int Kr, long n_qh) {
+// T: value/output element type; TL: sampling_loc / attn_weight element type; xs: elements between x-neighbouring
+// pixels of `value` (H*D for the reference layout; larger when the value maps of several layers are interleaved).
+template <typename T, typename TL, int KT>
+__device__ __forceinline__ void msda_fwd_group(const T *__restrict__ value, const int64_t *__restrict__ shapes,
+                                               const int64_t *__restrict__ lsi, const TL *__restrict__ loc,
+                                               const TL *__restrict__ attn, T *__restrict__ out, int S, int H, int L,
+                                               int Lq, int Kr, int xs, long qh, int sub) {
   constexpr int D = 32;
   constexpr int CH = Row<T>::CH;
-  constexpr int G = D / CH;  // lanes per (b,q,head)
-  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long qh = tid / G;
-  if (qh >= n_qh) return;
-  const int sub = (int)(tid % G);
   const int m = (int)(qh % H);
   const int b = (int)((qh / H) / Lq);
   const int K = KT ? KT : Kr;
-  const int xs = H * D;  // elements between x-neighbours
   const long pbase = qh * L * K;
 
   float acc[CH];
@@ -108,8 +107,8 @@ msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
       unsigned okm[KT];  // bit0..3: corner valid, bit4: point contributes
 #pragma unroll
       for (int p = 0; p < KT; ++p) {
-        const float2 xy = LocIO<T>::xy(loc, pbase + l * KT + p);
-        aw[p] = LocIO<T>::w(attn, pbase + l * KT + p);
+        const float2 xy = LocIO<TL>::xy(loc, pbase + l * KT + p);
+        aw[p] = LocIO<TL>::w(attn, pbase + l * KT + p);
         const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
         const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
         const float hfl = floorf(h_im), wfl = floorf(w_im);
@@ -145,8 +144,8 @@ msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
       }
     } else {
       for (int p = 0; p < K; ++p) {
-        const float2 xy = LocIO<T>::xy(loc, pbase + l * K + p);
-        const float aw = LocIO<T>::w(attn, pbase + l * K + p);
+        const float2 xy = LocIO<TL>::xy(loc, pbase + l * K + p);
+        const float aw = LocIO<TL>::w(attn, pbase + l * K + p);
         const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
         if (h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf) {
           const float hfl = floorf(h_im), wfl = floorf(w_im);
@@ -172,6 +171,59 @@ msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
     }
   }
   Row<T>::store(out + qh * D + sub * CH, acc);
+}
+
+// Mapping A ("linear"): consecutive lane groups take consecutive (b,q,head).  Any Lq.
+template <typename T, typename TL, int KT>
+__global__ void __launch_bounds__(256)
+msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+             const TL *__restrict__ loc, const TL *__restrict__ attn, T *__restrict__ out, int S, int H, int L, int Lq,
+             int Kr, int xs, long n_qh) {
+  constexpr int G = 32 / Row<T>::CH;  // lanes per (b,q,head)
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long qh = tid / G;
+  if (qh >= n_qh) return;
+  msda_fwd_group<T, TL, KT>(value, shapes, lsi, loc, attn, out, S, H, L, Lq, Kr, xs, qh, (int)(tid % G));
+}
+
+// Mapping B ("tiled"), used when Lq == S, i.e. the queries ARE the pixels of the pyramid (encoder self-attention,
+// deformable_encoder.py:124): a CTA takes an 8x8 patch of queries of one level for ONE head.  Neighbouring queries
+// sample neighbouring pixels, so the patch's corner reads (64 queries x L*K points x 4 corners of 128 B) fall into a
+// few-KB window of that head's value map and are served by L1 instead of L2.  Pure re-ordering of the work: every
+// (b,q,head) is still computed exactly once by the same code, so results are identical to mapping A.
+// Persistent-style grid: CTAs stride over (batch, head, tile); the tile table is derived on the device from
+// spatial_shapes (the host never reads them -- no sync).
+constexpr int kTile = 8;
+template <typename T, typename TL, int KT>
+__global__ void __launch_bounds__(kTile *kTile * (32 / Row<T>::CH))
+msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+               const TL *__restrict__ loc, const TL *__restrict__ attn, T *__restrict__ out, int B, int S, int H, int L,
+               int Kr, int xs) {
+  constexpr int G = 32 / Row<T>::CH;
+  const int g = threadIdx.x / G, sub = threadIdx.x % G;  // g: query slot inside the 8x8 patch
+  const int gy = g / kTile, gx = g % kTile;
+  int n_tiles = 0;
+  for (int l = 0; l < L; ++l)
+    n_tiles += ceil_div((int)__ldg(shapes + 2 * l), kTile) * ceil_div((int)__ldg(shapes + 2 * l + 1), kTile);
+  const long n_work = (long)B * H * n_tiles;
+  for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+    int t = (int)(w % n_tiles);
+    const int m = (int)((w / n_tiles) % H);
+    const int b = (int)(w / ((long)n_tiles * H));
+    int l = 0, Hh = 0, Ww = 0, tx_n = 0;
+    for (; l < L; ++l) {
+      Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
+      tx_n = ceil_div(Ww, kTile);
+      const int n = ceil_div(Hh, kTile) * tx_n;
+      if (t < n) break;
+      t -= n;
+    }
+    const int y = (t / tx_n) * kTile + gy, x = (t % tx_n) * kTile + gx;
+    if (y < Hh && x < Ww) {
+      const long q = __ldg(lsi + l) + (long)y * Ww + x;
+      msda_fwd_group<T, TL, KT>(value, shapes, lsi, loc, attn, out, S, H, L, S, Kr, xs, ((long)b * S + q) * H + m, sub);
+    }
+  }
 }
 
 // ---- generic: any D, float / double; one thread per output scalar ------------------------------------------
@@ -223,23 +275,42 @@ msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes
   }
 }
 
-template <typename T>
+template <typename T, typename TL>
 static int launch_vec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
-                      void *out, int B, int S, int H, int L, int Lq, int K, cudaStream_t st) {
+                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st) {
   constexpr int G = 32 / Row<T>::CH;
   const long n_qh = (long)B * Lq * H;
+  const char *force = getenv("MEMOTR_MSDA_MAPPING");  // debugging override: "linear" | "tiled"
+  const bool tiled = force ? (force[0] == 't' && Lq == S) : (Lq == S && n_qh >= 4096);
+  if (tiled) {
+    // upper bound on the work items without reading the device-side shapes: every 8x8 patch holds >= 1 pixel
+    const long max_work = (long)B * H * S;
+    const int grid_t = (int)(max_work < (long)kNumSMs * 32 ? max_work : (long)kNumSMs * 32);
+    auto at = [&](auto kern) {
+      kern<<<grid_t, kTile * kTile * G, 0, st>>>((const T *)value, shapes, lsi, (const TL *)loc, (const TL *)attn,
+                                                   (T *)out, B, S, H, L, K, xs);
+    };
+    switch (K) {
+      case 1: at(msda_fwd_tiled<T, TL, 1>); break;
+      case 2: at(msda_fwd_tiled<T, TL, 2>); break;
+      case 4: at(msda_fwd_tiled<T, TL, 4>); break;
+      case 8: at(msda_fwd_tiled<T, TL, 8>); break;
+      default: at(msda_fwd_tiled<T, TL, 0>); break;
+    }
+    return check_launch("msda_fwd_tiled");
+  }
   const long threads = n_qh * G;
   const int grid = (int)((threads + 255) / 256);
   auto a = [&](auto kern) {
-    kern<<<grid, 256, 0, st>>>((const T *)value, shapes, lsi, (const T *)loc, (const T *)attn, (T *)out, S, H, L, Lq,
-                               K, n_qh);
+    kern<<<grid, 256, 0, st>>>((const T *)value, shapes, lsi, (const TL *)loc, (const TL *)attn, (T *)out, S, H, L, Lq,
+                               K, xs, n_qh);
   };
   switch (K) {
-    case 1: a(msda_fwd_vec<T, 1>); break;
-    case 2: a(msda_fwd_vec<T, 2>); break;
-    case 4: a(msda_fwd_vec<T, 4>); break;
-    case 8: a(msda_fwd_vec<T, 8>); break;
-    default: a(msda_fwd_vec<T, 0>); break;
+    case 1: a(msda_fwd_vec<T, TL, 1>); break;
+    case 2: a(msda_fwd_vec<T, TL, 2>); break;
+    case 4: a(msda_fwd_vec<T, TL, 4>); break;
+    case 8: a(msda_fwd_vec<T, TL, 8>); break;
+    default: a(msda_fwd_vec<T, TL, 0>); break;
   }
   return check_launch("msda_fwd_vec");
 }
@@ -260,12 +331,12 @@ extern "C" int memotr_msda_forward(const void *value, const int64_t *spatial_sha
   const bool vec_ok = (D == 32) && aligned16(value) && aligned16(output) &&
                       ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0);
   if (dtype == MEMOTR_F32 && vec_ok)
-    return launch_vec<float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L, Lq,
-                             K, st);
+    return launch_vec<float, float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H,
+                                    L, Lq, K, H * D, st);
   if (dtype == MEMOTR_BF16) {
     MEMOTR_REQUIRE(vec_ok, "msda_forward: bf16 requires D == 32 and 16-byte aligned buffers");
-    return launch_vec<__nv_bfloat16>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S,
-                                     H, L, Lq, K, st);
+    return launch_vec<__nv_bfloat16, __nv_bfloat16>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight,
+                                                    output, B, S, H, L, Lq, K, H * D, st);
   }
   const long n_out = (long)B * Lq * H * D;
   const int grid = (int)((n_out + 255) / 256 > (1L << 30) ? (1L << 30) : (n_out + 255) / 256);
@@ -281,4 +352,31 @@ extern "C" int memotr_msda_forward(const void *value, const int64_t *spatial_sha
     return fail(MEMOTR_EINVAL, "msda_forward: unknown dtype %d", dtype);
   }
   return check_launch("msda_fwd_generic");
+}
+
+// Engine variant: value/output in `dtype` (f32 or bf16), sampling locations and attention weights always fp32 (they
+// come straight from memotr_msda_prep), D == 32, and an explicit pixel stride so the value maps of all decoder layers
+// can live interleaved in one (S, n_layers*256) buffer written by a single GEMM.
+extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                      const int64_t *level_start_idx, const float *sampling_loc,
+                                      const float *attn_weight, void *output, int B, int S, int H, int L, int Lq, int K,
+                                      int dtype, void *stream) {
+  MEMOTR_REQUIRE(B >= 0 && S > 0 && H > 0 && L > 0 && Lq >= 0 && K > 0, "msda_forward_ex: bad sizes");
+  MEMOTR_REQUIRE(value_pixel_stride >= H * 32, "msda_forward_ex: pixel stride < H*32");
+  MEMOTR_REQUIRE((long)B * S * value_pixel_stride < (1L << 31), "msda_forward_ex: value spans >= 2^31 elements");
+  if ((long)B * Lq == 0) return MEMOTR_OK;
+  MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && sampling_loc && attn_weight && output,
+                 "msda_forward_ex: null pointer");
+  const int al = dtype == MEMOTR_BF16 ? 8 : 4;
+  MEMOTR_REQUIRE(aligned16(value) && aligned16(output) && value_pixel_stride % al == 0 &&
+                     ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
+                 "msda_forward_ex: misaligned buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MEMOTR_F32)
+    return launch_vec<float, float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H,
+                                    L, Lq, K, value_pixel_stride, st);
+  if (dtype == MEMOTR_BF16)
+    return launch_vec<__nv_bfloat16, float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output,
+                                            B, S, H, L, Lq, K, value_pixel_stride, st);
+  return fail(MEMOTR_EINVAL, "msda_forward_ex: dtype must be f32 or bf16");
 }

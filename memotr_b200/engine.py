@@ -1,0 +1,441 @@
+"""memotr_b200/engine.py -- the per-frame hot path of MeMOTR on one B200, every kernel our own.
+
+`FrameEngine` runs what `MeMOTR.forward` does after the backbone / input projections
+(/root/reference/models/memotr.py:128-195: reference-point/query assembly, DeformableTransformer.forward
+deformable_transformer.py:192-259, the per-layer heads) and `QueryUpdater.update_tracks_embedding`
+(models/query_updater.py:82-166), for batch size 1 and the DAB configuration the released MeMOTR checkpoints use
+(USE_DAB True, iterative box refinement, MERGE_DET_TRACK_LAYER 1).  It consumes the reference's own state_dict (same
+keys/shapes), packs the weights once into the layouts the kernels want, owns a fixed workspace in HBM, and issues
+nothing but C-ABI calls (include/memotr_b200.h) on the current CUDA stream -- so a whole frame can be captured into a
+CUDA graph (`capture()`), which removes the per-launch host cost and the host syncs listed in SURVEY.md 2.2.
+
+Two arithmetic modes:
+  "fp32"  fp32 storage, fp32 CUDA-core GEMMs -> matches the reference's fp32 (TF32-off) path to <= 1e-4
+  "bf16"  bf16 activations/weights, tcgen05 tensor-core GEMMs with fp32 accumulation, fp32 LayerNorm statistics,
+          fp32 geometry (reference points, sampling locations, boxes, logits) -> <= 1e-2
+"""
+import math
+
+import torch
+
+from . import _lib
+
+F32, BF16 = _lib.F32, _lib.BF16
+
+
+def _p(t):
+    return _lib.ptr(t)
+
+
+class _Lin:
+    """One nn.Linear packed for the kernels: weight (N,K) in the activation dtype, bias fp32."""
+
+    def __init__(self, w, b, dtype, device):
+        self.N, self.K = w.shape
+        self.w = w.to(device=device, dtype=dtype).contiguous()
+        self.b = b.to(device=device, dtype=torch.float32).contiguous() if b is not None else None
+
+
+class FrameEngine:
+    def __init__(self, state_dict, cfg, shapes, n_tracks, device="cuda", mode="fp32"):
+        assert mode in ("fp32", "bf16")
+        self.cfg, self.mode = dict(cfg), mode
+        self.dev = torch.device(device)
+        self.ta = torch.float32 if mode == "fp32" else torch.bfloat16
+        self.dt = F32 if mode == "fp32" else BF16
+        self.shapes = [(int(h), int(w)) for h, w in shapes]
+        self.L = len(self.shapes)
+        self.C, self.H, self.Fd = cfg["d_model"], cfg["n_heads"], cfg["d_ffn"]
+        assert self.C == 256 and self.C // self.H == 32, "kernels are specialised for d_model 256 / head dim 32"
+        assert self.L == cfg["n_levels"]
+        self.S = sum(h * w for h, w in self.shapes)
+        self.nd, self.nt = cfg["n_det_queries"], int(n_tracks)
+        self.nq = self.nd + self.nt
+        self.ncls = cfg["num_classes"]
+        self.n_enc, self.n_dec = cfg["n_enc_layers"], cfg["n_dec_layers"]
+        self.merge = cfg["merge_det_track_layer"]
+        self.lib = _lib.lib()
+        self.launches = 0
+        self._pack(state_dict)
+        self._alloc()
+        self.graph = None
+
+    # ------------------------------------------------------------------------------------------------ weights
+    def _pack(self, sd):
+        dev, ta = self.dev, self.ta
+        lin = lambda k: _Lin(sd[k + ".weight"], sd[k + ".bias"], ta, dev)          # noqa: E731
+        f32 = lambda k: sd[k].to(device=dev, dtype=torch.float32).contiguous()     # noqa: E731
+
+        def msda(k):
+            ol_w = torch.cat([sd[k + ".sampling_offsets.weight"], sd[k + ".attention_weights.weight"]], 0)
+            ol_b = torch.cat([sd[k + ".sampling_offsets.bias"], sd[k + ".attention_weights.bias"]], 0)
+            return {"ol": _Lin(ol_w, ol_b, ta, dev), "value": lin(k + ".value_proj"), "out": lin(k + ".output_proj")}
+
+        def ln(k):
+            return f32(k + ".weight"), f32(k + ".bias")
+
+        def mha(k):
+            w, b = sd[k + ".in_proj_weight"], sd[k + ".in_proj_bias"]
+            C = self.C
+            return {"q": _Lin(w[:C], b[:C], ta, dev), "k": _Lin(w[C:2 * C], b[C:2 * C], ta, dev),
+                    "qk": _Lin(w[:2 * C], b[:2 * C], ta, dev), "v": _Lin(w[2 * C:], b[2 * C:], ta, dev),
+                    "out": lin(k + ".out_proj")}
+
+        self.level_embed = f32("transformer.level_embed")
+        self.enc = []
+        for i in range(self.n_enc):
+            k = f"transformer.encoder.layers.{i}"
+            self.enc.append({"attn": msda(k + ".self_attn"), "norm1": ln(k + ".norm1"), "lin1": lin(k + ".linear1"),
+                             "lin2": lin(k + ".linear2"), "norm2": ln(k + ".norm2")})
+        self.dec = []
+        for i in range(self.n_dec):
+            k = f"transformer.decoder.layers.{i}"
+            self.dec.append({"self": mha(k + ".self_attn"), "norm2": ln(k + ".norm2"), "attn": msda(k + ".cross_attn"),
+                             "norm1": ln(k + ".norm1"), "lin1": lin(k + ".linear1"), "lin2": lin(k + ".linear2"),
+                             "norm3": ln(k + ".norm3"),
+                             "bbox": [lin(f"bbox_embed.{i}.layers.{j}") for j in range(3)],
+                             "cls": lin(f"class_embed.{i}")})
+        # value projections of all decoder layers share the input (the encoder memory): one stacked GEMM
+        self.dec_value = _Lin(torch.cat([sd[f"transformer.decoder.layers.{i}.cross_attn.value_proj.weight"]
+                                         for i in range(self.n_dec)], 0),
+                              torch.cat([sd[f"transformer.decoder.layers.{i}.cross_attn.value_proj.bias"]
+                                         for i in range(self.n_dec)], 0), ta, dev)
+        self.query_scale = [lin(f"transformer.decoder.query_scale.layers.{j}") for j in range(2)]
+        self.ref_point_head = [lin(f"transformer.decoder.ref_point_head.layers.{j}") for j in range(2)]
+        self.det_anchor = f32("det_anchor")
+        self.det_query_embed = f32("det_query_embed")
+        q = "query_updater"
+        self.upd = {
+            "conf": [lin(f"{q}.confidence_weight_net.0.layers.{j}") for j in range(2)],
+            "fusion": [lin(f"{q}.short_memory_fusion.layers.{j}") for j in range(2)],
+            "pos_head": [lin(f"{q}.query_pos_head.layers.{j}") for j in range(2)],
+            "attn": mha(f"{q}.memory_attn"), "memory_norm": ln(f"{q}.memory_norm"),
+            "mffn": (lin(f"{q}.memory_ffn.linear1"), lin(f"{q}.memory_ffn.linear2"), ln(f"{q}.memory_ffn.norm")),
+            "feat_norm": ln(f"{q}.query_feat_norm"),
+            "fffn": (lin(f"{q}.query_feat_ffn.linear1"), lin(f"{q}.query_feat_ffn.linear2"),
+                     ln(f"{q}.query_feat_ffn.norm")),
+        }
+        i = torch.arange(128, dtype=torch.float32)                                   # models/utils.py:80-81
+        self.dim_t = (10000 ** (2 * torch.div(i, 2, rounding_mode="trunc") / 128)).to(dev)
+
+    # ------------------------------------------------------------------------------------------------ workspace
+    def _alloc(self):
+        dev, ta, S, C, nq, nt = self.dev, self.ta, self.S, self.C, self.nq, self.nt
+        e = lambda *s, dtype=ta: torch.empty(*s, dtype=dtype, device=dev)            # noqa: E731
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)              # noqa: E731
+        LK = self.L * max(self.cfg["n_enc_points"], self.cfg["n_dec_points"])
+        self.shapes_t = torch.as_tensor(self.shapes, dtype=torch.long, device=dev)
+        sizes = [h * w for h, w in self.shapes]
+        self.lsi_host = [sum(sizes[:i]) for i in range(self.L)]
+        self.lsi_t = torch.as_tensor(self.lsi_host, dtype=torch.long, device=dev)
+        # static inputs (filled by load_frame; fixed addresses so a captured graph can be replayed)
+        self.in_src = [f(C, h * w) for h, w in self.shapes]
+        self.in_pos = [f(C, h * w) for h, w in self.shapes]
+        self.in_mask = [torch.zeros(h * w, dtype=torch.uint8, device=dev) for h, w in self.shapes]
+        self.in_track_ref = f(nt, 4)
+        self.in_track_embed = f(nt, C)
+        # encoder
+        self.mask_flat = torch.zeros(S, dtype=torch.uint8, device=dev)
+        self.vr = f(self.L, 2)
+        self.src_tok, self.pos_tok, self.q_tok = e(S, C), e(S, C), e(S, C)
+        self.value = e(S, C)
+        self.ol = f(S, 3 * self.H * LK)
+        self.loc = f(S, self.H, LK, 2)
+        self.attw = f(S, self.H, LK)
+        self.att = e(S, C)
+        self.pre = f(S, C) if self.mode == "fp32" else e(S, C)       # pre-LayerNorm GEMM output
+        self.src1 = e(S, C)
+        self.hid = e(S, self.Fd)
+        self.value_all = e(S, self.n_dec * C)
+        # decoder (Nq rows)
+        self.ref = [f(nq, 4) for _ in range(self.n_dec + 1)]         # ref[0] = init (sigmoid), ref[l+1] after layer l
+        self.pred_box = [f(nq, 4) for _ in range(self.n_dec)]
+        self.pred_logit = [f(nq, self.ncls) for _ in range(self.n_dec)]
+        self.tgt = [e(nq, C) for _ in range(self.n_dec + 1)]         # tgt[0] = queries, tgt[l+1] = output of layer l
+        self.ref_raw = f(nq, 4)
+        self.vr_scale4 = f(4)
+        self.anchor = e(nq, 2 * C)
+        self.d_a, self.d_b, self.d_c = e(nq, C), e(nq, C), e(nq, C)
+        self.query_pos = e(nq, C)
+        self.qk_in = e(nq, C)
+        self.qk = e(nq, 2 * C)
+        self.v = e(nq, C)
+        self.t1, self.t1q, self.t2 = e(nq, C), e(nq, C), e(nq, C)
+        self.d_hid = e(nq, self.Fd)
+        self.delta = f(nq, 4)
+        self.out32 = f(nq, C)
+        self.last_ref_pts, self.init_ref_pts = f(nq, 4), f(nq, 4)
+        # query updater (Nt rows); the track state itself is fp32 (TrackInstances fields)
+        self.st = {k: f(nt, C) for k in ("query_embed", "output_embed", "last_output", "long_memory")}
+        self.st["ref_pts"], self.st["boxes"], self.st["logits"] = f(nt, 4), f(nt, 4), f(nt, self.ncls)
+        self.is_pos = torch.zeros(nt, dtype=torch.uint8, device=dev)
+        self.u_ref = f(nt, 4)
+        self.u_sine = e(nt, 2 * C)
+        self.u_oe, self.u_last, self.u_long = e(nt, C), e(nt, C), e(nt, C)
+        self.u_cat = e(nt, 2 * C)
+        self.u_a, self.u_b, self.u_c, self.u_d = e(nt, C), e(nt, C), e(nt, C), e(nt, C)
+        self.u_big = e(nt, 2 * C)
+        self.u_q, self.u_k, self.u_v = e(nt, C), e(nt, C), e(nt, C)
+        self.u_hid = e(nt, self.Fd)
+
+    # ------------------------------------------------------------------------------------------------ launch helpers
+    def _st(self):
+        return _lib.stream_ptr(self.dev)
+
+    def _ck(self, rc, what):
+        self.launches += 1
+        _lib.check(rc, what)
+
+    def lin(self, x, ldx, L, out, ldo, M, act=0, mul=None, ldmul=0, add=None, ldadd=0, rowzero=None, c_dtype=None,
+            path=0):
+        cd = self.dt if c_dtype is None else c_dtype
+        self._ck(self.lib.memotr_linear(_p(x), ldx, _p(L.w), L.K, _p(L.b), _p(mul), ldmul, _p(add), ldadd, _p(rowzero),
+                                        _p(out), ldo, M, L.N, L.K, self.dt, cd, act, path, self._st()), "linear")
+
+    def ln(self, x, x_dtype, ldx, wb, y, ldy, M, x2=None, ldx2=0, pos=None, ldpos=0, ypos=None, ldypos=0, y32=None,
+           ldy32=0):
+        self._ck(self.lib.memotr_layernorm(_p(x), x_dtype, ldx, _p(x2), ldx2, _p(wb[0]), _p(wb[1]), 1e-5, _p(y), self.dt,
+                                           ldy, _p(pos), ldpos, _p(ypos), ldypos, _p(y32), ldy32, M, self.C, self._st()),
+                 "layernorm")
+
+    def add(self, a, lda, b, ldb, out, ldo, M, N):
+        self._ck(self.lib.memotr_add(_p(a), lda, _p(b), ldb, _p(out), ldo, M, N, self.dt, self._st()), "add")
+
+    def convert(self, src, sdt, lds, dst, ddt, ldd, M, N):
+        self._ck(self.lib.memotr_convert(_p(src), sdt, lds, _p(dst), ddt, ldd, M, N, self._st()), "convert")
+
+    def msda(self, value, stride, ol, ldol, mode, ref4, out, Lq, K):
+        self._ck(self.lib.memotr_msda_prep(_p(ol), ldol, _p(self.shapes_t), _p(self.lsi_t), _p(self.vr), _p(ref4), mode,
+                                           _p(self.loc), _p(self.attw), Lq, self.H, self.L, K, self._st()), "msda_prep")
+        self._ck(self.lib.memotr_msda_forward_ex(_p(value), stride, _p(self.shapes_t), _p(self.lsi_t), _p(self.loc),
+                                                 _p(self.attw), _p(out), 1, self.S, self.H, self.L, Lq, K, self.dt,
+                                                 self._st()), "msda_forward_ex")
+
+    def mha(self, q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, kpm=None):
+        self._ck(self.lib.memotr_mha(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(kpm), _p(out), ldo, Nq, Nk, self.H, 32,
+                                     self.dt, self._st()), "mha")
+
+    def sine(self, pts, scale4, sigmoid, out, N):
+        self._ck(self.lib.memotr_sine_embed(_p(pts), 4, _p(scale4), int(sigmoid), _p(self.dim_t), _p(out), 2 * self.C, N,
+                                            self.dt, self._st()), "sine_embed")
+
+    # ------------------------------------------------------------------------------------------------ inputs
+    def load_frame(self, srcs, masks, pos, track_ref_pts, track_query_embed, non_blocking=True):
+        """Copy one frame's inputs (host or device tensors, fp32 NCHW with batch 1) into the static input buffers."""
+        for l in range(self.L):
+            self.in_src[l].copy_(srcs[l].reshape(self.C, -1), non_blocking=non_blocking)
+            self.in_pos[l].copy_(pos[l].reshape(self.C, -1), non_blocking=non_blocking)
+            self.in_mask[l].copy_(masks[l].reshape(-1).to(torch.uint8), non_blocking=non_blocking)
+        self.in_track_ref.copy_(track_ref_pts, non_blocking=non_blocking)
+        self.in_track_embed.copy_(track_query_embed, non_blocking=non_blocking)
+
+    def load_tracks(self, tracks, non_blocking=True):
+        for k in ("query_embed", "output_embed", "last_output", "long_memory", "ref_pts", "boxes", "logits"):
+            self.st[k].copy_(tracks[k], non_blocking=non_blocking)
+
+    # ------------------------------------------------------------------------------------------------ the frame
+    def forward(self):
+        """Transformer + heads on the loaded frame.  Results stay in the workspace; see results()."""
+        C, S, H, L, dt = self.C, self.S, self.H, self.L, self.dt
+        st = self._st
+        # -- level flattening, level embedding, valid ratios (deformable_transformer.py:196-220)
+        for l, (h, w) in enumerate(self.shapes):
+            self._ck(self.lib.memotr_tokens_from_nchw(_p(self.in_src[l]), _p(self.in_pos[l]), _p(self.level_embed[l]),
+                                                      _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok), C, h * w,
+                                                      self.lsi_host[l], C, dt, st()), "tokens")
+            self._ck(self.lib.memotr_valid_ratio(_p(self.in_mask[l]), h, w, _p(self.vr[l]), st()), "valid_ratio")
+            self.convert_u8(self.in_mask[l], self.mask_flat[self.lsi_host[l]:], h * w)
+        # -- encoder (deformable_encoder.py:109-131)
+        Ke = self.cfg["n_enc_points"]
+        pre_dt = F32 if self.mode == "fp32" else BF16
+        for i, ly in enumerate(self.enc):
+            a = ly["attn"]
+            self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat)
+            self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
+            self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
+            self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=pre_dt)
+            self.ln(self.pre, pre_dt, C, ly["norm1"], self.src1, C, S, x2=self.src_tok, ldx2=C)
+            self.lin(self.src1, C, ly["lin1"], self.hid, self.Fd, S, act=1)
+            self.lin(self.hid, self.Fd, ly["lin2"], self.pre, C, S, c_dtype=pre_dt)
+            self.ln(self.pre, pre_dt, C, ly["norm2"], self.src_tok, C, S, x2=self.src1, ldx2=C,
+                    pos=self.pos_tok, ldpos=C, ypos=self.q_tok, ldypos=C)
+        memory = self.src_tok
+        # -- decoder inputs (memotr.py:209-278, deformable_transformer.py:239-242)
+        nd, nt, nq = self.nd, self.nt, self.nq
+        self.convert(self.det_anchor, F32, 4, self.ref_raw, F32, 4, nd, 4)
+        self.convert(self.in_track_ref, F32, 4, self.ref_raw[nd:], F32, 4, nt, 4)
+        self._ck(self.lib.memotr_unary(_p(self.ref_raw), _p(self.ref[0]), nq * 4, 0, st()), "sigmoid")
+        self.convert(self.det_query_embed, F32, C, self.tgt[0], dt, C, nd, C)
+        self.convert(self.in_track_embed, F32, C, self.tgt[0][nd:], dt, C, nt, C)
+        self.convert(self.vr, F32, 2, self.vr_scale4, F32, 2, 1, 2)          # (vr0.w, vr0.h, vr0.w, vr0.h)
+        self.convert(self.vr, F32, 2, self.vr_scale4[2:], F32, 2, 1, 2)
+        # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
+        self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat)
+        Kd = self.cfg["n_dec_points"]
+        for lid, ly in enumerate(self.dec):
+            out, ref = self.tgt[lid], self.ref[lid]
+            n = nq if lid >= self.merge else nd              # det/track split before the merge layer (:292-297)
+            # DAB positional query (deformable_decoder.py:88-95)
+            self.sine(ref, self.vr_scale4, False, self.anchor, nq)
+            self.lin(self.anchor, 2 * C, self.ref_point_head[0], self.d_a, C, nq, act=1)
+            if lid == 0:
+                self.lin(self.d_a, C, self.ref_point_head[1], self.query_pos, C, nq)
+            else:
+                self.lin(self.d_a, C, self.ref_point_head[1], self.d_b, C, nq)
+                self.lin(out, C, self.query_scale[0], self.d_c, C, nq, act=1)
+                self.lin(self.d_c, C, self.query_scale[1], self.query_pos, C, nq, mul=self.d_b, ldmul=C)
+            # self-attention (deformable_decoder.py:245-252)
+            sa = ly["self"]
+            self.add(out, C, self.query_pos, C, self.qk_in, C, n, C)
+            self.lin(self.qk_in, C, sa["qk"], self.qk, 2 * C, n)
+            self.lin(out, C, sa["v"], self.v, C, n)
+            self.mha(self.qk, 2 * C, self.qk[:, C:], 2 * C, self.v, C, self.d_a, C, n, n)
+            self.lin(self.d_a, C, sa["out"], self.d_b, C, n)
+            self.ln(self.d_b, dt, C, ly["norm2"], self.t1, C, n, x2=out, ldx2=C, pos=self.query_pos, ldpos=C,
+                    ypos=self.t1q, ldypos=C)
+            # cross-attention into the encoder memory (deformable_decoder.py:303-313)
+            a = ly["attn"]
+            self.lin(self.t1q, C, a["ol"], self.ol, a["ol"].N, n, c_dtype=F32)
+            self.msda(self.value_all[:, lid * C:], self.n_dec * C, self.ol, a["ol"].N, 1, ref, self.d_a, n, Kd)
+            self.lin(self.d_a, C, a["out"], self.d_b, C, n)
+            self.ln(self.d_b, dt, C, ly["norm1"], self.t2, C, n, x2=self.t1, ldx2=C)
+            # FFN (deformable_decoder.py:263-273)
+            self.lin(self.t2, C, ly["lin1"], self.d_hid, self.Fd, n, act=1)
+            self.lin(self.d_hid, self.Fd, ly["lin2"], self.d_b, C, n)
+            new = self.tgt[lid + 1]
+            last = lid == self.n_dec - 1
+            self.ln(self.d_b, dt, C, ly["norm3"], new, C, n, x2=self.t2, ldx2=C, y32=self.out32 if last else None,
+                    ldy32=C)
+            if n < nq:                                       # track queries bypass the layer (:316-317)
+                self.convert(out[n:], dt, C, new[n:], dt, C, nq - n, C)
+            # box refinement + heads (deformable_decoder.py:139-159, memotr.py:147-162)
+            bb = ly["bbox"]
+            self.lin(new, C, bb[0], self.d_a, C, nq, act=1)
+            self.lin(self.d_a, C, bb[1], self.d_c, C, nq, act=1)
+            self.lin(self.d_c, C, bb[2], self.delta, 4, nq, c_dtype=F32)
+            self._ck(self.lib.memotr_box_refine(_p(self.delta), _p(ref), _p(self.pred_box[lid]), _p(self.ref[lid + 1]),
+                                                nq, nq if lid >= self.merge else nd, st()), "box_refine")
+            self.lin(new, C, ly["cls"], self.pred_logit[lid], self.ncls, nq, c_dtype=F32)
+        self._ck(self.lib.memotr_unary(_p(self.ref[self.n_dec - 1]), _p(self.last_ref_pts), nq * 4, 1, st()), "inv_sig")
+        self._ck(self.lib.memotr_unary(_p(self.ref[0]), _p(self.init_ref_pts), nq * 4, 1, st()), "inv_sig")
+
+    def convert_u8(self, src, dst, n):
+        dst[:n].copy_(src)       # device-to-device byte copy on the current stream (cudaMemcpyAsync; graph-capturable)
+
+    def results(self):
+        """The reference's output dict (memotr.py:180-195), fp32, batch dimension restored."""
+        n = self.n_dec
+        f = lambda t: t.float()[None]                                                  # noqa: E731
+        return {
+            "pred_logits": self.pred_logit[n - 1][None], "pred_bboxes": self.pred_box[n - 1][None],
+            "last_ref_pts": self.last_ref_pts[None], "init_ref_pts": self.init_ref_pts[None],
+            "outputs": self.out32[None],
+            "aux_logits": torch.stack(self.pred_logit[:-1])[:, None], "aux_bboxes": torch.stack(self.pred_box[:-1])[:, None],
+            "aux_queries": torch.stack([f(t)[0] for t in self.tgt[1:n]])[:, None],
+            "memory": f(self.src_tok),
+        }
+
+    # ------------------------------------------------------------------------------------------------ query updater
+    def tracks_from_frame(self):
+        """What RuntimeTracker.update writes into the track instances before the updater runs
+        (runtime_tracker.py:43-45): boxes, logits and output_embed of the track rows of this frame."""
+        nd, nt, C, n = self.nd, self.nt, self.C, self.n_dec
+        self.convert(self.pred_box[n - 1][nd:], F32, 4, self.st["boxes"], F32, 4, nt, 4)
+        self.convert(self.pred_logit[n - 1][nd:], F32, self.ncls, self.st["logits"], F32, self.ncls, nt, self.ncls)
+        self.convert(self.out32[nd:], F32, C, self.st["output_embed"], F32, C, nt, C)
+
+    def update_tracks(self):
+        """QueryUpdater.update_tracks_embedding on the fp32 track state in self.st (query_updater.py:82-166)."""
+        C, nt, dt, st, u = self.C, self.nt, self.dt, self.st, self.upd
+        self._ck(self.lib.memotr_upd_prepare(_p(st["logits"]), self.ncls, _p(st["boxes"]), _p(st["ref_pts"]),
+                                             float(self.cfg["update_thresh"]), _p(self.is_pos), _p(self.u_ref), nt,
+                                             self._st()), "upd_prepare")
+        self.sine(self.u_ref, None, True, self.u_sine, nt)
+        self.convert(st["output_embed"], F32, C, self.u_oe, dt, C, nt, C)
+        self.convert(st["last_output"], F32, C, self.u_cat[:, C:], dt, 2 * C, nt, C)
+        self.convert(st["long_memory"], F32, C, self.u_long, dt, C, nt, C)
+        # confidence gate and short-memory fusion (:109-118)
+        self.lin(self.u_oe, C, u["conf"][0], self.u_a, C, nt, act=1)
+        self.lin(self.u_a, C, u["conf"][1], self.u_cat, 2 * C, nt, act=2, mul=self.u_oe, ldmul=C)
+        self.lin(self.u_cat, 2 * C, u["fusion"][0], self.u_big, 2 * C, nt, act=1)
+        self.lin(self.u_big, 2 * C, u["fusion"][1], self.u_a, C, nt)                 # short memory
+        self.lin(self.u_sine, 2 * C, u["pos_head"][0], self.u_b, C, nt, act=1)
+        self.lin(self.u_b, C, u["pos_head"][1], self.u_c, C, nt)                     # query_pos
+        self.add(self.u_a, C, self.u_c, C, self.u_b, C, nt, C)                        # q = short + pos
+        self.add(self.u_long, C, self.u_c, C, self.u_d, C, nt, C)                     # k = long + pos
+        # long-term-memory attention (:125-128)
+        ma = u["attn"]
+        self.lin(self.u_b, C, ma["q"], self.u_q, C, nt)
+        self.lin(self.u_d, C, ma["k"], self.u_k, C, nt)
+        self.lin(self.u_oe, C, ma["v"], self.u_v, C, nt)
+        self.mha(self.u_q, C, self.u_k, C, self.u_v, C, self.u_a, C, nt, nt)
+        self.lin(self.u_a, C, ma["out"], self.u_b, C, nt)
+        self.ln(self.u_b, dt, C, u["memory_norm"], self.u_a, C, nt, x2=self.u_oe, ldx2=C)
+        l1, l2, nrm = u["mffn"]
+        self.lin(self.u_a, C, l1, self.u_hid, self.Fd, nt, act=1)
+        self.lin(self.u_hid, self.Fd, l2, self.u_b, C, nt)
+        self.ln(self.u_b, dt, C, nrm, self.u_c, C, nt, x2=self.u_a, ldx2=C)
+        # long-memory residual branch (:130-133)
+        self.ln(self.u_c, dt, C, u["feat_norm"], self.u_a, C, nt, x2=self.u_long, ldx2=C)
+        l1, l2, nrm = u["fffn"]
+        self.lin(self.u_a, C, l1, self.u_hid, self.Fd, nt, act=1)
+        self.lin(self.u_hid, self.Fd, l2, self.u_b, C, nt)
+        self.ln(self.u_b, dt, C, nrm, self.u_c, C, nt, x2=self.u_a, ldx2=C)           # query_feat
+        # masked state writes (:135-147); ref_pts was already replaced where is_pos (:99-102)
+        self._ck(self.lib.memotr_upd_finalize(_p(self.is_pos), _p(self.u_c), dt, C, _p(st["output_embed"]),
+                                              _p(st["query_embed"]), _p(st["long_memory"]), _p(st["last_output"]),
+                                              float(self.cfg["long_memory_lambda"]), nt, C, self._st()), "upd_finalize")
+        self.convert(self.u_ref, F32, 4, st["ref_pts"], F32, 4, nt, 4)
+
+    def track_state(self):
+        return {k: v.clone() for k, v in self.st.items()}
+
+    # ------------------------------------------------------------------------------------------------ whole step
+    def step(self):
+        """One hot-path step: frame forward, hand the track rows to the updater, update the track embeddings, and
+        feed the updated (ref_pts, query_embed) back as the next frame's track queries (submit_engine.py:64-72 with
+        the host-side RuntimeTracker glue reduced to the field hand-off of runtime_tracker.py:43-45)."""
+        self.forward()
+        self.tracks_from_frame()
+        self.update_tracks()
+        self.convert(self.st["ref_pts"], F32, 4, self.in_track_ref, F32, 4, self.nt, 4)
+        self.convert(self.st["query_embed"], F32, self.C, self.in_track_embed, F32, self.C, self.nt, self.C)
+
+    def capture(self, fn=None):
+        """Record `fn` (default: step) into a CUDA graph; replay() then re-issues the whole frame with one launch."""
+        fn = fn or self.step
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            fn()                                            # warm-up outside capture (one-time attribute calls etc.)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.launches = 0
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        self.graph, self.graph_launches = g, self.launches
+        return g
+
+    def replay(self):
+        self.graph.replay()
+
+
+def smoke(dev):
+    """Tiny end-to-end engine run against the CPU oracle (called by __graft_entry__.smoke)."""
+    from oracle import frame as oframe
+    from oracle import synth
+    cfg = synth.small_cfg()
+    sd = synth.hot_path_state_dict(cfg, seed=0)
+    x = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 5, seed=1)
+    eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 5, dev, mode="fp32")
+    eng.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
+    eng.forward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = oframe.frame_forward(sd, x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"],
+                                    x["tracks"]["query_embed"], cfg)
+    got = eng.results()
+    for k in ("pred_logits", "pred_bboxes", "outputs"):
+        err = (got[k].cpu() - want[k]).abs().max() / want[k].abs().max()
+        assert err < 1e-4, (k, float(err))

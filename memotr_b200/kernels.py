@@ -1,0 +1,111 @@
+"""memotr_b200/kernels.py -- tensor-level wrappers of the individual C-ABI kernels (allocation + argument plumbing).
+
+The frame engine calls the library directly on its pre-allocated workspace; these functional forms exist for the
+module mirrors, the unit tests and ad-hoc use.  All tensors must be CUDA tensors; nothing here falls back to torch math.
+"""
+import torch
+
+from . import _lib
+
+_ACT = {None: 0, "none": 0, "relu": 1, "sigmoid": 2}
+_PATH = {"auto": 0, "simt": 1, "tc": 2}
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a 2-d tensor with unit column stride"
+    return t.stride(0)
+
+
+def linear(x, weight, bias=None, act=None, mul=None, add=None, rowzero=None, out_dtype=None, path="auto", out=None):
+    """act(x @ weight.T + bias) [* mul] [+ add], rows with rowzero != 0 zeroed.  x (M,K), weight (N,K)."""
+    M, K = x.shape
+    N = weight.shape[0]
+    assert weight.shape[1] == K and x.dtype == weight.dtype
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    if bias is not None:
+        bias = bias.float().contiguous()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_linear(
+            _lib.ptr(x), _ld(x), _lib.ptr(weight), _ld(weight), _lib.ptr(bias), _lib.ptr(mul), _ld(mul) if mul is not None else 0,
+            _lib.ptr(add), _ld(add) if add is not None else 0, _lib.ptr(rowzero), _lib.ptr(out), _ld(out), M, N, K,
+            _lib.dtype_code(x), _lib.dtype_code(out), _ACT[act], _PATH[path], _lib.stream_ptr())
+    _lib.check(rc, "memotr_linear")
+    return out
+
+
+def layernorm(x, gamma, beta, x2=None, pos=None, eps=1e-5, out_dtype=None, want_f32=False):
+    """LayerNorm(x [+ x2]) over the last (256-wide) dimension; returns y, or (y, y + pos), plus an fp32 copy on request."""
+    M, C = x.shape
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((M, C), dtype=out_dtype, device=x.device)
+    ypos = torch.empty_like(y) if pos is not None else None
+    y32 = torch.empty((M, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_layernorm(
+            _lib.ptr(x), _lib.dtype_code(x), _ld(x), _lib.ptr(x2), _ld(x2) if x2 is not None else 0,
+            _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.ptr(y), _lib.dtype_code(y), C, _lib.ptr(pos),
+            _ld(pos) if pos is not None else 0, _lib.ptr(ypos), C, _lib.ptr(y32), C, M, C, _lib.stream_ptr())
+    _lib.check(rc, "memotr_layernorm")
+    res = (y,) + ((ypos,) if pos is not None else ()) + ((y32,) if want_f32 else ())
+    return res[0] if len(res) == 1 else res
+
+
+def mha(q, k, v, n_heads, key_padding_mask=None):
+    """softmax(q k^T / sqrt(32) + mask) v per head; q (Nq, n_heads*32), k/v (Nk, n_heads*32)."""
+    Nq, C = q.shape
+    Nk = k.shape[0]
+    out = torch.empty((Nq, C), dtype=q.dtype, device=q.device)
+    kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().memotr_mha(_lib.ptr(q), _ld(q), _lib.ptr(k), _ld(k), _lib.ptr(v), _ld(v), _lib.ptr(kpm),
+                                   _lib.ptr(out), C, Nq, Nk, n_heads, C // n_heads, _lib.dtype_code(q),
+                                   _lib.stream_ptr())
+    _lib.check(rc, "memotr_mha")
+    return out
+
+
+def msda_prep(ol, spatial_shapes, level_start_index, valid_ratios, n_heads, n_levels, n_points, ref4=None):
+    """-> sampling_loc (Lq,H,L,K,2), attn_weight (Lq,H,L,K).  ref4=None: encoder mode (queries are the pixels)."""
+    Lq = ol.shape[0]
+    loc = torch.empty((Lq, n_heads, n_levels, n_points, 2), dtype=torch.float32, device=ol.device)
+    attn = torch.empty((Lq, n_heads, n_levels, n_points), dtype=torch.float32, device=ol.device)
+    with torch.cuda.device(ol.device):
+        rc = _lib.lib().memotr_msda_prep(_lib.ptr(ol), _ld(ol), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
+                                         _lib.ptr(valid_ratios), _lib.ptr(ref4), 0 if ref4 is None else 1, _lib.ptr(loc),
+                                         _lib.ptr(attn), Lq, n_heads, n_levels, n_points, _lib.stream_ptr())
+    _lib.check(rc, "memotr_msda_prep")
+    return loc, attn
+
+
+def msda_forward_ex(value, spatial_shapes, level_start_index, loc, attn, n_heads):
+    """value (S, >=H*32 columns; may be a column slice of a wider buffer) f32/bf16; loc/attn fp32 -> (Lq, H*32)."""
+    S = value.shape[0]
+    Lq, H, L, K = attn.shape
+    out = torch.empty((Lq, H * 32), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().memotr_msda_forward_ex(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
+                                               _lib.ptr(level_start_index), _lib.ptr(loc), _lib.ptr(attn), _lib.ptr(out),
+                                               1, S, H, L, Lq, K, _lib.dtype_code(value), _lib.stream_ptr())
+    _lib.check(rc, "memotr_msda_forward_ex")
+    return out
+
+
+def sine_embed(pts, dim_t, scale4=None, apply_sigmoid=False, out_dtype=torch.float32):
+    N = pts.shape[0]
+    out = torch.empty((N, 512), dtype=out_dtype, device=pts.device)
+    with torch.cuda.device(pts.device):
+        rc = _lib.lib().memotr_sine_embed(_lib.ptr(pts), _ld(pts), _lib.ptr(scale4), int(apply_sigmoid), _lib.ptr(dim_t),
+                                          _lib.ptr(out), 512, N, _lib.dtype_code(out), _lib.stream_ptr())
+    _lib.check(rc, "memotr_sine_embed")
+    return out
+
+
+def box_refine(delta, ref, n_take):
+    new_ref, ref_next = torch.empty_like(ref), torch.empty_like(ref)
+    with torch.cuda.device(ref.device):
+        rc = _lib.lib().memotr_box_refine(_lib.ptr(delta), _lib.ptr(ref), _lib.ptr(new_ref), _lib.ptr(ref_next),
+                                          ref.shape[0], n_take, _lib.stream_ptr())
+    _lib.check(rc, "memotr_box_refine")
+    return new_ref, ref_next

@@ -75,7 +75,13 @@ def main():
         for lname, lc in locs.items():
             nbytes = (S * 256 + Lq * 8 * 4 * K * 3 + Lq * 256) * 4
             row = {"case": tag, "loc": lname, "Lq": Lq, "K": K, "fp32_bytes": nbytes}
+            if Lq == S:
+                os.environ["MEMOTR_MSDA_MAPPING"] = "linear"
+                row["ours_fwd_fp32_linear_us"], _ = timeit(
+                    lambda: memotr_b200.ms_deform_attn_forward(value, shp, lsi, lc, attn, 64), flush=flush)
+                os.environ["MEMOTR_MSDA_MAPPING"] = "tiled"
             t, tmin = timeit(lambda: memotr_b200.ms_deform_attn_forward(value, shp, lsi, lc, attn, 64), flush=flush)
+            os.environ.pop("MEMOTR_MSDA_MAPPING", None)
             row["ours_fwd_fp32_us"], row["ours_fwd_fp32_min_us"] = t, tmin
             row["ours_fwd_fp32_gbs"] = nbytes / t / 1e3
             row["ours_fwd_fp32_frac"] = row["ours_fwd_fp32_gbs"] / PEAK
