@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the MeMOTR per-frame hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode bf16|fp32] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one frame through the hot path: level flattening -> 6-layer deformable encoder -> 6-layer decoder (300
+detect + 100 track queries) -> class/box heads -> QueryUpdater.update_tracks_embedding, on a synthetic 1333x800
+4-scale pyramid (S = 22323 tokens), DanceTrack hyper-parameters (BASELINE.json configs[1] minus the ResNet-50
+backbone, which SURVEY.md section 8 marks out of scope).  The track queries a step produces feed the next step, so K
+steps are a K-frame clip.
+
+  value   frames/s with the frame inputs already resident in HBM (CUDA-graph replay of the whole step; 4 distinct
+          frames rotate through the input buffers, device-to-device, inside the timed region).
+  e2e     the same metric through the public API with HOST buffers: every step copies the frame (4 feature maps,
+          4 position maps, 4 masks, track queries) from pinned host memory, runs the step and reads pred_logits /
+          pred_bboxes / track embeddings back.
+  roofline   MSDA forward (encoder-shaped launch, the dominant kernel): algorithmic bytes / duration, duration from CUDA
+          events recorded inside the captured graph around that launch.
+  cpu_baseline / --impl reference   the reference's CPU path (oracle/frame.py, the torch restatement pinned against the
+          reference modules) on the host cores.
+N > 1: every rank runs its own sub-clip of K frames (weak scaling) and the ranks exchange their packed track-query
+memory with ONE NCCL all-gather at the end of the clip; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec at 1333x800, 300 det+100 track queries"
+N_TRACKS = 100
+N_ROT = 4   # distinct resident frames rotating through the input buffers (4 x 45.8 MB > 126 MB L2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_fps(steps, warmup):
+    """The reference's CPU path (torch fp32 on all host cores) through the functional oracle."""
+    from oracle import frame as oframe
+    from oracle import synth
+    cfg = oframe.dancetrack_cfg()
+    sd = synth.hot_path_state_dict(cfg, seed=0)
+    x = synth.frame_inputs(cfg, synth.DANCETRACK_SHAPES, N_TRACKS, seed=1)
+    torch.set_num_threads(os.cpu_count())
+    tracks = dict(x["tracks"])
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = oframe.frame_forward(sd, x["srcs"], x["masks"], x["pos"], tracks["ref_pts"], tracks["query_embed"], cfg)
+            nd = cfg["n_det_queries"]
+            tracks.update(boxes=res["pred_bboxes"][0, nd:], logits=res["pred_logits"][0, nd:],
+                          output_embed=res["outputs"][0, nd:])
+            tracks.update({k: v for k, v in oframe.update_tracks(sd, tracks, cfg).items() if k != "is_pos"})
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return len(times) / sum(times), torch.get_num_threads()
+
+
+def gpu_reference_fps(dev, steps, warmup):
+    """The reference GPU path restated: stock PyTorch fp32 ops (TF32 off, main.py:96-97) + the reference's own CUDA op
+    compiled into oracle/_ref.  Reported beside our numbers; None when the .so did not travel."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "MultiScaleDeformableAttention.so")):
+        return None
+    sys.path.insert(0, ref_dir)
+    import MultiScaleDeformableAttention as MSDA
+    from oracle import frame as oframe
+    from oracle import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = oframe.dancetrack_cfg()
+    sd = {k: v.to(dev) for k, v in synth.hot_path_state_dict(cfg, seed=0).items()}
+    x = synth.frame_inputs(cfg, synth.DANCETRACK_SHAPES, N_TRACKS, seed=1)
+    srcs, masks, pos = ([t.to(dev) for t in x[k]] for k in ("srcs", "masks", "pos"))
+    tracks = {k: v.to(dev) for k, v in x["tracks"].items()}
+
+    def core(value, shapes_t, lsi, loc, attn):
+        return MSDA.ms_deform_attn_forward(value.contiguous(), shapes_t, lsi, loc.contiguous(), attn.contiguous(), 64)
+
+    def step():
+        res = oframe.frame_forward(sd, srcs, masks, pos, tracks["ref_pts"], tracks["query_embed"], cfg, core=core)
+        nd = cfg["n_det_queries"]
+        tracks.update(boxes=res["pred_bboxes"][0, nd:], logits=res["pred_logits"][0, nd:],
+                      output_embed=res["outputs"][0, nd:])
+        tracks.update({k: v for k, v in oframe.update_tracks(sd, tracks, cfg).items() if k != "is_pos"})
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            step()
+        e.record()
+        torch.cuda.synchronize(dev)
+    return steps / (s.elapsed_time(e) * 1e-3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / gpu_reference legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+    workload = "DanceTrack hot path: transformer(6 enc + 6 dec, d256, ffn2048, 4 levels S=22323) + heads + " \
+               "QueryUpdater, 300 det + 100 track queries, batch 1, synthetic 1333x800 pyramid, backbone excluded"
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path, all host threads, rank 0 only
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 8))              # bounded sample: one step is one full frame (seconds of CPU)
+        fps, cores = cpu_reference_fps(steps, min(W, 2))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(W, 2), "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "note": "reference CPU path = PyTorch fp32 ops on the host cores with "
+                       "ms_deform_attn_core_pytorch as the sampling core (oracle/frame.py, pinned to the reference modules)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} full frames after {min(W, 2)} warm-up"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from memotr_b200 import synthetic as synth
+    from memotr_b200.engine import FrameEngine
+    cfg = synth.dancetrack_cfg()
+    sd = synth.hot_path_state_dict(cfg, seed=0)
+    frames = [synth.frame_inputs(cfg, synth.DANCETRACK_SHAPES, N_TRACKS, seed=1 + i + 17 * rank) for i in range(N_ROT)]
+    eng = FrameEngine(sd, cfg, synth.DANCETRACK_SHAPES, N_TRACKS, dev, mode=args.mode)
+    eng.enable_msda_timer()
+    L, C, K = eng.L, eng.C, args.steps
+
+    # resident copies of the rotating frames + pinned host copies for the e2e leg
+    res_src = [[f["srcs"][l].reshape(C, -1).to(dev) for l in range(L)] for f in frames]
+    res_pos = [[f["pos"][l].reshape(C, -1).to(dev) for l in range(L)] for f in frames]
+    pin = lambda t: t.contiguous().pin_memory()                                      # noqa: E731
+    host = [{"srcs": [pin(t) for t in f["srcs"]], "pos": [pin(t) for t in f["pos"]],
+             "masks": [pin(t.to(torch.uint8)) for t in f["masks"]]} for f in frames]
+    x0 = frames[0]
+    eng.load_frame(x0["srcs"], x0["masks"], x0["pos"], x0["tracks"]["ref_pts"], x0["tracks"]["query_embed"])
+    eng.load_tracks(x0["tracks"])
+    eng.capture()                                       # records step(): forward + hand-off + updater + feedback
+
+    def feed_resident(i):
+        for l in range(L):
+            eng.in_src[l].copy_(res_src[i % N_ROT][l], non_blocking=True)
+            eng.in_pos[l].copy_(res_pos[i % N_ROT][l], non_blocking=True)
+
+    def reset_clip():
+        eng.in_track_ref.copy_(x0["tracks"]["ref_pts"])
+        eng.in_track_embed.copy_(x0["tracks"]["query_embed"])
+        eng.load_tracks(x0["tracks"], non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def clip_exchange():
+        """One NCCL all-gather of the packed track-query memory per clip."""
+        if world == 1:
+            return None
+        packed = torch.cat([eng.st[k].reshape(-1) for k in ("query_embed", "long_memory", "last_output", "output_embed",
+                                                           "ref_pts", "boxes", "logits")])
+        out = torch.empty(world * packed.numel(), dtype=packed.dtype, device=dev)
+        dist.all_gather_into_tensor(out, packed)
+        return out
+
+    # ---- resident-input throughput ("value") -----------------------------------------------------------------
+    reset_clip()
+    for i in range(W):
+        feed_resident(i)
+        eng.replay()
+    clip_exchange()
+    reset_clip()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(K):
+        feed_resident(i)
+        eng.replay()
+    clip_exchange()
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    msda_us = eng.msda_times_us()                       # the 6 encoder MSDA launches of the last timed step
+
+    # ---- end to end through the public API with host buffers ("e2e") ----------------------------------------------
+    nd = cfg["n_det_queries"]
+    h_logits = torch.empty(eng.nq, eng.ncls).pin_memory()
+    h_boxes = torch.empty(eng.nq, 4).pin_memory()
+    h_embed = torch.empty(eng.nt, C).pin_memory()
+    h_ref = torch.empty(eng.nt, 4).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for k in ("srcs", "pos", "masks") for t in host[0][k])
+    d2h = sum(t.numel() * t.element_size() for t in (h_logits, h_boxes, h_embed, h_ref))
+
+    def e2e_step(i):
+        h = host[i % N_ROT]
+        for l in range(L):
+            eng.in_src[l].copy_(h["srcs"][l].reshape(C, -1), non_blocking=True)
+            eng.in_pos[l].copy_(h["pos"][l].reshape(C, -1), non_blocking=True)
+            eng.in_mask[l].copy_(h["masks"][l].reshape(-1), non_blocking=True)
+        eng.replay()
+        n = eng.n_dec
+        h_logits.copy_(eng.pred_logit[n - 1], non_blocking=True)
+        h_boxes.copy_(eng.pred_box[n - 1], non_blocking=True)
+        h_embed.copy_(eng.st["query_embed"], non_blocking=True)
+        h_ref.copy_(eng.st["ref_pts"], non_blocking=True)
+
+    reset_clip()
+    for i in range(W):
+        e2e_step(i)
+    reset_clip()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    clip_exchange()
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_fps = world * K / (float(ems.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (MSDA forward, encoder-shaped launch) ----------------------------------------
+    S, H, LK = eng.S, eng.H, eng.L * cfg["n_enc_points"]
+    esz = 2 if args.mode == "bf16" else 4
+    # value read once + output written once (activation dtype) + sampling locations and weights (fp32): BASELINE.md sec. 3
+    alg_bytes = S * H * 32 * esz + S * H * 32 * esz + S * H * LK * 3 * 4
+    peak, peak_src = peaks()
+    dur = sum(msda_us) / len(msda_us)
+    achieved = alg_bytes / dur / 1e3
+    fps = world * K / (ms_total * 1e-3)
+    out = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload, "clip": f"{K} chained frames per GPU; N>1: one NCCL all-gather of the packed "
+                   "track-query memory per clip", "l2": f"inputs larger than L2: {N_ROT} resident frames x 45.8 MB rotate "
+                   "through the input buffers and a step touches ~0.5 GB of workspace (L2 = 126 MB)",
+                   "arithmetic": "bf16 GEMM operands + fp32 accumulate/residual/LayerNorm/geometry" if args.mode == "bf16"
+                   else "fp32 everywhere (TF32 off, as the reference)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": eng.graph_launches * K,
+        "roofline": {"kernel": "msda_fwd_vec (encoder-shaped launch, Lq = S = 22323)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "duration_us": dur,
+                     "samples": f"{len(msda_us)} launches (the encoder layers of the last timed step), CUDA events "
+                                "recorded inside the captured graph",
+                     "ceiling_note": "on-chip gather traffic (S*H*L*K*4 corners*32 ch) is ~18x the algorithmic bytes; see DESIGN.md"},
+    }
+    if not args.no_baselines:
+        cpu_fps, cores = cpu_reference_fps(3, 1)
+        out["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": "3 full frames after 1 warm-up (oracle/frame.py on the host cores, torch fp32)"}
+        g = gpu_reference_fps(dev, 10, 3)
+        out["gpu_reference"] = {"value": g, "unit": "frames/s",
+                                "what": "reference models/ops CUDA op (oracle/_ref, compiled from /root/reference) + stock "
+                                        "PyTorch fp32 eager modules (TF32 off) on the same GPU and inputs"} if g else None
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,11 +137,12 @@ MEMOTR_API int memotr_mha(const void *Q, int ldq, const void *K, int ldk, const 
                           const unsigned char *key_padding_mask, void *O, int ldo, int Nq, int Nk, int n_heads,
                           int head_dim, int dtype, void *stream);
 
-/* One pyramid level, (C,HW) fp32 maps -> token rows [row0,row0+HW): src^T, pos^T+level_embed, and their sum.
+/* One pyramid level, (C,HW) fp32 maps -> token rows [row0,row0+HW): src^T, pos^T+level_embed, and their sum, in
+ * `dtype`; src_tok32 (optional) additionally keeps src^T in fp32 (the residual stream of the bf16 engine).
  * models/deformable_transformer.py:200-216 (+ with_pos_embed, models/deformable_encoder.py:124). */
 MEMOTR_API int memotr_tokens_from_nchw(const float *src, const float *pos, const float *level_embed, void *src_tok,
-                                       void *pos_tok, void *q_tok, int C, int HW, int row0, int ld, int dtype,
-                                       void *stream);
+                                       void *pos_tok, void *q_tok, float *src_tok32, int C, int HW, int row0, int ld,
+                                       int dtype, void *stream);
 
 /* valid ratio (w,h) of one level's (H,W) uint8 padding mask -- models/deformable_transformer.py:175-190 */
 MEMOTR_API int memotr_valid_ratio(const unsigned char *mask, int H, int W, float *out2, void *stream);
@@ -176,6 +177,17 @@ MEMOTR_API int memotr_upd_prepare(const float *logits, int ncls, const float *bo
 MEMOTR_API int memotr_upd_finalize(const unsigned char *is_pos, const void *feat, int feat_dtype, int ldf,
                                    const float *out_e, float *query_embed, float *long_memory, float *last_output,
                                    float lam, int Nt, int C, void *stream);
+
+/*
+ * Interval timer for measurement (bench.py): n CUDA events; memotr_timer_record enqueues event `idx` on `stream`
+ * (as an external event-record node when the stream is being captured into a CUDA graph), memotr_timer_elapsed_ms
+ * reads the time between two recorded events after the work has completed.  No reference counterpart (the reference
+ * times with time.time(), train_engine.py:191,251-252).
+ */
+MEMOTR_API void *memotr_timer_create(int n_events);
+MEMOTR_API void memotr_timer_destroy(void *timer);
+MEMOTR_API int memotr_timer_record(void *timer, int idx, void *stream);
+MEMOTR_API int memotr_timer_elapsed_ms(void *timer, int idx_start, int idx_stop, float *ms);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ _SIGNATURES = {
     "memotr_linear": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 7 + [_vp], _i),
     "memotr_layernorm": ([_vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp], _i),
     "memotr_mha": ([_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 5 + [_vp], _i),
-    "memotr_tokens_from_nchw": ([_vp] * 6 + [_i] * 5 + [_vp], _i),
+    "memotr_tokens_from_nchw": ([_vp] * 7 + [_i] * 5 + [_vp], _i),
     "memotr_valid_ratio": ([_vp, _i, _i, _vp, _vp], _i),
     "memotr_sine_embed": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp], _i),
     "memotr_add": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
@@ -38,6 +38,10 @@ _SIGNATURES = {
     "memotr_unary": ([_vp, _vp, _l, _i, _vp], _i),
     "memotr_upd_prepare": ([_vp, _i, _vp, _vp, _f, _vp, _vp, _i, _vp], _i),
     "memotr_upd_finalize": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp], _i),
+    "memotr_timer_create": ([_i], _vp),
+    "memotr_timer_destroy": ([_vp], None),
+    "memotr_timer_record": ([_vp, _i, _vp], _i),
+    "memotr_timer_elapsed_ms": ([_vp, _i, _i, _vp], _i),
 }
 
 

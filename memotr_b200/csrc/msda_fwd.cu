@@ -280,8 +280,11 @@ static int launch_vec(const void *value, const int64_t *shapes, const int64_t *l
                       void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st) {
   constexpr int G = 32 / Row<T>::CH;
   const long n_qh = (long)B * Lq * H;
-  const char *force = getenv("MEMOTR_MSDA_MAPPING");  // debugging override: "linear" | "tiled"
-  const bool tiled = force ? (force[0] == 't' && Lq == S) : (Lq == S && n_qh >= 4096);
+  // Mapping B measured SLOWER than mapping A on B200 (profiles/r01_micro_msda_v2_tiled.json: 125 vs 104 us on the
+  // encoder-shaped call even with spatially coherent samples), i.e. the kernel is not bound by L1/L2 hit rates; it
+  // stays available for experiments through MEMOTR_MSDA_MAPPING=tiled.
+  const char *force = getenv("MEMOTR_MSDA_MAPPING");
+  const bool tiled = force && force[0] == 't' && Lq == S;
   if (tiled) {
     // upper bound on the work items without reading the device-side shapes: every 8x8 patch holds >= 1 pixel
     const long max_work = (long)B * H * S;

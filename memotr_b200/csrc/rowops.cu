@@ -77,12 +77,11 @@ layernorm256_kernel(const TX *__restrict__ x, int ldx, const TX *__restrict__ x2
   store8<TY>(y + (long)row * ldy + c0, v);
   if (y32) store8<float>(y32 + (long)row * ldy32 + c0, v);
   if (ypos) {
-    float p[8], r[8];
+    float p[8];
     load8<TY>(pos + (long)row * ldpos + c0, p);
-    load8<TY>(y + (long)row * ldy + c0, r);  // the value as stored (rounded to TY), as the reference adds tensors
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] += p[i];
-    store8<TY>(ypos + (long)row * ldypos + c0, r);
+    for (int i = 0; i < 8; ++i) p[i] += v[i];  // fp32 sum, rounded once on store
+    store8<TY>(ypos + (long)row * ldypos + c0, p);
   }
 }
 
@@ -157,7 +156,8 @@ msda_prep_kernel(const float *__restrict__ ol, int ldol, const int64_t *__restri
 template <typename T>
 __global__ void __launch_bounds__(256)
 tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, const float *__restrict__ lvl_embed,
-              T *__restrict__ src_tok, T *__restrict__ pos_tok, T *__restrict__ q_tok, int C, int HW, int row0, int ld) {
+              T *__restrict__ src_tok, T *__restrict__ pos_tok, T *__restrict__ q_tok, float *__restrict__ src_tok32,
+              int C, int HW, int row0, int ld) {
   __shared__ float ts[32][33], tp[32][33];
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -175,6 +175,7 @@ tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, cons
       const float pe = tp[tx][i] + lvl_embed[c];
       const long o = (long)(row0 + p) * ld + c;
       src_tok[o] = from_f32<T>(s);
+      if (src_tok32) src_tok32[o] = s;
       pos_tok[o] = from_f32<T>(pe);
       q_tok[o] = from_f32<T>(s + pe);
     }
@@ -347,8 +348,8 @@ extern "C" int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatia
 }
 
 extern "C" int memotr_tokens_from_nchw(const float *src, const float *pos, const float *level_embed, void *src_tok,
-                                       void *pos_tok, void *q_tok, int C, int HW, int row0, int ld, int dtype,
-                                       void *stream) {
+                                       void *pos_tok, void *q_tok, float *src_tok32, int C, int HW, int row0, int ld,
+                                       int dtype, void *stream) {
   MEMOTR_REQUIRE(src && pos && level_embed && src_tok && pos_tok && q_tok && C > 0 && HW > 0 && ld >= C,
                  "tokens_from_nchw: bad arguments");
   MEMOTR_DTYPE_AB(dtype);
@@ -356,10 +357,11 @@ extern "C" int memotr_tokens_from_nchw(const float *src, const float *pos, const
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MEMOTR_F32)
     tokens_kernel<float><<<grid, 256, 0, st>>>(src, pos, level_embed, (float *)src_tok, (float *)pos_tok,
-                                               (float *)q_tok, C, HW, row0, ld);
+                                               (float *)q_tok, src_tok32, C, HW, row0, ld);
   else
     tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, pos, level_embed, (__nv_bfloat16 *)src_tok,
-                                                       (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, C, HW, row0, ld);
+                                                       (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, HW,
+                                                       row0, ld);
   return check_launch("tokens_from_nchw");
 }
 

@@ -11,8 +11,9 @@ CUDA graph (`capture()`), which removes the per-launch host cost and the host sy
 
 Two arithmetic modes:
   "fp32"  fp32 storage, fp32 CUDA-core GEMMs -> matches the reference's fp32 (TF32-off) path to <= 1e-4
-  "bf16"  bf16 activations/weights, tcgen05 tensor-core GEMMs with fp32 accumulation, fp32 LayerNorm statistics,
-          fp32 geometry (reference points, sampling locations, boxes, logits) -> <= 1e-2
+  "bf16"  bf16 GEMM operands (activations fed to GEMMs, weights, value maps), tcgen05 tensor-core GEMMs with fp32
+          accumulation; the residual stream, the pre-LayerNorm sums, LayerNorm itself and all geometry (reference points,
+          sampling locations, boxes, logits) stay fp32 -> <= 1e-2
 """
 import math
 
@@ -59,6 +60,23 @@ class FrameEngine:
         self._pack(state_dict)
         self._alloc()
         self.graph = None
+        self.timer = None
+
+    # ------------------------------------------------------------------------------------------------ measurement
+    def enable_msda_timer(self):
+        """Bracket every encoder-layer MSDA forward launch with a pair of (graph-capturable) CUDA events."""
+        self.timer = self.lib.memotr_timer_create(2 * self.n_enc)
+        self._timer_slot = 0
+
+    def msda_times_us(self):
+        """Durations of the encoder MSDA forward launches of the most recent step (call after a synchronize)."""
+        import ctypes
+        out = []
+        ms = ctypes.c_float()
+        for i in range(self.n_enc):
+            _lib.check(self.lib.memotr_timer_elapsed_ms(self.timer, 2 * i, 2 * i + 1, ctypes.byref(ms)), "timer_elapsed")
+            out.append(ms.value * 1e3)
+        return out
 
     # ------------------------------------------------------------------------------------------------ weights
     def _pack(self, sd):
@@ -143,8 +161,12 @@ class FrameEngine:
         self.loc = f(S, self.H, LK, 2)
         self.attw = f(S, self.H, LK)
         self.att = e(S, C)
-        self.pre = f(S, C) if self.mode == "fp32" else e(S, C)       # pre-LayerNorm GEMM output
+        self.pre = f(S, C)                                           # pre-LayerNorm GEMM output, always fp32
         self.src1 = e(S, C)
+        # fp32 residual stream: in fp32 mode the activation buffers are their own masters
+        fp32 = self.mode == "fp32"
+        self.src32 = self.src_tok if fp32 else f(S, C)
+        self.src1_32 = self.src1 if fp32 else f(S, C)
         self.hid = e(S, self.Fd)
         self.value_all = e(S, self.n_dec * C)
         # decoder (Nq rows)
@@ -152,6 +174,7 @@ class FrameEngine:
         self.pred_box = [f(nq, 4) for _ in range(self.n_dec)]
         self.pred_logit = [f(nq, self.ncls) for _ in range(self.n_dec)]
         self.tgt = [e(nq, C) for _ in range(self.n_dec + 1)]         # tgt[0] = queries, tgt[l+1] = output of layer l
+        self.tgt32 = self.tgt if fp32 else [f(nq, C) for _ in range(self.n_dec + 1)]
         self.ref_raw = f(nq, 4)
         self.vr_scale4 = f(4)
         self.anchor = e(nq, 2 * C)
@@ -161,9 +184,11 @@ class FrameEngine:
         self.qk = e(nq, 2 * C)
         self.v = e(nq, C)
         self.t1, self.t1q, self.t2 = e(nq, C), e(nq, C), e(nq, C)
+        self.t1_32 = self.t1 if fp32 else f(nq, C)
+        self.t2_32 = self.t2 if fp32 else f(nq, C)
+        self.d_pre = f(nq, C)
         self.d_hid = e(nq, self.Fd)
         self.delta = f(nq, 4)
-        self.out32 = f(nq, C)
         self.last_ref_pts, self.init_ref_pts = f(nq, 4), f(nq, 4)
         # query updater (Nt rows); the track state itself is fp32 (TrackInstances fields)
         self.st = {k: f(nt, C) for k in ("query_embed", "output_embed", "last_output", "long_memory")}
@@ -177,6 +202,9 @@ class FrameEngine:
         self.u_big = e(nt, 2 * C)
         self.u_q, self.u_k, self.u_v = e(nt, C), e(nt, C), e(nt, C)
         self.u_hid = e(nt, self.Fd)
+        self.u_pre = f(nt, C)
+        self.u_a32 = self.u_a if fp32 else f(nt, C)
+        self.u_c32 = self.u_c if fp32 else f(nt, C)
 
     # ------------------------------------------------------------------------------------------------ launch helpers
     def _st(self):
@@ -192,11 +220,13 @@ class FrameEngine:
         self._ck(self.lib.memotr_linear(_p(x), ldx, _p(L.w), L.K, _p(L.b), _p(mul), ldmul, _p(add), ldadd, _p(rowzero),
                                         _p(out), ldo, M, L.N, L.K, self.dt, cd, act, path, self._st()), "linear")
 
-    def ln(self, x, x_dtype, ldx, wb, y, ldy, M, x2=None, ldx2=0, pos=None, ldpos=0, ypos=None, ldypos=0, y32=None,
-           ldy32=0):
-        self._ck(self.lib.memotr_layernorm(_p(x), x_dtype, ldx, _p(x2), ldx2, _p(wb[0]), _p(wb[1]), 1e-5, _p(y), self.dt,
-                                           ldy, _p(pos), ldpos, _p(ypos), ldypos, _p(y32), ldy32, M, self.C, self._st()),
-                 "layernorm")
+    def ln(self, x, wb, y, M, x2=None, y32=None, pos=None, ypos=None):
+        """y = LN(x + x2) in the activation dtype (+ fp32 master y32, + ypos = y + pos).  x, x2, y32: fp32, ld = C."""
+        C = self.C
+        if y32 is not None and y32.data_ptr() == y.data_ptr():
+            y32 = None                                           # fp32 mode: y is its own master
+        self._ck(self.lib.memotr_layernorm(_p(x), F32, C, _p(x2), C, _p(wb[0]), _p(wb[1]), 1e-5, _p(y), self.dt, C,
+                                           _p(pos), C, _p(ypos), C, _p(y32), C, M, C, self._st()), "layernorm")
 
     def add(self, a, lda, b, ldb, out, ldo, M, N):
         self._ck(self.lib.memotr_add(_p(a), lda, _p(b), ldb, _p(out), ldo, M, N, self.dt, self._st()), "add")
@@ -207,9 +237,16 @@ class FrameEngine:
     def msda(self, value, stride, ol, ldol, mode, ref4, out, Lq, K):
         self._ck(self.lib.memotr_msda_prep(_p(ol), ldol, _p(self.shapes_t), _p(self.lsi_t), _p(self.vr), _p(ref4), mode,
                                            _p(self.loc), _p(self.attw), Lq, self.H, self.L, K, self._st()), "msda_prep")
+        timed = self.timer is not None and mode == 0
+        if timed:
+            slot = self._timer_slot % self.n_enc
+            self._timer_slot += 1
+            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
         self._ck(self.lib.memotr_msda_forward_ex(_p(value), stride, _p(self.shapes_t), _p(self.lsi_t), _p(self.loc),
                                                  _p(self.attw), _p(out), 1, self.S, self.H, self.L, Lq, K, self.dt,
                                                  self._st()), "msda_forward_ex")
+        if timed:
+            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
 
     def mha(self, q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, kpm=None):
         self._ck(self.lib.memotr_mha(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(kpm), _p(out), ldo, Nq, Nk, self.H, 32,
@@ -241,32 +278,34 @@ class FrameEngine:
         # -- level flattening, level embedding, valid ratios (deformable_transformer.py:196-220)
         for l, (h, w) in enumerate(self.shapes):
             self._ck(self.lib.memotr_tokens_from_nchw(_p(self.in_src[l]), _p(self.in_pos[l]), _p(self.level_embed[l]),
-                                                      _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok), C, h * w,
+                                                      _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
+                                                      _p(None if self.mode == "fp32" else self.src32), C, h * w,
                                                       self.lsi_host[l], C, dt, st()), "tokens")
             self._ck(self.lib.memotr_valid_ratio(_p(self.in_mask[l]), h, w, _p(self.vr[l]), st()), "valid_ratio")
             self.convert_u8(self.in_mask[l], self.mask_flat[self.lsi_host[l]:], h * w)
         # -- encoder (deformable_encoder.py:109-131)
         Ke = self.cfg["n_enc_points"]
-        pre_dt = F32 if self.mode == "fp32" else BF16
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
             self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat)
             self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
             self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
-            self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=pre_dt)
-            self.ln(self.pre, pre_dt, C, ly["norm1"], self.src1, C, S, x2=self.src_tok, ldx2=C)
+            self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
+            self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
             self.lin(self.src1, C, ly["lin1"], self.hid, self.Fd, S, act=1)
-            self.lin(self.hid, self.Fd, ly["lin2"], self.pre, C, S, c_dtype=pre_dt)
-            self.ln(self.pre, pre_dt, C, ly["norm2"], self.src_tok, C, S, x2=self.src1, ldx2=C,
-                    pos=self.pos_tok, ldpos=C, ypos=self.q_tok, ldypos=C)
+            self.lin(self.hid, self.Fd, ly["lin2"], self.pre, C, S, c_dtype=F32)
+            self.ln(self.pre, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
+                    ypos=self.q_tok)
         memory = self.src_tok
         # -- decoder inputs (memotr.py:209-278, deformable_transformer.py:239-242)
         nd, nt, nq = self.nd, self.nt, self.nq
         self.convert(self.det_anchor, F32, 4, self.ref_raw, F32, 4, nd, 4)
         self.convert(self.in_track_ref, F32, 4, self.ref_raw[nd:], F32, 4, nt, 4)
         self._ck(self.lib.memotr_unary(_p(self.ref_raw), _p(self.ref[0]), nq * 4, 0, st()), "sigmoid")
-        self.convert(self.det_query_embed, F32, C, self.tgt[0], dt, C, nd, C)
-        self.convert(self.in_track_embed, F32, C, self.tgt[0][nd:], dt, C, nt, C)
+        self.convert(self.det_query_embed, F32, C, self.tgt32[0], F32, C, nd, C)
+        self.convert(self.in_track_embed, F32, C, self.tgt32[0][nd:], F32, C, nt, C)
+        if self.mode != "fp32":
+            self.convert(self.tgt32[0], F32, C, self.tgt[0], dt, C, nq, C)
         self.convert(self.vr, F32, 2, self.vr_scale4, F32, 2, 1, 2)          # (vr0.w, vr0.h, vr0.w, vr0.h)
         self.convert(self.vr, F32, 2, self.vr_scale4[2:], F32, 2, 1, 2)
         # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
@@ -290,24 +329,24 @@ class FrameEngine:
             self.lin(self.qk_in, C, sa["qk"], self.qk, 2 * C, n)
             self.lin(out, C, sa["v"], self.v, C, n)
             self.mha(self.qk, 2 * C, self.qk[:, C:], 2 * C, self.v, C, self.d_a, C, n, n)
-            self.lin(self.d_a, C, sa["out"], self.d_b, C, n)
-            self.ln(self.d_b, dt, C, ly["norm2"], self.t1, C, n, x2=out, ldx2=C, pos=self.query_pos, ldpos=C,
-                    ypos=self.t1q, ldypos=C)
+            self.lin(self.d_a, C, sa["out"], self.d_pre, C, n, c_dtype=F32)
+            self.ln(self.d_pre, ly["norm2"], self.t1, n, x2=self.tgt32[lid], y32=self.t1_32, pos=self.query_pos,
+                    ypos=self.t1q)
             # cross-attention into the encoder memory (deformable_decoder.py:303-313)
             a = ly["attn"]
             self.lin(self.t1q, C, a["ol"], self.ol, a["ol"].N, n, c_dtype=F32)
             self.msda(self.value_all[:, lid * C:], self.n_dec * C, self.ol, a["ol"].N, 1, ref, self.d_a, n, Kd)
-            self.lin(self.d_a, C, a["out"], self.d_b, C, n)
-            self.ln(self.d_b, dt, C, ly["norm1"], self.t2, C, n, x2=self.t1, ldx2=C)
+            self.lin(self.d_a, C, a["out"], self.d_pre, C, n, c_dtype=F32)
+            self.ln(self.d_pre, ly["norm1"], self.t2, n, x2=self.t1_32, y32=self.t2_32)
             # FFN (deformable_decoder.py:263-273)
             self.lin(self.t2, C, ly["lin1"], self.d_hid, self.Fd, n, act=1)
-            self.lin(self.d_hid, self.Fd, ly["lin2"], self.d_b, C, n)
-            new = self.tgt[lid + 1]
-            last = lid == self.n_dec - 1
-            self.ln(self.d_b, dt, C, ly["norm3"], new, C, n, x2=self.t2, ldx2=C, y32=self.out32 if last else None,
-                    ldy32=C)
+            self.lin(self.d_hid, self.Fd, ly["lin2"], self.d_pre, C, n, c_dtype=F32)
+            new, new32 = self.tgt[lid + 1], self.tgt32[lid + 1]
+            self.ln(self.d_pre, ly["norm3"], new, n, x2=self.t2_32, y32=new32)
             if n < nq:                                       # track queries bypass the layer (:316-317)
-                self.convert(out[n:], dt, C, new[n:], dt, C, nq - n, C)
+                self.convert(self.tgt32[lid][n:], F32, C, new32[n:], F32, C, nq - n, C)
+                if self.mode != "fp32":
+                    self.convert(out[n:], dt, C, new[n:], dt, C, nq - n, C)
             # box refinement + heads (deformable_decoder.py:139-159, memotr.py:147-162)
             bb = ly["bbox"]
             self.lin(new, C, bb[0], self.d_a, C, nq, act=1)
@@ -329,9 +368,9 @@ class FrameEngine:
         return {
             "pred_logits": self.pred_logit[n - 1][None], "pred_bboxes": self.pred_box[n - 1][None],
             "last_ref_pts": self.last_ref_pts[None], "init_ref_pts": self.init_ref_pts[None],
-            "outputs": self.out32[None],
+            "outputs": self.tgt32[n][None],
             "aux_logits": torch.stack(self.pred_logit[:-1])[:, None], "aux_bboxes": torch.stack(self.pred_box[:-1])[:, None],
-            "aux_queries": torch.stack([f(t)[0] for t in self.tgt[1:n]])[:, None],
+            "aux_queries": torch.stack(self.tgt32[1:n])[:, None],
             "memory": f(self.src_tok),
         }
 
@@ -342,7 +381,7 @@ class FrameEngine:
         nd, nt, C, n = self.nd, self.nt, self.C, self.n_dec
         self.convert(self.pred_box[n - 1][nd:], F32, 4, self.st["boxes"], F32, 4, nt, 4)
         self.convert(self.pred_logit[n - 1][nd:], F32, self.ncls, self.st["logits"], F32, self.ncls, nt, self.ncls)
-        self.convert(self.out32[nd:], F32, C, self.st["output_embed"], F32, C, nt, C)
+        self.convert(self.tgt32[n][nd:], F32, C, self.st["output_embed"], F32, C, nt, C)
 
     def update_tracks(self):
         """QueryUpdater.update_tracks_embedding on the fp32 track state in self.st (query_updater.py:82-166)."""
@@ -369,20 +408,20 @@ class FrameEngine:
         self.lin(self.u_d, C, ma["k"], self.u_k, C, nt)
         self.lin(self.u_oe, C, ma["v"], self.u_v, C, nt)
         self.mha(self.u_q, C, self.u_k, C, self.u_v, C, self.u_a, C, nt, nt)
-        self.lin(self.u_a, C, ma["out"], self.u_b, C, nt)
-        self.ln(self.u_b, dt, C, u["memory_norm"], self.u_a, C, nt, x2=self.u_oe, ldx2=C)
+        self.lin(self.u_a, C, ma["out"], self.u_pre, C, nt, c_dtype=F32)
+        self.ln(self.u_pre, u["memory_norm"], self.u_a, nt, x2=st["output_embed"], y32=self.u_a32)
         l1, l2, nrm = u["mffn"]
         self.lin(self.u_a, C, l1, self.u_hid, self.Fd, nt, act=1)
-        self.lin(self.u_hid, self.Fd, l2, self.u_b, C, nt)
-        self.ln(self.u_b, dt, C, nrm, self.u_c, C, nt, x2=self.u_a, ldx2=C)
+        self.lin(self.u_hid, self.Fd, l2, self.u_pre, C, nt, c_dtype=F32)
+        self.ln(self.u_pre, nrm, self.u_c, nt, x2=self.u_a32, y32=self.u_c32)
         # long-memory residual branch (:130-133)
-        self.ln(self.u_c, dt, C, u["feat_norm"], self.u_a, C, nt, x2=self.u_long, ldx2=C)
+        self.ln(self.u_c32, u["feat_norm"], self.u_a, nt, x2=st["long_memory"], y32=self.u_a32)
         l1, l2, nrm = u["fffn"]
         self.lin(self.u_a, C, l1, self.u_hid, self.Fd, nt, act=1)
-        self.lin(self.u_hid, self.Fd, l2, self.u_b, C, nt)
-        self.ln(self.u_b, dt, C, nrm, self.u_c, C, nt, x2=self.u_a, ldx2=C)           # query_feat
+        self.lin(self.u_hid, self.Fd, l2, self.u_pre, C, nt, c_dtype=F32)
+        self.ln(self.u_pre, nrm, self.u_c, nt, x2=self.u_a32, y32=self.u_c32)        # query_feat
         # masked state writes (:135-147); ref_pts was already replaced where is_pos (:99-102)
-        self._ck(self.lib.memotr_upd_finalize(_p(self.is_pos), _p(self.u_c), dt, C, _p(st["output_embed"]),
+        self._ck(self.lib.memotr_upd_finalize(_p(self.is_pos), _p(self.u_c32), F32, C, _p(st["output_embed"]),
                                               _p(st["query_embed"]), _p(st["long_memory"]), _p(st["last_output"]),
                                               float(self.cfg["long_memory_lambda"]), nt, C, self._st()), "upd_finalize")
         self.convert(self.u_ref, F32, 4, st["ref_pts"], F32, 4, nt, 4)
@@ -423,8 +462,8 @@ class FrameEngine:
 
 def smoke(dev):
     """Tiny end-to-end engine run against the CPU oracle (called by __graft_entry__.smoke)."""
-    from oracle import frame as oframe
-    from oracle import synth
+    from oracle import frame as oframe          # checker, smoke only
+    from . import synthetic as synth
     cfg = synth.small_cfg()
     sd = synth.hot_path_state_dict(cfg, seed=0)
     x = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 5, seed=1)

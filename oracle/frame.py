@@ -305,10 +305,8 @@ def update_tracks(sd, t, cfg, key="query_updater"):
 
 # ----------------------------------------------------------------------------------------------- configs
 def dancetrack_cfg():
-    """Hot-path hyper-parameters of configs/train_dancetrack.yaml:60-75,89-90."""
-    return dict(d_model=256, d_ffn=2048, n_levels=4, n_heads=8, n_enc_points=4, n_dec_points=4, n_enc_layers=6,
-                n_dec_layers=6, merge_det_track_layer=1, n_det_queries=300, update_thresh=0.5,
-                long_memory_lambda=0.01, num_classes=1)
+    from memotr_b200.synthetic import dancetrack_cfg as _cfg
+    return _cfg()
 
 
 def to_reference_config(cfg):

@@ -1,177 +1,4 @@
-"""oracle/synth.py -- deterministic synthetic weights and inputs for the hot path.  TEST INFRASTRUCTURE ONLY.
-
-Everything is drawn from a seeded *CPU* torch.Generator, so the authoring container (where the reference is
-importable and golden outputs are produced, oracle/make_golden.py) and the GPU box (where only this repo
-exists) regenerate bit-identical tensors from (cfg, seed) and the golden files only need to hold outputs.
-
-Input recipes follow SURVEY.md section 8d:
-  op level    models/ops/test.py:33-36  (value = rand*0.01, loc = rand [or rand*1.2-0.1 for the border
-              variant], attention weights = rand+1e-5 normalised over (L,K))
-  frame level srcs/pos = randn(1,C,H_l,W_l), masks all-False or right/bottom padded, det_anchor/det_query_embed
-              = randn, Nt synthetic tracks with randn embeddings and logits kept >= 0.1 away from the 0.5 score
-              threshold.
-"""
-import math
-
-import torch
-
-DANCETRACK_SHAPES = ((100, 168), (50, 84), (25, 42), (13, 21))          # 1333x800 -> padded 800x1344, S=22323
-BDD_SHAPES = ((92, 160), (46, 80), (23, 40), (12, 20))                  # 1280x720 -> padded 736x1280, S=19560
-BDD_SHAPES_L5 = BDD_SHAPES + ((6, 10),)
-
-
-def _gen(seed):
-    g = torch.Generator(device="cpu")
-    g.manual_seed(int(seed))
-    return g
-
-
-def msda_inputs(shapes, B=1, H=8, D=32, K=4, Lq=100, seed=3, border=False, dtype=torch.float32):
-    """-> value (B,S,H,D), shapes (L,2) i64, level_start_index (L,) i64, loc (B,Lq,H,L,K,2), attn (B,Lq,H,L,K)."""
-    g = _gen(seed)
-    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
-    L = shapes_t.shape[0]
-    S = int((shapes_t[:, 0] * shapes_t[:, 1]).sum())
-    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
-    value = torch.rand(B, S, H, D, generator=g) * 0.01
-    loc = torch.rand(B, Lq, H, L, K, 2, generator=g)
-    if border:
-        loc = loc * 1.2 - 0.1
-    attn = torch.rand(B, Lq, H, L, K, generator=g) + 1e-5
-    attn = attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
-    return value.to(dtype), shapes_t, lsi, loc.to(dtype), attn.to(dtype)
-
-
-def hot_path_param_shapes(cfg):
-    """Key -> shape for every hot-path parameter, in the reference's state_dict naming.
-    oracle/make_golden.py asserts this table against the instantiated reference modules."""
-    C, Fd, H, L = cfg["d_model"], cfg["d_ffn"], cfg["n_heads"], cfg["n_levels"]
-    ncls = cfg["num_classes"]
-    t = {}
-
-    def lin(key, o, i):
-        t[key + ".weight"] = (o, i)
-        t[key + ".bias"] = (o,)
-
-    def ln(key):
-        t[key + ".weight"] = (C,)
-        t[key + ".bias"] = (C,)
-
-    def msda(key, K):
-        lin(key + ".sampling_offsets", H * L * K * 2, C)
-        lin(key + ".attention_weights", H * L * K, C)
-        lin(key + ".value_proj", C, C)
-        lin(key + ".output_proj", C, C)
-
-    t["transformer.level_embed"] = (L, C)
-    for i in range(cfg["n_enc_layers"]):
-        k = f"transformer.encoder.layers.{i}"
-        msda(k + ".self_attn", cfg["n_enc_points"])
-        ln(k + ".norm1"); lin(k + ".linear1", Fd, C); lin(k + ".linear2", C, Fd); ln(k + ".norm2")
-    for i in range(cfg["n_dec_layers"]):
-        k = f"transformer.decoder.layers.{i}"
-        t[k + ".self_attn.in_proj_weight"] = (3 * C, C)
-        t[k + ".self_attn.in_proj_bias"] = (3 * C,)
-        lin(k + ".self_attn.out_proj", C, C)
-        ln(k + ".norm2")
-        msda(k + ".cross_attn", cfg["n_dec_points"])
-        ln(k + ".norm1"); lin(k + ".linear1", Fd, C); lin(k + ".linear2", C, Fd); ln(k + ".norm3")
-    lin("transformer.decoder.query_scale.layers.0", C, C)
-    lin("transformer.decoder.query_scale.layers.1", C, C)
-    lin("transformer.decoder.ref_point_head.layers.0", C, 2 * C)
-    lin("transformer.decoder.ref_point_head.layers.1", C, C)
-    q = "query_updater"
-    lin(q + ".confidence_weight_net.0.layers.0", C, C)
-    lin(q + ".confidence_weight_net.0.layers.1", C, C)
-    lin(q + ".short_memory_fusion.layers.0", 2 * C, 2 * C)
-    lin(q + ".short_memory_fusion.layers.1", C, 2 * C)
-    t[q + ".memory_attn.in_proj_weight"] = (3 * C, C)
-    t[q + ".memory_attn.in_proj_bias"] = (3 * C,)
-    lin(q + ".memory_attn.out_proj", C, C)
-    ln(q + ".memory_norm")
-    lin(q + ".memory_ffn.linear1", Fd, C); lin(q + ".memory_ffn.linear2", C, Fd); ln(q + ".memory_ffn.norm")
-    ln(q + ".query_feat_norm")
-    lin(q + ".query_feat_ffn.linear1", Fd, C); lin(q + ".query_feat_ffn.linear2", C, Fd); ln(q + ".query_feat_ffn.norm")
-    lin(q + ".query_pos_head.layers.0", C, 2 * C)
-    lin(q + ".query_pos_head.layers.1", C, C)
-    for i in range(cfg["n_dec_layers"]):
-        lin(f"class_embed.{i}", ncls, C)
-        lin(f"bbox_embed.{i}.layers.0", C, C)
-        lin(f"bbox_embed.{i}.layers.1", C, C)
-        lin(f"bbox_embed.{i}.layers.2", 4, C)
-    t["det_anchor"] = (cfg["n_det_queries"], 4)
-    t["det_query_embed"] = (cfg["n_det_queries"], C)
-    return t
-
-
-def hot_path_state_dict(cfg, seed=0):
-    """Deterministic fp32 weights with magnitudes that keep the graph well-conditioned: fan-in scaled normal
-    weights, small biases, LayerNorm gains near 1, sampling-offset biases on the reference's ring pattern
-    (ms_deform_attn.py:72-81) plus noise so the samples spread a few pixels around each reference point."""
-    g = _gen(seed)
-    sd = {}
-    for key, shape in hot_path_param_shapes(cfg).items():
-        parts = key.split(".")
-        leaf = parts[-1]
-        is_norm = len(parts) >= 2 and "norm" in parts[-2]
-        if is_norm and leaf == "weight":
-            v = 1.0 + 0.1 * torch.randn(shape, generator=g)
-        elif is_norm and leaf == "bias":
-            v = 0.1 * torch.randn(shape, generator=g)
-        elif key.endswith("sampling_offsets.bias"):
-            H, L = cfg["n_heads"], cfg["n_levels"]
-            K = shape[0] // (H * L * 2)
-            th = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
-            ring = torch.stack([th.cos(), th.sin()], -1)
-            ring = (ring / ring.abs().max(-1, keepdim=True)[0]).view(H, 1, 1, 2).repeat(1, L, K, 1)
-            ring = ring * torch.arange(1, K + 1, dtype=torch.float32).view(1, 1, K, 1)
-            v = ring.reshape(-1) + 0.5 * torch.randn(shape, generator=g)
-        elif key.endswith("sampling_offsets.weight"):
-            v = torch.randn(shape, generator=g) * (0.5 / math.sqrt(shape[1]))
-        elif key in ("det_anchor", "det_query_embed", "transformer.level_embed"):
-            v = torch.randn(shape, generator=g)
-        elif leaf in ("weight", "in_proj_weight"):
-            v = torch.randn(shape, generator=g) / math.sqrt(shape[1])
-        else:
-            v = 0.05 * torch.randn(shape, generator=g)
-        sd[key] = v.float()
-    return sd
-
-
-def frame_inputs(cfg, shapes=DANCETRACK_SHAPES, n_tracks=100, seed=1, padded=False):
-    """One synthetic frame for batch size 1.  -> dict(srcs, masks, pos: lists per level;  tracks: dict)."""
-    g = _gen(seed)
-    C = cfg["d_model"]
-    srcs = [torch.randn(1, C, h, w, generator=g) for h, w in shapes]
-    pos = [torch.randn(1, C, h, w, generator=g) for h, w in shapes]
-    masks = []
-    for h, w in shapes:
-        m = torch.zeros(1, h, w, dtype=torch.bool)
-        if padded:                                   # valid region = 1333/1344 wide and 7/8 high
-            m[:, :, int(math.ceil(w * 1333 / 1344)):] = True
-            m[:, int(math.ceil(h * 0.875)):, :] = True
-        masks.append(m)
-    nt = n_tracks
-    logits = torch.randn(nt, cfg["num_classes"], generator=g)
-    logits = logits + torch.sign(logits) * 0.5       # |logit| >= 0.5 => score at least 0.12 away from 0.5
-    tracks = {
-        "ref_pts": torch.randn(nt, 4, generator=g),
-        "query_embed": torch.randn(nt, C, generator=g),
-        "output_embed": torch.randn(nt, C, generator=g),
-        "last_output": torch.randn(nt, C, generator=g),
-        "long_memory": torch.randn(nt, C, generator=g),
-        "logits": logits,
-        "boxes": torch.rand(nt, 4, generator=g) * 0.8 + 0.1,
-    }
-    return {"srcs": srcs, "masks": masks, "pos": pos, "tracks": tracks}
-
-
-def small_cfg():
-    """A reduced configuration (same head dim 32 / d_model 256 as DanceTrack, fewer layers, FFN 256,
-    12 detect queries) used for the committed golden file."""
-    return dict(d_model=256, d_ffn=256, n_levels=4, n_heads=8, n_enc_points=4, n_dec_points=4, n_enc_layers=2,
-                n_dec_layers=3, merge_det_track_layer=1, n_det_queries=12, update_thresh=0.5,
-                long_memory_lambda=0.01, num_classes=1)
-
-
-SMALL_SHAPES = ((12, 20), (6, 10), (3, 5), (2, 3))
+"""oracle/synth.py -- re-export of the synthetic data generator (memotr_b200/synthetic.py: pure tensor generation from
+seeds, no model arithmetic) under its historical name, so checker code reads `from oracle import synth`."""
+from memotr_b200.synthetic import *  # noqa: F401,F403
+from memotr_b200.synthetic import _gen  # noqa: F401
