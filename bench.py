@@ -12,9 +12,10 @@ steps are a K-frame clip.
 
   value   frames/s with the frame inputs already resident in HBM (CUDA-graph replay of the whole step; 4 distinct
           frames rotate through the input buffers, device-to-device, inside the timed region).
-  e2e     the same metric through the public API with HOST buffers: every step copies the frame (4 feature maps,
-          4 position maps, 4 masks, track queries) from pinned host memory, runs the step and reads pred_logits /
-          pred_bboxes / track embeddings back.
+  e2e     the same metric through the public API (memotr_b200.engine.ClipRunner) with HOST buffers: every step copies
+          the frame (4 feature maps, 4 position maps, 4 masks) from pinned host memory -- on a copy stream, double
+          buffered, so the transfer of frame i+1 overlaps the compute of frame i -- runs the step and reads pred_logits /
+          pred_bboxes / the updated track queries back to pinned host memory.
   roofline   MSDA forward (encoder-shaped launch, the dominant kernel): algorithmic bytes / duration, duration from CUDA
           events recorded inside the captured graph around that launch.
   cpu_baseline / --impl reference   the reference's CPU path (oracle/frame.py, the torch restatement pinned against the
@@ -84,14 +85,38 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _pick_cpu_threads(sd, x, cfg):
+    """torch intra-op thread count that runs the reference CPU path fastest on this host.  "All the host threads" is
+    not automatically the fastest setting: on the 128-core GPU hosts the default (one thread per core) ran a frame in
+    52 s against a few seconds with fewer threads (oversubscription on many small ops).  Probe = one encoder layer."""
+    from oracle import frame as oframe
+    src, mask, pos, shapes, lsi, vr = oframe.flatten_levels(sd, "transformer", x["srcs"], x["masks"], x["pos"])
+    ref = oframe.encoder_reference_points(shapes, vr, "cpu")
+    n_cpu = os.cpu_count() or 1
+    best, best_t = None, float("inf")
+    for t in sorted({min(c, n_cpu) for c in (8, 16, 32, 64, n_cpu)}):
+        torch.set_num_threads(t)
+        with torch.no_grad():
+            for rep in range(2):
+                t0 = time.perf_counter()
+                oframe.encoder_layer(sd, "transformer.encoder.layers.0", src, pos, ref, shapes, lsi, mask, cfg)
+                dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = t, dt
+        if dt > 4 * best_t:
+            break
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_fps(steps, warmup):
-    """The reference's CPU path (torch fp32 on all host cores) through the functional oracle."""
+    """The reference's CPU path (torch fp32 on the host cores) through the functional oracle."""
     from oracle import frame as oframe
     from oracle import synth
     cfg = oframe.dancetrack_cfg()
     sd = synth.hot_path_state_dict(cfg, seed=0)
     x = synth.frame_inputs(cfg, synth.DANCETRACK_SHAPES, N_TRACKS, seed=1)
-    torch.set_num_threads(os.cpu_count())
+    threads = _pick_cpu_threads(sd, x, cfg)
     tracks = dict(x["tracks"])
     times = []
     with torch.no_grad():
@@ -104,7 +129,7 @@ def cpu_reference_fps(steps, warmup):
             tracks.update({k: v for k, v in oframe.update_tracks(sd, tracks, cfg).items() if k != "is_pos"})
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return len(times) / sum(times), torch.get_num_threads()
+    return len(times) / sum(times), threads
 
 
 def gpu_reference_fps(dev, steps, warmup):
@@ -177,7 +202,8 @@ def main():
             "config": {"workload": workload, "note": "reference CPU path = PyTorch fp32 ops on the host cores with "
                        "ms_deform_attn_core_pytorch as the sampling core (oracle/frame.py, pinned to the reference modules)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full frames after {min(W, 2)} warm-up"},
+                             "sample": f"{steps} full frames after {min(W, 2)} warm-up; thread count = fastest of "
+                                       f"8/16/32/64/{os.cpu_count()} on a one-encoder-layer probe"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -261,36 +287,25 @@ def main():
     msda_us = eng.msda_times_us()                       # the 6 encoder MSDA launches of the last timed step
 
     # ---- end to end through the public API with host buffers ("e2e") ----------------------------------------------
-    nd = cfg["n_det_queries"]
-    h_logits = torch.empty(eng.nq, eng.ncls).pin_memory()
-    h_boxes = torch.empty(eng.nq, 4).pin_memory()
-    h_embed = torch.empty(eng.nt, C).pin_memory()
-    h_ref = torch.empty(eng.nt, 4).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for k in ("srcs", "pos", "masks") for t in host[0][k])
-    d2h = sum(t.numel() * t.element_size() for t in (h_logits, h_boxes, h_embed, h_ref))
+    from memotr_b200.engine import ClipRunner
+    runner = ClipRunner(eng)
+    h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
+    hf = [(h["srcs"], h["pos"], h["masks"]) for h in host]
 
-    def e2e_step(i):
-        h = host[i % N_ROT]
-        for l in range(L):
-            eng.in_src[l].copy_(h["srcs"][l].reshape(C, -1), non_blocking=True)
-            eng.in_pos[l].copy_(h["pos"][l].reshape(C, -1), non_blocking=True)
-            eng.in_mask[l].copy_(h["masks"][l].reshape(-1), non_blocking=True)
-        eng.replay()
-        n = eng.n_dec
-        h_logits.copy_(eng.pred_logit[n - 1], non_blocking=True)
-        h_boxes.copy_(eng.pred_box[n - 1], non_blocking=True)
-        h_embed.copy_(eng.st["query_embed"], non_blocking=True)
-        h_ref.copy_(eng.st["ref_pts"], non_blocking=True)
+    def e2e_clip(n):
+        runner.prefetch(0, *hf[0])
+        for i in range(n):
+            if i + 1 < n:
+                runner.prefetch((i + 1) % 2, *hf[(i + 1) % N_ROT])
+            runner.run(i % 2)
 
     reset_clip()
-    for i in range(W):
-        e2e_step(i)
+    e2e_clip(W)
     reset_clip()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
-        e2e_step(i)
+    e2e_clip(K)
     clip_exchange()
     e1.record()
     barrier()
@@ -335,7 +350,8 @@ def main():
     if not args.no_baselines:
         cpu_fps, cores = cpu_reference_fps(3, 1)
         out["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                               "sample": "3 full frames after 1 warm-up (oracle/frame.py on the host cores, torch fp32)"}
+                               "sample": "3 full frames after 1 warm-up (oracle/frame.py on the host cores, torch fp32; "
+                                         f"thread count = fastest of 8/16/32/64/{os.cpu_count()} on a one-layer probe)"}
         g = gpu_reference_fps(dev, 10, 3)
         out["gpu_reference"] = {"value": g, "unit": "frames/s",
                                 "what": "reference models/ops CUDA op (oracle/_ref, compiled from /root/reference) + stock "

@@ -130,12 +130,13 @@ MEMOTR_API int memotr_layernorm(const void *x, int x_dtype, int ldx, const void 
 
 /*
  * Multi-head attention core (head_dim 32): O = softmax(Q K^T / sqrt(32) + key_padding_mask) V per head.
- * Q (Nq, n_heads*32) ldq, K/V (Nk, n_heads*32); key_padding_mask (Nk) uint8 or NULL (1 = ignore key).
+ * Q (Nq, n_heads*32) ldq, K/V (Nk, n_heads*32) in in_dtype; O in out_dtype; key_padding_mask (Nk) uint8 or NULL
+ * (1 = ignore key).  The bf16 engine keeps the projected Q/K/V in fp32 (in_dtype F32) and takes O as bf16.
  * nn.MultiheadAttention math path at models/deformable_decoder.py:245-252 and models/query_updater.py:125.
  */
 MEMOTR_API int memotr_mha(const void *Q, int ldq, const void *K, int ldk, const void *V, int ldv,
                           const unsigned char *key_padding_mask, void *O, int ldo, int Nq, int Nk, int n_heads,
-                          int head_dim, int dtype, void *stream);
+                          int head_dim, int in_dtype, int out_dtype, void *stream);
 
 /* One pyramid level, (C,HW) fp32 maps -> token rows [row0,row0+HW): src^T, pos^T+level_embed, and their sum, in
  * `dtype`; src_tok32 (optional) additionally keeps src^T in fp32 (the residual stream of the bf16 engine).

@@ -82,9 +82,52 @@ gemm_simt_kernel(const TA *__restrict__ A, int lda, const TA *__restrict__ W, in
   }
 }
 
+
+// Skinny outputs (N <= 8: the 4-wide box-delta layer and the 1..8-wide class heads, memotr.py:153-154): one warp per
+// row of A, lanes stride over K, N running sums reduced with xor-shuffles.  The tiled kernels would leave 15/16 of a
+// 64-wide tile empty and launch only M/32 CTAs.
+template <typename TA, typename TC>
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const TA *__restrict__ A, int lda, const TA *__restrict__ W, int ldw, TC *__restrict__ C, int ldc, int M,
+                 int N, int K, Epilogue ep) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float a = to_f32<TA>(A[(long)row * lda + k]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) acc[n] = fmaf(a, to_f32<TA>(W[(long)n * ldw + k]), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], s);
+  if (lane < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (lane == n) v = acc[n];
+    if (ep.bias) v += ep.bias[lane];
+    if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
+    if (ep.act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    if (ep.mul) v *= to_f32<TA>(((const TA *)ep.mul)[(long)row * ep.ldmul + lane]);
+    if (ep.add) v += to_f32<TA>(((const TA *)ep.add)[(long)row * ep.ldadd + lane]);
+    if (ep.rowzero && ep.rowzero[row]) v = 0.f;
+    C[(long)row * ldc + lane] = from_f32<TC>(v);
+  }
+}
+
 template <typename TA, typename TC>
 static int launch_simt(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
                        const Epilogue &ep, cudaStream_t st) {
+  if (N <= 8) {
+    gemv_rows_kernel<TA, TC><<<ceil_div(M, 8), 256, 0, st>>>((const TA *)A, lda, (const TA *)W, ldw, (TC *)C, ldc, M, N,
+                                                             K, ep);
+    return check_launch("gemv_rows");
+  }
   // big problems: 128x128 tiles (8x8 per thread); small ones (decoder / updater rows): 32x64 tiles for more CTAs
   if ((long)M * N >= 128L * 128 * kNumSMs) {
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128));

@@ -357,6 +357,145 @@ extern "C" int memotr_msda_forward(const void *value, const int64_t *spatial_sha
   return check_launch("msda_fwd_generic");
 }
 
+// =====================================================================================================================
+// v2 gather ("decode once"), used by the engine entry point.
+//
+// ncu on v1 (profiles/r01_msda_fwd_v1_ncu.md): issue slots 80 % busy, L1 61 %, DRAM 7 % -- the kernel is bound by
+// instruction issue, and more than half of its instructions are the per-point decode (floor, bilinear weights,
+// bounds tests, addresses) that all G lanes of a group repeat.  Here a CTA first decodes every point of its
+// (b,q,head) groups exactly once -- one point per thread, coalesced reads of sampling_loc / attn_weight -- into a
+// shared-memory record of 4 clamped element offsets + 4 corner weights pre-multiplied by the attention weight (zero for
+// out-of-range corners / non-contributing points, so the gather needs no predicates), then the lane groups stream the
+// records (conflict-free 16-byte broadcasts) and do nothing but 16-byte loads and FMAs.
+// Arithmetic differs from the reference order only by the pre-multiplication (<= 1 ulp per term); the bit-exact
+// reference sequence stays in v1, which memotr_msda_forward (the MSDeformAttnFunction path) keeps using.
+namespace memotr {
+
+struct __align__(16) TapRec {
+  int off[4];   // element offsets of the 4 corners from the (batch, head, lane) base pointer, always in range
+  float c[4];   // bilinear weight x attention weight; 0 where the corner / point does not contribute
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fwd_v2(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+            const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int H, int L,
+            int Lq, int K, int xs, long n_qh) {
+  constexpr int D = 32, CH = Row<T>::CH, G = D / CH, GROUPS = 256 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int P = L * K;
+  const int gstride = P * 8 + 4;  // words per group: records + 16 B pad => the groups of a warp hit disjoint banks
+  float *recs = reinterpret_cast<float *>(smem_raw);
+  const long qh0 = (long)blockIdx.x * GROUPS;
+
+  // ---- phase 1: decode, one point per thread --------------------------------------------------------------------
+  for (int idx = threadIdx.x; idx < GROUPS * P; idx += 256) {
+    const int g = idx / P, i = idx - g * P;
+    const long qh = qh0 + g;
+    TapRec r;
+    r.off[0] = r.off[1] = r.off[2] = r.off[3] = 0;
+    r.c[0] = r.c[1] = r.c[2] = r.c[3] = 0.f;
+    if (qh < n_qh) {
+      const int l = i / K;
+      const int Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
+      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + qh * P + i);
+      const float aw = __ldg(attn + qh * P + i);
+      const float h_im = __fmaf_rn(xy.y, (float)Hh, -0.5f), w_im = __fmaf_rn(xy.x, (float)Ww, -0.5f);
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)Hh && w_im < (float)Ww) {
+        const float hfl = floorf(h_im), wfl = floorf(w_im);
+        const int y0 = (int)hfl, x0 = (int)wfl;
+        const float lh = h_im - hfl, lw = w_im - wfl, hh = 1.f - lh, hw = 1.f - lw;
+        const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
+        const int yc0 = max(y0, 0), yc1 = min(y0 + 1, Hh - 1), xc0 = max(x0, 0), xc1 = min(x0 + 1, Ww - 1);
+        const int base = (int)__ldg(lsi + l) * xs;
+        const int ys = Ww * xs;
+        r.off[0] = base + yc0 * ys + xc0 * xs;
+        r.off[1] = base + yc0 * ys + xc1 * xs;
+        r.off[2] = base + yc1 * ys + xc0 * xs;
+        r.off[3] = base + yc1 * ys + xc1 * xs;
+        r.c[0] = (y0ok && x0ok) ? hh * hw * aw : 0.f;
+        r.c[1] = (y0ok && x1ok) ? hh * lw * aw : 0.f;
+        r.c[2] = (y1ok && x0ok) ? lh * hw * aw : 0.f;
+        r.c[3] = (y1ok && x1ok) ? lh * lw * aw : 0.f;
+      }
+    }
+    float4 *dst = reinterpret_cast<float4 *>(recs + g * gstride + i * 8);
+    dst[0] = make_float4(__int_as_float(r.off[0]), __int_as_float(r.off[1]), __int_as_float(r.off[2]),
+                         __int_as_float(r.off[3]));
+    dst[1] = make_float4(r.c[0], r.c[1], r.c[2], r.c[3]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: gather + blend ---------------------------------------------------------------------------------
+  const int g = threadIdx.x / G, sub = threadIdx.x % G;
+  const long qh = qh0 + g;
+  if (qh >= n_qh) return;
+  const int m = (int)(qh % H);
+  const int b = (int)((qh / H) / Lq);
+  const T *vb = value + (long)b * S * xs + m * D + sub * CH;
+  const float4 *rp = reinterpret_cast<const float4 *>(recs + g * gstride);
+  float acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+  constexpr int U = 2;  // points per batch of loads (8 x 16-byte loads in flight per lane)
+  int i = 0;
+  for (; i + U <= P; i += U) {
+    float4 o[U], w[U];
+    float v[U][4][CH];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      o[u] = rp[(i + u) * 2];
+      w[u] = rp[(i + u) * 2 + 1];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      Row<T>::load(vb + __float_as_int(o[u].x), true, v[u][0]);
+      Row<T>::load(vb + __float_as_int(o[u].y), true, v[u][1]);
+      Row<T>::load(vb + __float_as_int(o[u].z), true, v[u][2]);
+      Row<T>::load(vb + __float_as_int(o[u].w), true, v[u][3]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        acc[c] = fmaf(w[u].w, v[u][3][c], fmaf(w[u].z, v[u][2][c], fmaf(w[u].y, v[u][1][c], fmaf(w[u].x, v[u][0][c], acc[c]))));
+  }
+  for (; i < P; ++i) {
+    const float4 o = rp[i * 2], w = rp[i * 2 + 1];
+    float v0[CH], v1[CH], v2[CH], v3[CH];
+    Row<T>::load(vb + __float_as_int(o.x), true, v0);
+    Row<T>::load(vb + __float_as_int(o.y), true, v1);
+    Row<T>::load(vb + __float_as_int(o.z), true, v2);
+    Row<T>::load(vb + __float_as_int(o.w), true, v3);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = fmaf(w.w, v3[c], fmaf(w.z, v2[c], fmaf(w.y, v1[c], fmaf(w.x, v0[c], acc[c]))));
+  }
+  Row<T>::store(out + qh * D + sub * CH, acc);
+}
+
+template <typename T>
+static int launch_v2(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                     void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, bool *handled) {
+  constexpr int GROUPS = 256 / (32 / Row<T>::CH);
+  const size_t smem = (size_t)GROUPS * (L * K * 8 + 4) * sizeof(float);
+  *handled = smem <= 160 * 1024;
+  if (!*handled) return MEMOTR_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(msda_fwd_v2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "msda_fwd_v2: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long n_qh = (long)B * Lq * H;
+  const int grid = (int)((n_qh + GROUPS - 1) / GROUPS);
+  msda_fwd_v2<T><<<grid, 256, smem, st>>>((const T *)value, shapes, lsi, loc, attn, (T *)out, S, H, L, Lq, K, xs, n_qh);
+  return check_launch("msda_fwd_v2");
+}
+
+}  // namespace memotr
+
+using namespace memotr;
+
 // Engine variant: value/output in `dtype` (f32 or bf16), sampling locations and attention weights always fp32 (they
 // come straight from memotr_msda_prep), D == 32, and an explicit pixel stride so the value maps of all decoder layers
 // can live interleaved in one (S, n_layers*256) buffer written by a single GEMM.
@@ -375,6 +514,18 @@ extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
                      ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
                  "msda_forward_ex: misaligned buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  const char *force = getenv("MEMOTR_MSDA_KERNEL");  // debugging override: "v1" keeps the reference-order kernel
+  if (!(force && force[0] == 'v' && force[1] == '1')) {
+    bool handled = false;
+    int rc = dtype == MEMOTR_F32
+                 ? launch_v2<float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L,
+                                    Lq, K, value_pixel_stride, st, &handled)
+                 : dtype == MEMOTR_BF16
+                       ? launch_v2<__nv_bfloat16>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight,
+                                                  output, B, S, H, L, Lq, K, value_pixel_stride, st, &handled)
+                       : fail(MEMOTR_EINVAL, "msda_forward_ex: dtype must be f32 or bf16");
+    if (rc != MEMOTR_OK || handled) return rc;
+  }
   if (dtype == MEMOTR_F32)
     return launch_vec<float, float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H,
                                     L, Lq, K, value_pixel_stride, st);

@@ -148,6 +148,56 @@ msda_prep_kernel(const float *__restrict__ ol, int ldol, const int64_t *__restri
   }
 }
 
+
+// Fast path of the same computation for L*K in {4, 8, 16, 32}: one thread per (q, head, point).  The L*K lanes of a
+// (q, head) are adjacent lanes of one warp, so the softmax max / sum are xor-shuffles, and every global access is
+// fully coalesced (the one-thread-per-(q,head) form above walks 128-byte rows per thread).
+template <int LK>
+__global__ void __launch_bounds__(256)
+msda_prep_fast_kernel(const float *__restrict__ ol, int ldol, const int64_t *__restrict__ shapes,
+                      const int64_t *__restrict__ lsi, const float *__restrict__ vr, const float *__restrict__ ref4,
+                      int mode, float *__restrict__ loc, float *__restrict__ attn, int Lq, int H, int L, int K) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx < (long)Lq * H * LK;
+  const long cidx = live ? idx : (long)Lq * H * LK - 1;  // tail lanes shadow the last element (shuffles stay full-warp)
+  const int i = (int)(cidx % LK);
+  const long qh = cidx / LK;
+  const int q = (int)(qh / H), h = (int)(qh % H);
+  const float *row = ol + (long)q * ldol;
+  const float2 off = *reinterpret_cast<const float2 *>(row + ((long)h * LK + i) * 2);
+  const float logit = row[(long)H * LK * 2 + (long)h * LK + i];
+  float mx = logit;
+#pragma unroll
+  for (int s = LK / 2; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  const float e = expf(logit - mx);
+  float sum = e;
+#pragma unroll
+  for (int s = LK / 2; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const int l = i / K;
+  const float vx = vr[2 * l], vy = vr[2 * l + 1];
+  float lx, ly;
+  if (mode == 0) {
+    int lq = 0;
+    for (int t = 1; t < L; ++t)
+      if (q >= (int)lsi[t]) lq = t;
+    const int Wq = (int)shapes[2 * lq + 1], Hq = (int)shapes[2 * lq];
+    const int p = q - (int)lsi[lq];
+    const int y = p / Wq, x = p - y * Wq;
+    const float bx = ((float)x + 0.5f) / (vr[2 * lq] * (float)Wq);
+    const float by = ((float)y + 0.5f) / (vr[2 * lq + 1] * (float)Hq);
+    lx = bx * vx + off.x / (float)shapes[2 * l + 1];
+    ly = by * vy + off.y / (float)shapes[2 * l];
+  } else {
+    const float4 r = *reinterpret_cast<const float4 *>(ref4 + 4 * q);
+    lx = r.x * vx + off.x / (float)K * (r.z * vx) * 0.5f;
+    ly = r.y * vy + off.y / (float)K * (r.w * vy) * 0.5f;
+  }
+  if (live) {
+    *reinterpret_cast<float2 *>(loc + idx * 2) = make_float2(lx, ly);
+    attn[idx] = e / sum;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // (C, HW) fp32 feature map + position map of one level -> token-major rows [row0, row0+HW) of three (S, C) buffers:
 //   src_tok = src^T ;  pos_tok = pos^T + level_embed ;  q_tok = src_tok + pos_tok
@@ -341,9 +391,26 @@ extern "C" int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatia
   MEMOTR_REQUIRE(mode == 0 || (mode == 1 && ref4), "msda_prep: mode must be 0 (encoder) or 1 (decoder, needs ref4)");
   MEMOTR_REQUIRE(ldol >= 3 * H * L * K, "msda_prep: ldol too small");
   if (Lq == 0) return MEMOTR_OK;
+  const int LK = L * K;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = (ldol % 2 == 0) && ((reinterpret_cast<uintptr_t>(ol) & 7u) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) && (mode == 0 || aligned16(ref4));
+  if (vec_ok && (LK == 4 || LK == 8 || LK == 16 || LK == 32)) {
+    const long nt = (long)Lq * H * LK;
+    const int grid = (int)((nt + 255) / 256);
+#define PREP_FAST(N)                                                                                             \
+  msda_prep_fast_kernel<N><<<grid, 256, 0, st>>>(ol, ldol, spatial_shapes, level_start_idx, valid_ratios, ref4, \
+                                                 mode, sampling_loc, attn_weight, Lq, H, L, K)
+    if (LK == 4) PREP_FAST(4);
+    else if (LK == 8) PREP_FAST(8);
+    else if (LK == 16) PREP_FAST(16);
+    else PREP_FAST(32);
+#undef PREP_FAST
+    return check_launch("msda_prep_fast");
+  }
   const long n = (long)Lq * H;
-  msda_prep_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      ol, ldol, spatial_shapes, level_start_idx, valid_ratios, ref4, mode, sampling_loc, attn_weight, Lq, H, L, K);
+  msda_prep_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(ol, ldol, spatial_shapes, level_start_idx, valid_ratios,
+                                                          ref4, mode, sampling_loc, attn_weight, Lq, H, L, K);
   return check_launch("msda_prep");
 }
 

@@ -181,8 +181,8 @@ class FrameEngine:
         self.d_a, self.d_b, self.d_c = e(nq, C), e(nq, C), e(nq, C)
         self.query_pos = e(nq, C)
         self.qk_in = e(nq, C)
-        self.qk = e(nq, 2 * C)
-        self.v = e(nq, C)
+        self.qk = f(nq, 2 * C)                                        # projected q|k and v stay fp32 (see mha())
+        self.v = f(nq, C)
         self.t1, self.t1q, self.t2 = e(nq, C), e(nq, C), e(nq, C)
         self.t1_32 = self.t1 if fp32 else f(nq, C)
         self.t2_32 = self.t2 if fp32 else f(nq, C)
@@ -200,7 +200,7 @@ class FrameEngine:
         self.u_cat = e(nt, 2 * C)
         self.u_a, self.u_b, self.u_c, self.u_d = e(nt, C), e(nt, C), e(nt, C), e(nt, C)
         self.u_big = e(nt, 2 * C)
-        self.u_q, self.u_k, self.u_v = e(nt, C), e(nt, C), e(nt, C)
+        self.u_q, self.u_k, self.u_v = f(nt, C), f(nt, C), f(nt, C)
         self.u_hid = e(nt, self.Fd)
         self.u_pre = f(nt, C)
         self.u_a32 = self.u_a if fp32 else f(nt, C)
@@ -249,8 +249,10 @@ class FrameEngine:
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
 
     def mha(self, q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, kpm=None):
+        """q/k/v are the fp32 projections (kept in fp32 in both modes: rounding them to bf16 perturbs the attention
+        logits by ~1e-2); the output is an activation (GEMM operand) in the engine dtype."""
         self._ck(self.lib.memotr_mha(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(kpm), _p(out), ldo, Nq, Nk, self.H, 32,
-                                     self.dt, self._st()), "mha")
+                                     F32, self.dt, self._st()), "mha")
 
     def sine(self, pts, scale4, sigmoid, out, N):
         self._ck(self.lib.memotr_sine_embed(_p(pts), 4, _p(scale4), int(sigmoid), _p(self.dim_t), _p(out), 2 * self.C, N,
@@ -326,8 +328,8 @@ class FrameEngine:
             # self-attention (deformable_decoder.py:245-252)
             sa = ly["self"]
             self.add(out, C, self.query_pos, C, self.qk_in, C, n, C)
-            self.lin(self.qk_in, C, sa["qk"], self.qk, 2 * C, n)
-            self.lin(out, C, sa["v"], self.v, C, n)
+            self.lin(self.qk_in, C, sa["qk"], self.qk, 2 * C, n, c_dtype=F32)
+            self.lin(out, C, sa["v"], self.v, C, n, c_dtype=F32)
             self.mha(self.qk, 2 * C, self.qk[:, C:], 2 * C, self.v, C, self.d_a, C, n, n)
             self.lin(self.d_a, C, sa["out"], self.d_pre, C, n, c_dtype=F32)
             self.ln(self.d_pre, ly["norm2"], self.t1, n, x2=self.tgt32[lid], y32=self.t1_32, pos=self.query_pos,
@@ -404,9 +406,9 @@ class FrameEngine:
         self.add(self.u_long, C, self.u_c, C, self.u_d, C, nt, C)                     # k = long + pos
         # long-term-memory attention (:125-128)
         ma = u["attn"]
-        self.lin(self.u_b, C, ma["q"], self.u_q, C, nt)
-        self.lin(self.u_d, C, ma["k"], self.u_k, C, nt)
-        self.lin(self.u_oe, C, ma["v"], self.u_v, C, nt)
+        self.lin(self.u_b, C, ma["q"], self.u_q, C, nt, c_dtype=F32)
+        self.lin(self.u_d, C, ma["k"], self.u_k, C, nt, c_dtype=F32)
+        self.lin(self.u_oe, C, ma["v"], self.u_v, C, nt, c_dtype=F32)
         self.mha(self.u_q, C, self.u_k, C, self.u_v, C, self.u_a, C, nt, nt)
         self.lin(self.u_a, C, ma["out"], self.u_pre, C, nt, c_dtype=F32)
         self.ln(self.u_pre, u["memory_norm"], self.u_a, nt, x2=st["output_embed"], y32=self.u_a32)
@@ -458,6 +460,79 @@ class FrameEngine:
 
     def replay(self):
         self.graph.replay()
+
+
+class ClipRunner:
+    """Public host-buffer API for a clip: frames arrive as pinned HOST tensors, results go back to pinned host tensors.
+
+    The host->device copy of frame i+1 runs on a dedicated copy stream into one of two device staging slots while the
+    captured step of frame i runs on the compute stream (events order slot reuse), so the PCIe transfer (45.7 MB per
+    1333x800 frame) overlaps the compute instead of preceding it.  One replayed CUDA graph per frame; results of frame i
+    are read back asynchronously into pinned host buffers.
+    """
+
+    def __init__(self, eng: "FrameEngine"):
+        self.eng = eng
+        dev = eng.dev
+        if eng.graph is None:
+            eng.capture()
+        self.copy_stream = torch.cuda.Stream(dev)
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)              # noqa: E731
+        self.stage = [{"src": [f(eng.C, h * w) for h, w in eng.shapes], "pos": [f(eng.C, h * w) for h, w in eng.shapes],
+                       "mask": [torch.zeros(h * w, dtype=torch.uint8, device=dev) for h, w in eng.shapes]}
+                      for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(dev))
+        self.host_out = {
+            "pred_logits": torch.empty(eng.nq, eng.ncls).pin_memory(), "pred_bboxes": torch.empty(eng.nq, 4).pin_memory(),
+            "track_query_embed": torch.empty(eng.nt, eng.C).pin_memory(), "track_ref_pts": torch.empty(eng.nt, 4).pin_memory(),
+        }
+        self.h2d_bytes = sum(t.numel() * t.element_size() for k in ("src", "pos", "mask") for t in self.stage[0][k])
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out.values())
+
+    def prefetch(self, slot, srcs, pos, masks):
+        """Enqueue the H2D copy of one frame (pinned host tensors: per level (1,C,H,W) fp32 x2 and (1,H,W) uint8/bool)."""
+        eng, st = self.eng, self.stage[slot]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])
+            for l in range(eng.L):
+                st["src"][l].copy_(srcs[l].reshape(eng.C, -1), non_blocking=True)
+                st["pos"][l].copy_(pos[l].reshape(eng.C, -1), non_blocking=True)
+                st["mask"][l].copy_(masks[l].reshape(-1), non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, slot):
+        """Run the hot-path step on the frame staged in `slot`; enqueue the read-back of its results."""
+        eng, st = self.eng, self.stage[slot]
+        cur = torch.cuda.current_stream(eng.dev)
+        cur.wait_event(self.ready[slot])
+        for l in range(eng.L):
+            eng.in_src[l].copy_(st["src"][l], non_blocking=True)
+            eng.in_pos[l].copy_(st["pos"][l], non_blocking=True)
+            eng.in_mask[l].copy_(st["mask"][l], non_blocking=True)
+        self.free[slot].record(cur)
+        eng.replay()
+        n = eng.n_dec
+        self.host_out["pred_logits"].copy_(eng.pred_logit[n - 1], non_blocking=True)
+        self.host_out["pred_bboxes"].copy_(eng.pred_box[n - 1], non_blocking=True)
+        self.host_out["track_query_embed"].copy_(eng.st["query_embed"], non_blocking=True)
+        self.host_out["track_ref_pts"].copy_(eng.st["ref_pts"], non_blocking=True)
+        return self.host_out
+
+    def run_clip(self, frames):
+        """frames: iterable of (srcs, pos, masks) pinned host tensors.  Returns the last frame's host outputs."""
+        frames = list(frames)
+        if not frames:
+            return None
+        self.prefetch(0, *frames[0])
+        out = None
+        for i in range(len(frames)):
+            if i + 1 < len(frames):
+                self.prefetch((i + 1) % 2, *frames[i + 1])
+            out = self.run(i % 2)
+        return out
 
 
 def smoke(dev):

@@ -52,16 +52,16 @@ def layernorm(x, gamma, beta, x2=None, pos=None, eps=1e-5, out_dtype=None, want_
     return res[0] if len(res) == 1 else res
 
 
-def mha(q, k, v, n_heads, key_padding_mask=None):
+def mha(q, k, v, n_heads, key_padding_mask=None, out_dtype=None):
     """softmax(q k^T / sqrt(32) + mask) v per head; q (Nq, n_heads*32), k/v (Nk, n_heads*32)."""
     Nq, C = q.shape
     Nk = k.shape[0]
-    out = torch.empty((Nq, C), dtype=q.dtype, device=q.device)
+    out = torch.empty((Nq, C), dtype=out_dtype or q.dtype, device=q.device)
     kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
     with torch.cuda.device(q.device):
         rc = _lib.lib().memotr_mha(_lib.ptr(q), _ld(q), _lib.ptr(k), _ld(k), _lib.ptr(v), _ld(v), _lib.ptr(kpm),
                                    _lib.ptr(out), C, Nq, Nk, n_heads, C // n_heads, _lib.dtype_code(q),
-                                   _lib.stream_ptr())
+                                   _lib.dtype_code(out), _lib.stream_ptr())
     _lib.check(rc, "memotr_mha")
     return out
 

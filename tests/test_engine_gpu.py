@@ -135,15 +135,37 @@ def test_mha_core(dtype, Nq, Nk, masked):
     want = (torch.softmax(logits, -1) @ vd).transpose(0, 1).reshape(Nq, 256)
     got = K().mha(q.to(DEV), k.to(DEV), v.to(DEV), 8, kpm.to(DEV) if masked else None).float().cpu()
     assert rel_err(got, want) < (1e-5 if dtype == torch.float32 else 5e-3)
+    if dtype == torch.float32:       # the bf16 engine's configuration: fp32 projections in, bf16 activation out
+        got = K().mha(q.to(DEV), k.to(DEV), v.to(DEV), 8, kpm.to(DEV) if masked else None,
+                      out_dtype=torch.bfloat16).float().cpu()
+        assert rel_err(got, want) < 5e-3
 
 
-@pytest.mark.parametrize("mode", ["enc", "dec"])
-def test_msda_prep_matches_module_arithmetic(mode):
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Kp,shapes", [(4, synth.DANCETRACK_SHAPES), (8, synth.BDD_SHAPES), (4, synth.BDD_SHAPES_L5),
+                                       (3, synth.SMALL_SHAPES)])
+def test_msda_forward_ex_decode_once_kernel(dtype, Kp, shapes):
+    """The engine's gather kernel (v2: points decoded once into shared memory, pre-multiplied weights) against the C
+    oracle, on a column slice of a wider value buffer (the interleaved decoder value maps) with border samples."""
+    from oracle import msda as omsda
+    value, shp, lsi, loc, attn = synth.msda_inputs(shapes, B=1, H=8, D=32, K=Kp, Lq=333, seed=60 + Kp, border=True)
+    S = value.shape[1]
+    wide = torch.randn(S, 3 * 256, generator=_g(1)).to(dtype)
+    wide[:, 256:512] = value.reshape(S, 256).to(dtype)
+    v_used = wide[:, 256:512].float().reshape(1, S, 8, 32)
+    want = omsda.forward(v_used.numpy(), shp.numpy(), lsi.numpy(), loc.numpy(), attn.numpy(), fma=True)[0]
+    got = K().msda_forward_ex(wide.to(DEV)[:, 256:512], shp.to(DEV), lsi.to(DEV), loc[0].contiguous().to(DEV),
+                              attn[0].contiguous().to(DEV), 8).float().cpu().numpy()
+    assert rel_err(got, want) < (2e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("mode,L,Kp", [("enc", 4, 4), ("dec", 4, 4), ("enc", 4, 8), ("dec", 4, 3), ("enc", 5, 4)])
+def test_msda_prep_matches_module_arithmetic(mode, L, Kp):
     """Sampling locations / attention weights against the torch expressions of ms_deform_attn.py:108-120 with the
     reference points of deformable_encoder.py:29-40 / deformable_decoder.py:82-84, padded (valid ratio < 1) case."""
     g = _g(5)
-    shapes = synth.SMALL_SHAPES
-    H, L, Kp = 8, 4, 4
+    shapes = synth.SMALL_SHAPES if L == 4 else synth.SMALL_SHAPES + ((1, 2),)
+    H = 8
     S = sum(h * w for h, w in shapes)
     vr = torch.rand(1, L, 2, generator=g) * 0.3 + 0.7
     shp = torch.as_tensor(shapes, dtype=torch.long)

@@ -89,6 +89,13 @@ def main():
             t, tmin = timeit(lambda: memotr_b200.ms_deform_attn_forward(vb, shp, lsi, lb, ab, 64), flush=flush)
             row["ours_fwd_bf16_us"] = t
             row["ours_fwd_bf16_gbs"] = nbytes / 2 / t / 1e3
+            from memotr_b200 import kernels
+            for nm, vv in (("fp32", value.reshape(S, 256)), ("bf16", value.reshape(S, 256).bfloat16())):
+                for kern in ("v1", "v2"):
+                    os.environ["MEMOTR_MSDA_KERNEL"] = kern
+                    t, _ = timeit(lambda: kernels.msda_forward_ex(vv, shp, lsi, lc[0], attn[0], 8), flush=flush)
+                    row[f"ex_{kern}_{nm}_us"] = t
+            os.environ.pop("MEMOTR_MSDA_KERNEL", None)
             if K == 4:
                 go = torch.randn(1, Lq, 256, device=DEV)
                 t, _ = timeit(lambda: memotr_b200.ms_deform_attn_backward(value, shp, lsi, lc, attn, go, 64), flush=flush)
