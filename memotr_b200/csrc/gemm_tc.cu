@@ -12,8 +12,11 @@
 //            bf16 x bf16 -> fp32 accumulator in TMEM), 4 per k-block; tcgen05.commit frees the smem stage and, after the
 //            last k-block, signals the epilogue.
 //   warps 2-5 epilogue: tcgen05.ld 32x32b (one accumulator row per thread, 32 columns at a time) -> bias / ReLU /
-//            sigmoid / multiplier / residual / padding-mask -> 16-byte stores.
-// Rows beyond M are zero-filled by TMA on load and masked on store.  96 KB (BN=128) or 72 KB (BN=64) of shared memory
+//            sigmoid / multiplier / residual / padding-mask -> 16-byte st.shared into the (by then dead) pipeline
+//            stages, laid out as 128-row x 128-byte panels with the 128B swizzle -> one TMA store per panel
+//            (cp.async.bulk.tensor.2d.global.shared::cta).  v1 wrote one row per thread straight to global memory
+//            (32 scattered 16-byte sectors per store instruction); the panels make every global write a full line.
+// Rows beyond M are zero-filled by TMA on load and clipped by TMA on store.  96 KB (BN=128) or 72 KB (BN=64) of shared memory
 // and BN TMEM columns per CTA, so 2-3 CTAs are resident per SM and one tile's epilogue overlaps another's main loop.
 #include <cuda.h>
 
@@ -104,8 +107,8 @@ struct Smem {
 
 template <int BN, typename TC>
 __global__ void __launch_bounds__(192)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TC *__restrict__ C,
-               int ldc, int M, int N, int K, Epilogue ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   using SM = Smem<BN>;
@@ -121,6 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
@@ -169,20 +173,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) ----
-    mbar_wait(tmem_full, 0);
+    mbar_wait(tmem_full, 0);   // all MMAs have completed => every smem stage has been consumed and may be reused
     tcgen05_fence_after();
     const int quarter = warp & 3;
-    const int row = m_blk * BM + quarter * 32 + lane;
+    const int r_in = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const int row = m_blk * BM + r_in;
     const bool row_ok = row < M;
     const bool zero_row = row_ok && ep.rowzero && ep.rowzero[row];
     const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
     const __nv_bfloat16 *addp = (const __nv_bfloat16 *)ep.add + (long)row * ep.ldadd;
+    constexpr int PANEL_COLS = 128 / (int)sizeof(TC);       // columns per 128-byte panel row: 32 (fp32) or 64 (bf16)
+    constexpr int N_PANELS = BN / PANEL_COLS;
+    static_assert(N_PANELS * BM * 128 <= STAGES * SM::STAGE_BYTES, "staging panels must fit in the dead pipeline stages");
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
       const int col0 = n_blk * BN + c0;
-      if (!row_ok) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -200,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
       }
-      if (ep.mul) {
+      if (ep.mul && row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float t[8];
@@ -209,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 8; ++i) v[j + i] *= t[i];
         }
       }
-      if (ep.add) {
+      if (ep.add && row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float t[8];
@@ -222,20 +229,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      TC *dst = C + (long)row * ldc + col0;
+      // stage: panel p holds PANEL_COLS columns; row r_in occupies 128 bytes; 16-byte chunk k sits at k ^ (r_in & 7)
+      const int panel = c0 / PANEL_COLS;
+      uint8_t *prow = smem + panel * (BM * 128) + r_in * 128;
       if constexpr (sizeof(TC) == 4) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4 *>(prow + ((k ^ (r_in & 7)) << 4)) =
+              make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       } else {
+        const int kbase = (c0 % PANEL_COLS) / 8;  // 0 or 4: which half of the 64-column panel row
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
+        for (int k = 0; k < 4; ++k) {
           float t[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = v[j + i];
-          *reinterpret_cast<uint4 *>(dst + j) = f32x8_to_bf16(t);
+          for (int i = 0; i < 8; ++i) t[i] = v[8 * k + i];
+          *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t);
         }
       }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to TMA
+    asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps only
+    if (warp == 2 && lane == 0) {
+#pragma unroll 1
+      for (int p = 0; p < N_PANELS; ++p)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                     "r"(smem_u32(smem + p * (BM * 128))), "r"(n_blk * BN + p * PANEL_COLS), "r"(m_blk * BM)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must stay intact until TMA has read it
     }
   }
   tcgen05_fence_before();
@@ -263,24 +285,26 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major (rows, cols) with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle
-static bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows) {
+// 2-D row-major (rows, cols) with leading dimension ld (elements); box = box_rows x (128 bytes of columns), 128B swizzle
+static bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows, bool f32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
+  const int esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BN, typename TC>
 static int launch(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
                   const Epilogue &ep, cudaStream_t st) {
-  CUtensorMap tmA, tmW;
-  if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN))
+  CUtensorMap tmA, tmW, tmC;
+  if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN) ||
+      !make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4))
     return fail(MEMOTR_ECUDA, "linear(tc): cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   auto kern = gemm_tc_kernel<BN, TC>;
   static bool attr_set = false;  // idempotent attribute; benign if two threads race to set the same value
@@ -290,7 +314,7 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
     attr_set = true;
   }
   dim3 grid(N / BN, ceil_div(M, BM));
-  kern<<<grid, 192, Smem<BN>::TOTAL, st>>>(tmA, tmW, (TC *)C, ldc, M, N, K, ep);
+  kern<<<grid, 192, Smem<BN>::TOTAL, st>>>(tmA, tmW, tmC, M, N, K, ep);
   return check_launch("gemm_tc");
 }
 

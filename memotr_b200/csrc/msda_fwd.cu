@@ -376,26 +376,55 @@ struct __align__(16) TapRec {
   float c[4];   // bilinear weight x attention weight; 0 where the corner / point does not contribute
 };
 
+// raw 16-byte row slices as loaded (conversion to fp32 is deferred to the blend so that a batch in flight costs 4
+// registers per corner for either element type)
 template <typename T>
+struct Raw;
+template <>
+struct Raw<float> {
+  using type = float4;
+  static __device__ __forceinline__ float4 ld(const float *p) { return ldg_f4(p); }
+  static __device__ __forceinline__ void fma_into(float (&acc)[4], float w, const float4 &r) {
+    acc[0] = fmaf(w, r.x, acc[0]), acc[1] = fmaf(w, r.y, acc[1]), acc[2] = fmaf(w, r.z, acc[2]), acc[3] = fmaf(w, r.w, acc[3]);
+  }
+};
+template <>
+struct Raw<__nv_bfloat16> {
+  using type = uint4;
+  static __device__ __forceinline__ uint4 ld(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+  static __device__ __forceinline__ void fma_into(float (&acc)[8], float w, const uint4 &r) {
+    float f[8];
+    bf16x8_to_f32(r, f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+  }
+};
+
+// U = points per batch.  The gather loop is software-pipelined by hand (ping-pong register batches A/B): the 4U
+// 16-byte loads of batch i+1 are issued BEFORE the blend of batch i, so every warp keeps 4U loads in flight while it
+// computes -- left to itself the compiler interleaves each load with its consumer (1-2 loads in flight per warp) and
+// the kernel becomes latency-bound (measured: 106 us vs 78 us for v1 on the encoder-shaped bf16 launch).
+template <typename T, int U>
 __global__ void __launch_bounds__(256)
 msda_fwd_v2(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int H, int L,
             int Lq, int K, int xs, long n_qh) {
   constexpr int D = 32, CH = Row<T>::CH, G = D / CH, GROUPS = 256 / G;
+  using RawT = typename Raw<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int P = L * K;
-  const int gstride = P * 8 + 4;  // words per group: records + 16 B pad => the groups of a warp hit disjoint banks
+  const int Pp = (P + U - 1) / U * U;   // records per group, padded with zero-weight taps to a multiple of U
+  const int gstride = Pp * 8 + 4;       // words per group: records + 16 B pad => the groups of a warp hit disjoint banks
   float *recs = reinterpret_cast<float *>(smem_raw);
   const long qh0 = (long)blockIdx.x * GROUPS;
 
   // ---- phase 1: decode, one point per thread --------------------------------------------------------------------
-  for (int idx = threadIdx.x; idx < GROUPS * P; idx += 256) {
-    const int g = idx / P, i = idx - g * P;
+  for (int idx = threadIdx.x; idx < GROUPS * Pp; idx += 256) {
+    const int g = idx / Pp, i = idx - g * Pp;
     const long qh = qh0 + g;
-    TapRec r;
-    r.off[0] = r.off[1] = r.off[2] = r.off[3] = 0;
-    r.c[0] = r.c[1] = r.c[2] = r.c[3] = 0.f;
-    if (qh < n_qh) {
+    int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    if (qh < n_qh && i < P) {
       const int l = i / K;
       const int Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
       const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + qh * P + i);
@@ -409,24 +438,23 @@ msda_fwd_v2(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
         const int yc0 = max(y0, 0), yc1 = min(y0 + 1, Hh - 1), xc0 = max(x0, 0), xc1 = min(x0 + 1, Ww - 1);
         const int base = (int)__ldg(lsi + l) * xs;
         const int ys = Ww * xs;
-        r.off[0] = base + yc0 * ys + xc0 * xs;
-        r.off[1] = base + yc0 * ys + xc1 * xs;
-        r.off[2] = base + yc1 * ys + xc0 * xs;
-        r.off[3] = base + yc1 * ys + xc1 * xs;
-        r.c[0] = (y0ok && x0ok) ? hh * hw * aw : 0.f;
-        r.c[1] = (y0ok && x1ok) ? hh * lw * aw : 0.f;
-        r.c[2] = (y1ok && x0ok) ? lh * hw * aw : 0.f;
-        r.c[3] = (y1ok && x1ok) ? lh * lw * aw : 0.f;
+        o0 = base + yc0 * ys + xc0 * xs;
+        o1 = base + yc0 * ys + xc1 * xs;
+        o2 = base + yc1 * ys + xc0 * xs;
+        o3 = base + yc1 * ys + xc1 * xs;
+        c0 = (y0ok && x0ok) ? hh * hw * aw : 0.f;
+        c1 = (y0ok && x1ok) ? hh * lw * aw : 0.f;
+        c2 = (y1ok && x0ok) ? lh * hw * aw : 0.f;
+        c3 = (y1ok && x1ok) ? lh * lw * aw : 0.f;
       }
     }
     float4 *dst = reinterpret_cast<float4 *>(recs + g * gstride + i * 8);
-    dst[0] = make_float4(__int_as_float(r.off[0]), __int_as_float(r.off[1]), __int_as_float(r.off[2]),
-                         __int_as_float(r.off[3]));
-    dst[1] = make_float4(r.c[0], r.c[1], r.c[2], r.c[3]);
+    dst[0] = make_float4(__int_as_float(o0), __int_as_float(o1), __int_as_float(o2), __int_as_float(o3));
+    dst[1] = make_float4(c0, c1, c2, c3);
   }
   __syncthreads();
 
-  // ---- phase 2: gather + blend ---------------------------------------------------------------------------------
+  // ---- phase 2: gather + blend, ping-pong pipelined -------------------------------------------------------------
   const int g = threadIdx.x / G, sub = threadIdx.x % G;
   const long qh = qh0 + g;
   if (qh >= n_qh) return;
@@ -437,59 +465,71 @@ msda_fwd_v2(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
   float acc[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) acc[c] = 0.f;
-  constexpr int U = 2;  // points per batch of loads (8 x 16-byte loads in flight per lane)
+
+  float4 wA[U], wB[U];
+  RawT rA[U][4], rB[U][4];
+#define MSDA_LOAD(W_, R_, i0)                                       \
+  _Pragma("unroll") for (int u = 0; u < U; ++u) {                   \
+    const float4 o = rp[((i0) + u) * 2];                            \
+    W_[u] = rp[((i0) + u) * 2 + 1];                                 \
+    R_[u][0] = Raw<T>::ld(vb + __float_as_int(o.x));                \
+    R_[u][1] = Raw<T>::ld(vb + __float_as_int(o.y));                \
+    R_[u][2] = Raw<T>::ld(vb + __float_as_int(o.z));                \
+    R_[u][3] = Raw<T>::ld(vb + __float_as_int(o.w));                \
+  }
+#define MSDA_BLEND(W_, R_)                                          \
+  _Pragma("unroll") for (int u = 0; u < U; ++u) {                   \
+    Raw<T>::fma_into(acc, W_[u].x, R_[u][0]);                       \
+    Raw<T>::fma_into(acc, W_[u].y, R_[u][1]);                       \
+    Raw<T>::fma_into(acc, W_[u].z, R_[u][2]);                       \
+    Raw<T>::fma_into(acc, W_[u].w, R_[u][3]);                       \
+  }
   int i = 0;
-  for (; i + U <= P; i += U) {
-    float4 o[U], w[U];
-    float v[U][4][CH];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      o[u] = rp[(i + u) * 2];
-      w[u] = rp[(i + u) * 2 + 1];
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      Row<T>::load(vb + __float_as_int(o[u].x), true, v[u][0]);
-      Row<T>::load(vb + __float_as_int(o[u].y), true, v[u][1]);
-      Row<T>::load(vb + __float_as_int(o[u].z), true, v[u][2]);
-      Row<T>::load(vb + __float_as_int(o[u].w), true, v[u][3]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        acc[c] = fmaf(w[u].w, v[u][3][c], fmaf(w[u].z, v[u][2][c], fmaf(w[u].y, v[u][1][c], fmaf(w[u].x, v[u][0][c], acc[c]))));
+  MSDA_LOAD(wA, rA, 0)
+  while (true) {
+    if (i + U < Pp) { MSDA_LOAD(wB, rB, i + U) }
+    MSDA_BLEND(wA, rA)
+    i += U;
+    if (i >= Pp) break;
+    if (i + U < Pp) { MSDA_LOAD(wA, rA, i + U) }
+    MSDA_BLEND(wB, rB)
+    i += U;
+    if (i >= Pp) break;
   }
-  for (; i < P; ++i) {
-    const float4 o = rp[i * 2], w = rp[i * 2 + 1];
-    float v0[CH], v1[CH], v2[CH], v3[CH];
-    Row<T>::load(vb + __float_as_int(o.x), true, v0);
-    Row<T>::load(vb + __float_as_int(o.y), true, v1);
-    Row<T>::load(vb + __float_as_int(o.z), true, v2);
-    Row<T>::load(vb + __float_as_int(o.w), true, v3);
-#pragma unroll
-    for (int c = 0; c < CH; ++c) acc[c] = fmaf(w.w, v3[c], fmaf(w.z, v2[c], fmaf(w.y, v1[c], fmaf(w.x, v0[c], acc[c]))));
-  }
+#undef MSDA_LOAD
+#undef MSDA_BLEND
   Row<T>::store(out + qh * D + sub * CH, acc);
 }
 
-template <typename T>
-static int launch_v2(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
-                     void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, bool *handled) {
+template <typename T, int U>
+static int launch_v2u(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, bool *handled) {
   constexpr int GROUPS = 256 / (32 / Row<T>::CH);
-  const size_t smem = (size_t)GROUPS * (L * K * 8 + 4) * sizeof(float);
+  const int Pp = (L * K + U - 1) / U * U;
+  const size_t smem = (size_t)GROUPS * (Pp * 8 + 4) * sizeof(float);
   *handled = smem <= 160 * 1024;
   if (!*handled) return MEMOTR_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(msda_fwd_v2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(msda_fwd_v2<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "msda_fwd_v2: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const long n_qh = (long)B * Lq * H;
   const int grid = (int)((n_qh + GROUPS - 1) / GROUPS);
-  msda_fwd_v2<T><<<grid, 256, smem, st>>>((const T *)value, shapes, lsi, loc, attn, (T *)out, S, H, L, Lq, K, xs, n_qh);
+  msda_fwd_v2<T, U><<<grid, 256, smem, st>>>((const T *)value, shapes, lsi, loc, attn, (T *)out, S, H, L, Lq, K, xs,
+                                             n_qh);
   return check_launch("msda_fwd_v2");
+}
+
+template <typename T>
+static int launch_v2(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                     void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, bool *handled) {
+  const char *u = getenv("MEMOTR_MSDA_U");  // tuning knob: points per in-flight batch (1, 2 or 4)
+  const int U = u ? atoi(u) : 2;
+  if (U == 1) return launch_v2u<T, 1>(value, shapes, lsi, loc, attn, out, B, S, H, L, Lq, K, xs, st, handled);
+  if (U == 4) return launch_v2u<T, 4>(value, shapes, lsi, loc, attn, out, B, S, H, L, Lq, K, xs, st, handled);
+  return launch_v2u<T, 2>(value, shapes, lsi, loc, attn, out, B, S, H, L, Lq, K, xs, st, handled);
 }
 
 }  // namespace memotr

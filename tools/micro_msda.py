@@ -91,11 +91,13 @@ def main():
             row["ours_fwd_bf16_gbs"] = nbytes / 2 / t / 1e3
             from memotr_b200 import kernels
             for nm, vv in (("fp32", value.reshape(S, 256)), ("bf16", value.reshape(S, 256).bfloat16())):
-                for kern in ("v1", "v2"):
+                for kern, U in (("v1", "2"), ("v2", "1"), ("v2", "2"), ("v2", "4")):
                     os.environ["MEMOTR_MSDA_KERNEL"] = kern
+                    os.environ["MEMOTR_MSDA_U"] = U
                     t, _ = timeit(lambda: kernels.msda_forward_ex(vv, shp, lsi, lc[0], attn[0], 8), flush=flush)
-                    row[f"ex_{kern}_{nm}_us"] = t
+                    row[f"ex_{kern}{'_U' + U if kern == 'v2' else ''}_{nm}_us"] = t
             os.environ.pop("MEMOTR_MSDA_KERNEL", None)
+            os.environ.pop("MEMOTR_MSDA_U", None)
             if K == 4:
                 go = torch.randn(1, Lq, 256, device=DEV)
                 t, _ = timeit(lambda: memotr_b200.ms_deform_attn_backward(value, shp, lsi, lc, attn, go, 64), flush=flush)
