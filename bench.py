@@ -250,15 +250,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from memotr_b200 import clip as clip_mod
+
     def clip_exchange():
-        """One NCCL all-gather of the packed track-query memory per clip."""
-        if world == 1:
-            return None
-        packed = torch.cat([eng.st[k].reshape(-1) for k in ("query_embed", "long_memory", "last_output", "output_embed",
-                                                           "ref_pts", "boxes", "logits")])
-        out = torch.empty(world * packed.numel(), dtype=packed.dtype, device=dev)
-        dist.all_gather_into_tensor(out, packed)
-        return out
+        """One NCCL all-gather of the packed track-query memory per clip (memotr_b200/clip.py)."""
+        return clip_mod.gather_track_memory(eng.st) if world > 1 else None
 
     # ---- resident-input throughput ("value") -----------------------------------------------------------------
     reset_clip()

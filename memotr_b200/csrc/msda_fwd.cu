@@ -554,8 +554,10 @@ extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
                      ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
                  "msda_forward_ex: misaligned buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  const char *force = getenv("MEMOTR_MSDA_KERNEL");  // debugging override: "v1" keeps the reference-order kernel
-  if (!(force && force[0] == 'v' && force[1] == '1')) {
+  // v2 (decode-once) measured no faster than v1 on B200 (profiles/r01_micro_msda_v3_decode_once.json), so the
+  // reference-order kernel stays the default; MEMOTR_MSDA_KERNEL=v2 [MEMOTR_MSDA_U=1|2|4] selects the experiment.
+  const char *force = getenv("MEMOTR_MSDA_KERNEL");
+  if (force && force[0] == 'v' && force[1] == '2') {
     bool handled = false;
     int rc = dtype == MEMOTR_F32
                  ? launch_v2<float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L,
