@@ -281,6 +281,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     msda_us = eng.msda_times_us()                       # the 6 encoder MSDA launches of the last timed step
+    sections = eng.section_times_us()
 
     # ---- end to end through the public API with host buffers ("e2e") ----------------------------------------------
     from memotr_b200.engine import ClipRunner
@@ -336,6 +337,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": eng.graph_launches * K,
+        "sections_us": {k: round(v, 1) for k, v in sections.items()},
         "roofline": {"kernel": "msda_fwd_vec (encoder-shaped launch, Lq = S = 22323)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "duration_us": dur,

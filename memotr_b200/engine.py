@@ -64,9 +64,23 @@ class FrameEngine:
 
     # ------------------------------------------------------------------------------------------------ measurement
     def enable_msda_timer(self):
-        """Bracket every encoder-layer MSDA forward launch with a pair of (graph-capturable) CUDA events."""
-        self.timer = self.lib.memotr_timer_create(2 * self.n_enc)
+        """Bracket every encoder-layer MSDA forward launch with a pair of (graph-capturable) CUDA events, and mark the
+        section boundaries of a step (prep | encoder | decoder | updater) with five more."""
+        self.timer = self.lib.memotr_timer_create(2 * self.n_enc + 5)
         self._timer_slot = 0
+
+    def _mark(self, i):
+        if self.timer is not None:
+            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + i, self._st()), "timer_record")
+
+    def section_times_us(self):
+        """(prep, encoder, decoder+heads, updater) durations of the most recent step."""
+        import ctypes
+        ms, out, b = ctypes.c_float(), {}, 2 * self.n_enc
+        for i, name in enumerate(("prep", "encoder", "decoder_heads", "updater")):
+            _lib.check(self.lib.memotr_timer_elapsed_ms(self.timer, b + i, b + i + 1, ctypes.byref(ms)), "timer_elapsed")
+            out[name] = ms.value * 1e3
+        return out
 
     def msda_times_us(self):
         """Durations of the encoder MSDA forward launches of the most recent step (call after a synchronize)."""
@@ -277,6 +291,7 @@ class FrameEngine:
         """Transformer + heads on the loaded frame.  Results stay in the workspace; see results()."""
         C, S, H, L, dt = self.C, self.S, self.H, self.L, self.dt
         st = self._st
+        self._mark(0)
         # -- level flattening, level embedding, valid ratios (deformable_transformer.py:196-220)
         for l, (h, w) in enumerate(self.shapes):
             self._ck(self.lib.memotr_tokens_from_nchw(_p(self.in_src[l]), _p(self.in_pos[l]), _p(self.level_embed[l]),
@@ -286,6 +301,7 @@ class FrameEngine:
             self._ck(self.lib.memotr_valid_ratio(_p(self.in_mask[l]), h, w, _p(self.vr[l]), st()), "valid_ratio")
             self.convert_u8(self.in_mask[l], self.mask_flat[self.lsi_host[l]:], h * w)
         # -- encoder (deformable_encoder.py:109-131)
+        self._mark(1)
         Ke = self.cfg["n_enc_points"]
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
@@ -299,6 +315,7 @@ class FrameEngine:
             self.ln(self.pre, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
                     ypos=self.q_tok)
         memory = self.src_tok
+        self._mark(2)
         # -- decoder inputs (memotr.py:209-278, deformable_transformer.py:239-242)
         nd, nt, nq = self.nd, self.nt, self.nq
         self.convert(self.det_anchor, F32, 4, self.ref_raw, F32, 4, nd, 4)
@@ -359,6 +376,7 @@ class FrameEngine:
             self.lin(new, C, ly["cls"], self.pred_logit[lid], self.ncls, nq, c_dtype=F32)
         self._ck(self.lib.memotr_unary(_p(self.ref[self.n_dec - 1]), _p(self.last_ref_pts), nq * 4, 1, st()), "inv_sig")
         self._ck(self.lib.memotr_unary(_p(self.ref[0]), _p(self.init_ref_pts), nq * 4, 1, st()), "inv_sig")
+        self._mark(3)
 
     def convert_u8(self, src, dst, n):
         dst[:n].copy_(src)       # device-to-device byte copy on the current stream (cudaMemcpyAsync; graph-capturable)
@@ -441,6 +459,7 @@ class FrameEngine:
         self.update_tracks()
         self.convert(self.st["ref_pts"], F32, 4, self.in_track_ref, F32, 4, self.nt, 4)
         self.convert(self.st["query_embed"], F32, self.C, self.in_track_embed, F32, self.C, self.nt, self.C)
+        self._mark(4)
 
     def capture(self, fn=None):
         """Record `fn` (default: step) into a CUDA graph; replay() then re-issues the whole frame with one launch."""

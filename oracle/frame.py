@@ -199,10 +199,10 @@ def decoder(sd, key, bbox_key, tgt, ref, memory, shapes, lsi, valid_ratios, quer
         out = decoder_layer(sd, f"{key}.layers.{lid}", out, query_pos, ref_in, memory, shapes, lsi, query_mask,
                             mem_mask, cfg, merge=(lid >= merge_layer), core=core)
         new_ref = (mlp(sd, f"{bbox_key}.{lid}", out, 3) + inverse_sigmoid(ref)).sigmoid()
-        if lid < merge_layer:
-            ref = torch.cat((new_ref[:, :nd], ref[:, nd:]), dim=1)
+        if lid < merge_layer:                  # refined points are detached (deformable_decoder.py:150-159)
+            ref = torch.cat((new_ref[:, :nd].detach(), ref[:, nd:]), dim=1)
         else:
-            ref = new_ref
+            ref = new_ref.detach()
         outs.append(out)
         refs.append(ref)
     return torch.stack(outs), torch.stack(refs), torch.stack(queries)
