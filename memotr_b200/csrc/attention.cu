@@ -28,6 +28,7 @@ template <typename T, typename TO>
 __global__ void mha32_kernel(const T *__restrict__ Q, int ldq, const T *__restrict__ K, int ldk,
                              const T *__restrict__ V, int ldv, const unsigned char *__restrict__ kpm,
                              TO *__restrict__ O, int ldo, int Nq, int Nk, float scale, int qpb) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   float *Ks = sm;             // [Nk][33]
   float *Vs = Ks + Nk * 33;   // [Nk][32]
@@ -118,7 +119,7 @@ extern "C" int memotr_mha(const void *Q, int ldq, const void *K, int ldk, const 
     attr_set = true;
   }
 #define MHA_LAUNCH(TI, TO_)                                                                                          \
-  mha32_kernel<TI, TO_><<<grid, threads, smem, st>>>((const TI *)Q, ldq, (const TI *)K, ldk, (const TI *)V, ldv,      \
+  MEMOTR_LAUNCH((mha32_kernel<TI, TO_>), grid, threads, smem, st, (const TI *)Q, ldq, (const TI *)K, ldk, (const TI *)V, ldv,      \
                                                      key_padding_mask, (TO_ *)O, ldo, Nq, Nk, scale, qpb)
   if (in_dtype == MEMOTR_F32 && out_dtype == MEMOTR_F32) MHA_LAUNCH(float, float);
   else if (in_dtype == MEMOTR_F32) MHA_LAUNCH(float, bf);

@@ -6,6 +6,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/memotr_b200.h"
 
@@ -37,6 +39,43 @@ inline int check_launch(const char *what) {
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// Half of a frame is ~200 small kernels on <= 400 rows whose cost is launch latency, not work.  Every kernel of this
+// library starts with pdl_grid_sync() (griddepcontrol.wait: returns once the preceding grid in the stream has completed
+// and its writes are visible -- the ordinary stream-order guarantee) followed by griddepcontrol.launch_dependents, and
+// is launched with the programmatic-stream-serialization attribute, so the NEXT kernel's launch, block scheduling and
+// (for the GEMM) barrier/TMEM set-up overlap the tail of this one instead of following it.  Semantics are unchanged:
+// no dependent data is touched before the wait.  MEMOTR_PDL=0 launches plainly (A/B measurement, debugging).
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = []() {
+    const char *e = getenv("MEMOTR_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);  // errors: check_launch()
+}
+#define MEMOTR_LAUNCH(kern, grid, block, smem, st, ...) \
+  ::memotr::launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

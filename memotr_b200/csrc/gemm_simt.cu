@@ -19,6 +19,7 @@ template <typename TA, typename TC, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA *__restrict__ A, int lda, const TA *__restrict__ W, int ldw, TC *__restrict__ C, int ldc,
                  int M, int N, int K, Epilogue ep) {
+  pdl_grid_sync();
   constexpr int BK = 16;
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads per CTA");
   __shared__ float As[BK][BM + 4];
@@ -90,6 +91,7 @@ template <typename TA, typename TC>
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const TA *__restrict__ A, int lda, const TA *__restrict__ W, int ldw, TC *__restrict__ C, int ldc, int M,
                  int N, int K, Epilogue ep) {
+  pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   float acc[8];
@@ -124,18 +126,18 @@ template <typename TA, typename TC>
 static int launch_simt(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
                        const Epilogue &ep, cudaStream_t st) {
   if (N <= 8) {
-    gemv_rows_kernel<TA, TC><<<ceil_div(M, 8), 256, 0, st>>>((const TA *)A, lda, (const TA *)W, ldw, (TC *)C, ldc, M, N,
+    MEMOTR_LAUNCH((gemv_rows_kernel<TA, TC>), ceil_div(M, 8), 256, 0, st, (const TA *)A, lda, (const TA *)W, ldw, (TC *)C, ldc, M, N,
                                                              K, ep);
     return check_launch("gemv_rows");
   }
   // big problems: 128x128 tiles (8x8 per thread); small ones (decoder / updater rows): 32x64 tiles for more CTAs
   if ((long)M * N >= 128L * 128 * kNumSMs) {
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128));
-    gemm_simt_kernel<TA, TC, 128, 128, 8, 8><<<grid, 256, 0, st>>>((const TA *)A, lda, (const TA *)W, ldw, (TC *)C,
+    MEMOTR_LAUNCH((gemm_simt_kernel<TA, TC, 128, 128, 8, 8>), grid, 256, 0, st, (const TA *)A, lda, (const TA *)W, ldw, (TC *)C,
                                                                     ldc, M, N, K, ep);
   } else {
     dim3 grid(ceil_div(N, 64), ceil_div(M, 32));
-    gemm_simt_kernel<TA, TC, 32, 64, 2, 4><<<grid, 256, 0, st>>>((const TA *)A, lda, (const TA *)W, ldw, (TC *)C, ldc,
+    MEMOTR_LAUNCH((gemm_simt_kernel<TA, TC, 32, 64, 2, 4>), grid, 256, 0, st, (const TA *)A, lda, (const TA *)W, ldw, (TC *)C, ldc,
                                                                   M, N, K, ep);
   }
   return check_launch("gemm_simt");

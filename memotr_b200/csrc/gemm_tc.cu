@@ -141,6 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // everything above (descriptor prefetch, barrier init, TMEM allocation) overlapped the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -314,7 +315,7 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
     attr_set = true;
   }
   dim3 grid(N / BN, ceil_div(M, BM));
-  kern<<<grid, 192, Smem<BN>::TOTAL, st>>>(tmA, tmW, tmC, M, N, K, ep);
+  MEMOTR_LAUNCH((kern), grid, 192, Smem<BN>::TOTAL, st, tmA, tmW, tmC, M, N, K, ep);
   return check_launch("gemm_tc");
 }
 

@@ -31,6 +31,7 @@ msda_bwd_f32_d32(const float *__restrict__ value, const int64_t *__restrict__ sh
                  const int64_t *__restrict__ lsi, const float *__restrict__ loc, const float *__restrict__ attn,
                  const float *__restrict__ grad_out, float *__restrict__ grad_value, float *__restrict__ grad_loc,
                  float *__restrict__ grad_attn, int S, int H, int L, int Lq, int K, long n_qh) {
+  pdl_grid_sync();
   constexpr int D = 32;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long qh_raw = tid >> 3;
@@ -110,6 +111,7 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes
                  const T *__restrict__ loc, const T *__restrict__ attn, const T *__restrict__ grad_out,
                  T *__restrict__ grad_value, T *__restrict__ grad_loc, T *__restrict__ grad_attn, int S, int H, int D,
                  int L, int Lq, int K, long n_out) {
+  pdl_grid_sync();
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_out; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % D);
     const long qh = idx / D;
@@ -176,7 +178,7 @@ extern "C" int memotr_msda_backward(const void *value, const int64_t *spatial_sh
       ((reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0)) {
     const long threads = n_qh * 8;
     const int grid = (int)((threads + 255) / 256);
-    msda_bwd_f32_d32<<<grid, 256, 0, st>>>((const float *)value, spatial_shapes, level_start_idx,
+    MEMOTR_LAUNCH((msda_bwd_f32_d32), grid, 256, 0, st, (const float *)value, spatial_shapes, level_start_idx,
                                            (const float *)sampling_loc, (const float *)attn_weight,
                                            (const float *)grad_output, (float *)grad_value,
                                            (float *)grad_sampling_loc, (float *)grad_attn_weight, S, H, L, Lq, K,
@@ -193,13 +195,13 @@ extern "C" int memotr_msda_backward(const void *value, const int64_t *spatial_sh
   const long n_out = n_qh * D;
   const int grid = (int)((n_out + 255) / 256 > (1L << 30) ? (1L << 30) : (n_out + 255) / 256);
   if (dtype == MEMOTR_F32)
-    msda_bwd_generic<float><<<grid, 256, 0, st>>>((const float *)value, spatial_shapes, level_start_idx,
+    MEMOTR_LAUNCH((msda_bwd_generic<float>), grid, 256, 0, st, (const float *)value, spatial_shapes, level_start_idx,
                                                   (const float *)sampling_loc, (const float *)attn_weight,
                                                   (const float *)grad_output, (float *)grad_value,
                                                   (float *)grad_sampling_loc, (float *)grad_attn_weight, S, H, D, L,
                                                   Lq, K, n_out);
   else
-    msda_bwd_generic<double><<<grid, 256, 0, st>>>((const double *)value, spatial_shapes, level_start_idx,
+    MEMOTR_LAUNCH((msda_bwd_generic<double>), grid, 256, 0, st, (const double *)value, spatial_shapes, level_start_idx,
                                                    (const double *)sampling_loc, (const double *)attn_weight,
                                                    (const double *)grad_output, (double *)grad_value,
                                                    (double *)grad_sampling_loc, (double *)grad_attn_weight, S, H, D,

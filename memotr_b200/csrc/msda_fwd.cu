@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(256)
 msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const TL *__restrict__ loc, const TL *__restrict__ attn, T *__restrict__ out, int S, int H, int L, int Lq,
              int Kr, int xs, long n_qh) {
+  pdl_grid_sync();
   constexpr int G = 32 / Row<T>::CH;  // lanes per (b,q,head)
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long qh = tid / G;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kTile *kTile * (32 / Row<T>::CH))
 msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const TL *__restrict__ loc, const TL *__restrict__ attn, T *__restrict__ out, int B, int S, int H, int L,
                int Kr, int xs) {
+  pdl_grid_sync();
   constexpr int G = 32 / Row<T>::CH;
   const int g = threadIdx.x / G, sub = threadIdx.x % G;  // g: query slot inside the 8x8 patch
   const int gy = g / kTile, gx = g % kTile;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(256)
 msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                  const T *__restrict__ loc, const T *__restrict__ attn, T *__restrict__ out, int S, int H, int D,
                  int L, int Lq, int K, long n_out) {
+  pdl_grid_sync();
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_out; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % D);
     const long qh = idx / D;
@@ -290,7 +293,7 @@ static int launch_vec(const void *value, const int64_t *shapes, const int64_t *l
     const long max_work = (long)B * H * S;
     const int grid_t = (int)(max_work < (long)kNumSMs * 32 ? max_work : (long)kNumSMs * 32);
     auto at = [&](auto kern) {
-      kern<<<grid_t, kTile * kTile * G, 0, st>>>((const T *)value, shapes, lsi, (const TL *)loc, (const TL *)attn,
+      MEMOTR_LAUNCH((kern), grid_t, kTile * kTile * G, 0, st, (const T *)value, shapes, lsi, (const TL *)loc, (const TL *)attn,
                                                    (T *)out, B, S, H, L, K, xs);
     };
     switch (K) {
@@ -305,7 +308,7 @@ static int launch_vec(const void *value, const int64_t *shapes, const int64_t *l
   const long threads = n_qh * G;
   const int grid = (int)((threads + 255) / 256);
   auto a = [&](auto kern) {
-    kern<<<grid, 256, 0, st>>>((const T *)value, shapes, lsi, (const TL *)loc, (const TL *)attn, (T *)out, S, H, L, Lq,
+    MEMOTR_LAUNCH((kern), grid, 256, 0, st, (const T *)value, shapes, lsi, (const TL *)loc, (const TL *)attn, (T *)out, S, H, L, Lq,
                                K, xs, n_qh);
   };
   switch (K) {
@@ -344,11 +347,11 @@ extern "C" int memotr_msda_forward(const void *value, const int64_t *spatial_sha
   const long n_out = (long)B * Lq * H * D;
   const int grid = (int)((n_out + 255) / 256 > (1L << 30) ? (1L << 30) : (n_out + 255) / 256);
   if (dtype == MEMOTR_F32) {
-    msda_fwd_generic<float><<<grid, 256, 0, st>>>((const float *)value, spatial_shapes, level_start_idx,
+    MEMOTR_LAUNCH((msda_fwd_generic<float>), grid, 256, 0, st, (const float *)value, spatial_shapes, level_start_idx,
                                                   (const float *)sampling_loc, (const float *)attn_weight,
                                                   (float *)output, S, H, D, L, Lq, K, n_out);
   } else if (dtype == MEMOTR_F64) {
-    msda_fwd_generic<double><<<grid, 256, 0, st>>>((const double *)value, spatial_shapes, level_start_idx,
+    MEMOTR_LAUNCH((msda_fwd_generic<double>), grid, 256, 0, st, (const double *)value, spatial_shapes, level_start_idx,
                                                    (const double *)sampling_loc, (const double *)attn_weight,
                                                    (double *)output, S, H, D, L, Lq, K, n_out);
   } else {
@@ -409,6 +412,7 @@ __global__ void __launch_bounds__(256)
 msda_fwd_v2(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int H, int L,
             int Lq, int K, int xs, long n_qh) {
+  pdl_grid_sync();
   constexpr int D = 32, CH = Row<T>::CH, G = D / CH, GROUPS = 256 / G;
   using RawT = typename Raw<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -517,7 +521,7 @@ static int launch_v2u(const void *value, const int64_t *shapes, const int64_t *l
   }
   const long n_qh = (long)B * Lq * H;
   const int grid = (int)((n_qh + GROUPS - 1) / GROUPS);
-  msda_fwd_v2<T, U><<<grid, 256, smem, st>>>((const T *)value, shapes, lsi, loc, attn, (T *)out, S, H, L, Lq, K, xs,
+  MEMOTR_LAUNCH((msda_fwd_v2<T, U>), grid, 256, smem, st, (const T *)value, shapes, lsi, loc, attn, (T *)out, S, H, L, Lq, K, xs,
                                              n_qh);
   return check_launch("msda_fwd_v2");
 }

@@ -47,6 +47,7 @@ layernorm256_kernel(const TX *__restrict__ x, int ldx, const TX *__restrict__ x2
                     const float *__restrict__ gamma, const float *__restrict__ beta, float eps, TY *__restrict__ y,
                     int ldy, const TY *__restrict__ pos, int ldpos, TY *__restrict__ ypos, int ldypos,
                     float *__restrict__ y32, int ldy32, int M) {
+  pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int c0 = (threadIdx.x & 31) * 8;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256)
 msda_prep_kernel(const float *__restrict__ ol, int ldol, const int64_t *__restrict__ shapes,
                  const int64_t *__restrict__ lsi, const float *__restrict__ vr, const float *__restrict__ ref4, int mode,
                  float *__restrict__ loc, float *__restrict__ attn, int Lq, int H, int L, int K) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)Lq * H) return;
   const int q = (int)(idx / H), h = (int)(idx % H);
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(256)
 msda_prep_fast_kernel(const float *__restrict__ ol, int ldol, const int64_t *__restrict__ shapes,
                       const int64_t *__restrict__ lsi, const float *__restrict__ vr, const float *__restrict__ ref4,
                       int mode, float *__restrict__ loc, float *__restrict__ attn, int Lq, int H, int L, int K) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = idx < (long)Lq * H * LK;
   const long cidx = live ? idx : (long)Lq * H * LK - 1;  // tail lanes shadow the last element (shuffles stay full-warp)
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(256)
 tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, const float *__restrict__ lvl_embed,
               T *__restrict__ src_tok, T *__restrict__ pos_tok, T *__restrict__ q_tok, float *__restrict__ src_tok32,
               int C, int HW, int row0, int ld) {
+  pdl_grid_sync();
   __shared__ float ts[32][33], tp[32][33];
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -234,6 +238,7 @@ tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, cons
 
 // valid ratio of one level's padding mask (deformable_transformer.py:175-190): (#valid in row 0)/W, (#valid in col 0)/H
 __global__ void valid_ratio_kernel(const unsigned char *__restrict__ mask, int Hh, int Ww, float *__restrict__ out2) {
+  pdl_grid_sync();
   __shared__ int cnt[2];
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -258,6 +263,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 sine_embed_kernel(const float *__restrict__ pts, int ldp, const float *__restrict__ scale4, int apply_sigmoid,
                   const float *__restrict__ dim_t, T *__restrict__ out, int ldo, int N) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (n, coord, j)
   if (idx >= (long)N * 256) return;
   const int n = (int)(idx >> 8), c = (int)((idx >> 6) & 3), j = (int)(idx & 63);
@@ -275,6 +281,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 add_kernel(const T *__restrict__ a, int lda, const T *__restrict__ b, int ldb, T *__restrict__ out, int ldo, int M,
            int N) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)M * N) return;
   const int r = (int)(idx / N), c = (int)(idx % N);
@@ -285,6 +292,7 @@ add_kernel(const T *__restrict__ a, int lda, const T *__restrict__ b, int ldb, T
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256)
 convert_kernel(const TS *__restrict__ src, int lds, TD *__restrict__ dst, int ldd, int M, int N) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)M * N) return;
   const int r = (int)(idx / N), c = (int)(idx % N);
@@ -302,6 +310,7 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x
 // `new` for all rows is also the layer's predicted box (memotr.py:147-160 computes the same expression).
 __global__ void box_refine_kernel(const float *__restrict__ delta, const float *__restrict__ ref,
                                   float *__restrict__ new_ref, float *__restrict__ ref_next, int N, int n_take) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * 4) return;
   const float r = ref[idx];
@@ -312,6 +321,7 @@ __global__ void box_refine_kernel(const float *__restrict__ delta, const float *
 
 // op 0: sigmoid, op 1: inverse_sigmoid  (deformable_transformer.py:241 ; memotr.py:183-187)
 __global__ void unary_kernel(const float *__restrict__ in, float *__restrict__ out, long n, int op) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   out[idx] = op == 0 ? sigmoidf(in[idx]) : inv_sigmoid(in[idx]);
@@ -322,6 +332,7 @@ __global__ void unary_kernel(const float *__restrict__ in, float *__restrict__ o
 __global__ void upd_prepare_kernel(const float *__restrict__ logits, int ncls, const float *__restrict__ boxes,
                                    const float *__restrict__ ref_pts, float thr, unsigned char *__restrict__ is_pos,
                                    float *__restrict__ ref_new, int Nt) {
+  pdl_grid_sync();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Nt) return;
   float s = -INFINITY;
@@ -340,6 +351,7 @@ __global__ void __launch_bounds__(256)
 upd_finalize_kernel(const unsigned char *__restrict__ is_pos, const T *__restrict__ feat, int ldf,
                     const float *__restrict__ out_e, float *__restrict__ query_embed, float *__restrict__ long_memory,
                     float *__restrict__ last_output, float lam, int Nt, int C) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)Nt * C) return;
   const int n = (int)(idx / C), c = (int)(idx % C);
@@ -371,7 +383,7 @@ extern "C" int memotr_layernorm(const void *x, int x_dtype, int ldx, const void 
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(M, 8);
 #define LN_LAUNCH(TX, TY)                                                                                         \
-  layernorm256_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX *)x, ldx, (const TX *)x2, ldx2, gamma, beta, eps,   \
+  MEMOTR_LAUNCH((layernorm256_kernel<TX, TY>), grid, 256, 0, st, (const TX *)x, ldx, (const TX *)x2, ldx2, gamma, beta, eps,   \
                                                     (TY *)y, ldy, (const TY *)pos, ldpos, (TY *)ypos, ldypos, y32, \
                                                     ldy32, M)
   if (x_dtype == MEMOTR_F32 && y_dtype == MEMOTR_F32) LN_LAUNCH(float, float);
@@ -399,7 +411,7 @@ extern "C" int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatia
     const long nt = (long)Lq * H * LK;
     const int grid = (int)((nt + 255) / 256);
 #define PREP_FAST(N)                                                                                             \
-  msda_prep_fast_kernel<N><<<grid, 256, 0, st>>>(ol, ldol, spatial_shapes, level_start_idx, valid_ratios, ref4, \
+  MEMOTR_LAUNCH((msda_prep_fast_kernel<N>), grid, 256, 0, st, ol, ldol, spatial_shapes, level_start_idx, valid_ratios, ref4, \
                                                  mode, sampling_loc, attn_weight, Lq, H, L, K)
     if (LK == 4) PREP_FAST(4);
     else if (LK == 8) PREP_FAST(8);
@@ -409,7 +421,7 @@ extern "C" int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatia
     return check_launch("msda_prep_fast");
   }
   const long n = (long)Lq * H;
-  msda_prep_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(ol, ldol, spatial_shapes, level_start_idx, valid_ratios,
+  MEMOTR_LAUNCH((msda_prep_kernel), (int)((n + 255) / 256), 256, 0, st, ol, ldol, spatial_shapes, level_start_idx, valid_ratios,
                                                           ref4, mode, sampling_loc, attn_weight, Lq, H, L, K);
   return check_launch("msda_prep");
 }
@@ -423,10 +435,10 @@ extern "C" int memotr_tokens_from_nchw(const float *src, const float *pos, const
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MEMOTR_F32)
-    tokens_kernel<float><<<grid, 256, 0, st>>>(src, pos, level_embed, (float *)src_tok, (float *)pos_tok,
+    MEMOTR_LAUNCH((tokens_kernel<float>), grid, 256, 0, st, src, pos, level_embed, (float *)src_tok, (float *)pos_tok,
                                                (float *)q_tok, src_tok32, C, HW, row0, ld);
   else
-    tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, pos, level_embed, (__nv_bfloat16 *)src_tok,
+    MEMOTR_LAUNCH((tokens_kernel<__nv_bfloat16>), grid, 256, 0, st, src, pos, level_embed, (__nv_bfloat16 *)src_tok,
                                                        (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, HW,
                                                        row0, ld);
   return check_launch("tokens_from_nchw");
@@ -434,7 +446,7 @@ extern "C" int memotr_tokens_from_nchw(const float *src, const float *pos, const
 
 extern "C" int memotr_valid_ratio(const unsigned char *mask, int Hh, int Ww, float *out2, void *stream) {
   MEMOTR_REQUIRE(mask && out2 && Hh > 0 && Ww > 0, "valid_ratio: bad arguments");
-  valid_ratio_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mask, Hh, Ww, out2);
+  MEMOTR_LAUNCH((valid_ratio_kernel), 1, 256, 0, (cudaStream_t)stream, mask, Hh, Ww, out2);
   return check_launch("valid_ratio");
 }
 
@@ -447,9 +459,9 @@ extern "C" int memotr_sine_embed(const float *pts, int ldp, const float *scale4,
   const int grid = (int)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == MEMOTR_F32)
-    sine_embed_kernel<float><<<grid, 256, 0, st>>>(pts, ldp, scale4, apply_sigmoid, dim_t, (float *)out, ldo, N);
+    MEMOTR_LAUNCH((sine_embed_kernel<float>), grid, 256, 0, st, pts, ldp, scale4, apply_sigmoid, dim_t, (float *)out, ldo, N);
   else
-    sine_embed_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pts, ldp, scale4, apply_sigmoid, dim_t, (__nv_bfloat16 *)out,
+    MEMOTR_LAUNCH((sine_embed_kernel<__nv_bfloat16>), grid, 256, 0, st, pts, ldp, scale4, apply_sigmoid, dim_t, (__nv_bfloat16 *)out,
                                                            ldo, N);
   return check_launch("sine_embed");
 }
@@ -463,9 +475,9 @@ extern "C" int memotr_add(const void *a, int lda, const void *b, int ldb, void *
   const int grid = (int)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MEMOTR_F32)
-    add_kernel<float><<<grid, 256, 0, st>>>((const float *)a, lda, (const float *)b, ldb, (float *)out, ldo, M, N);
+    MEMOTR_LAUNCH((add_kernel<float>), grid, 256, 0, st, (const float *)a, lda, (const float *)b, ldb, (float *)out, ldo, M, N);
   else
-    add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)a, lda, (const __nv_bfloat16 *)b, ldb,
+    MEMOTR_LAUNCH((add_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16 *)a, lda, (const __nv_bfloat16 *)b, ldb,
                                                     (__nv_bfloat16 *)out, ldo, M, N);
   return check_launch("add");
 }
@@ -481,13 +493,13 @@ extern "C" int memotr_convert(const void *src, int src_dtype, int lds, void *dst
   cudaStream_t st = (cudaStream_t)stream;
   using bf = __nv_bfloat16;
   if (src_dtype == MEMOTR_F32 && dst_dtype == MEMOTR_F32)
-    convert_kernel<float, float><<<grid, 256, 0, st>>>((const float *)src, lds, (float *)dst, ldd, M, N);
+    MEMOTR_LAUNCH((convert_kernel<float, float>), grid, 256, 0, st, (const float *)src, lds, (float *)dst, ldd, M, N);
   else if (src_dtype == MEMOTR_F32)
-    convert_kernel<float, bf><<<grid, 256, 0, st>>>((const float *)src, lds, (bf *)dst, ldd, M, N);
+    MEMOTR_LAUNCH((convert_kernel<float, bf>), grid, 256, 0, st, (const float *)src, lds, (bf *)dst, ldd, M, N);
   else if (dst_dtype == MEMOTR_F32)
-    convert_kernel<bf, float><<<grid, 256, 0, st>>>((const bf *)src, lds, (float *)dst, ldd, M, N);
+    MEMOTR_LAUNCH((convert_kernel<bf, float>), grid, 256, 0, st, (const bf *)src, lds, (float *)dst, ldd, M, N);
   else
-    convert_kernel<bf, bf><<<grid, 256, 0, st>>>((const bf *)src, lds, (bf *)dst, ldd, M, N);
+    MEMOTR_LAUNCH((convert_kernel<bf, bf>), grid, 256, 0, st, (const bf *)src, lds, (bf *)dst, ldd, M, N);
   return check_launch("convert");
 }
 
@@ -495,14 +507,14 @@ extern "C" int memotr_box_refine(const float *delta, const float *ref, float *ne
                                  int n_take, void *stream) {
   MEMOTR_REQUIRE(delta && ref && new_ref && ref_next && N >= 0, "box_refine: bad arguments");
   if (N == 0) return MEMOTR_OK;
-  box_refine_kernel<<<ceil_div(N * 4, 256), 256, 0, (cudaStream_t)stream>>>(delta, ref, new_ref, ref_next, N, n_take);
+  MEMOTR_LAUNCH((box_refine_kernel), ceil_div(N * 4, 256), 256, 0, (cudaStream_t)stream, delta, ref, new_ref, ref_next, N, n_take);
   return check_launch("box_refine");
 }
 
 extern "C" int memotr_unary(const float *in, float *out, long n, int op, void *stream) {
   MEMOTR_REQUIRE(in && out && n >= 0 && (op == 0 || op == 1), "unary: bad arguments");
   if (n == 0) return MEMOTR_OK;
-  unary_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, op);
+  MEMOTR_LAUNCH((unary_kernel), (int)((n + 255) / 256), 256, 0, (cudaStream_t)stream, in, out, n, op);
   return check_launch("unary");
 }
 
@@ -510,7 +522,7 @@ extern "C" int memotr_upd_prepare(const float *logits, int ncls, const float *bo
                                   unsigned char *is_pos, float *ref_new, int Nt, void *stream) {
   MEMOTR_REQUIRE(logits && boxes && ref_pts && is_pos && ref_new && ncls > 0 && Nt >= 0, "upd_prepare: bad arguments");
   if (Nt == 0) return MEMOTR_OK;
-  upd_prepare_kernel<<<ceil_div(Nt, 128), 128, 0, (cudaStream_t)stream>>>(logits, ncls, boxes, ref_pts, thr, is_pos,
+  MEMOTR_LAUNCH((upd_prepare_kernel), ceil_div(Nt, 128), 128, 0, (cudaStream_t)stream, logits, ncls, boxes, ref_pts, thr, is_pos,
                                                                          ref_new, Nt);
   return check_launch("upd_prepare");
 }
@@ -526,10 +538,10 @@ extern "C" int memotr_upd_finalize(const unsigned char *is_pos, const void *feat
   const int grid = (int)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (feat_dtype == MEMOTR_F32)
-    upd_finalize_kernel<float><<<grid, 256, 0, st>>>(is_pos, (const float *)feat, ldf, out_e, query_embed, long_memory,
+    MEMOTR_LAUNCH((upd_finalize_kernel<float>), grid, 256, 0, st, is_pos, (const float *)feat, ldf, out_e, query_embed, long_memory,
                                                      last_output, lam, Nt, C);
   else
-    upd_finalize_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(is_pos, (const __nv_bfloat16 *)feat, ldf, out_e,
+    MEMOTR_LAUNCH((upd_finalize_kernel<__nv_bfloat16>), grid, 256, 0, st, is_pos, (const __nv_bfloat16 *)feat, ldf, out_e,
                                                              query_embed, long_memory, last_output, lam, Nt, C);
   return check_launch("upd_finalize");
 }
