@@ -120,6 +120,17 @@ MEMOTR_API int memotr_linear(const void *A, int lda, const void *W, int ldw, con
                              int M, int N, int K, int ab_dtype, int c_dtype, int act, int path, void *stream);
 
 /*
+ * Fused two-layer MLP / FFN on the tensor cores (bf16 operands, fp32 accumulate):
+ *   C = act2( relu(X . W1^T + b1) . W2^T + b2 ) [* mul],   X (M,256) ldx, W1 (Hd,256), W2 (256,Hd), Hd %% 128 == 0,
+ * C (M,256) ldc in c_dtype (F32 or BF16); the (M,Hd) hidden activation stays in shared memory / TMEM.
+ * Replaces linear2(activation(linear1(x))) of models/deformable_encoder.py:97-107, models/deformable_decoder.py:263-273,
+ * models/ffn.py:15-22 and the 256-input two-layer MLPs (models/mlp.py:22-25).
+ */
+MEMOTR_API int memotr_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, const float *b2,
+                           const void *mul, int ldmul, void *C, int ldc, int M, int K1, int Hd, int N2, int c_dtype,
+                           int act2, void *stream);
+
+/*
  * y = LayerNorm(x [+ x2]) (C == 256, eps as given, affine fp32); optional ypos = y + pos and fp32 copy y32.
  * models/deformable_encoder.py:124-130, models/deformable_decoder.py:251-252,313-318, models/ffn.py:23-24,
  * models/query_updater.py:126-133.

@@ -1,0 +1,330 @@
+// mlp_tc.cu -- fused two-layer MLP / FFN on the tensor cores:  C = epi( relu(X . W1^T + b1) . W2^T + b2 ),
+// X (M,256) bf16, W1 (Hd,256), W2 (256,Hd), Hd a multiple of 128 (256 for the MLPs, 2048 for the FFNs).
+//
+// Replaces `linear2(dropout(activation(linear1(x))))` of the encoder / decoder FFNs
+// (models/deformable_encoder.py:97-107, models/deformable_decoder.py:263-273, models/ffn.py:15-22) and the two-layer
+// MLPs with 256-wide input (models/mlp.py:22-25 as used at deformable_decoder.py:93 query_scale, :140 bbox_embed layers
+// 0-1, query_updater.py:109 confidence net).  The reference materialises the (M, Hd) hidden activation in HBM
+// (91 MB per encoder layer in bf16, written once and read once); here it never leaves the SM.
+//
+// One CTA owns a 128-row tile of X (TMA-loaded once, 64 KB) and walks the hidden dimension in chunks of 128:
+//     GEMM1(c): acc1[c&1] (TMEM, 128 cols) = X . W1[c]^T                 4 k-blocks, tcgen05.mma M128 N128 K16
+//     epi1(c) : acc1 -> +b1 -> ReLU -> bf16 -> shared memory H[c&1]      written directly in the 128B-swizzled K-major
+//                                                                        layout UMMA wants for an A operand
+//     GEMM2(c): acc2 (TMEM, 256 cols) += H[c&1] . W2[:, c]^T             2 k-panels, tcgen05.mma M128 N256 K16
+// Warp roles: 0 = TMA producer streaming W1/W2 chunks through a 3-slot x 32 KB ring, 1 = MMA issuer (GEMM1 runs one
+// chunk ahead of GEMM2 so epi1(c) overlaps GEMM1(c+1)), 2-5 = epilogue.  acc1 and H are double-buffered; all hand-offs
+// are mbarriers (TMA expect_tx, tcgen05.commit, and 128-thread arrives from the epilogue warps).  TMEM: 2x128 + 256 =
+// 512 columns.  Shared memory: X 64 KB + ring 96 KB + H 64 KB = 224 KB (one CTA per SM).  Final epilogue as in
+// gemm_tc.cu: bias / activation / multiplier -> swizzled panels in the (dead) X+ring memory -> TMA store.
+#include "tc_common.cuh"
+
+namespace memotr {
+namespace tc {
+
+namespace mlp {
+constexpr int K1 = 256, N2 = 256, HC = 128;
+constexpr int XP = K1 / BK;                     // 4 X panels of 128 rows x 64 cols
+constexpr int PANEL = BM * 128;                 // 16 KB: 128 rows x 128 bytes
+constexpr int X_BYTES = XP * PANEL;             // 64 KB
+constexpr int SLOT = 2 * PANEL;                 // 32 KB: two W1 k-blocks (128 rows) or one W2 k-panel (256 rows)
+constexpr int NSLOT = 3;
+constexpr int H_BYTES = 2 * PANEL;              // one hidden chunk as A operand: 2 panels of 64 columns
+constexpr int OFF_RING = X_BYTES;
+constexpr int OFF_H = OFF_RING + NSLOT * SLOT;
+constexpr int OFF_BAR = OFF_H + 2 * H_BYTES;    // 224 KB
+constexpr int TOTAL = OFF_BAR + 256 + 1024;
+}  // namespace mlp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(192, 1)
+mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
+               const float *__restrict__ b1, int M, int Hd, Epilogue ep) {
+  using namespace mlp;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  uint64_t *x_full = bars, *full = bars + 1, *empty = full + NSLOT, *acc1_full = empty + NSLOT, *acc1_empty = acc1_full + 2,
+           *h_full = acc1_empty + 2, *h_empty = h_full + 2, *acc2_full = h_empty + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc2_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x;
+  const int NC = Hd / HC;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    mbar_init(x_full, 1);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc1_full + b, 1);
+      mbar_init(acc1_empty + b, 128);
+      mbar_init(h_full + b, 128);
+      mbar_init(h_empty + b, 1);
+    }
+    mbar_init(acc2_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();
+
+  uint8_t *ring = smem + OFF_RING;
+  uint8_t *hbuf = smem + OFF_H;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: X once, then W1(0), [W1(c+1), W2(c)] ... in exactly the order the MMA warp consumes ----
+      mbar_expect_tx(x_full, X_BYTES);
+      for (int p = 0; p < XP; ++p) tma_load_2d(smem + p * PANEL, &tmX, x_full, p * BK, m_blk * BM);
+      int t = 0;
+      auto load_w1 = [&](int c) {
+        for (int half = 0; half < 2; ++half, ++t) {
+          const int s = t % NSLOT;
+          mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
+          mbar_expect_tx(full + s, SLOT);
+          tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, c * HC);
+          tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, c * HC);
+        }
+      };
+      auto load_w2 = [&](int c) {
+        for (int j = 0; j < 2; ++j, ++t) {
+          const int s = t % NSLOT;
+          mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
+          mbar_expect_tx(full + s, SLOT);
+          tma_load_2d(ring + s * SLOT, &tmW2, full + s, c * HC + j * BK, 0);
+        }
+      };
+      load_w1(0);
+      for (int c = 0; c < NC; ++c) {
+        if (c + 1 < NC) load_w1(c + 1);
+        load_w2(c);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      constexpr uint32_t idesc1 = umma_idesc(HC), idesc2 = umma_idesc(N2);
+      mbar_wait(x_full, 0);
+      tcgen05_fence_after();
+      const uint32_t x_addr = smem_u32(smem), ring_addr = smem_u32(ring), h_addr = smem_u32(hbuf);
+      int t = 0;
+      auto gemm1 = [&](int c) {
+        const int b = c & 1;
+        mbar_wait(acc1_empty + b, ((c >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        for (int half = 0; half < 2; ++half, ++t) {
+          const int s = t % NSLOT;
+          mbar_wait(full + s, (t / NSLOT) & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int kb = 2 * half + kk;
+            const uint64_t adesc = umma_desc(x_addr + kb * PANEL), bdesc = umma_desc(ring_addr + s * SLOT + kk * PANEL);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_base + b * HC, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0);
+          }
+          umma_commit(empty + s);
+        }
+        umma_commit(acc1_full + b);
+      };
+      auto gemm2 = [&](int c) {
+        const int b = c & 1;
+        mbar_wait(h_full + b, (c >> 1) & 1);
+        tcgen05_fence_after();
+        for (int j = 0; j < 2; ++j, ++t) {
+          const int s = t % NSLOT;
+          mbar_wait(full + s, (t / NSLOT) & 1);
+          tcgen05_fence_after();
+          const uint64_t adesc = umma_desc(h_addr + b * H_BYTES + j * PANEL), bdesc = umma_desc(ring_addr + s * SLOT);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_base + 2 * HC, adesc + 2 * k, bdesc + 2 * k, idesc2, (c | j | k) != 0);
+          umma_commit(empty + s);
+        }
+        umma_commit(h_empty + b);
+      };
+      gemm1(0);
+      for (int c = 0; c < NC; ++c) {
+        if (c + 1 < NC) gemm1(c + 1);
+        gemm2(c);
+      }
+      umma_commit(acc2_full);
+    }
+  } else {
+    // ---- epilogue warps: lane quarter = warp % 4, one accumulator row per thread ----
+    const int quarter = warp & 3;
+    const int r_in = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    for (int c = 0; c < NC; ++c) {
+      const int b = c & 1;
+      mbar_wait(acc1_full + b, (c >> 1) & 1);
+      tcgen05_fence_after();
+      mbar_wait(h_empty + b, ((c >> 1) & 1) ^ 1);   // GEMM2(c-2) has finished reading this H buffer
+      uint8_t *hrow = hbuf + b * H_BYTES + r_in * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HC; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(b * HC + c0), r);
+        const float *bias = b1 + c * HC + c0;
+        uint8_t *prow = hrow + (c0 / 64) * PANEL;
+        const int kbase = (c0 % 64) / 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k));
+          const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k + 4));
+          float t8[8];
+          t8[0] = fmaxf(__uint_as_float(r[8 * k + 0]) + ba.x, 0.f);
+          t8[1] = fmaxf(__uint_as_float(r[8 * k + 1]) + ba.y, 0.f);
+          t8[2] = fmaxf(__uint_as_float(r[8 * k + 2]) + ba.z, 0.f);
+          t8[3] = fmaxf(__uint_as_float(r[8 * k + 3]) + ba.w, 0.f);
+          t8[4] = fmaxf(__uint_as_float(r[8 * k + 4]) + bb.x, 0.f);
+          t8[5] = fmaxf(__uint_as_float(r[8 * k + 5]) + bb.y, 0.f);
+          t8[6] = fmaxf(__uint_as_float(r[8 * k + 6]) + bb.z, 0.f);
+          t8[7] = fmaxf(__uint_as_float(r[8 * k + 7]) + bb.w, 0.f);
+          *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t8);
+        }
+      }
+      tcgen05_fence_before();                                        // TMEM reads ordered before the hand-off
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the UMMA (async proxy)
+      mbar_arrive(acc1_empty + b);
+      mbar_arrive(h_full + b);
+    }
+    // ---- final epilogue: acc2 (+b2, activation, multiplier) -> swizzled panels in the dead X/ring memory -> TMA store
+    mbar_wait(acc2_full, 0);
+    tcgen05_fence_after();
+    const int row = m_blk * BM + r_in;
+    const bool row_ok = row < M;
+    const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
+    constexpr int PANEL_COLS = 128 / (int)sizeof(TC);
+    constexpr int N_PANELS = N2 / PANEL_COLS;
+    static_assert(N_PANELS * PANEL <= OFF_H, "staging must fit in the X + ring area");
+#pragma unroll 1
+    for (int c0 = 0; c0 < N2; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_off + (uint32_t)(2 * HC + c0), r);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4 *>(ep.bias + c0 + j));
+          v[j] += bb.x, v[j + 1] += bb.y, v[j + 2] += bb.z, v[j + 3] += bb.w;
+        }
+      }
+      if (ep.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (ep.act == ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      }
+      if (ep.mul && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float t[8];
+          bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(mulp + c0 + j)), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j + i] *= t[i];
+        }
+      }
+      uint8_t *prow = smem + (c0 / PANEL_COLS) * PANEL + r_in * 128;
+      if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4 *>(prow + ((k ^ (r_in & 7)) << 4)) =
+              make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      } else {
+        const int kbase = (c0 % PANEL_COLS) / 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = v[8 * k + i];
+          *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+#pragma unroll 1
+      for (int p = 0; p < N_PANELS; ++p)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                     "r"(smem_u32(smem + p * PANEL)), "r"(p * PANEL_COLS), "r"(m_blk * BM)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+template <typename TC>
+static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
+                       int Hd, const Epilogue &ep, cudaStream_t st) {
+  using namespace mlp;
+  CUtensorMap tmX, tmW1, tmW2, tmC;
+  if (!make_map(&tmX, X, M, K1, ldx, BM) || !make_map(&tmW1, W1, Hd, K1, K1, HC) || !make_map(&tmW2, W2, N2, Hd, Hd, N2) ||
+      !make_map(&tmC, C, M, N2, ldc, BM, sizeof(TC) == 4))
+    return fail(MEMOTR_ECUDA, "mlp2(tc): cuTensorMapEncodeTiled failed (M=%d Hd=%d)", M, Hd);
+  auto kern = mlp2_tc_kernel<TC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL);
+    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  MEMOTR_LAUNCH((kern), ceil_div(M, BM), 192, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
+  return check_launch("mlp2_tc");
+}
+
+}  // namespace tc
+}  // namespace memotr
+
+using namespace memotr;
+
+extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, const float *b2,
+                           const void *mul, int ldmul, void *C, int ldc, int M, int K1, int Hd, int N2, int c_dtype,
+                           int act2, void *stream) {
+  MEMOTR_REQUIRE(M >= 0 && X && W1 && b1 && W2 && C, "mlp2: bad arguments");
+  MEMOTR_REQUIRE(K1 == tc::mlp::K1 && N2 == tc::mlp::N2 && Hd > 0 && Hd % tc::mlp::HC == 0,
+                 "mlp2: needs K1 == 256, N2 == 256, hidden %% 128 == 0 (got %d, %d, %d)", K1, N2, Hd);
+  MEMOTR_REQUIRE(c_dtype == MEMOTR_F32 || c_dtype == MEMOTR_BF16, "mlp2: output dtype must be f32 or bf16");
+  MEMOTR_REQUIRE(act2 >= 0 && act2 <= 2, "mlp2: unknown activation");
+  const int cal = c_dtype == MEMOTR_F32 ? 4 : 8;
+  MEMOTR_REQUIRE(ldx % 8 == 0 && ldc % cal == 0 && aligned16(X) && aligned16(W1) && aligned16(W2) && aligned16(C) &&
+                     aligned16(b1) && (!b2 || aligned16(b2)) && (!mul || (aligned16(mul) && ldmul % 8 == 0)),
+                 "mlp2: misaligned buffer");
+  MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "mlp2: cuTensorMapEncodeTiled unavailable");
+  if (M == 0) return MEMOTR_OK;
+  Epilogue ep{b2, mul, nullptr, nullptr, ldmul, 0, act2};
+  cudaStream_t st = (cudaStream_t)stream;
+  return c_dtype == MEMOTR_F32 ? tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
+                               : tc::launch_mlp2<__nv_bfloat16>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
+}

@@ -57,6 +57,8 @@ class FrameEngine:
         self.merge = cfg["merge_det_track_layer"]
         self.lib = _lib.lib()
         self.launches = 0
+        import os
+        self.fused_mlp = os.environ.get("MEMOTR_FUSED_MLP", "1") != "0"   # A/B switch for the on-chip FFN/MLP kernel
         self._pack(state_dict)
         self._alloc()
         self.graph = None
@@ -234,6 +236,17 @@ class FrameEngine:
         self._ck(self.lib.memotr_linear(_p(x), ldx, _p(L.w), L.K, _p(L.b), _p(mul), ldmul, _p(add), ldadd, _p(rowzero),
                                         _p(out), ldo, M, L.N, L.K, self.dt, cd, act, path, self._st()), "linear")
 
+    def mlp2(self, x, ldx, L1, L2, out, ldo, M, hid, act2=0, mul=None, ldmul=0, c_dtype=None):
+        """out = act2(relu(x L1^T + b1) L2^T + b2) [* mul].  bf16 mode with a 256-wide input/output: ONE tensor-core kernel
+        with the hidden activation kept on chip (memotr_mlp2); otherwise two GEMMs through the scratch buffer `hid`."""
+        cd = self.dt if c_dtype is None else c_dtype
+        if self.fused_mlp and self.mode == "bf16" and L1.K == 256 and L2.N == 256 and L1.N % 128 == 0 and L2.K == L1.N:
+            self._ck(self.lib.memotr_mlp2(_p(x), ldx, _p(L1.w), _p(L1.b), _p(L2.w), _p(L2.b), _p(mul), ldmul, _p(out), ldo,
+                                          M, L1.K, L1.N, L2.N, cd, act2, self._st()), "mlp2")
+            return
+        self.lin(x, ldx, L1, hid, L1.N, M, act=1)
+        self.lin(hid, L1.N, L2, out, ldo, M, act=act2, mul=mul, ldmul=ldmul, c_dtype=cd)
+
     def ln(self, x, wb, y, M, x2=None, y32=None, pos=None, ypos=None):
         """y = LN(x + x2) in the activation dtype (+ fp32 master y32, + ypos = y + pos).  x, x2, y32: fp32, ld = C."""
         C = self.C
@@ -310,8 +323,7 @@ class FrameEngine:
             self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
             self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
             self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
-            self.lin(self.src1, C, ly["lin1"], self.hid, self.Fd, S, act=1)
-            self.lin(self.hid, self.Fd, ly["lin2"], self.pre, C, S, c_dtype=F32)
+            self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)
             self.ln(self.pre, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
                     ypos=self.q_tok)
         memory = self.src_tok
@@ -340,8 +352,8 @@ class FrameEngine:
                 self.lin(self.d_a, C, self.ref_point_head[1], self.query_pos, C, nq)
             else:
                 self.lin(self.d_a, C, self.ref_point_head[1], self.d_b, C, nq)
-                self.lin(out, C, self.query_scale[0], self.d_c, C, nq, act=1)
-                self.lin(self.d_c, C, self.query_scale[1], self.query_pos, C, nq, mul=self.d_b, ldmul=C)
+                self.mlp2(out, C, self.query_scale[0], self.query_scale[1], self.query_pos, C, nq, self.d_c,
+                          mul=self.d_b, ldmul=C)
             # self-attention (deformable_decoder.py:245-252)
             sa = ly["self"]
             self.add(out, C, self.query_pos, C, self.qk_in, C, n, C)
@@ -358,8 +370,7 @@ class FrameEngine:
             self.lin(self.d_a, C, a["out"], self.d_pre, C, n, c_dtype=F32)
             self.ln(self.d_pre, ly["norm1"], self.t2, n, x2=self.t1_32, y32=self.t2_32)
             # FFN (deformable_decoder.py:263-273)
-            self.lin(self.t2, C, ly["lin1"], self.d_hid, self.Fd, n, act=1)
-            self.lin(self.d_hid, self.Fd, ly["lin2"], self.d_pre, C, n, c_dtype=F32)
+            self.mlp2(self.t2, C, ly["lin1"], ly["lin2"], self.d_pre, C, n, self.d_hid, c_dtype=F32)
             new, new32 = self.tgt[lid + 1], self.tgt32[lid + 1]
             self.ln(self.d_pre, ly["norm3"], new, n, x2=self.t2_32, y32=new32)
             if n < nq:                                       # track queries bypass the layer (:316-317)
@@ -368,8 +379,7 @@ class FrameEngine:
                     self.convert(out[n:], dt, C, new[n:], dt, C, nq - n, C)
             # box refinement + heads (deformable_decoder.py:139-159, memotr.py:147-162)
             bb = ly["bbox"]
-            self.lin(new, C, bb[0], self.d_a, C, nq, act=1)
-            self.lin(self.d_a, C, bb[1], self.d_c, C, nq, act=1)
+            self.mlp2(new, C, bb[0], bb[1], self.d_c, C, nq, self.d_a, act2=1)
             self.lin(self.d_c, C, bb[2], self.delta, 4, nq, c_dtype=F32)
             self._ck(self.lib.memotr_box_refine(_p(self.delta), _p(ref), _p(self.pred_box[lid]), _p(self.ref[lid + 1]),
                                                 nq, nq if lid >= self.merge else nd, st()), "box_refine")
@@ -414,8 +424,8 @@ class FrameEngine:
         self.convert(st["last_output"], F32, C, self.u_cat[:, C:], dt, 2 * C, nt, C)
         self.convert(st["long_memory"], F32, C, self.u_long, dt, C, nt, C)
         # confidence gate and short-memory fusion (:109-118)
-        self.lin(self.u_oe, C, u["conf"][0], self.u_a, C, nt, act=1)
-        self.lin(self.u_a, C, u["conf"][1], self.u_cat, 2 * C, nt, act=2, mul=self.u_oe, ldmul=C)
+        self.mlp2(self.u_oe, C, u["conf"][0], u["conf"][1], self.u_cat, 2 * C, nt, self.u_a, act2=2, mul=self.u_oe,
+                  ldmul=C)
         self.lin(self.u_cat, 2 * C, u["fusion"][0], self.u_big, 2 * C, nt, act=1)
         self.lin(self.u_big, 2 * C, u["fusion"][1], self.u_a, C, nt)                 # short memory
         self.lin(self.u_sine, 2 * C, u["pos_head"][0], self.u_b, C, nt, act=1)
@@ -431,14 +441,12 @@ class FrameEngine:
         self.lin(self.u_a, C, ma["out"], self.u_pre, C, nt, c_dtype=F32)
         self.ln(self.u_pre, u["memory_norm"], self.u_a, nt, x2=st["output_embed"], y32=self.u_a32)
         l1, l2, nrm = u["mffn"]
-        self.lin(self.u_a, C, l1, self.u_hid, self.Fd, nt, act=1)
-        self.lin(self.u_hid, self.Fd, l2, self.u_pre, C, nt, c_dtype=F32)
+        self.mlp2(self.u_a, C, l1, l2, self.u_pre, C, nt, self.u_hid, c_dtype=F32)
         self.ln(self.u_pre, nrm, self.u_c, nt, x2=self.u_a32, y32=self.u_c32)
         # long-memory residual branch (:130-133)
         self.ln(self.u_c32, u["feat_norm"], self.u_a, nt, x2=st["long_memory"], y32=self.u_a32)
         l1, l2, nrm = u["fffn"]
-        self.lin(self.u_a, C, l1, self.u_hid, self.Fd, nt, act=1)
-        self.lin(self.u_hid, self.Fd, l2, self.u_pre, C, nt, c_dtype=F32)
+        self.mlp2(self.u_a, C, l1, l2, self.u_pre, C, nt, self.u_hid, c_dtype=F32)
         self.ln(self.u_pre, nrm, self.u_c, nt, x2=self.u_a32, y32=self.u_c32)        # query_feat
         # masked state writes (:135-147); ref_pts was already replaced where is_pos (:99-102)
         self._ck(self.lib.memotr_upd_finalize(_p(self.is_pos), _p(self.u_c32), F32, C, _p(st["output_embed"]),

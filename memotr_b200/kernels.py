@@ -35,6 +35,22 @@ def linear(x, weight, bias=None, act=None, mul=None, add=None, rowzero=None, out
     return out
 
 
+def mlp2(x, w1, b1, w2, b2=None, act2=None, mul=None, out_dtype=None, out=None):
+    """act2(relu(x @ w1.T + b1) @ w2.T + b2) [* mul] in one tensor-core kernel; x (M,256), w1 (Hd,256), w2 (256,Hd) bf16."""
+    M, K1 = x.shape
+    Hd, N2 = w1.shape[0], w2.shape[0]
+    if out is None:
+        out = torch.empty((M, N2), dtype=out_dtype or x.dtype, device=x.device)
+    b1 = b1.float().contiguous()
+    b2 = b2.float().contiguous() if b2 is not None else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_mlp2(_lib.ptr(x), _ld(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                    _lib.ptr(mul), _ld(mul) if mul is not None else 0, _lib.ptr(out), _ld(out), M, K1, Hd,
+                                    N2, _lib.dtype_code(out), _ACT[act2], _lib.stream_ptr())
+    _lib.check(rc, "memotr_mlp2")
+    return out
+
+
 def layernorm(x, gamma, beta, x2=None, pos=None, eps=1e-5, out_dtype=None, want_f32=False):
     """LayerNorm(x [+ x2]) over the last (256-wide) dimension; returns y, or (y, y + pos), plus an fp32 copy on request."""
     M, C = x.shape
