@@ -240,7 +240,12 @@ class FrameEngine:
         """out = act2(relu(x L1^T + b1) L2^T + b2) [* mul].  bf16 mode with a 256-wide input/output: ONE tensor-core kernel
         with the hidden activation kept on chip (memotr_mlp2); otherwise two GEMMs through the scratch buffer `hid`."""
         cd = self.dt if c_dtype is None else c_dtype
-        if self.fused_mlp and self.mode == "bf16" and L1.K == 256 and L2.N == 256 and L1.N % 128 == 0 and L2.K == L1.N:
+        # one CTA per 128 rows walks the hidden chunks serially: worth it when there are enough row tiles to fill the
+        # GPU (encoder, 175 tiles) or the chain is short (256-wide hidden = 2 chunks); the 2048-wide FFN on <= 400 decoder
+        # rows is faster as two GEMMs (measured 51 vs 30 us, profiles/r01_micro_gemm_v3_fused.json)
+        worth = M >= 2048 or L1.N <= 256
+        if self.fused_mlp and worth and self.mode == "bf16" and L1.K == 256 and L2.N == 256 and L1.N % 128 == 0 \
+                and L2.K == L1.N:
             self._ck(self.lib.memotr_mlp2(_p(x), ldx, _p(L1.w), _p(L1.b), _p(L2.w), _p(L2.b), _p(mul), ldmul, _p(out), ldo,
                                           M, L1.K, L1.N, L2.N, cd, act2, self._st()), "mlp2")
             return
