@@ -91,6 +91,20 @@ MEMOTR_API int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
                                       int K, int dtype, void *stream);
 
 /*
+ * Encoder-shaped bf16 fast path of the forward op on a re-laid-out value map.
+ * memotr_msda_pairs_layout: value (S, >=H*32 per pixel, bf16) -> pairs (H, S, 2, 32) bf16: entry s = pixel (y,x) holds the
+ *   32 channels of head h of that pixel followed by those of its right neighbour (y,x+1) (zeros at the end of a row), so
+ *   the two x-corners of a bilinear footprint are one aligned 128-byte line (the L1 serves one line per clock).
+ * memotr_msda_forward_pairs: same arithmetic as memotr_msda_forward_ex (B = 1, D = 32, fp32 loc/attn, bf16 output
+ *   (Lq, H*32)) reading that layout: 2 lines and 2 loads per sampling point instead of 4 and 4.  K in {1,2,4,8}.
+ */
+MEMOTR_API int memotr_msda_pairs_layout(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                        const int64_t *level_start_idx, void *pairs, int S, int H, int L, void *stream);
+MEMOTR_API int memotr_msda_forward_pairs(const void *pairs, const int64_t *spatial_shapes, const int64_t *level_start_idx,
+                                         const float *sampling_loc, const float *attn_weight, void *output, int S, int H,
+                                         int L, int Lq, int K, void *stream);
+
+/*
  * Sampling locations + attention weights from the raw projections -- models/ops/modules/ms_deform_attn.py:108-120.
  *   ol            (Lq, ldol) fp32: per row [ offsets (H,L,K,2) | logits (H,L*K) ]  (one GEMM with the stacked
  *                 sampling_offsets / attention_weights weights)

@@ -580,3 +580,141 @@ extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
                                             B, S, H, L, Lq, K, value_pixel_stride, st);
   return fail(MEMOTR_EINVAL, "msda_forward_ex: dtype must be f32 or bf16");
 }
+
+// =====================================================================================================================
+// v3 gather for the encoder-shaped launch (bf16): "pair-duplicated head-major" value map.
+//
+// The L1 cache serves one 128-byte line per clock per SM, and in the reference's pixel-major layout every corner of
+// every head is its own line (4 lines per sampling point; profiles/r01_msda_fwd_v1_ncu.md).  memotr_msda_pairs_layout
+// rewrites a value map once per layer as  pairs[h][s][2][32] (bf16):  entry s = pixel (y,x) of its level holds that
+// pixel's 32 channels of head h followed by those of its RIGHT neighbour (y,x+1) (zeros at the end of a row), i.e. the
+// two x-corners of a bilinear footprint are one aligned 128-byte line.  A group of 8 lanes then fetches BOTH corners of
+// one footprint row with a single 16-byte load per lane: 2 lines and 2 load instructions per point instead of 4 and 4.
+// Lanes 0-3 blend the x0 column, lanes 4-7 the x1 column; the halves are added with one xor-shuffle per channel at the end.
+namespace memotr {
+
+__global__ void __launch_bounds__(256)
+msda_pairs_layout_kernel(const __nv_bfloat16 *__restrict__ value, int xs, const int64_t *__restrict__ shapes,
+                         const int64_t *__restrict__ lsi, __nv_bfloat16 *__restrict__ pairs, int S, int H, int L) {
+  pdl_grid_sync();
+  // one thread per (s, head, half, 16-byte quarter): 8 threads move the 128-byte entry of one (s, head)
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)S * H * 8) return;
+  const int part = (int)(idx & 7), h = (int)((idx >> 3) % H), s = (int)(idx / (8 * H));
+  const int half = part >> 2, q = part & 3;
+  int l = 0;
+  for (int t = 1; t < L; ++t)
+    if (s >= (int)lsi[t]) l = t;
+  const int Ww = (int)shapes[2 * l + 1];
+  const int x = (s - (int)lsi[l]) % Ww;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (half == 0 || x + 1 < Ww) v = __ldg(reinterpret_cast<const uint4 *>(value + (long)(s + half) * xs + h * 32 + q * 8));
+  *reinterpret_cast<uint4 *>(pairs + (((long)h * S + s) * 2 + half) * 32 + q * 8) = v;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+msda_fwd_pairs(const __nv_bfloat16 *__restrict__ pairs, const int64_t *__restrict__ shapes,
+               const int64_t *__restrict__ lsi, const float *__restrict__ loc, const float *__restrict__ attn,
+               __nv_bfloat16 *__restrict__ out, int S, int H, int L, int Lq, long n_qh) {
+  pdl_grid_sync();
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long qh_raw = tid >> 3;
+  const bool live = qh_raw < n_qh;
+  const long qh = live ? qh_raw : n_qh - 1;            // tail lanes shadow a valid group (shuffles stay full-warp)
+  const int sub = (int)(tid & 7), xsel = sub >> 2, c8 = sub & 3;
+  const int m = (int)(qh % H);
+  const __nv_bfloat16 *plane = pairs + (long)m * S * 64 + c8 * 8;   // + entry * 64 + half * 32
+  const long pbase = qh * L * KT;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const int Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
+    const float Hf = (float)Hh, Wf = (float)Ww;
+    const int base = (int)__ldg(lsi + l);
+    float w0[KT], w1[KT];
+    int o0[KT], o1[KT];
+#pragma unroll
+    for (int p = 0; p < KT; ++p) {
+      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + pbase + l * KT + p);
+      const float aw = __ldg(attn + pbase + l * KT + p);
+      const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
+      const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
+      const float hfl = floorf(h_im), wfl = floorf(w_im);
+      const int y0 = (int)hfl, x0 = (int)wfl;
+      const float lh = h_im - hfl, lw = w_im - wfl;
+      const float wx = (xsel ? lw : 1.f - lw) * aw;          // this lane's column weight (x0 or x1)
+      const int xc = x0 + xsel;                              // this lane's column
+      const bool xok = inside && xc >= 0 && xc <= Ww - 1;
+      // entry = pixel max(x0,0); its half 0 is column max(x0,0), half 1 the column to its right
+      const int xe = max(x0, 0), hsel = xc - xe;             // hsel in {0,1} whenever xok
+      const int yc0 = min(max(y0, 0), Hh - 1), yc1 = min(max(y0 + 1, 0), Hh - 1);
+      const int xec = min(xe, Ww - 1), hs = xok ? hsel : 0;
+      o0[p] = ((base + yc0 * Ww + xec) * 2 + hs) * 32;
+      o1[p] = ((base + yc1 * Ww + xec) * 2 + hs) * 32;
+      w0[p] = (xok && y0 >= 0) ? (1.f - lh) * wx : 0.f;
+      w1[p] = (xok && y0 + 1 <= Hh - 1) ? lh * wx : 0.f;
+    }
+    uint4 r0[KT], r1[KT];
+#pragma unroll
+    for (int p = 0; p < KT; ++p) {
+      r0[p] = __ldg(reinterpret_cast<const uint4 *>(plane + o0[p]));
+      r1[p] = __ldg(reinterpret_cast<const uint4 *>(plane + o1[p]));
+    }
+#pragma unroll
+    for (int p = 0; p < KT; ++p) {
+      float f0[8], f1[8];
+      bf16x8_to_f32(r0[p], f0);
+      bf16x8_to_f32(r1[p], f1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(w1[p], f1[c], fmaf(w0[p], f0[c], acc[c]));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);   // x0 half + x1 half
+  if (live && xsel == 0) *reinterpret_cast<uint4 *>(out + qh * 32 + c8 * 8) = f32x8_to_bf16(acc);
+}
+
+}  // namespace memotr
+
+extern "C" int memotr_msda_pairs_layout(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                        const int64_t *level_start_idx, void *pairs, int S, int H, int L, void *stream) {
+  MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && pairs && S > 0 && H > 0 && L > 0,
+                 "msda_pairs_layout: bad arguments");
+  MEMOTR_REQUIRE(value_pixel_stride >= H * 32 && value_pixel_stride % 8 == 0 && aligned16(value) && aligned16(pairs),
+                 "msda_pairs_layout: misaligned buffer");
+  const long n = (long)S * H * 8;
+  MEMOTR_LAUNCH((msda_pairs_layout_kernel), (int)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
+                (const __nv_bfloat16 *)value, value_pixel_stride, spatial_shapes, level_start_idx, (__nv_bfloat16 *)pairs,
+                S, H, L);
+  return check_launch("msda_pairs_layout");
+}
+
+extern "C" int memotr_msda_forward_pairs(const void *pairs, const int64_t *spatial_shapes, const int64_t *level_start_idx,
+                                         const float *sampling_loc, const float *attn_weight, void *output, int S, int H,
+                                         int L, int Lq, int K, void *stream) {
+  MEMOTR_REQUIRE(pairs && spatial_shapes && level_start_idx && sampling_loc && attn_weight && output && S > 0 && H > 0 &&
+                     L > 0 && Lq >= 0,
+                 "msda_forward_pairs: bad arguments");
+  MEMOTR_REQUIRE((long)S * H * 64 < (1L << 31), "msda_forward_pairs: value map too large");
+  MEMOTR_REQUIRE(aligned16(pairs) && aligned16(output) && ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
+                 "msda_forward_pairs: misaligned buffer");
+  if (Lq == 0) return MEMOTR_OK;
+  const long n_qh = (long)Lq * H;
+  const int grid = (int)((n_qh * 8 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  using bf = __nv_bfloat16;
+#define PAIRS_LAUNCH(KT_)                                                                                       \
+  MEMOTR_LAUNCH((msda_fwd_pairs<KT_>), grid, 256, 0, st, (const bf *)pairs, spatial_shapes, level_start_idx,   \
+                sampling_loc, attn_weight, (bf *)output, S, H, L, Lq, n_qh)
+  switch (K) {
+    case 1: PAIRS_LAUNCH(1); break;
+    case 2: PAIRS_LAUNCH(2); break;
+    case 4: PAIRS_LAUNCH(4); break;
+    case 8: PAIRS_LAUNCH(8); break;
+    default: return fail(MEMOTR_ENOSYS, "msda_forward_pairs: K must be 1, 2, 4 or 8 (got %d)", K);
+  }
+#undef PAIRS_LAUNCH
+  return check_launch("msda_fwd_pairs");
+}

@@ -59,6 +59,9 @@ class FrameEngine:
         self.launches = 0
         import os
         self.fused_mlp = os.environ.get("MEMOTR_FUSED_MLP", "1") != "0"   # A/B switch for the on-chip FFN/MLP kernel
+        # encoder MSDA on the pair-duplicated head-major value map (bf16 mode, K in {1,2,4,8}); A/B switch
+        self.use_pairs = (os.environ.get("MEMOTR_MSDA_PAIRS", "1") != "0" and mode == "bf16"
+                          and cfg["n_enc_points"] in (1, 2, 4, 8))
         self._pack(state_dict)
         self._alloc()
         self.graph = None
@@ -173,6 +176,7 @@ class FrameEngine:
         self.vr = f(self.L, 2)
         self.src_tok, self.pos_tok, self.q_tok = e(S, C), e(S, C), e(S, C)
         self.value = e(S, C)
+        self.pairs = e(self.H, S, 2, 32) if self.use_pairs else None
         self.ol = f(S, 3 * self.H * LK)
         self.loc = f(S, self.H, LK, 2)
         self.attw = f(S, self.H, LK)
@@ -241,9 +245,9 @@ class FrameEngine:
         with the hidden activation kept on chip (memotr_mlp2); otherwise two GEMMs through the scratch buffer `hid`."""
         cd = self.dt if c_dtype is None else c_dtype
         # one CTA per 128 rows walks the hidden chunks serially: worth it when there are enough row tiles to fill the
-        # GPU (encoder, 175 tiles) or the chain is short (256-wide hidden = 2 chunks); the 2048-wide FFN on <= 400 decoder
-        # rows is faster as two GEMMs (measured 51 vs 30 us, profiles/r01_micro_gemm_v3_fused.json)
-        worth = M >= 2048 or L1.N <= 256
+        # GPU (encoder, 175 tiles); on <= 400 decoder rows two GEMMs are as fast or faster (measured 51 vs 30 us for the
+        # 2048-wide FFN, 22.5 vs 21.4 us for the 256-wide MLPs; profiles/r01_micro_gemm_v3_fused.json)
+        worth = M >= 2048
         if self.fused_mlp and worth and self.mode == "bf16" and L1.K == 256 and L2.N == 256 and L1.N % 128 == 0 \
                 and L2.K == L1.N:
             self._ck(self.lib.memotr_mlp2(_p(x), ldx, _p(L1.w), _p(L1.b), _p(L2.w), _p(L2.b), _p(mul), ldmul, _p(out), ldo,
@@ -270,6 +274,19 @@ class FrameEngine:
         self._ck(self.lib.memotr_msda_prep(_p(ol), ldol, _p(self.shapes_t), _p(self.lsi_t), _p(self.vr), _p(ref4), mode,
                                            _p(self.loc), _p(self.attw), Lq, self.H, self.L, K, self._st()), "msda_prep")
         timed = self.timer is not None and mode == 0
+        if mode == 0 and self.use_pairs:
+            self._ck(self.lib.memotr_msda_pairs_layout(_p(value), stride, _p(self.shapes_t), _p(self.lsi_t),
+                                                       _p(self.pairs), self.S, self.H, self.L, self._st()), "pairs_layout")
+            if timed:
+                slot = self._timer_slot % self.n_enc
+                self._timer_slot += 1
+                _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
+            self._ck(self.lib.memotr_msda_forward_pairs(_p(self.pairs), _p(self.shapes_t), _p(self.lsi_t), _p(self.loc),
+                                                        _p(self.attw), _p(out), self.S, self.H, self.L, Lq, K,
+                                                        self._st()), "msda_forward_pairs")
+            if timed:
+                _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
+            return
         if timed:
             slot = self._timer_slot % self.n_enc
             self._timer_slot += 1

@@ -125,3 +125,27 @@ def box_refine(delta, ref, n_take):
                                           ref.shape[0], n_take, _lib.stream_ptr())
     _lib.check(rc, "memotr_box_refine")
     return new_ref, ref_next
+
+
+def msda_pairs_layout(value, spatial_shapes, level_start_index, n_heads):
+    """(S, >=H*32) bf16 pixel-major value map -> (H, S, 2, 32) pair-duplicated head-major map."""
+    S = value.shape[0]
+    pairs = torch.empty((n_heads, S, 2, 32), dtype=torch.bfloat16, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().memotr_msda_pairs_layout(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
+                                                 _lib.ptr(level_start_index), _lib.ptr(pairs), S, n_heads,
+                                                 spatial_shapes.shape[0], _lib.stream_ptr())
+    _lib.check(rc, "memotr_msda_pairs_layout")
+    return pairs
+
+
+def msda_forward_pairs(pairs, spatial_shapes, level_start_index, loc, attn):
+    H, S = pairs.shape[0], pairs.shape[1]
+    Lq, _, L, K = attn.shape
+    out = torch.empty((Lq, H * 32), dtype=torch.bfloat16, device=pairs.device)
+    with torch.cuda.device(pairs.device):
+        rc = _lib.lib().memotr_msda_forward_pairs(_lib.ptr(pairs), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
+                                                  _lib.ptr(loc), _lib.ptr(attn), _lib.ptr(out), S, H, L, Lq, K,
+                                                  _lib.stream_ptr())
+    _lib.check(rc, "memotr_msda_forward_pairs")
+    return out

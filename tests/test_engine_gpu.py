@@ -196,6 +196,31 @@ def test_msda_forward_ex_decode_once_kernel(dtype, Kp, shapes):
     assert rel_err(got, want) < (2e-6 if dtype == torch.float32 else 4e-3)
 
 
+@pytest.mark.parametrize("Kp,shapes,Lq", [(4, synth.DANCETRACK_SHAPES, 777), (8, synth.BDD_SHAPES, 100), (4, synth.BDD_SHAPES_L5, 64),
+                                          (2, synth.SMALL_SHAPES, 50), (1, ((1, 1), (2, 3)), 9)])
+def test_msda_pairs_layout_and_gather(Kp, shapes, Lq):
+    """Encoder fast path: pair-duplicated head-major value map + 2-loads-per-point gather, against the C oracle (border
+    samples included: x0 = -1, x1 = W, y out of range), reading the value map through a pixel stride."""
+    from oracle import msda as omsda
+    value, shp, lsi, loc, attn = synth.msda_inputs(shapes, B=1, H=8, D=32, K=Kp, Lq=Lq, seed=70 + Kp, border=True)
+    S = value.shape[1]
+    wide = torch.randn(S, 2 * 256, generator=_g(2)).bfloat16()
+    wide[:, 256:] = value.reshape(S, 256).bfloat16()
+    v_used = wide[:, 256:].float().reshape(1, S, 8, 32)
+    want = omsda.forward(v_used.numpy(), shp.numpy(), lsi.numpy(), loc.numpy(), attn.numpy(), fma=True)[0]
+    pairs = K().msda_pairs_layout(wide.to(DEV)[:, 256:], shp.to(DEV), lsi.to(DEV), 8)
+    # layout property: half 0 is the pixel itself, half 1 its right neighbour (zeros at row ends)
+    hm = v_used[0].permute(1, 0, 2)                                       # (H, S, 32)
+    assert torch.equal(pairs[:, :, 0].float().cpu(), hm)
+    x_idx = torch.cat([torch.arange(h * w) % w for h, w in shapes])
+    w_of = torch.cat([torch.full((h * w,), w) for h, w in shapes])
+    right = torch.roll(hm, -1, dims=1) * (x_idx + 1 < w_of)[None, :, None]
+    assert torch.equal(pairs[:, :, 1].float().cpu(), right)
+    got = K().msda_forward_pairs(pairs, shp.to(DEV), lsi.to(DEV), loc[0].contiguous().to(DEV),
+                                 attn[0].contiguous().to(DEV)).float().cpu().numpy()
+    assert rel_err(got, want) < 4e-3
+
+
 @pytest.mark.parametrize("mode,L,Kp", [("enc", 4, 4), ("dec", 4, 4), ("enc", 4, 8), ("dec", 4, 3), ("enc", 5, 4)])
 def test_msda_prep_matches_module_arithmetic(mode, L, Kp):
     """Sampling locations / attention weights against the torch expressions of ms_deform_attn.py:108-120 with the

@@ -98,6 +98,11 @@ def main():
                     row[f"ex_{kern}{'_U' + U if kern == 'v2' else ''}_{nm}_us"] = t
             os.environ.pop("MEMOTR_MSDA_KERNEL", None)
             os.environ.pop("MEMOTR_MSDA_U", None)
+            if K in (4, 8):
+                vb16 = value.reshape(S, 256).bfloat16()
+                row["pairs_layout_us"], _ = timeit(lambda: kernels.msda_pairs_layout(vb16, shp, lsi, 8), flush=flush)
+                pr = kernels.msda_pairs_layout(vb16, shp, lsi, 8)
+                row["pairs_gather_us"], _ = timeit(lambda: kernels.msda_forward_pairs(pr, shp, lsi, lc[0], attn[0]), flush=flush)
             if K == 4:
                 go = torch.randn(1, Lq, 256, device=DEV)
                 t, _ = timeit(lambda: memotr_b200.ms_deform_attn_backward(value, shp, lsi, lc, attn, go, 64), flush=flush)
