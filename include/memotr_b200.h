@@ -40,6 +40,7 @@ extern "C" {
 #define MEMOTR_F32 0
 #define MEMOTR_F64 1
 #define MEMOTR_BF16 2
+#define MEMOTR_F16 3  /* value maps only: memotr_linear output, memotr_msda_forward_ex input */
 
 /* return codes */
 #define MEMOTR_OK 0
@@ -80,7 +81,7 @@ MEMOTR_API int memotr_msda_backward(const void *value, const int64_t *spatial_sh
 
 
 /*
- * Engine variant of the forward op: value/output in `dtype` (F32 or BF16), sampling locations and attention
+ * Engine variant of the forward op: value/output in `dtype` (F32 or BF16; F16 = fp16 value map with bf16 output), sampling locations and attention
  * weights always fp32 (the outputs of memotr_msda_prep), D == 32, and an explicit pixel stride (elements between
  * consecutive pixels of `value`, >= H*32) so that the value maps of all decoder layers can live interleaved in one
  * (S, n_layers*256) buffer written by a single GEMM.  Same arithmetic as memotr_msda_forward.
@@ -120,6 +121,7 @@ MEMOTR_API int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatia
                                 float *sampling_loc, float *attn_weight, int Lq, int H, int L, int K, void *stream);
 
 /*
+ * (c_dtype MEMOTR_F16 is additionally accepted on the tensor-core path: the value maps the sampling kernel reads.)
  * C = epilogue(A . W^T):  v = acc + bias;  act (0 none, 1 ReLU, 2 sigmoid);  v *= mul;  v += add;  rows with
  * rowzero[m] != 0 are written as zeros.  A (M,K) lda, W (N,K) ldw, both `ab_dtype` (F32 or BF16); C (M,N) ldc in
  * `c_dtype` (F32, or BF16 when ab_dtype is BF16); mul/add (M,N) in ab_dtype; bias fp32; fp32 accumulation.

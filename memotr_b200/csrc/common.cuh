@@ -1,6 +1,7 @@
 // common.cuh -- shared helpers for the sm_100a kernels behind the C ABI (include/memotr_b200.h).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -99,6 +100,21 @@ __device__ __forceinline__ uint4 f32x8_to_bf16(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return u;
 }
+
+__device__ __forceinline__ uint4 f32x8_to_f16(const float (&f)[8]) {
+  uint4 u;
+  __half2 *h = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+// 8 floats -> 16 bytes of the 2-byte type T (bf16 or fp16)
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]);
+template <>
+__device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&f)[8]) { return f32x8_to_bf16(f); }
+template <>
+__device__ __forceinline__ uint4 pack8<__half>(const float (&f)[8]) { return f32x8_to_f16(f); }
 
 // ---- dtype conversion + the GEMM epilogue description shared by gemm_simt.cu and gemm_tc.cu -------------------------
 template <typename T>

@@ -161,8 +161,8 @@ extern "C" int memotr_linear(const void *A, int lda, const void *W, int ldw, con
   MEMOTR_REQUIRE(lda >= K && ldw >= K && ldc >= N, "linear: leading dimension too small");
   MEMOTR_REQUIRE(act >= 0 && act <= 2, "linear: unknown activation %d", act);
   MEMOTR_REQUIRE(ab_dtype == MEMOTR_F32 || ab_dtype == MEMOTR_BF16, "linear: A/W dtype must be f32 or bf16");
-  MEMOTR_REQUIRE(c_dtype == MEMOTR_F32 || (c_dtype == MEMOTR_BF16 && ab_dtype == MEMOTR_BF16),
-                 "linear: output dtype must be f32, or bf16 with bf16 inputs");
+  MEMOTR_REQUIRE(c_dtype == MEMOTR_F32 || ((c_dtype == MEMOTR_BF16 || c_dtype == MEMOTR_F16) && ab_dtype == MEMOTR_BF16),
+                 "linear: output dtype must be f32, or bf16/fp16 with bf16 inputs");
   cudaStream_t st = (cudaStream_t)stream;
   Epilogue ep{bias, mul, add, rowzero, ldmul, ldadd, act};
   // path: 0 = auto, 1 = force CUDA-core kernel, 2 = force tensor-core kernel
@@ -171,6 +171,7 @@ extern "C" int memotr_linear(const void *A, int lda, const void *W, int ldw, con
     if (ok) return linear_tc_bf16(A, lda, W, ldw, C, ldc, c_dtype, M, N, K, ep, st);
     if (path == 2) return fail(MEMOTR_ENOSYS, "linear: shape M=%d N=%d K=%d not supported by the tcgen05 path", M, N, K);
   }
+  MEMOTR_REQUIRE(c_dtype != MEMOTR_F16, "linear: fp16 output is only produced by the tensor-core path");
   if (ab_dtype == MEMOTR_F32) return launch_simt<float, float>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);
   if (c_dtype == MEMOTR_F32) return launch_simt<__nv_bfloat16, float>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);
   return launch_simt<__nv_bfloat16, __nv_bfloat16>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);

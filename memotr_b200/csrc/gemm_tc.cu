@@ -18,6 +18,8 @@
 //            (32 scattered 16-byte sectors per store instruction); the panels make every global write a full line.
 // Rows beyond M are zero-filled by TMA on load and clipped by TMA on store.  96 KB (BN=128) or 72 KB (BN=64) of shared memory
 // and BN TMEM columns per CTA, so 2-3 CTAs are resident per SM and one tile's epilogue overlaps another's main loop.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace memotr {
@@ -175,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float t[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) t[i] = v[8 * k + i];
-          *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t);
+          *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = pack8<TC>(t);
         }
       }
     }
@@ -204,7 +206,7 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
                   const Epilogue &ep, cudaStream_t st) {
   CUtensorMap tmA, tmW, tmC;
   if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN) ||
-      !make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4))
+      !make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4, std::is_same<TC, __half>::value))
     return fail(MEMOTR_ECUDA, "linear(tc): cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   auto kern = gemm_tc_kernel<BN, TC>;
   static bool attr_set = false;  // idempotent attribute; benign if two threads race to set the same value
@@ -223,7 +225,7 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
 bool linear_tc_supported(int lda, int ldw, int ldc, int c_dtype, int M, int N, int K, const void *A, const void *W,
                          const void *C) {
   (void)M;
-  const int cal = c_dtype == MEMOTR_F32 ? 4 : 8;  // 16-byte row segments on store
+  const int cal = c_dtype == MEMOTR_F32 ? 4 : 8;  // 16-byte row segments on store (bf16 / fp16: 8 elements)
   return N % 64 == 0 && K % tc::BK == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % cal == 0 && aligned16(A) &&
          aligned16(W) && aligned16(C) && tc::encode_fn() != nullptr;
 }
@@ -234,6 +236,9 @@ int linear_tc_bf16(const void *A, int lda, const void *W, int ldw, void *C, int 
   if (ep.add && (ep.ldadd % 8 != 0 || !aligned16(ep.add))) return fail(MEMOTR_EINVAL, "linear(tc): add misaligned");
   if (ep.bias && !aligned16(ep.bias)) return fail(MEMOTR_EINVAL, "linear(tc): bias misaligned");
   const bool wide = N % 128 == 0;
+  if (c_dtype == MEMOTR_F16)
+    return wide ? tc::launch<128, __half>(A, lda, W, ldw, C, ldc, M, N, K, ep, st)
+                : tc::launch<64, __half>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);
   if (c_dtype == MEMOTR_F32)
     return wide ? tc::launch<128, float>(A, lda, W, ldw, C, ldc, M, N, K, ep, st)
                 : tc::launch<64, float>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);

@@ -538,6 +538,10 @@ static int launch_v2(const void *value, const int64_t *shapes, const int64_t *ls
 
 }  // namespace memotr
 
+namespace memotr {
+static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st);
+}
 using namespace memotr;
 
 // Engine variant: value/output in `dtype` (f32 or bf16), sampling locations and attention weights always fp32 (they
@@ -553,11 +557,14 @@ extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
   if ((long)B * Lq == 0) return MEMOTR_OK;
   MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && sampling_loc && attn_weight && output,
                  "msda_forward_ex: null pointer");
-  const int al = dtype == MEMOTR_BF16 ? 8 : 4;
+  const int al = dtype == MEMOTR_F32 ? 4 : 8;
   MEMOTR_REQUIRE(aligned16(value) && aligned16(output) && value_pixel_stride % al == 0 &&
                      ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
                  "msda_forward_ex: misaligned buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MEMOTR_F16)  // fp16 value map -> bf16 output, packed-half blend (v4)
+    return launch_h16(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L, Lq, K,
+                      value_pixel_stride, st);
   // v2 (decode-once) measured no faster than v1 on B200 (profiles/r01_micro_msda_v3_decode_once.json), so the
   // reference-order kernel stays the default; MEMOTR_MSDA_KERNEL=v2 [MEMOTR_MSDA_U=1|2|4] selects the experiment.
   const char *force = getenv("MEMOTR_MSDA_KERNEL");
@@ -718,3 +725,124 @@ extern "C" int memotr_msda_forward_pairs(const void *pairs, const int64_t *spati
 #undef PAIRS_LAUNCH
   return check_launch("msda_fwd_pairs");
 }
+
+// =====================================================================================================================
+// v4 gather: fp16 value map, packed-half blending.
+//
+// ncu on v1/v2/v3 (profiles/r01_msda_variants_ncu.md): with a bf16 value map the kernel is bound by the ALU pipe
+// (72 % busy) -- one integer op per element just to widen bf16 to fp32 (32 per point per lane), on top of addressing --
+// whatever the thread mapping or layout.  Storing the value map in fp16 (11-bit mantissa: MORE accurate than bf16 for
+// this read-only intermediate; the value_proj GEMM epilogue writes it) lets the 4-corner blend run as packed HFMA2 on
+// 2 channels per instruction with no widening at all; the fp16 partial sum of one level's K points is widened and
+// added into the fp32 accumulator once per level.  Corner weights (bilinear x attention, <= 1) are rounded to fp16;
+// out-of-range corners get weight 0 and a clamped address, so the loads are unpredicated.
+namespace memotr {
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+             const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
+             int L, int Lq, int Kr, int xs, long n_qh) {
+  pdl_grid_sync();
+  constexpr int D = 32, G = 4;
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long qh = tid / G;
+  if (qh >= n_qh) return;
+  const int sub = (int)(tid % G);
+  const int m = (int)(qh % H);
+  const int b = (int)((qh / H) / Lq);
+  const int K = KT ? KT : Kr;
+  const long pbase = qh * L * K;
+  const __half *vb = value + (long)b * S * xs + m * D + sub * 8;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+
+  for (int l = 0; l < L; ++l) {
+    const int Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
+    const float Hf = (float)Hh, Wf = (float)Ww;
+    const int base = (int)__ldg(lsi + l) * xs, ys = Ww * xs;
+    __half2 a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = __float2half2_rn(0.f);
+
+    auto point = [&](int p, __half2 (&w)[4], int (&o)[4]) {
+      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + pbase + l * K + p);
+      const float aw = __ldg(attn + pbase + l * K + p);
+      const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
+      const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
+      const float hfl = floorf(h_im), wfl = floorf(w_im);
+      const int y0 = (int)hfl, x0 = (int)wfl;
+      const float lh = h_im - hfl, lw = w_im - wfl, hh = 1.f - lh, hw = 1.f - lw;
+      const bool y0ok = inside && y0 >= 0, y1ok = inside && y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
+      const int yc0 = min(max(y0, 0), Hh - 1), yc1 = min(max(y0 + 1, 0), Hh - 1);
+      const int xc0 = min(max(x0, 0), Ww - 1), xc1 = min(max(x0 + 1, 0), Ww - 1);
+      o[0] = base + yc0 * ys + xc0 * xs;
+      o[1] = base + yc0 * ys + xc1 * xs;
+      o[2] = base + yc1 * ys + xc0 * xs;
+      o[3] = base + yc1 * ys + xc1 * xs;
+      w[0] = __float2half2_rn((y0ok && x0ok) ? hh * hw * aw : 0.f);
+      w[1] = __float2half2_rn((y0ok && x1ok) ? hh * lw * aw : 0.f);
+      w[2] = __float2half2_rn((y1ok && x0ok) ? lh * hw * aw : 0.f);
+      w[3] = __float2half2_rn((y1ok && x1ok) ? lh * lw * aw : 0.f);
+    };
+    auto blend = [&](const __half2 (&w)[4], const uint4 (&r)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const __half2 *v = reinterpret_cast<const __half2 *>(&r[c]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = __hfma2(w[c], v[j], a[j]);
+      }
+    };
+    if constexpr (KT > 0) {
+      __half2 w[KT][4];
+      int o[KT][4];
+      uint4 r[KT][4];
+#pragma unroll
+      for (int p = 0; p < KT; ++p) point(p, w[p], o[p]);
+#pragma unroll
+      for (int p = 0; p < KT; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[p][c] = __ldg(reinterpret_cast<const uint4 *>(vb + o[p][c]));
+#pragma unroll
+      for (int p = 0; p < KT; ++p) blend(w[p], r[p]);
+    } else {
+      for (int p = 0; p < K; ++p) {
+        __half2 w[4];
+        int o[4];
+        uint4 r[4];
+        point(p, w, o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[c] = __ldg(reinterpret_cast<const uint4 *>(vb + o[c]));
+        blend(w, r);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(a[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  }
+  *reinterpret_cast<uint4 *>(out + qh * D + sub * 8) = f32x8_to_bf16(acc);
+}
+
+static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st) {
+  const long n_qh = (long)B * Lq * H;
+  const int grid = (int)((n_qh * 4 + 255) / 256);
+#define H16_LAUNCH(KT_)                                                                                      \
+  MEMOTR_LAUNCH((msda_fwd_h16<KT_>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,       \
+                (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh)
+  switch (K) {
+    case 1: H16_LAUNCH(1); break;
+    case 2: H16_LAUNCH(2); break;
+    case 4: H16_LAUNCH(4); break;
+    case 8: H16_LAUNCH(8); break;
+    default: H16_LAUNCH(0); break;
+  }
+#undef H16_LAUNCH
+  return check_launch("msda_fwd_h16");
+}
+
+}  // namespace memotr

@@ -96,7 +96,8 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // 2-D row-major (rows, cols) with leading dimension ld (elements); box = box_rows x (128 bytes of columns), 128B swizzle
-inline bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows, bool f32 = false) {
+inline bool make_map(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_rows, bool f32 = false,
+                     bool f16 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const int esz = f32 ? 4 : 2;
@@ -104,7 +105,10 @@ inline bool make_map(CUtensorMap *map, const void *base, long rows, long cols, l
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+  const CUtensorMapDataType dt = f32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                       : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  return fn(map, dt, 2, const_cast<void *>(base),
             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-F32, BF16 = _lib.F32, _lib.BF16
+F32, BF16, F16 = _lib.F32, _lib.BF16, _lib.F16
 
 
 def _p(t):
@@ -60,8 +60,14 @@ class FrameEngine:
         import os
         self.fused_mlp = os.environ.get("MEMOTR_FUSED_MLP", "1") != "0"   # A/B switch for the on-chip FFN/MLP kernel
         # encoder MSDA on the pair-duplicated head-major value map (bf16 mode, K in {1,2,4,8}); A/B switch
-        self.use_pairs = (os.environ.get("MEMOTR_MSDA_PAIRS", "1") != "0" and mode == "bf16"
+        # (measured slower than the plain layout -- the gather is ALU-bound, not L1-bound -- so off by default)
+        self.use_pairs = (os.environ.get("MEMOTR_MSDA_PAIRS", "0") == "1" and mode == "bf16"
                           and cfg["n_enc_points"] in (1, 2, 4, 8))
+        # value maps in fp16 (bf16 mode): more mantissa than bf16 for this read-only intermediate, and the gather can
+        # blend corners with packed HFMA2 instead of widening every bf16 element on the (binding) ALU pipe; A/B switch
+        self.value_f16 = mode == "bf16" and os.environ.get("MEMOTR_VALUE_F16", "1") != "0" and not self.use_pairs
+        self.vdt = F16 if self.value_f16 else self.dt
+        self.tv = torch.float16 if self.value_f16 else self.ta
         self._pack(state_dict)
         self._alloc()
         self.graph = None
@@ -175,7 +181,7 @@ class FrameEngine:
         self.mask_flat = torch.zeros(S, dtype=torch.uint8, device=dev)
         self.vr = f(self.L, 2)
         self.src_tok, self.pos_tok, self.q_tok = e(S, C), e(S, C), e(S, C)
-        self.value = e(S, C)
+        self.value = e(S, C, dtype=self.tv)
         self.pairs = e(self.H, S, 2, 32) if self.use_pairs else None
         self.ol = f(S, 3 * self.H * LK)
         self.loc = f(S, self.H, LK, 2)
@@ -188,7 +194,7 @@ class FrameEngine:
         self.src32 = self.src_tok if fp32 else f(S, C)
         self.src1_32 = self.src1 if fp32 else f(S, C)
         self.hid = e(S, self.Fd)
-        self.value_all = e(S, self.n_dec * C)
+        self.value_all = e(S, self.n_dec * C, dtype=self.tv)
         # decoder (Nq rows)
         self.ref = [f(nq, 4) for _ in range(self.n_dec + 1)]         # ref[0] = init (sigmoid), ref[l+1] after layer l
         self.pred_box = [f(nq, 4) for _ in range(self.n_dec)]
@@ -292,7 +298,7 @@ class FrameEngine:
             self._timer_slot += 1
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
         self._ck(self.lib.memotr_msda_forward_ex(_p(value), stride, _p(self.shapes_t), _p(self.lsi_t), _p(self.loc),
-                                                 _p(self.attw), _p(out), 1, self.S, self.H, self.L, Lq, K, self.dt,
+                                                 _p(self.attw), _p(out), 1, self.S, self.H, self.L, Lq, K, self.vdt,
                                                  self._st()), "msda_forward_ex")
         if timed:
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
@@ -340,7 +346,7 @@ class FrameEngine:
         Ke = self.cfg["n_enc_points"]
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
-            self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat)
+            self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
             self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
             self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
             self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
@@ -362,7 +368,7 @@ class FrameEngine:
         self.convert(self.vr, F32, 2, self.vr_scale4, F32, 2, 1, 2)          # (vr0.w, vr0.h, vr0.w, vr0.h)
         self.convert(self.vr, F32, 2, self.vr_scale4[2:], F32, 2, 1, 2)
         # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
-        self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat)
+        self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
         Kd = self.cfg["n_dec_points"]
         for lid, ly in enumerate(self.dec):
             out, ref = self.tgt[lid], self.ref[lid]

@@ -99,7 +99,8 @@ def msda_forward_ex(value, spatial_shapes, level_start_index, loc, attn, n_heads
     """value (S, >=H*32 columns; may be a column slice of a wider buffer) f32/bf16; loc/attn fp32 -> (Lq, H*32)."""
     S = value.shape[0]
     Lq, H, L, K = attn.shape
-    out = torch.empty((Lq, H * 32), dtype=value.dtype, device=value.device)
+    out_dtype = torch.bfloat16 if value.dtype == torch.float16 else value.dtype     # fp16 value maps feed bf16 GEMMs
+    out = torch.empty((Lq, H * 32), dtype=out_dtype, device=value.device)
     with torch.cuda.device(value.device):
         rc = _lib.lib().memotr_msda_forward_ex(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
                                                _lib.ptr(level_start_index), _lib.ptr(loc), _lib.ptr(attn), _lib.ptr(out),

@@ -65,7 +65,7 @@ def test_linear_fp32_epilogues():
 
 @pytest.mark.parametrize("M,N,K_", [(128, 64, 64), (1, 128, 256), (300, 384, 256), (400, 256, 512), (4000, 2048, 256),
                                     (1025, 256, 2048), (22323, 256, 256), (22323, 1536, 256)])
-@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32, torch.float16])
 def test_linear_bf16_tensor_core(M, N, K_, out_dtype):
     g = _g(M + N + 1)
     x = torch.randn(M, K_, generator=g).bfloat16()
@@ -73,7 +73,7 @@ def test_linear_bf16_tensor_core(M, N, K_, out_dtype):
     b = torch.randn(N, generator=g)
     want = F.linear(x.double(), w.double(), b.double())        # exact product of the bf16-rounded operands
     got = K().linear(x.to(DEV), w.to(DEV), b.to(DEV), out_dtype=out_dtype, path="tc").float().cpu()
-    tol = 1e-5 if out_dtype == torch.float32 else 6e-3        # fp32 accumulate; bf16 output rounding 2^-8
+    tol = {torch.float32: 1e-5, torch.bfloat16: 6e-3, torch.float16: 8e-4}[out_dtype]   # output rounding 2^-8 / 2^-11
     assert rel_err(got, want) < tol
 
 
@@ -178,7 +178,7 @@ def test_mha_core(dtype, Nq, Nk, masked):
         assert rel_err(got, want) < 5e-3
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("Kp,shapes", [(4, synth.DANCETRACK_SHAPES), (8, synth.BDD_SHAPES), (4, synth.BDD_SHAPES_L5),
                                        (3, synth.SMALL_SHAPES)])
 def test_msda_forward_ex_decode_once_kernel(dtype, Kp, shapes):
@@ -193,7 +193,24 @@ def test_msda_forward_ex_decode_once_kernel(dtype, Kp, shapes):
     want = omsda.forward(v_used.numpy(), shp.numpy(), lsi.numpy(), loc.numpy(), attn.numpy(), fma=True)[0]
     got = K().msda_forward_ex(wide.to(DEV)[:, 256:512], shp.to(DEV), lsi.to(DEV), loc[0].contiguous().to(DEV),
                               attn[0].contiguous().to(DEV), 8).float().cpu().numpy()
+    # fp16 value map (packed-half blend, bf16 output): the output rounding to bf16 (2^-9) dominates
     assert rel_err(got, want) < (2e-6 if dtype == torch.float32 else 4e-3)
+
+
+def test_msda_forward_ex_fp16_value_map_is_tighter_than_bf16():
+    """Same inputs, fp16 vs bf16 value maps, each against the fp32 oracle on the UNROUNDED value: the fp16 path (more
+    mantissa in the map, fp16 corner blend) must not be worse than the bf16 path."""
+    from oracle import msda as omsda
+    value, shp, lsi, loc, attn = synth.msda_inputs(synth.DANCETRACK_SHAPES, B=1, H=8, D=32, K=4, Lq=2000, seed=81, border=True)
+    S = value.shape[1]
+    v2d = (value.reshape(S, 256) * 100).contiguous()            # O(1) magnitudes like a real value_proj output
+    want = omsda.forward(v2d.reshape(1, S, 8, 32).numpy(), shp.numpy(), lsi.numpy(), loc.numpy(), attn.numpy())[0]
+    d = lambda t: t.to(DEV)                                                                  # noqa: E731
+    err = {}
+    for dt in (torch.bfloat16, torch.float16):
+        got = K().msda_forward_ex(d(v2d.to(dt)), d(shp), d(lsi), d(loc[0].contiguous()), d(attn[0].contiguous()), 8)
+        err[dt] = rel_err(got.float().cpu().numpy(), want)
+    assert err[torch.float16] <= err[torch.bfloat16] * 1.05 and err[torch.float16] < 5e-3, err
 
 
 @pytest.mark.parametrize("Kp,shapes,Lq", [(4, synth.DANCETRACK_SHAPES, 777), (8, synth.BDD_SHAPES, 100), (4, synth.BDD_SHAPES_L5, 64),

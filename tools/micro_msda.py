@@ -98,6 +98,8 @@ def main():
                     row[f"ex_{kern}{'_U' + U if kern == 'v2' else ''}_{nm}_us"] = t
             os.environ.pop("MEMOTR_MSDA_KERNEL", None)
             os.environ.pop("MEMOTR_MSDA_U", None)
+            vh16 = value.reshape(S, 256).half()
+            row["ex_v4_fp16_us"], _ = timeit(lambda: kernels.msda_forward_ex(vh16, shp, lsi, lc[0], attn[0], 8), flush=flush)
             if K in (4, 8):
                 vb16 = value.reshape(S, 256).bfloat16()
                 row["pairs_layout_us"], _ = timeit(lambda: kernels.msda_pairs_layout(vb16, shp, lsi, 8), flush=flush)
