@@ -338,7 +338,8 @@ def main():
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": eng.graph_launches * K,
         "sections_us": {k: round(v, 1) for k, v in sections.items()},
-        "roofline": {"kernel": "msda_fwd_vec (encoder-shaped launch, Lq = S = 22323)", "bound": "hbm",
+        "roofline": {"kernel": ("msda_fwd_h16 (fp16 value map)" if eng.value_f16 else "msda_fwd_vec") +
+                               " -- encoder-shaped launch, Lq = S = 22323", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "duration_us": dur,
                      "samples": f"{len(msda_us)} launches (the encoder layers of the last timed step), CUDA events "

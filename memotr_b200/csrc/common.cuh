@@ -75,6 +75,26 @@ inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);  // errors: check_launch()
 }
+// same, for kernels launched as thread-block clusters of `cluster_x` CTAs (TMA multicast between neighbouring SMs)
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  unsigned cluster_x, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 #define MEMOTR_LAUNCH(kern, grid, block, smem, st, ...) \
   ::memotr::launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 

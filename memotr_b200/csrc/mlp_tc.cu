@@ -17,6 +17,13 @@
 // are mbarriers (TMA expect_tx, tcgen05.commit, and 128-thread arrives from the epilogue warps).  TMEM: 2x128 + 256 =
 // 512 columns.  Shared memory: X 64 KB + ring 96 KB + H 64 KB = 224 KB (one CTA per SM).  Final epilogue as in
 // gemm_tc.cu: bias / activation / multiplier -> swizzled panels in the (dead) X+ring memory -> TMA store.
+//
+// Thread-block clusters (CS = 2 or 4 CTAs on neighbouring SMs, different row tiles): every CTA needs the SAME W1/W2
+// chunks, and with one CTA per SM the kernel is bound by the per-SM L2->SM bandwidth (2 MB of weights per 128-row tile;
+// measured 82 us per encoder FFN vs a ~17 us MMA bound).  Each CTA of a cluster therefore loads 1/CS of every ring slot
+// and TMA-multicasts it into the shared memory of all CS CTAs (cp.async.bulk.tensor ... .multicast::cluster); the slot's
+// `full` mbarrier in every CTA counts the bytes arriving from all issuers, and a slot is re-filled only after the MMA
+// warps of ALL CTAs released it (tcgen05.commit ... multicast::cluster onto every CTA's `empty` barrier, count CS).
 #include "tc_common.cuh"
 
 namespace memotr {
@@ -39,8 +46,31 @@ constexpr int TOTAL = OFF_BAR + 256 + 1024;
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], "
+      "[%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 
-template <typename TC>
+template <typename TC, int CS>
 __global__ void __launch_bounds__(192, 1)
 mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
@@ -56,6 +86,8 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x;
   const int NC = Hd / HC;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -65,7 +97,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     mbar_init(x_full, 1);
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
+      mbar_init(empty + s, CS);   // released by the MMA warps of all CTAs of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc1_full + b, 1);
@@ -82,7 +114,8 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_grid_sync();
@@ -96,21 +129,33 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_expect_tx(x_full, X_BYTES);
       for (int p = 0; p < XP; ++p) tma_load_2d(smem + p * PANEL, &tmX, x_full, p * BK, m_blk * BM);
       int t = 0;
-      auto load_w1 = [&](int c) {
+      // a ring slot is 256 row-units of 128 B; this CTA loads units [crank*UNITS, (crank+1)*UNITS) and multicasts them
+      constexpr int UNITS = 256 / CS;
+      auto load_w1 = [&](int c) {          // slot = [k-block 2*half: 128 rows][k-block 2*half+1: 128 rows]
         for (int half = 0; half < 2; ++half, ++t) {
           const int s = t % NSLOT;
           mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + s, SLOT);
-          tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, c * HC);
-          tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, c * HC);
+          if constexpr (CS == 1) {
+            tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, c * HC);
+            tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, c * HC);
+          } else {
+            const int u0 = crank * UNITS, kb = 2 * half + u0 / 128, r0 = u0 % 128;
+            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW1, full + s, kb * BK, c * HC + r0, MC_MASK);
+          }
         }
       };
-      auto load_w2 = [&](int c) {
+      auto load_w2 = [&](int c) {          // slot = 256 output rows x 64 hidden columns
         for (int j = 0; j < 2; ++j, ++t) {
           const int s = t % NSLOT;
           mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + s, SLOT);
-          tma_load_2d(ring + s * SLOT, &tmW2, full + s, c * HC + j * BK, 0);
+          if constexpr (CS == 1) {
+            tma_load_2d(ring + s * SLOT, &tmW2, full + s, c * HC + j * BK, 0);
+          } else {
+            const int u0 = crank * UNITS;
+            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW2, full + s, c * HC + j * BK, u0, MC_MASK);
+          }
         }
       };
       load_w1(0);
@@ -143,7 +188,8 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int k = 0; k < BK / 16; ++k)
               umma_bf16(tmem_base + b * HC, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0);
           }
-          umma_commit(empty + s);
+          if constexpr (CS > 1) umma_commit_mc(empty + s, MC_MASK);
+          else umma_commit(empty + s);
         }
         umma_commit(acc1_full + b);
       };
@@ -159,7 +205,8 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_base + 2 * HC, adesc + 2 * k, bdesc + 2 * k, idesc2, (c | j | k) != 0);
-          umma_commit(empty + s);
+          if constexpr (CS > 1) umma_commit_mc(empty + s, MC_MASK);
+          else umma_commit(empty + s);
         }
         umma_commit(h_empty + b);
       };
@@ -278,29 +325,39 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / arrive on it
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
-template <typename TC>
+template <typename TC, int CS>
 static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
                        int Hd, const Epilogue &ep, cudaStream_t st) {
   using namespace mlp;
   CUtensorMap tmX, tmW1, tmW2, tmC;
-  if (!make_map(&tmX, X, M, K1, ldx, BM) || !make_map(&tmW1, W1, Hd, K1, K1, HC) || !make_map(&tmW2, W2, N2, Hd, Hd, N2) ||
+  constexpr int W1_BOX = CS == 1 ? HC : (256 / CS < 128 ? 256 / CS : 128), W2_BOX = 256 / CS;
+  if (!make_map(&tmX, X, M, K1, ldx, BM) || !make_map(&tmW1, W1, Hd, K1, K1, W1_BOX) ||
+      !make_map(&tmW2, W2, N2, Hd, Hd, W2_BOX) ||
       !make_map(&tmC, C, M, N2, ldc, BM, sizeof(TC) == 4))
     return fail(MEMOTR_ECUDA, "mlp2(tc): cuTensorMapEncodeTiled failed (M=%d Hd=%d)", M, Hd);
-  auto kern = mlp2_tc_kernel<TC>;
+  auto kern = mlp2_tc_kernel<TC, CS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL);
     if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  MEMOTR_LAUNCH((kern), ceil_div(M, BM), 192, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
+  const int tiles = ceil_div(M, BM);
+  if constexpr (CS == 1) {
+    MEMOTR_LAUNCH((kern), tiles, 192, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
+  } else {
+    // CTAs beyond the last tile (grid rounded up to a whole cluster) see zero-filled X and have their stores clipped
+    launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(192), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
+                          M, Hd, ep);
+  }
   return check_launch("mlp2_tc");
 }
 
@@ -325,6 +382,19 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   if (M == 0) return MEMOTR_OK;
   Epilogue ep{b2, mul, nullptr, nullptr, ldmul, 0, act2};
   cudaStream_t st = (cudaStream_t)stream;
-  return c_dtype == MEMOTR_F32 ? tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
-                               : tc::launch_mlp2<__nv_bfloat16>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
+  // cluster size: enough row tiles to fill the GPU with clusters -> multicast the weights (MEMOTR_MLP_CLUSTER = 1|2|4)
+  const char *cs_str = getenv("MEMOTR_MLP_CLUSTER");
+  const int cs_env = cs_str ? atoi(cs_str) : 0;
+  const int tiles = ceil_div(M, tc::BM);
+  const int cs = cs_env ? cs_env : (tiles >= 2 * kNumSMs / 2 ? 2 : 1);
+#define MLP2_GO(TC_, CS_) return tc::launch_mlp2<TC_, CS_>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
+  if (c_dtype == MEMOTR_F32) {
+    if (cs == 4) MLP2_GO(float, 4);
+    if (cs == 2) MLP2_GO(float, 2);
+    MLP2_GO(float, 1);
+  }
+  if (cs == 4) MLP2_GO(__nv_bfloat16, 4);
+  if (cs == 2) MLP2_GO(__nv_bfloat16, 2);
+  MLP2_GO(__nv_bfloat16, 1);
+#undef MLP2_GO
 }

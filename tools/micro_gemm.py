@@ -65,13 +65,18 @@ def main():
         b1, b2 = torch.randn(Hd, device=DEV), torch.randn(256, device=DEV)
         out = torch.empty(M, 256, device=DEV)
         t = timeit(lambda: kernels.mlp2(x, w1, b1, w2, b2, out=out), flush=flush)
+        extra = {}
+        for cs in ("1", "2", "4"):
+            os.environ["MEMOTR_MLP_CLUSTER"] = cs
+            extra[f"fused_cluster{cs}_us"] = timeit(lambda: kernels.mlp2(x, w1, b1, w2, b2, out=out), flush=flush)
+        os.environ.pop("MEMOTR_MLP_CLUSTER", None)
         hid = torch.empty(M, Hd, device=DEV, dtype=torch.bfloat16)
 
         def two():
             kernels.linear(x, w1, b1, act="relu", out=hid, path="tc")
             kernels.linear(hid, w2, b2, out=out, path="tc")
         t2 = timeit(two, flush=flush)
-        row = {"gemm": name, "M": M, "fused_us": t, "Hd": Hd, "fused_tflops": 2 * 2 * M * Hd * 256 / t / 1e6, "two_gemms_us": t2}
+        row = {"gemm": name, "M": M, "fused_us": t, "Hd": Hd, "fused_tflops": 2 * 2 * M * Hd * 256 / t / 1e6, "two_gemms_us": t2, **extra}
         print(json.dumps(row), flush=True)
         res.append(row)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
