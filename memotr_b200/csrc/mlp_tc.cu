@@ -13,7 +13,9 @@
 //                                                                        layout UMMA wants for an A operand
 //     GEMM2(c): acc2 (TMEM, 256 cols) += H[c&1] . W2[:, c]^T             2 k-panels, tcgen05.mma M128 N256 K16
 // Warp roles: 0 = TMA producer streaming W1/W2 chunks through a 3-slot x 32 KB ring, 1 = MMA issuer (GEMM1 runs one
-// chunk ahead of GEMM2 so epi1(c) overlaps GEMM1(c+1)), 2-5 = epilogue.  acc1 and H are double-buffered; all hand-offs
+// chunk ahead of GEMM2 so epi1(c) overlaps GEMM1(c+1)), 2-9 = epilogue (two warps per TMEM lane quarter, each taking half
+// of the columns, two tcgen05.ld in flight per warp: with four warps the per-chunk epilogue, ~4000 clk, was the critical
+// path -- 82 us per encoder FFN whatever the weight-load strategy).  acc1 and H are double-buffered; all hand-offs
 // are mbarriers (TMA expect_tx, tcgen05.commit, and 128-thread arrives from the epilogue warps).  TMEM: 2x128 + 256 =
 // 512 columns.  Shared memory: X 64 KB + ring 96 KB + H 64 KB = 224 KB (one CTA per SM).  Final epilogue as in
 // gemm_tc.cu: bias / activation / multiplier -> swizzled panels in the (dead) X+ring memory -> TMA store.
@@ -71,7 +73,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 
 template <typename TC, int CS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
                const float *__restrict__ b1, int M, int Hd, Epilogue ep) {
@@ -101,8 +103,8 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc1_full + b, 1);
-      mbar_init(acc1_empty + b, 128);
-      mbar_init(h_full + b, 128);
+      mbar_init(acc1_empty + b, 256);
+      mbar_init(h_full + b, 256);
       mbar_init(h_empty + b, 1);
     }
     mbar_init(acc2_full, 1);
@@ -218,8 +220,8 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       umma_commit(acc2_full);
     }
   } else {
-    // ---- epilogue warps: lane quarter = warp % 4, one accumulator row per thread ----
-    const int quarter = warp & 3;
+    // ---- epilogue warps 2..9: lane quarter = warp % 4 (one accumulator row per thread), column half = (warp - 2) / 4 ----
+    const int quarter = warp & 3, chalf = (warp - 2) >> 2;
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     for (int c = 0; c < NC; ++c) {
@@ -227,36 +229,37 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(acc1_full + b, (c >> 1) & 1);
       tcgen05_fence_after();
       mbar_wait(h_empty + b, ((c >> 1) & 1) ^ 1);   // GEMM2(c-2) has finished reading this H buffer
-      uint8_t *hrow = hbuf + b * H_BYTES + r_in * 128;
-#pragma unroll 1
-      for (int c0 = 0; c0 < HC; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + (uint32_t)(b * HC + c0), r);
-        const float *bias = b1 + c * HC + c0;
-        uint8_t *prow = hrow + (c0 / 64) * PANEL;
-        const int kbase = (c0 % 64) / 8;
+      // this warp: hidden columns [chalf*64, chalf*64+64) of the chunk = H panel `chalf`, both 32-column halves in flight
+      uint32_t r0[32], r1[32];
+      tmem_ld32_issue(tmem_base + lane_off + (uint32_t)(b * HC + chalf * 64), r0);
+      tmem_ld32_issue(tmem_base + lane_off + (uint32_t)(b * HC + chalf * 64 + 32), r1);
+      tmem_ld_wait();
+      uint8_t *prow = hbuf + b * H_BYTES + chalf * PANEL + r_in * 128;
+      const float *bias = b1 + c * HC + chalf * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k));
-          const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k + 4));
-          float t8[8];
-          t8[0] = fmaxf(__uint_as_float(r[8 * k + 0]) + ba.x, 0.f);
-          t8[1] = fmaxf(__uint_as_float(r[8 * k + 1]) + ba.y, 0.f);
-          t8[2] = fmaxf(__uint_as_float(r[8 * k + 2]) + ba.z, 0.f);
-          t8[3] = fmaxf(__uint_as_float(r[8 * k + 3]) + ba.w, 0.f);
-          t8[4] = fmaxf(__uint_as_float(r[8 * k + 4]) + bb.x, 0.f);
-          t8[5] = fmaxf(__uint_as_float(r[8 * k + 5]) + bb.y, 0.f);
-          t8[6] = fmaxf(__uint_as_float(r[8 * k + 6]) + bb.z, 0.f);
-          t8[7] = fmaxf(__uint_as_float(r[8 * k + 7]) + bb.w, 0.f);
-          *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t8);
-        }
+      for (int k = 0; k < 8; ++k) {
+        const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k));
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k + 4));
+        float t8[8];
+#define RV(i) __uint_as_float(k < 4 ? r0[8 * k + (i)] : r1[8 * (k - 4) + (i)])
+        t8[0] = fmaxf(RV(0) + ba.x, 0.f);
+        t8[1] = fmaxf(RV(1) + ba.y, 0.f);
+        t8[2] = fmaxf(RV(2) + ba.z, 0.f);
+        t8[3] = fmaxf(RV(3) + ba.w, 0.f);
+        t8[4] = fmaxf(RV(4) + bb.x, 0.f);
+        t8[5] = fmaxf(RV(5) + bb.y, 0.f);
+        t8[6] = fmaxf(RV(6) + bb.z, 0.f);
+        t8[7] = fmaxf(RV(7) + bb.w, 0.f);
+#undef RV
+        *reinterpret_cast<uint4 *>(prow + ((k ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t8);
       }
       tcgen05_fence_before();                                        // TMEM reads ordered before the hand-off
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the UMMA (async proxy)
       mbar_arrive(acc1_empty + b);
       mbar_arrive(h_full + b);
     }
-    // ---- final epilogue: acc2 (+b2, activation, multiplier) -> swizzled panels in the dead X/ring memory -> TMA store
+    // ---- final epilogue: acc2 (+b2, activation, multiplier) -> swizzled panels in the dead X/ring memory -> TMA store;
+    //      this warp takes output columns [chalf*128, chalf*128+128)
     mbar_wait(acc2_full, 0);
     tcgen05_fence_after();
     const int row = m_blk * BM + r_in;
@@ -266,7 +269,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     constexpr int N_PANELS = N2 / PANEL_COLS;
     static_assert(N_PANELS * PANEL <= OFF_H, "staging must fit in the X + ring area");
 #pragma unroll 1
-    for (int c0 = 0; c0 < N2; c0 += 32) {
+    for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + lane_off + (uint32_t)(2 * HC + c0), r);
       float v[32];
@@ -313,7 +316,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (warp == 2 && lane == 0) {
 #pragma unroll 1
       for (int p = 0; p < N_PANELS; ++p)
@@ -352,10 +355,10 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
   }
   const int tiles = ceil_div(M, BM);
   if constexpr (CS == 1) {
-    MEMOTR_LAUNCH((kern), tiles, 192, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
+    MEMOTR_LAUNCH((kern), tiles, 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
   } else {
     // CTAs beyond the last tile (grid rounded up to a whole cluster) see zero-filled X and have their stores clipped
-    launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(192), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
+    launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(320), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
                           M, Hd, ep);
   }
   return check_launch("mlp2_tc");
@@ -386,7 +389,8 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   const char *cs_str = getenv("MEMOTR_MLP_CLUSTER");
   const int cs_env = cs_str ? atoi(cs_str) : 0;
   const int tiles = ceil_div(M, tc::BM);
-  const int cs = cs_env ? cs_env : (tiles >= 2 * kNumSMs / 2 ? 2 : 1);
+  (void)tiles;
+  const int cs = cs_env ? cs_env : 1;   // measured: the kernel is epilogue-bound, multicast gives nothing yet (profiles/)
 #define MLP2_GO(TC_, CS_) return tc::launch_mlp2<TC_, CS_>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
   if (c_dtype == MEMOTR_F32) {
     if (cs == 4) MLP2_GO(float, 4);
