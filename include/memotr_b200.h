@@ -125,8 +125,9 @@ MEMOTR_API int memotr_msda_prep(const float *ol, int ldol, const int64_t *spatia
  * C = epilogue(A . W^T):  v = acc + bias;  act (0 none, 1 ReLU, 2 sigmoid);  v *= mul;  v += add;  rows with
  * rowzero[m] != 0 are written as zeros.  A (M,K) lda, W (N,K) ldw, both `ab_dtype` (F32 or BF16); C (M,N) ldc in
  * `c_dtype` (F32, or BF16 when ab_dtype is BF16); mul/add (M,N) in ab_dtype; bias fp32; fp32 accumulation.
- * path 0 = auto (bf16 with N % 64 == 0, K % 64 == 0 -> tcgen05/TMA tensor-core kernel, otherwise CUDA-core kernel),
- * 1 = force CUDA cores, 2 = force tensor cores (MEMOTR_ENOSYS if the shape is unsupported).
+ * path 0 = auto (bf16: M <= 1024 rows -> latency-optimised mma.sync kernel; otherwise N % 64 == 0, K % 64 == 0 ->
+ * tcgen05/TMA/TMEM kernel; otherwise CUDA-core kernel), 1 = force CUDA cores, 2 = force tcgen05, 3 = force mma.sync
+ * (MEMOTR_ENOSYS if the shape is unsupported by a forced path).
  * Replaces torch.nn.functional.linear at every call site of the hot path: models/ops/modules/ms_deform_attn.py:104-129,
  * models/deformable_encoder.py:97-107, models/deformable_decoder.py:245-273, models/mlp.py:22-25, models/ffn.py:15-25,
  * models/query_updater.py:109-132, models/memotr.py:153-154 (and the padding-mask fill of ms_deform_attn.py:106).

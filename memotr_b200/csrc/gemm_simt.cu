@@ -147,6 +147,10 @@ int linear_tc_bf16(const void *A, int lda, const void *W, int ldw, void *C, int 
                    const Epilogue &ep, cudaStream_t st);  // gemm_tc.cu
 bool linear_tc_supported(int lda, int ldw, int ldc, int c_dtype, int M, int N, int K, const void *A, const void *W,
                          const void *C);
+int linear_mma_bf16(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int c_dtype, int M, int N, int K,
+                    const Epilogue &ep, cudaStream_t st);  // gemm_mma.cu
+bool linear_mma_supported(int lda, int ldw, int ldc, int c_dtype, int M, int N, int K, const void *A, const void *W,
+                          const void *C);
 
 }  // namespace memotr
 
@@ -165,7 +169,12 @@ extern "C" int memotr_linear(const void *A, int lda, const void *W, int ldw, con
                  "linear: output dtype must be f32, or bf16/fp16 with bf16 inputs");
   cudaStream_t st = (cudaStream_t)stream;
   Epilogue ep{bias, mul, add, rowzero, ldmul, ldadd, act};
-  // path: 0 = auto, 1 = force CUDA-core kernel, 2 = force tensor-core kernel
+  // path: 0 = auto, 1 = force CUDA-core kernel, 2 = force tcgen05 kernel, 3 = force the few-rows mma.sync kernel
+  if (ab_dtype == MEMOTR_BF16 && (path == 3 || (path == 0 && M <= 1024))) {
+    const bool ok = linear_mma_supported(lda, ldw, ldc, c_dtype, M, N, K, A, W, C);
+    if (ok) return linear_mma_bf16(A, lda, W, ldw, C, ldc, c_dtype, M, N, K, ep, st);
+    if (path == 3) return fail(MEMOTR_ENOSYS, "linear: shape M=%d N=%d K=%d not supported by the mma.sync path", M, N, K);
+  }
   if (ab_dtype == MEMOTR_BF16 && path != 1) {
     const bool ok = linear_tc_supported(lda, ldw, ldc, c_dtype, M, N, K, A, W, C);
     if (ok) return linear_tc_bf16(A, lda, W, ldw, C, ldc, c_dtype, M, N, K, ep, st);

@@ -172,32 +172,39 @@ msda_prep_fast_kernel(const float *__restrict__ ol, int ldol, const int64_t *__r
   float mx = logit;
 #pragma unroll
   for (int s = LK / 2; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  const float e = expf(logit - mx);
+  const float e = __expf(logit - mx);
   float sum = e;
 #pragma unroll
   for (int s = LK / 2; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
   const int l = i / K;
-  const float vx = vr[2 * l], vy = vr[2 * l + 1];
+  const float vx = __ldg(vr + 2 * l), vy = __ldg(vr + 2 * l + 1);
+  // divisions: a / b is evaluated as a * rcp(b) with the correctly rounded reciprocal (<= 1 ulp from the quotient the
+  // reference's torch ops produce -- far inside the 1e-4 budget; a full IEEE division costs ~10 instructions each and
+  // this kernel is instruction-bound)
   float lx, ly;
   if (mode == 0) {
     int lq = 0;
     for (int t = 1; t < L; ++t)
-      if (q >= (int)lsi[t]) lq = t;
-    const int Wq = (int)shapes[2 * lq + 1], Hq = (int)shapes[2 * lq];
-    const int p = q - (int)lsi[lq];
-    const int y = p / Wq, x = p - y * Wq;
-    const float bx = ((float)x + 0.5f) / (vr[2 * lq] * (float)Wq);
-    const float by = ((float)y + 0.5f) / (vr[2 * lq + 1] * (float)Hq);
-    lx = bx * vx + off.x / (float)shapes[2 * l + 1];
-    ly = by * vy + off.y / (float)shapes[2 * l];
+      if (q >= (int)__ldg(lsi + t)) lq = t;
+    const int Wq = (int)__ldg(shapes + 2 * lq + 1), Hq = (int)__ldg(shapes + 2 * lq);
+    const int p = q - (int)__ldg(lsi + lq);
+    // p / Wq without an integer division: p < 2^24 and the fractional part of (p+0.5)/Wq is >= 0.5/Wq away from an
+    // integer, far above the float rounding error, so the truncation is exact
+    const int y = (int)(((float)p + 0.5f) * __frcp_rn((float)Wq));
+    const int x = p - y * Wq;
+    const float bx = ((float)x + 0.5f) * __frcp_rn(__ldg(vr + 2 * lq) * (float)Wq);
+    const float by = ((float)y + 0.5f) * __frcp_rn(__ldg(vr + 2 * lq + 1) * (float)Hq);
+    lx = bx * vx + off.x * __frcp_rn((float)__ldg(shapes + 2 * l + 1));
+    ly = by * vy + off.y * __frcp_rn((float)__ldg(shapes + 2 * l));
   } else {
-    const float4 r = *reinterpret_cast<const float4 *>(ref4 + 4 * q);
-    lx = r.x * vx + off.x / (float)K * (r.z * vx) * 0.5f;
-    ly = r.y * vy + off.y / (float)K * (r.w * vy) * 0.5f;
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(ref4 + 4 * q));
+    const float rk = __frcp_rn((float)K);
+    lx = r.x * vx + off.x * rk * (r.z * vx) * 0.5f;
+    ly = r.y * vy + off.y * rk * (r.w * vy) * 0.5f;
   }
   if (live) {
     *reinterpret_cast<float2 *>(loc + idx * 2) = make_float2(lx, ly);
-    attn[idx] = e / sum;
+    attn[idx] = e * __frcp_rn(sum);
   }
 }
 

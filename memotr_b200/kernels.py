@@ -8,7 +8,7 @@ import torch
 from . import _lib
 
 _ACT = {None: 0, "none": 0, "relu": 1, "sigmoid": 2}
-_PATH = {"auto": 0, "simt": 1, "tc": 2}
+_PATH = {"auto": 0, "simt": 1, "tc": 2, "mma": 3}
 
 
 def _ld(t):
