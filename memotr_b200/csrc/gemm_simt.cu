@@ -87,21 +87,48 @@ gemm_simt_kernel(const TA *__restrict__ A, int lda, const TA *__restrict__ W, in
 // Skinny outputs (N <= 8: the 4-wide box-delta layer and the 1..8-wide class heads, memotr.py:153-154): one warp per
 // row of A, lanes stride over K, N running sums reduced with xor-shuffles.  The tiled kernels would leave 15/16 of a
 // 64-wide tile empty and launch only M/32 CTAs.
+template <typename TA>
+__device__ __forceinline__ void load8_as_f32(const TA *p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8_as_f32<float>(const float *p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p + 4));
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8_as_f32<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[8]) {
+  bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(p)), v);
+}
+
 template <typename TA, typename TC>
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const TA *__restrict__ A, int lda, const TA *__restrict__ W, int ldw, TC *__restrict__ C, int ldc, int M,
-                 int N, int K, Epilogue ep) {
+                 int N, int K, Epilogue ep, int vec) {
   pdl_grid_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   float acc[8];
 #pragma unroll
   for (int n = 0; n < 8; ++n) acc[n] = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float a = to_f32<TA>(A[(long)row * lda + k]);
+  if (vec) {  // K % 8 == 0 and 16-byte aligned rows: 8 elements per lane per step, all loads issued before the math
+    for (int k = lane * 8; k < K; k += 256) {
+      float a[8];
+      load8_as_f32<TA>(A + (long)row * lda + k, a);
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
-      if (n < N) acc[n] = fmaf(a, to_f32<TA>(W[(long)n * ldw + k]), acc[n]);
+      for (int n = 0; n < 8; ++n)
+        if (n < N) {
+          float w[8];
+          load8_as_f32<TA>(W + (long)n * ldw + k, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[n] = fmaf(a[i], w[i], acc[n]);
+        }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float a = to_f32<TA>(A[(long)row * lda + k]);
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+        if (n < N) acc[n] = fmaf(a, to_f32<TA>(W[(long)n * ldw + k]), acc[n]);
+    }
   }
 #pragma unroll
   for (int n = 0; n < 8; ++n)
@@ -126,8 +153,9 @@ template <typename TA, typename TC>
 static int launch_simt(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
                        const Epilogue &ep, cudaStream_t st) {
   if (N <= 8) {
+    const int vec = (K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && aligned16(A) && aligned16(W)) ? 1 : 0;
     MEMOTR_LAUNCH((gemv_rows_kernel<TA, TC>), ceil_div(M, 8), 256, 0, st, (const TA *)A, lda, (const TA *)W, ldw, (TC *)C, ldc, M, N,
-                                                             K, ep);
+                                                             K, ep, vec);
     return check_launch("gemv_rows");
   }
   // big problems: 128x128 tiles (8x8 per thread); small ones (decoder / updater rows): 32x64 tiles for more CTAs

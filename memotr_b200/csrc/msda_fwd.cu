@@ -738,17 +738,23 @@ extern "C" int memotr_msda_forward_pairs(const void *pairs, const int64_t *spati
 // out-of-range corners get weight 0 and a clamped address, so the loads are unpredicated.
 namespace memotr {
 
-template <int KT>
+// SPLIT = 1: 4 lanes per (b,q,head) walk all levels (throughput shape: encoder, Lq = S).
+// SPLIT = 4: 16 lanes per (b,q,head), each 4-lane subgroup takes every 4th level and the partial sums are combined with
+//            two xor-shuffles per channel -- 4x the threads and a quarter of the dependent load->blend chain for the
+//            decoder-shaped launch (400 queries: 50 CTAs of serial work otherwise, 12.4 us measured).
+template <int KT, int SPLIT>
 __global__ void __launch_bounds__(256)
 msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
              int L, int Lq, int Kr, int xs, long n_qh) {
   pdl_grid_sync();
-  constexpr int D = 32, G = 4;
+  constexpr int D = 32, G = 4 * SPLIT;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long qh = tid / G;
-  if (qh >= n_qh) return;
-  const int sub = (int)(tid % G);
+  const long qh_raw = tid / G;
+  const bool live = qh_raw < n_qh;
+  if (SPLIT == 1 && !live) return;
+  const long qh = live ? qh_raw : n_qh - 1;     // SPLIT > 1: tail lanes shadow a valid group (shuffles stay full-warp)
+  const int sub = (int)(tid % 4), lvl0 = (int)((tid % G) / 4);
   const int m = (int)(qh % H);
   const int b = (int)((qh / H) / Lq);
   const int K = KT ? KT : Kr;
@@ -758,7 +764,7 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 
-  for (int l = 0; l < L; ++l) {
+  for (int l = lvl0; l < L; l += SPLIT) {
     const int Hh = (int)__ldg(shapes + 2 * l), Ww = (int)__ldg(shapes + 2 * l + 1);
     const float Hf = (float)Hh, Wf = (float)Ww;
     const int base = (int)__ldg(lsi + l) * xs, ys = Ww * xs;
@@ -824,16 +830,29 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
       acc[2 * j + 1] += f.y;
     }
   }
+  if constexpr (SPLIT > 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 8);
+    }
+    if (!live || lvl0 != 0) return;
+  }
   *reinterpret_cast<uint4 *>(out + qh * D + sub * 8) = f32x8_to_bf16(acc);
 }
 
 static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                       void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st) {
   const long n_qh = (long)B * Lq * H;
-  const int grid = (int)((n_qh * 4 + 255) / 256);
-#define H16_LAUNCH(KT_)                                                                                      \
-  MEMOTR_LAUNCH((msda_fwd_h16<KT_>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,       \
-                (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh)
+  const bool split = n_qh * 4 < (long)kNumSMs * 256 * 2;   // too few groups to fill the GPU: spread the levels over lanes
+  const int grid = (int)((n_qh * (split ? 16 : 4) + 255) / 256);
+#define H16_LAUNCH(KT_)                                                                                               \
+  if (split)                                                                                                          \
+    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh);                                                    \
+  else                                                                                                                \
+    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh)
   switch (K) {
     case 1: H16_LAUNCH(1); break;
     case 2: H16_LAUNCH(2); break;
