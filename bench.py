@@ -213,6 +213,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from memotr_b200 import synthetic as synth
@@ -269,9 +270,11 @@ def main():
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    host_t0 = time.perf_counter()
     for i in range(K):
         feed_resident(i)
         eng.replay()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / K     # CPU time to enqueue one step (must stay < GPU time)
     clip_exchange()
     t1.record()
     barrier()
@@ -338,6 +341,7 @@ def main():
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": eng.graph_launches * K,
         "sections_us": {k: round(v, 1) for k, v in sections.items()},
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "roofline": {"kernel": ("msda_fwd_h16 (fp16 value map)" if eng.value_f16 else "msda_fwd_vec") +
                                " -- encoder-shaped launch, Lq = S = 22323", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
