@@ -208,6 +208,48 @@ MEMOTR_API int memotr_upd_finalize(const unsigned char *is_pos, const void *feat
                                    float lam, int Nt, int C, void *stream);
 
 /*
+ * Tracker glue on the device (SURVEY.md section 8(f) "next" row 1).  The reference does this on the host with python
+ * loops over TrackInstances (structures/track_instances.py:11-38).  A track table here is a fixed-capacity
+ * structure-of-arrays in device memory; rows [0, *n_active) are live, in the reference's order.
+ */
+typedef struct memotr_track_table {
+  long long *ids, *labels, *disappear_time;                      /* (capacity) int64, as TrackInstances */
+  float *query_embed, *output_embed, *last_output, *long_memory; /* (capacity, C) */
+  float *ref_pts, *boxes, *logits;                               /* (capacity, 4), (capacity, 4), (capacity, ncls) */
+  int *n_active;                                                 /* device scalar */
+} memotr_track_table;
+
+/* the rows of MeMOTR.forward's output dict the tracker reads (models/memotr.py:180-195), (n_det + capacity) rows each:
+ * detect queries first, then one row per track-table row */
+typedef struct memotr_frame_outputs {
+  const float *pred_logits, *pred_boxes, *outputs, *last_ref_pts, *aux_queries; /* aux_outputs[-1]["queries"] */
+} memotr_frame_outputs;
+
+/*
+ * RuntimeTracker.update (models/runtime_tracker.py:29-101, use_motion=False) followed by
+ * QueryUpdater.select_active_tracks in eval mode (models/query_updater.py:243-254), in place on `tracks`:
+ *   previous track i: score = sigmoid(logits[n_det+i][labels[i]]); disappear_time = score < track_thresh ? +1 : 0;
+ *                     id = -1 once disappear_time >= miss_tolerance; boxes/logits/output_embed <- this frame's rows;
+ *   newborn: detect query j with max_c sigmoid(logits[j][c]) >= det_thresh: id = *max_obj_id + rank, label = argmax,
+ *            ref_pts = last_ref_pts[j], output_embed = last_output = outputs[j], query_embed = long_memory = aux_queries[j];
+ *   result = surviving previous tracks in order, then newborns in order; *max_obj_id advanced.
+ * `scratch` is a second table of the same capacity (work space), `src_index` (capacity) int32 work space,
+ * `track_pad` (capacity) receives 1 for rows >= *n_active (the key-padding mask of the track rows for the next frame).
+ * Newborns that do not fit are dropped and counted in *overflow (device int, accumulated) -- the caller must check it.
+ * No reference counterpart for the capacity: the reference's tensors grow.
+ */
+MEMOTR_API int memotr_tracker_update(const memotr_frame_outputs *frame, int n_det, int ncls, int C,
+                                     const memotr_track_table *tracks, const memotr_track_table *scratch, int capacity,
+                                     float det_thresh, float track_thresh, int miss_tolerance, long long *max_obj_id,
+                                     int *src_index, unsigned char *track_pad, int *overflow, void *stream);
+
+/* per-frame result rows (submit_engine.py:89-102): keep = live && max_c sigmoid(logits) > score_thresh &&
+ * w*ori_w*h*ori_h > area_thresh; boxes cxcywh (normalised) -> xyxy in pixels.  All outputs have `capacity` rows. */
+MEMOTR_API int memotr_tracker_results(const memotr_track_table *tracks, int capacity, int ncls, float score_thresh,
+                                      float area_thresh, float ori_w, float ori_h, long long *ids, float *boxes_xyxy,
+                                      float *scores, unsigned char *keep, void *stream);
+
+/*
  * Interval timer for measurement (bench.py): n CUDA events; memotr_timer_record enqueues event `idx` on `stream`
  * (as an external event-record node when the stream is being captured into a CUDA graph), memotr_timer_elapsed_ms
  * reads the time between two recorded events after the work has completed.  No reference counterpart (the reference

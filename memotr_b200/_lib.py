@@ -19,6 +19,19 @@ _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.f
 _lib = None
 
 _vp, _i, _f, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_long
+
+
+class TrackTable(ctypes.Structure):
+    """memotr_track_table (include/memotr_b200.h): device pointers of one fixed-capacity track table."""
+    _fields_ = [(k, ctypes.c_void_p) for k in ("ids", "labels", "disappear_time", "query_embed", "output_embed",
+                                               "last_output", "long_memory", "ref_pts", "boxes", "logits", "n_active")]
+
+
+class FrameOutputs(ctypes.Structure):
+    """memotr_frame_outputs (include/memotr_b200.h)."""
+    _fields_ = [(k, ctypes.c_void_p) for k in ("pred_logits", "pred_boxes", "outputs", "last_ref_pts", "aux_queries")]
+
+
 _SIGNATURES = {
     "memotr_abi_version": ([], _i),
     "memotr_last_error": ([], ctypes.c_char_p),
@@ -41,6 +54,8 @@ _SIGNATURES = {
     "memotr_unary": ([_vp, _vp, _l, _i, _vp], _i),
     "memotr_upd_prepare": ([_vp, _i, _vp, _vp, _f, _vp, _vp, _i, _vp], _i),
     "memotr_upd_finalize": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp], _i),
+    "memotr_tracker_update": ([_vp, _i, _i, _i, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "memotr_tracker_results": ([_vp, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),
     "memotr_timer_destroy": ([_vp], None),
     "memotr_timer_record": ([_vp, _i, _vp], _i),

@@ -39,7 +39,8 @@ __global__ void mha32_kernel(const T *__restrict__ Q, int ldq, const T *__restri
   for (int idx = threadIdx.x; idx < Nk * 32; idx += blockDim.x) {
     const int j = idx >> 5, d = idx & 31;
     Ks[j * 33 + d] = to_f32<T>(K[(long)j * ldk + h * 32 + d]);
-    Vs[j * 32 + d] = to_f32<T>(V[(long)j * ldv + h * 32 + d]);
+    // padded keys get probability 0; zero their values too so that 0 * (whatever a padding row holds, even NaN) = 0
+    Vs[j * 32 + d] = (kpm && kpm[j]) ? 0.f : to_f32<T>(V[(long)j * ldv + h * 32 + d]);
   }
   __syncthreads();
   const int q0 = blockIdx.x * qpb;
@@ -64,6 +65,7 @@ __global__ void mha32_kernel(const T *__restrict__ Q, int ldq, const T *__restri
       mx = fmaxf(mx, s);
     }
     mx = warp_max_f(mx);
+    if (mx == -INFINITY) mx = 0.f;  // every key padded (an empty track table): probabilities 0, output 0 (not NaN)
     float sum = 0.f;
     for (int j = lane; j < Nk; j += 32) {
       const float e = expf(P[j] - mx);
@@ -82,7 +84,7 @@ __global__ void mha32_kernel(const T *__restrict__ Q, int ldq, const T *__restri
     }
     for (; j < Nk; ++j) a0 = fmaf(P[j], Vs[j * 32 + lane], a0);
     const float acc = (a0 + a1) + (a2 + a3);
-    O[(long)qi * ldo + h * 32 + lane] = from_f32<TO>(acc / sum);
+    O[(long)qi * ldo + h * 32 + lane] = from_f32<TO>(sum > 0.f ? acc / sum : 0.f);
     __syncwarp();
   }
 }
@@ -109,7 +111,8 @@ mha32_v2_kernel(const T *__restrict__ Q, int ldq, const T *__restrict__ K, int l
     for (int idx = threadIdx.x; idx < Nk * 8; idx += 256) {
       const int j = idx >> 3, d4 = (idx & 7) * 4;
       const float4 kv = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(K) + (long)j * ldk + h * 32 + d4));
-      const float4 vv = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(V) + (long)j * ldv + h * 32 + d4));
+      float4 vv = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(V) + (long)j * ldv + h * 32 + d4));
+      if (kpm && kpm[j]) vv = make_float4(0.f, 0.f, 0.f, 0.f);  // padded key: probability 0 and value 0 (0 * NaN safe)
       Kt[(d4 + 0) * NkP + j] = kv.x, Kt[(d4 + 1) * NkP + j] = kv.y, Kt[(d4 + 2) * NkP + j] = kv.z, Kt[(d4 + 3) * NkP + j] = kv.w;
       *reinterpret_cast<float4 *>(Vs + j * 32 + d4) = vv;
     }
@@ -117,7 +120,7 @@ mha32_v2_kernel(const T *__restrict__ Q, int ldq, const T *__restrict__ K, int l
     for (int idx = threadIdx.x; idx < Nk * 32; idx += 256) {
       const int j = idx >> 5, d = idx & 31;
       Kt[d * NkP + j] = to_f32<T>(K[(long)j * ldk + h * 32 + d]);
-      Vs[j * 32 + d] = to_f32<T>(V[(long)j * ldv + h * 32 + d]);
+      Vs[j * 32 + d] = (kpm && kpm[j]) ? 0.f : to_f32<T>(V[(long)j * ldv + h * 32 + d]);
     }
   }
   const int q0 = blockIdx.x * 32 + warp * 4;
@@ -147,6 +150,7 @@ mha32_v2_kernel(const T *__restrict__ Q, int ldq, const T *__restrict__ K, int l
     mx.x = fmaxf(mx.x, s.x), mx.y = fmaxf(mx.y, s.y), mx.z = fmaxf(mx.z, s.z), mx.w = fmaxf(mx.w, s.w);
   }
   mx.x = warp_max_f(mx.x), mx.y = warp_max_f(mx.y), mx.z = warp_max_f(mx.z), mx.w = warp_max_f(mx.w);
+  if (mx.x == -INFINITY) mx = make_float4(0.f, 0.f, 0.f, 0.f);  // every key padded: output 0 instead of NaN
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j = lane; j < Nk; j += 32) {
     float4 e = P[j];
@@ -170,10 +174,11 @@ mha32_v2_kernel(const T *__restrict__ Q, int ldq, const T *__restrict__ K, int l
     a0.x = fmaf(p0.x, v0, a0.x), a0.y = fmaf(p0.y, v0, a0.y), a0.z = fmaf(p0.z, v0, a0.z), a0.w = fmaf(p0.w, v0, a0.w);
   }
   TO *o = O + (long)q0 * ldo + h * 32 + lane;
-  o[0] = from_f32<TO>((a0.x + a1.x) / sum.x);
-  if (q0 + 1 < Nq) o[ldo] = from_f32<TO>((a0.y + a1.y) / sum.y);
-  if (q0 + 2 < Nq) o[2 * (long)ldo] = from_f32<TO>((a0.z + a1.z) / sum.z);
-  if (q0 + 3 < Nq) o[3 * (long)ldo] = from_f32<TO>((a0.w + a1.w) / sum.w);
+  const bool live = sum.x > 0.f;  // the mask is per key: all four queries see the same keys
+  o[0] = from_f32<TO>(live ? (a0.x + a1.x) / sum.x : 0.f);
+  if (q0 + 1 < Nq) o[ldo] = from_f32<TO>(live ? (a0.y + a1.y) / sum.y : 0.f);
+  if (q0 + 2 < Nq) o[2 * (long)ldo] = from_f32<TO>(live ? (a0.z + a1.z) / sum.z : 0.f);
+  if (q0 + 3 < Nq) o[3 * (long)ldo] = from_f32<TO>(live ? (a0.w + a1.w) / sum.w : 0.f);
 }
 
 }  // namespace memotr

@@ -38,8 +38,15 @@ class _Lin:
 
 
 class FrameEngine:
-    def __init__(self, state_dict, cfg, shapes, n_tracks, device="cuda", mode="fp32"):
+    def __init__(self, state_dict, cfg, shapes, n_tracks, device="cuda", mode="fp32", tracker=None,
+                 ori_size=(1920, 1080)):
+        """`n_tracks` is the number of track-query rows (= the capacity of the track table).  `tracker=None`: the
+        caller owns the track bookkeeping and every row is live (the reference's model + query-updater path only).
+        `tracker=dict(det_score_thresh=, track_score_thresh=, miss_tolerance=, result_score_thresh=)`: the
+        RuntimeTracker glue runs on the device inside step() (memotr_b200/tracker.py) with a variable number of live
+        rows; `ori_size` = (width, height) of the original image for the result boxes (submit_engine.py:89-98)."""
         assert mode in ("fp32", "bf16")
+        self.tracker_cfg, self.ori_size = (dict(tracker) if tracker is not None else None), tuple(ori_size)
         self.cfg, self.mode = dict(cfg), mode
         self.dev = torch.device(device)
         self.ta = torch.float32 if mode == "fp32" else torch.bfloat16
@@ -175,8 +182,8 @@ class FrameEngine:
         self.in_src = [f(C, h * w) for h, w in self.shapes]
         self.in_pos = [f(C, h * w) for h, w in self.shapes]
         self.in_mask = [torch.zeros(h * w, dtype=torch.uint8, device=dev) for h, w in self.shapes]
-        self.in_track_ref = f(nt, 4)
-        self.in_track_embed = f(nt, C)
+        self.in_track_ref = torch.zeros(nt, 4, dtype=torch.float32, device=dev)
+        self.in_track_embed = torch.zeros(nt, C, dtype=torch.float32, device=dev)
         # encoder
         self.mask_flat = torch.zeros(S, dtype=torch.uint8, device=dev)
         self.vr = f(self.L, 2)
@@ -217,8 +224,15 @@ class FrameEngine:
         self.delta = f(nq, 4)
         self.last_ref_pts, self.init_ref_pts = f(nq, 4), f(nq, 4)
         # query updater (Nt rows); the track state itself is fp32 (TrackInstances fields)
-        self.st = {k: f(nt, C) for k in ("query_embed", "output_embed", "last_output", "long_memory")}
-        self.st["ref_pts"], self.st["boxes"], self.st["logits"] = f(nt, 4), f(nt, 4), f(nt, self.ncls)
+        from .tracker import TrackTable, DeviceTracker, FLOAT_FIELDS
+        self.table = TrackTable(nt, C, self.ncls, dev)
+        self.st = {k: self.table[k] for k in FLOAT_FIELDS}
+        self.query_pad = torch.zeros(nq, dtype=torch.uint8, device=dev)     # key-padding mask of the decoder queries
+        self.trk = None
+        if self.tracker_cfg is not None:
+            self.trk = DeviceTracker(self.table, self.nd, **self.tracker_cfg)
+            self.trk.track_pad = self.query_pad[self.nd:]                    # written by the tracker, read by the MHAs
+            self.trk.reset()
         self.is_pos = torch.zeros(nt, dtype=torch.uint8, device=dev)
         self.u_ref = f(nt, 4)
         self.u_sine = e(nt, 2 * C)
@@ -387,7 +401,8 @@ class FrameEngine:
             self.add(out, C, self.query_pos, C, self.qk_in, C, n, C)
             self.lin(self.qk_in, C, sa["qk"], self.qk, 2 * C, n, c_dtype=F32)
             self.lin(out, C, sa["v"], self.v, C, n, c_dtype=F32)
-            self.mha(self.qk, 2 * C, self.qk[:, C:], 2 * C, self.v, C, self.d_a, C, n, n)
+            self.mha(self.qk, 2 * C, self.qk[:, C:], 2 * C, self.v, C, self.d_a, C, n, n,
+                     kpm=self.query_pad if (self.trk is not None and n == nq) else None)
             self.lin(self.d_a, C, sa["out"], self.d_pre, C, n, c_dtype=F32)
             self.ln(self.d_pre, ly["norm2"], self.t1, n, x2=self.tgt32[lid], y32=self.t1_32, pos=self.query_pos,
                     ypos=self.t1q)
@@ -465,7 +480,8 @@ class FrameEngine:
         self.lin(self.u_b, C, ma["q"], self.u_q, C, nt, c_dtype=F32)
         self.lin(self.u_d, C, ma["k"], self.u_k, C, nt, c_dtype=F32)
         self.lin(self.u_oe, C, ma["v"], self.u_v, C, nt, c_dtype=F32)
-        self.mha(self.u_q, C, self.u_k, C, self.u_v, C, self.u_a, C, nt, nt)
+        self.mha(self.u_q, C, self.u_k, C, self.u_v, C, self.u_a, C, nt, nt,
+                 kpm=self.trk.track_pad if self.trk is not None else None)
         self.lin(self.u_a, C, ma["out"], self.u_pre, C, nt, c_dtype=F32)
         self.ln(self.u_pre, u["memory_norm"], self.u_a, nt, x2=st["output_embed"], y32=self.u_a32)
         l1, l2, nrm = u["mffn"]
@@ -491,8 +507,17 @@ class FrameEngine:
         feed the updated (ref_pts, query_embed) back as the next frame's track queries (submit_engine.py:64-72 with
         the host-side RuntimeTracker glue reduced to the field hand-off of runtime_tracker.py:43-45)."""
         self.forward()
-        self.tracks_from_frame()
+        if self.trk is None:
+            self.tracks_from_frame()
+        else:       # RuntimeTracker.update + select_active_tracks on the device (submit_engine.py:66-70)
+            n = self.n_dec
+            self.trk.update(self.pred_logit[n - 1], self.pred_box[n - 1], self.tgt32[n], self.last_ref_pts,
+                            self.tgt32[n - 1])
+            self.launches += 3
         self.update_tracks()
+        if self.trk is not None:
+            self.trk.results(*self.ori_size)
+            self.launches += 1
         self.convert(self.st["ref_pts"], F32, 4, self.in_track_ref, F32, 4, self.nt, 4)
         self.convert(self.st["query_embed"], F32, self.C, self.in_track_embed, F32, self.C, self.nt, self.C)
         self._mark(4)

@@ -182,10 +182,69 @@ def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
     print(f"frame_{tag}.npz:", {k: v.shape for k, v in arrays.items()})
 
 
+def golden_tracker():
+    """The reference's own RuntimeTracker / TrackInstances / QueryUpdater.select_active_tracks (eval) / result filter
+    driven for several frames with synthetic model outputs; inputs and outputs of every frame are stored."""
+    from models.runtime_tracker import RuntimeTracker
+    from models.query_updater import QueryUpdater
+    from structures.track_instances import TrackInstances
+    from utils.box_ops import box_cxcywh_to_xyxy
+    try:
+        from submit_engine import Submitter
+        filt_score, filt_area = Submitter.filter_by_score, Submitter.filter_by_area
+    except Exception as e:                                   # noqa: BLE001 -- heavy optional imports (datasets, tqdm ...)
+        print("submit_engine not importable here (%r); restating its two filters (submit_engine.py:118-127)" % (e,))
+        filt_score = lambda t, thresh: t[torch.max(t.scores, dim=-1).values > thresh]   # noqa: E731
+        filt_area = lambda t, thresh=100: t[t.area > thresh]                              # noqa: E731
+    arrays = {}
+    for case, (ncls, nd, C, det_t, trk_t, miss, res_t) in enumerate([(1, 24, 8, 0.7, 0.6, 2, 0.65), (3, 17, 8, 0.8, 0.5, 1, 0.5)]):
+        g = torch.Generator().manual_seed(100 + case)
+        tracker = RuntimeTracker(det_score_thresh=det_t, track_score_thresh=trk_t, miss_tolerance=miss, use_dab=True)
+        fake_self = types.SimpleNamespace(training=False, use_dab=True, hidden_dim=C)
+        tracks = [TrackInstances(hidden_dim=C, num_classes=ncls, use_dab=True)]
+        ori_w, ori_h = 1920, 1080
+        for t in range(6):
+            n = len(tracks[0])
+            nq = nd + n
+            res = {
+                "pred_logits": (torch.randn(1, nq, ncls, generator=g) * 1.5),
+                "pred_bboxes": torch.rand(1, nq, 4, generator=g) * torch.tensor([1.0, 1.0, 0.05, 0.05]),
+                "outputs": torch.randn(1, nq, C, generator=g), "last_ref_pts": torch.randn(1, nq, 4, generator=g),
+                "aux_outputs": [{"queries": torch.randn(1, nq, C, generator=g)}],
+                "det_query_embed": torch.zeros(nd, C),
+            }
+            pre = f"c{case}_f{t}_"
+            for k in ("pred_logits", "pred_bboxes", "outputs", "last_ref_pts"):
+                arrays[pre + "in_" + k] = res[k][0].numpy().copy()
+            arrays[pre + "in_aux_queries"] = res["aux_outputs"][-1]["queries"][0].numpy().copy()
+            prev, new = tracker.update(model_outputs=res, tracks=tracks)
+            tracks = QueryUpdater.select_active_tracks(fake_self, prev, new, None)
+            a = tracks[0]
+            for k in ("ids", "labels", "disappear_time", "boxes", "logits", "ref_pts", "query_embed", "output_embed",
+                      "last_output", "long_memory"):
+                arrays[pre + "out_" + k] = getattr(a, k).numpy().copy()
+            arrays[pre + "max_obj_id"] = np.asarray(tracker.max_obj_id, dtype=np.int64)
+            # result rows (submit_engine.py:88-98)
+            r = a.to(torch.device("cpu"))
+            r.scores = r.logits.sigmoid()           # the field the filter reads; set by model/tracker in the real loop
+            r.area = r.boxes[:, 2] * ori_w * r.boxes[:, 3] * ori_h
+            r = filt_area(filt_score(r, thresh=res_t))
+            r.boxes = box_cxcywh_to_xyxy(r.boxes) * torch.as_tensor([ori_w, ori_h, ori_w, ori_h], dtype=torch.float)
+            arrays[pre + "res_ids"] = r.ids.numpy().copy()
+            arrays[pre + "res_boxes"] = r.boxes.numpy().reshape(-1, 4).copy()
+        arrays[f"c{case}_meta"] = np.asarray([ncls, nd, C, miss, ori_w, ori_h], dtype=np.int64)
+        arrays[f"c{case}_thresh"] = np.asarray([det_t, trk_t, res_t], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "tracker.npz"), **arrays)
+    print("tracker.npz:", len(arrays), "arrays;", {k: v.tolist() for k, v in arrays.items() if k.endswith("out_ids")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     func = import_reference()
+    golden_tracker()
+    if "--tracker-only" in sys.argv:
+        sys.exit(0)
     golden_msda(func)
     golden_frame(synth.small_cfg(), synth.SMALL_SHAPES, n_tracks=5, seed_w=0, seed_x=1, padded=False, tag="small")
     golden_frame(synth.small_cfg(), synth.SMALL_SHAPES, n_tracks=5, seed_w=2, seed_x=3, padded=True, tag="small_padded")

@@ -1,0 +1,243 @@
+"""GPU parity tests of the device-side tracker glue (memotr_b200/tracker.py, csrc/tracker.cu; run with `pytest -m gpu`).
+
+Bar: every integer output (ids, labels, disappear_time, n_active, max_obj_id, which rows are kept) bit-exact, every
+float field bit-exact too (they are copies) against
+  * tests/golden/tracker.npz -- outputs of the reference's own RuntimeTracker / TrackInstances /
+    QueryUpdater.select_active_tracks / result filter (oracle/make_golden.py), and
+  * oracle/tracker.py on seeded inputs at sizes the goldens do not cover (capacity > 1024, births + deaths, overflow).
+The whole-loop test runs the engine with the tracker inside its CUDA graph for six frames against the functional
+oracle (fp32 mode: identities exact, boxes <= 1e-4 as max|a-b|/max|b|).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import synth
+from oracle import tracker as otr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+IN_KEYS = ("pred_logits", "pred_bboxes", "outputs", "last_ref_pts", "aux_queries")
+
+
+def _mk(cap, C, ncls, nd, **thr):
+    from memotr_b200.tracker import DeviceTracker, TrackTable
+    trk = DeviceTracker(TrackTable(cap, C, ncls, DEV), nd, **thr)
+    trk.reset()
+    return trk
+
+
+def _pad_inputs(out, nd, n, cap, g):
+    """Model outputs with nd + n rows -> nd + cap rows; the padding rows hold garbage that must be ignored."""
+    res = {}
+    for k in IN_KEYS:
+        x = out[k]
+        junk = torch.randn(cap - n, x.shape[1], generator=g) * 3
+        res[k] = torch.cat((x[:nd], x[nd:nd + n], junk)).contiguous().to(DEV)
+    return res
+
+
+def _check_active(trk, want, tag):
+    got = trk.table.active()
+    n = len(want["ids"])
+    assert len(got["ids"]) == n, (tag, len(got["ids"]), n)
+    for k in otr.INT_FIELDS + otr.FLOAT_FIELDS:
+        w = want[k] if isinstance(want[k], np.ndarray) else want[k].numpy()
+        assert np.array_equal(got[k].cpu().numpy(), w), (tag, k)
+    pad = trk.track_pad.cpu().numpy()
+    assert pad[:n].sum() == 0 and pad[n:].all(), tag
+
+
+def _check_results(trk, ids, boxes, tag):
+    torch.cuda.synchronize()
+    keep = trk.res_keep.cpu().bool()
+    assert np.array_equal(trk.res_ids.cpu()[keep].numpy(), ids), tag
+    assert np.array_equal(trk.res_boxes.cpu()[keep].numpy(), boxes), tag
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_tracker_matches_reference_golden(case):
+    g = np.load(f"{GOLDEN}/tracker.npz")
+    ncls, nd, C, miss, ow, oh = (int(v) for v in g[f"c{case}_meta"])
+    det_t, trk_t, res_t = (float(v) for v in g[f"c{case}_thresh"])
+    cap = 40
+    trk = _mk(cap, C, ncls, nd, det_score_thresh=det_t, track_score_thresh=trk_t, miss_tolerance=miss,
+              result_score_thresh=res_t)
+    gen = torch.Generator().manual_seed(case)
+    n = 0
+    for t in range(6):
+        pre = f"c{case}_f{t}_"
+        out = {k: torch.from_numpy(g[pre + "in_" + k]) for k in IN_KEYS}
+        assert out["pred_logits"].shape[0] == nd + n
+        x = _pad_inputs(out, nd, n, cap, gen)
+        trk.update(*(x[k] for k in IN_KEYS))
+        trk.results(ow, oh)
+        want = {k: g[pre + "out_" + k] for k in otr.INT_FIELDS + otr.FLOAT_FIELDS}
+        _check_active(trk, want, (case, t))
+        assert int(trk.max_obj_id.item()) == int(g[pre + "max_obj_id"])
+        _check_results(trk, g[pre + "res_ids"], g[pre + "res_boxes"], (case, t))
+        n = len(want["ids"])
+    trk.check_overflow()
+
+
+def _random_outputs(nd, n, C, ncls, g, scale=1.5):
+    nq = nd + n
+    return {"pred_logits": torch.randn(nq, ncls, generator=g) * scale,
+            "pred_bboxes": torch.rand(nq, 4, generator=g) * torch.tensor([1.0, 1.0, 0.2, 0.2]),
+            "outputs": torch.randn(nq, C, generator=g), "last_ref_pts": torch.randn(nq, 4, generator=g),
+            "aux_queries": torch.randn(nq, C, generator=g)}
+
+
+@pytest.mark.parametrize("nd,cap,ncls,C", [(300, 1500, 1, 256), (1100, 2100, 4, 32), (5, 3, 2, 16)])
+def test_tracker_vs_oracle_large_tables(nd, cap, ncls, C):
+    """More rows than one scan pass (1024) on both the track and the detect side; births and deaths for 5 frames."""
+    g = torch.Generator().manual_seed(nd + cap)
+    thr = dict(det_score_thresh=0.8 if cap > 10 else 0.9, track_score_thresh=0.45, miss_tolerance=2)
+    trk = _mk(cap, C, ncls, nd, result_score_thresh=0.5, **thr)
+    tracks, max_id = otr.empty_tracks(C, ncls), 0
+    for t in range(5):
+        n = len(tracks["ids"])
+        out = _random_outputs(nd, n, C, ncls, g)
+        prev, new, max_id2 = otr.runtime_tracker_update(out, tracks, max_id, thr["det_score_thresh"],
+                                                        thr["track_score_thresh"], thr["miss_tolerance"])
+        act = otr.select_active_tracks(prev, new)
+        if len(act["ids"]) > cap:           # keep the oracle inside the capacity: the overflow rule is tested below
+            act = {k: v[:cap] for k, v in act.items()}
+            max_id2 = max_id + (cap - int((prev["ids"] >= 0).sum()))
+        x = _pad_inputs(out, nd, n, cap, g)
+        trk.update(*(x[k] for k in IN_KEYS))
+        trk.results(1920, 1080)
+        _check_active(trk, act, (nd, cap, t))
+        assert int(trk.max_obj_id.item()) == max_id2
+        ids, boxes, _ = otr.frame_results(act, 0.5, 1920, 1080)
+        _check_results(trk, ids.numpy(), boxes.numpy().reshape(-1, 4), (nd, cap, t))
+        tracks, max_id = act, max_id2
+
+
+def test_tracker_overflow_is_counted_and_raises():
+    nd, cap, C = 50, 8, 16
+    trk = _mk(cap, C, 1, nd, det_score_thresh=0.5, track_score_thresh=0.0, miss_tolerance=5)
+    g = torch.Generator().manual_seed(3)
+    out = _random_outputs(nd, 0, C, 1, g)
+    born = int((out["pred_logits"].sigmoid()[:, 0] >= 0.5).sum())
+    assert born > cap
+    x = _pad_inputs(out, nd, 0, cap, g)
+    trk.update(*(x[k] for k in IN_KEYS))
+    assert int(trk.table.n_active.item()) == cap and int(trk.max_obj_id.item()) == cap
+    assert int(trk.overflow.item()) == born - cap
+    assert trk.table["ids"].cpu().tolist() == list(range(cap))          # the first `cap` newborns in detect order
+    with pytest.raises(RuntimeError, match="did not fit"):
+        trk.check_overflow()
+
+
+def test_tracker_all_tracks_die_and_empty_table():
+    nd, cap, C = 6, 4, 16
+    trk = _mk(cap, C, 1, nd, det_score_thresh=2.0, track_score_thresh=2.0, miss_tolerance=1)   # nothing born, all die
+    g = torch.Generator().manual_seed(4)
+    trk.reset({"query_embed": torch.randn(3, C, generator=g), "ref_pts": torch.randn(3, 4, generator=g),
+               "last_output": torch.randn(3, C, generator=g), "long_memory": torch.randn(3, C, generator=g)},
+              max_obj_id=3)
+    x = _pad_inputs(_random_outputs(nd, 3, C, 1, g), nd, 3, cap, g)
+    trk.update(*(x[k] for k in IN_KEYS))
+    assert int(trk.table.n_active.item()) == 0 and trk.track_pad.cpu().all() and int(trk.max_obj_id.item()) == 3
+    assert (trk.table["ids"].cpu() == -1).all()
+    trk.update(*(x[k] for k in IN_KEYS))                                  # update on the empty table
+    assert int(trk.table.n_active.item()) == 0
+    trk.results(100, 100)
+    assert not trk.res_keep.cpu().any()
+
+
+def test_tracker_rejects_bad_arguments():
+    trk = _mk(4, 16, 1, 6)
+    g = torch.Generator().manual_seed(5)
+    x = _pad_inputs(_random_outputs(6, 0, 16, 1, g), 6, 0, 4, g)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        trk.update(x["pred_logits"].cpu(), *(x[k] for k in IN_KEYS[1:]))
+    with pytest.raises(RuntimeError, match="contiguous fp32"):
+        trk.update(x["pred_logits"].double(), *(x[k] for k in IN_KEYS[1:]))
+    with pytest.raises(RuntimeError, match="contiguous fp32"):
+        trk.update(x["pred_logits"][:-1], *(x[k] for k in IN_KEYS[1:]))
+    from memotr_b200.tracker import TrackTable
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        TrackTable(4, 16, 1, "cpu")
+    with pytest.raises(RuntimeError, match="exceed the capacity"):
+        trk.table.load({"query_embed": torch.zeros(5, 16)})
+
+
+# ------------------------------------------------------------------------------------------------ the whole loop
+CLIP_THR = dict(det_score_thresh=0.66, track_score_thresh=0.6, miss_tolerance=2, result_score_thresh=0.62)
+
+
+def _clip_oracle(cfg, sd, n_frames):
+    tracks, max_id, per_frame, margin = otr.empty_tracks(cfg["d_model"], cfg["num_classes"]), 0, [], 1.0
+    for t in range(n_frames):
+        fr = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10 + t)
+        tracks, max_id, _, m = otr.clip_step(sd, cfg, fr, tracks, max_id, CLIP_THR["det_score_thresh"],
+                                             CLIP_THR["track_score_thresh"], CLIP_THR["miss_tolerance"])
+        margin = min(margin, m)
+        ids, boxes, _ = otr.frame_results(tracks, CLIP_THR["result_score_thresh"], 1920, 1080)
+        margin = min(margin, float((tracks["logits"].sigmoid().max(-1).values - CLIP_THR["result_score_thresh"]).abs().min())
+                     if len(tracks["ids"]) else 1.0)
+        per_frame.append(({k: v.clone() for k, v in tracks.items()}, max_id, ids, boxes))
+    return per_frame, margin
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_engine_clip_with_device_tracker_matches_oracle(graph):
+    """Six frames from an empty track table: births, misses, deaths.  Engine (fp32, capacity 10, tracker on the device,
+    optionally the whole step replayed as one CUDA graph) against the submit loop restated in oracle/."""
+    from memotr_b200.engine import FrameEngine
+    cfg = synth.small_cfg()
+    sd = synth.hot_path_state_dict(cfg, seed=5)
+    want, margin = _clip_oracle(cfg, sd, 6)
+    assert margin > 5e-4, f"a threshold decision of the oracle run is within {margin:.1e} of its threshold: re-seed"
+    assert max(len(w[0]["ids"]) for w in want) <= 10 and any(len(w[0]["ids"]) == 0 for w in want) is False
+    eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 10, DEV, mode="fp32", tracker=CLIP_THR, ori_size=(1920, 1080))
+    if graph:
+        fr = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10)
+        eng.load_frame(fr["srcs"], fr["masks"], fr["pos"], eng.in_track_ref, eng.in_track_embed)
+        eng.capture()
+        eng.trk.reset()                       # the warm-up steps of capture() advanced the table: start the clip over
+        eng.in_track_ref.zero_(), eng.in_track_embed.zero_()
+    seen_death = False
+    for t in range(6):
+        fr = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10 + t)
+        eng.load_frame(fr["srcs"], fr["masks"], fr["pos"], eng.in_track_ref, eng.in_track_embed)
+        eng.replay() if graph else eng.step()
+        torch.cuda.synchronize()
+        w, max_id, ids, boxes = want[t]
+        got = eng.table.active()
+        assert got["ids"].cpu().tolist() == w["ids"].tolist(), (t, got["ids"].tolist(), w["ids"].tolist())
+        assert got["disappear_time"].cpu().tolist() == w["disappear_time"].tolist(), t
+        assert got["labels"].cpu().tolist() == w["labels"].tolist(), t
+        assert int(eng.trk.max_obj_id.item()) == max_id
+        for k in ("boxes", "logits", "ref_pts", "query_embed", "output_embed", "last_output", "long_memory"):
+            assert rel_err(got[k].cpu().numpy(), w[k].numpy()) <= 1e-4, (t, k)
+        keep = eng.trk.res_keep.cpu().bool()
+        assert eng.trk.res_ids.cpu()[keep].tolist() == ids.tolist(), t
+        if len(ids):
+            assert rel_err(eng.trk.res_boxes.cpu()[keep].numpy(), boxes.numpy()) <= 1e-4, t
+        seen_death |= t > 0 and not set(want[t - 1][0]["ids"].tolist()) <= set(w["ids"].tolist())
+    assert seen_death, "the clip was meant to exercise track deaths"
+    eng.trk.check_overflow()
+
+
+def test_engine_padded_rows_do_not_change_live_rows():
+    """The same two frames with capacity 6 and capacity 16 give the same live rows: padding is inert (key-padding masks in
+    the decoder self-attention and in the updater's memory attention)."""
+    from memotr_b200.engine import FrameEngine
+    cfg = synth.small_cfg()
+    sd = synth.hot_path_state_dict(cfg, seed=5)
+    outs = []
+    for cap in (6, 16):
+        eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, cap, DEV, mode="fp32", tracker=CLIP_THR)
+        for t in range(2):
+            fr = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10 + t)
+            eng.load_frame(fr["srcs"], fr["masks"], fr["pos"], eng.in_track_ref, eng.in_track_embed)
+            eng.step()
+        torch.cuda.synchronize()
+        outs.append(eng.table.active())
+    assert outs[0]["ids"].tolist() == outs[1]["ids"].tolist() and len(outs[0]["ids"]) > 0
+    for k in ("boxes", "query_embed", "long_memory"):
+        assert rel_err(outs[0][k].cpu().numpy(), outs[1][k].cpu().numpy()) <= 1e-5, k
