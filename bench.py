@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / gpu_reference legs")
+    ap.add_argument("--no-tracker", action="store_true",
+                    help="leave the RuntimeTracker glue out of the step (A/B; default: on the device, inside the graph)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,7 +223,12 @@ def main():
     cfg = synth.dancetrack_cfg()
     sd = synth.hot_path_state_dict(cfg, seed=0)
     frames = [synth.frame_inputs(cfg, synth.DANCETRACK_SHAPES, N_TRACKS, seed=1 + i + 17 * rank) for i in range(N_ROT)]
-    eng = FrameEngine(sd, cfg, synth.DANCETRACK_SHAPES, N_TRACKS, dev, mode=args.mode)
+    # Tracker glue on the device (memotr_b200/tracker.py).  The weights are random, so the thresholds are pinned such that
+    # the 100 loaded tracks stay live and nothing is born: the step keeps BASELINE.json's 300 det + 100 track queries.
+    tracker = None if args.no_tracker else dict(det_score_thresh=2.0, track_score_thresh=0.0, miss_tolerance=30,
+                                                result_score_thresh=0.5)
+    eng = FrameEngine(sd, cfg, synth.DANCETRACK_SHAPES, N_TRACKS, dev, mode=args.mode, tracker=tracker,
+                      ori_size=(1920, 1080))
     eng.enable_msda_timer()
     L, C, K = eng.L, eng.C, args.steps
 
@@ -234,6 +241,8 @@ def main():
     x0 = frames[0]
     eng.load_frame(x0["srcs"], x0["masks"], x0["pos"], x0["tracks"]["ref_pts"], x0["tracks"]["query_embed"])
     eng.load_tracks(x0["tracks"])
+    if eng.trk is not None:
+        eng.trk.reset(x0["tracks"])
     eng.capture()                                       # records step(): forward + hand-off + updater + feedback
 
     def feed_resident(i):
@@ -245,6 +254,8 @@ def main():
         eng.in_track_ref.copy_(x0["tracks"]["ref_pts"])
         eng.in_track_embed.copy_(x0["tracks"]["query_embed"])
         eng.load_tracks(x0["tracks"], non_blocking=False)
+        if eng.trk is not None:
+            eng.trk.reset(x0["tracks"], max_obj_id=N_TRACKS)
 
     def barrier():
         if world > 1:
@@ -283,6 +294,10 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    tracks_live = int(eng.table.n_active.item()) if eng.trk is not None else N_TRACKS
+    if eng.trk is not None:
+        eng.trk.check_overflow()
+        assert tracks_live == N_TRACKS, f"the bench workload drifted: {tracks_live} live tracks instead of {N_TRACKS}"
     msda_us = eng.msda_times_us()                       # the 6 encoder MSDA launches of the last timed step
     sections = eng.section_times_us()
 
@@ -325,6 +340,11 @@ def main():
     # value read once + output written once (activation dtype) + sampling locations and weights (fp32): BASELINE.md sec. 3
     alg_bytes = S * H * 32 * esz + S * H * 32 * esz + S * H * LK * 3 * 4
     peak, peak_src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_msda_fwd_h16_traffic.json")
+    if eng.value_f16 and os.path.exists(tpath):          # dram bytes of this kernel from the committed ncu --set full capture
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     dur = sum(msda_us) / len(msda_us)
     achieved = alg_bytes / dur / 1e3
     fps = world * K / (ms_total * 1e-3)
@@ -335,6 +355,9 @@ def main():
         "config": {"workload": workload, "clip": f"{K} chained frames per GPU; N>1: one NCCL all-gather of the packed "
                    "track-query memory per clip", "l2": f"inputs larger than L2: {N_ROT} resident frames x 45.8 MB rotate "
                    "through the input buffers and a step touches ~0.5 GB of workspace (L2 = 126 MB)",
+                   "tracker": ("RuntimeTracker.update + select_active_tracks + result filter on the device inside the "
+                               f"captured step; thresholds pinned so that {tracks_live} tracks stay live and none is born")
+                   if eng.trk is not None else "off (--no-tracker)",
                    "arithmetic": "bf16 GEMM operands + fp32 accumulate/residual/LayerNorm/geometry" if args.mode == "bf16"
                    else "fp32 everywhere (TF32 off, as the reference)"},
         "clocks": clocks,
@@ -344,7 +367,8 @@ def main():
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "roofline": {"kernel": ("msda_fwd_h16 (fp16 value map)" if eng.value_f16 else "msda_fwd_vec") +
                                " -- encoder-shaped launch, Lq = S = 22323", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/r01_msda_fwd_h16_traffic.json (ncu --set full)" if traffic else None,
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "duration_us": dur,
                      "samples": f"{len(msda_us)} launches (the encoder layers of the last timed step), CUDA events "
                                 "recorded inside the captured graph",

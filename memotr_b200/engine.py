@@ -567,8 +567,16 @@ class ClipRunner:
             e.record(torch.cuda.current_stream(dev))
         self.host_out = {
             "pred_logits": torch.empty(eng.nq, eng.ncls).pin_memory(), "pred_bboxes": torch.empty(eng.nq, 4).pin_memory(),
-            "track_query_embed": torch.empty(eng.nt, eng.C).pin_memory(), "track_ref_pts": torch.empty(eng.nt, 4).pin_memory(),
         }
+        if eng.trk is None:     # the caller keeps the tracks: hand the updated track queries back
+            self.host_out["track_query_embed"] = torch.empty(eng.nt, eng.C).pin_memory()
+            self.host_out["track_ref_pts"] = torch.empty(eng.nt, 4).pin_memory()
+        else:                   # tracks live on the device: only the frame's result rows travel (submit_engine.py:99-102)
+            self.host_out["ids"] = torch.empty(eng.nt, dtype=torch.long).pin_memory()
+            self.host_out["boxes_xyxy"] = torch.empty(eng.nt, 4).pin_memory()
+            self.host_out["scores"] = torch.empty(eng.nt).pin_memory()
+            self.host_out["keep"] = torch.empty(eng.nt, dtype=torch.uint8).pin_memory()
+            self.host_out["n_active"] = torch.empty(1, dtype=torch.int32).pin_memory()
         self.h2d_bytes = sum(t.numel() * t.element_size() for k in ("src", "pos", "mask") for t in self.stage[0][k])
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out.values())
 
@@ -597,8 +605,16 @@ class ClipRunner:
         n = eng.n_dec
         self.host_out["pred_logits"].copy_(eng.pred_logit[n - 1], non_blocking=True)
         self.host_out["pred_bboxes"].copy_(eng.pred_box[n - 1], non_blocking=True)
-        self.host_out["track_query_embed"].copy_(eng.st["query_embed"], non_blocking=True)
-        self.host_out["track_ref_pts"].copy_(eng.st["ref_pts"], non_blocking=True)
+        if eng.trk is None:
+            self.host_out["track_query_embed"].copy_(eng.st["query_embed"], non_blocking=True)
+            self.host_out["track_ref_pts"].copy_(eng.st["ref_pts"], non_blocking=True)
+        else:
+            t = eng.trk
+            self.host_out["ids"].copy_(t.res_ids, non_blocking=True)
+            self.host_out["boxes_xyxy"].copy_(t.res_boxes, non_blocking=True)
+            self.host_out["scores"].copy_(t.res_scores, non_blocking=True)
+            self.host_out["keep"].copy_(t.res_keep, non_blocking=True)
+            self.host_out["n_active"].copy_(eng.table.n_active, non_blocking=True)
         return self.host_out
 
     def run_clip(self, frames):
@@ -633,3 +649,20 @@ def smoke(dev):
     for k in ("pred_logits", "pred_bboxes", "outputs"):
         err = (got[k].cpu() - want[k]).abs().max() / want[k].abs().max()
         assert err < 1e-4, (k, float(err))
+    # the whole submit loop with the tracker glue on the device: three frames from an empty table against the oracle
+    from oracle import tracker as otr           # checker, smoke only
+    thr = dict(det_score_thresh=0.66, track_score_thresh=0.6, miss_tolerance=2, result_score_thresh=0.62)
+    sd = synth.hot_path_state_dict(cfg, seed=5)
+    eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 10, dev, mode="fp32", tracker=thr)
+    tracks, max_id = otr.empty_tracks(cfg["d_model"], cfg["num_classes"]), 0
+    for t in range(3):
+        fr = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10 + t)
+        eng.load_frame(fr["srcs"], fr["masks"], fr["pos"], eng.in_track_ref, eng.in_track_embed)
+        eng.step()
+        tracks, max_id, _, _ = otr.clip_step(sd, cfg, fr, tracks, max_id, thr["det_score_thresh"],
+                                             thr["track_score_thresh"], thr["miss_tolerance"])
+        got = eng.table.active()
+        assert got["ids"].cpu().tolist() == tracks["ids"].tolist(), (t, got["ids"].tolist(), tracks["ids"].tolist())
+        assert got["disappear_time"].cpu().tolist() == tracks["disappear_time"].tolist(), t
+        err = (got["boxes"].cpu() - tracks["boxes"]).abs().max() / tracks["boxes"].abs().max()
+        assert err < 1e-4, (t, float(err))
