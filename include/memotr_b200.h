@@ -250,6 +250,42 @@ MEMOTR_API int memotr_tracker_results(const memotr_track_table *tracks, int capa
                                       float *scores, unsigned char *keep, void *stream);
 
 /*
+ * The whole DeformableDecoder (all layers) + per-layer box / class heads as one persistent kernel, bf16 engine
+ * (models/deformable_decoder.py:56-160,276-319; models/memotr.py:147-162).  One CTA per block of 16 query rows, one grid
+ * barrier per layer (keys / values of the self-attention), weights streamed from L2 in program order.
+ * All pointers are device pointers; the struct itself lives on the host and is passed by value to the kernel.
+ */
+#define MEMOTR_DEC_MAX_LAYERS 8
+typedef struct memotr_dec_gemm { /* one dense layer of the weight program: W (N, K) bf16, K-major, row stride ldw */
+  const void *W;
+  int ldw, N, K, pad_;
+} memotr_dec_gemm;
+
+typedef struct memotr_dec_layer {
+  const float *qk_b, *v_b, *sao_b, *ol_b, *cao_b, *f1_b, *f2_b, *bb0_b, *bb1_b, *bb2_b, *cls_b; /* biases, fp32 */
+  const float *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;                                          /* LayerNorm */
+  const void *bb2_w, *cls_w;  /* (4, 256) and (ncls, 256) bf16: the two skinny heads, read directly */
+  const void *value;          /* this layer's value map: fp16, pixel-major, `value_stride` elements between pixels */
+  float *tgt_out, *ref_out, *pred_box, *pred_logit; /* (nq,256) layer output, (nq,4) next reference, (nq,4), (nq,ncls) */
+} memotr_dec_layer;
+
+typedef struct memotr_dec_params {
+  const memotr_dec_gemm *prog; /* device array, program order: per layer rph0, rph1, [qs0, qs1 if layer > 0], qk, v,
+                                  sa_out, ol, ca_out, ffn1/ffn2 (in two halves of the hidden dimension when d_ffn > 1024), bb0, bb1 */
+  int n_prog, n_layers, nq, nd, merge, ncls, n_levels, n_points, d_ffn, value_stride, np, pad_;
+  const float *rph0_b, *rph1_b, *qs0_b, *qs1_b; /* biases of the shared ref_point_head / query_scale MLPs */
+  const float *tgt_in, *ref_in;                 /* (nq,256) decoder input, (nq,4) initial reference boxes (sigmoid space) */
+  const float *vr_scale4, *valid_ratios, *dim_t; /* (4) level-0 ratios x2, (n_levels,2), (128) sine temperatures */
+  const unsigned char *query_pad;               /* (nq) key-padding mask or NULL */
+  void *kbuf, *vbuf;                            /* scratch: 2 x (np,256) fp16 keys, 2 x (256,np) fp16 values (transposed) */
+  unsigned int *barrier;                        /* scratch: one counter */
+  int shapes[16], lsi[8];                       /* (H, W) and first pixel of every level */
+  memotr_dec_layer layers[MEMOTR_DEC_MAX_LAYERS];
+} memotr_dec_params;
+
+MEMOTR_API int memotr_decoder_forward(const memotr_dec_params *params, void *stream);
+
+/*
  * Interval timer for measurement (bench.py): n CUDA events; memotr_timer_record enqueues event `idx` on `stream`
  * (as an external event-record node when the stream is being captured into a CUDA graph), memotr_timer_elapsed_ms
  * reads the time between two recorded events after the work has completed.  No reference counterpart (the reference

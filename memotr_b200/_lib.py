@@ -32,6 +32,34 @@ class FrameOutputs(ctypes.Structure):
     _fields_ = [(k, ctypes.c_void_p) for k in ("pred_logits", "pred_boxes", "outputs", "last_ref_pts", "aux_queries")]
 
 
+MEMOTR_DEC_MAX_LAYERS = 8
+
+
+class DecGemm(ctypes.Structure):
+    """memotr_dec_gemm (include/memotr_b200.h)."""
+    _fields_ = [("W", ctypes.c_void_p), ("ldw", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+                ("pad_", ctypes.c_int)]
+
+
+class DecLayer(ctypes.Structure):
+    """memotr_dec_layer (include/memotr_b200.h)."""
+    _fields_ = [(k, ctypes.c_void_p) for k in (
+        "qk_b", "v_b", "sao_b", "ol_b", "cao_b", "f1_b", "f2_b", "bb0_b", "bb1_b", "bb2_b", "cls_b",
+        "n1_g", "n1_b", "n2_g", "n2_b", "n3_g", "n3_b", "bb2_w", "cls_w", "value",
+        "tgt_out", "ref_out", "pred_box", "pred_logit")]
+
+
+class DecParams(ctypes.Structure):
+    """memotr_dec_params (include/memotr_b200.h)."""
+    _fields_ = ([("prog", ctypes.c_void_p)] +
+                [(k, ctypes.c_int) for k in ("n_prog", "n_layers", "nq", "nd", "merge", "ncls", "n_levels", "n_points",
+                                             "d_ffn", "value_stride", "np", "pad_")] +
+                [(k, ctypes.c_void_p) for k in ("rph0_b", "rph1_b", "qs0_b", "qs1_b", "tgt_in", "ref_in", "vr_scale4",
+                                                "valid_ratios", "dim_t", "query_pad", "kbuf", "vbuf", "barrier")] +
+                [("shapes", ctypes.c_int * 16), ("lsi", ctypes.c_int * 8),
+                 ("layers", DecLayer * MEMOTR_DEC_MAX_LAYERS)])
+
+
 _SIGNATURES = {
     "memotr_abi_version": ([], _i),
     "memotr_last_error": ([], ctypes.c_char_p),
@@ -56,6 +84,7 @@ _SIGNATURES = {
     "memotr_upd_finalize": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp], _i),
     "memotr_tracker_update": ([_vp, _i, _i, _i, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "memotr_tracker_results": ([_vp, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
+    "memotr_decoder_forward": ([_vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),
     "memotr_timer_destroy": ([_vp], None),
     "memotr_timer_record": ([_vp, _i, _vp], _i),

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(320, 1)
 mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
                const float *__restrict__ b1, int M, int Hd, Epilogue ep) {
+  // gridDim.y > 1: split-K over the hidden dimension -- CTA (x, y) handles hidden chunks [y*NC, (y+1)*NC) of row tile x
+  // and ADDS its partial product into the (zero-initialised, fp32) output with a TMA reduce-store; bias from split 0.
   using namespace mlp;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -87,7 +89,9 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x;
-  const int NC = Hd / HC;
+  const int NC = Hd / HC / (int)gridDim.y;          // hidden chunks of this CTA
+  const int c_off = (int)blockIdx.y * NC;           // first hidden chunk of this CTA
+  const bool split = gridDim.y > 1;
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1);
 
@@ -139,11 +143,11 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + s, SLOT);
           if constexpr (CS == 1) {
-            tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, c * HC);
-            tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, c * HC);
+            tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, (c_off + c) * HC);
+            tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, (c_off + c) * HC);
           } else {
             const int u0 = crank * UNITS, kb = 2 * half + u0 / 128, r0 = u0 % 128;
-            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW1, full + s, kb * BK, c * HC + r0, MC_MASK);
+            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW1, full + s, kb * BK, (c_off + c) * HC + r0, MC_MASK);
           }
         }
       };
@@ -153,10 +157,10 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + s, SLOT);
           if constexpr (CS == 1) {
-            tma_load_2d(ring + s * SLOT, &tmW2, full + s, c * HC + j * BK, 0);
+            tma_load_2d(ring + s * SLOT, &tmW2, full + s, (c_off + c) * HC + j * BK, 0);
           } else {
             const int u0 = crank * UNITS;
-            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW2, full + s, c * HC + j * BK, u0, MC_MASK);
+            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW2, full + s, (c_off + c) * HC + j * BK, u0, MC_MASK);
           }
         }
       };
@@ -235,7 +239,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tmem_ld32_issue(tmem_base + lane_off + (uint32_t)(b * HC + chalf * 64 + 32), r1);
       tmem_ld_wait();
       uint8_t *prow = hbuf + b * H_BYTES + chalf * PANEL + r_in * 128;
-      const float *bias = b1 + c * HC + chalf * 64;
+      const float *bias = b1 + (c_off + c) * HC + chalf * 64;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + 8 * k));
@@ -275,7 +279,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (ep.bias) {
+      if (ep.bias && blockIdx.y == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 bb = __ldg(reinterpret_cast<const float4 *>(ep.bias + c0 + j));
@@ -319,10 +323,17 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (warp == 2 && lane == 0) {
 #pragma unroll 1
-      for (int p = 0; p < N_PANELS; ++p)
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
-                     "r"(smem_u32(smem + p * PANEL)), "r"(p * PANEL_COLS), "r"(m_blk * BM)
-                     : "memory");
+      for (int p = 0; p < N_PANELS; ++p) {
+        if (split)
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           &tmC),
+                       "r"(smem_u32(smem + p * PANEL)), "r"(p * PANEL_COLS), "r"(m_blk * BM)
+                       : "memory");
+        else
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                       "r"(smem_u32(smem + p * PANEL)), "r"(p * PANEL_COLS), "r"(m_blk * BM)
+                       : "memory");
+      }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -338,7 +349,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 template <typename TC, int CS>
 static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
-                       int Hd, const Epilogue &ep, cudaStream_t st) {
+                       int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1) {
   using namespace mlp;
   CUtensorMap tmX, tmW1, tmW2, tmC;
   constexpr int W1_BOX = CS == 1 ? HC : (256 / CS < 128 ? 256 / CS : 128), W2_BOX = 256 / CS;
@@ -355,7 +366,11 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
   }
   const int tiles = ceil_div(M, BM);
   if constexpr (CS == 1) {
-    MEMOTR_LAUNCH((kern), tiles, 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
+    if (nsplit > 1) {   // partial products are reduce-added: start from zero (a memset node when captured into a graph)
+      const cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(TC), 0, (size_t)N2 * sizeof(TC), M, st);
+      if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
+    }
+    MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
   } else {
     // CTAs beyond the last tile (grid rounded up to a whole cluster) see zero-filled X and have their stores clipped
     launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(320), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
@@ -390,8 +405,32 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   const int cs_env = cs_str ? atoi(cs_str) : 0;
   const int tiles = ceil_div(M, tc::BM);
   (void)tiles;
-  const int cs = cs_env ? cs_env : 1;   // measured: the kernel is epilogue-bound, multicast gives nothing yet (profiles/)
+  const int cs = cs_env ? cs_env : 1;   // measured: the kernel is shared-memory-bound, multicast gives nothing (profiles/)
 #define MLP2_GO(TC_, CS_) return tc::launch_mlp2<TC_, CS_>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
+  // Split-K over the hidden dimension when the row tiles alone leave SMs idle (one CTA per SM: 175 tiles on 148 SMs are
+  // two rounds, the second 18 % full).  CTA (tile, split) handles Hd/nsplit hidden columns and reduce-adds into the fp32
+  // output; nsplit minimises rounds x (chunks per CTA x ~2 us + ~3 us fixed cost).  MEMOTR_MLP_SPLIT=1|2|4|8 overrides.
+  if (c_dtype == MEMOTR_F32 && cs == 1 && act2 == 0 && !mul) {
+    static int n_sm = 0;
+    if (!n_sm) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const char *sp = getenv("MEMOTR_MLP_SPLIT");
+    int nsplit = sp ? atoi(sp) : 0;
+    const int chunks = Hd / tc::mlp::HC;
+    if (nsplit <= 0) {
+      float best = 1e30f;
+      nsplit = 1;
+      for (int ns = 1; ns <= 8 && ns <= chunks; ns *= 2) {
+        if (chunks % ns) break;
+        const float cost = (float)ceil_div(tiles * ns, n_sm) * ((float)(chunks / ns) * 2.1f + 3.f) + (ns > 1 ? 4.f : 0.f);
+        if (cost < best - 0.5f) best = cost, nsplit = ns;
+      }
+    }
+    if (nsplit > 1 && chunks % nsplit == 0) return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, nsplit);
+  }
   if (c_dtype == MEMOTR_F32) {
     if (cs == 4) MLP2_GO(float, 4);
     if (cs == 2) MLP2_GO(float, 2);

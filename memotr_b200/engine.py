@@ -75,8 +75,15 @@ class FrameEngine:
         self.value_f16 = mode == "bf16" and os.environ.get("MEMOTR_VALUE_F16", "1") != "0" and not self.use_pairs
         self.vdt = F16 if self.value_f16 else self.dt
         self.tv = torch.float16 if self.value_f16 else self.ta
+        # the whole decoder + heads as one persistent kernel (csrc/decoder_fused.cu); A/B switch
+        self.dec_fused = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_DEC_FUSED", "1") != "0"
+                          and self.nq <= 16 * 132
+                          and (cfg["d_ffn"] % 256 == 0 if cfg["d_ffn"] <= 1024 else cfg["d_ffn"] in (1536, 2048))
+                          and cfg["n_levels"] * cfg["n_dec_points"] * 24 <= 512)
         self._pack(state_dict)
         self._alloc()
+        if self.dec_fused:
+            self._build_decoder_program()
         self.graph = None
         self.timer = None
 
@@ -246,6 +253,66 @@ class FrameEngine:
         self.u_a32 = self.u_a if fp32 else f(nt, C)
         self.u_c32 = self.u_c if fp32 else f(nt, C)
 
+    # ------------------------------------------------------------------------------------------------ fused decoder
+    def _build_decoder_program(self):
+        """Weight program + parameter block of memotr_decoder_forward (include/memotr_b200.h, csrc/decoder_fused.cu)."""
+        import ctypes
+        C, nq, dev, nl = self.C, self.nq, self.dev, self.n_dec
+        F = self.Fd
+        prog = []
+
+        def g(L, row0=0, rows=None, col0=0, K=None):
+            rows, K = (L.N if rows is None else rows), (L.K if K is None else K)
+            assert rows % 64 == 0 and K % 256 == 0 and L.w.dtype == torch.bfloat16
+            prog.append((L.w.data_ptr() + (row0 * L.K + col0) * 2, L.K, rows, K))
+
+        for lid, ly in enumerate(self.dec):
+            g(self.ref_point_head[0]), g(self.ref_point_head[1])
+            if lid > 0:
+                g(self.query_scale[0]), g(self.query_scale[1])
+            g(ly["self"]["qk"]), g(ly["self"]["v"]), g(ly["self"]["out"]), g(ly["attn"]["ol"]), g(ly["attn"]["out"])
+            nh = 2 if F > 1024 else 1
+            for half in range(nh):
+                g(ly["lin1"], row0=half * F // nh, rows=F // nh)
+                g(ly["lin2"], col0=half * F // nh, K=F // nh)
+            g(ly["bbox"][0]), g(ly["bbox"][1])
+        arr = (_lib.DecGemm * len(prog))(*[_lib.DecGemm(w, ldw, n, k, 0) for (w, ldw, n, k) in prog])
+        self.dec_prog = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.dec_np = (nq + 63) // 64 * 64
+        self.dec_kbuf = torch.zeros(2, self.dec_np, C, dtype=torch.float16, device=dev)
+        self.dec_vbuf = torch.zeros(2, C, self.dec_np, dtype=torch.float16, device=dev)
+        self.dec_barrier = torch.zeros(1, dtype=torch.int32, device=dev)
+        P = _lib.DecParams()
+        P.prog, P.n_prog, P.n_layers, P.nq, P.nd, P.merge = self.dec_prog.data_ptr(), len(prog), nl, nq, self.nd, self.merge
+        P.ncls, P.n_levels, P.n_points, P.d_ffn = self.ncls, self.L, self.cfg["n_dec_points"], F
+        P.value_stride, P.np = nl * C, self.dec_np
+        P.rph0_b, P.rph1_b = self.ref_point_head[0].b.data_ptr(), self.ref_point_head[1].b.data_ptr()
+        P.qs0_b, P.qs1_b = self.query_scale[0].b.data_ptr(), self.query_scale[1].b.data_ptr()
+        P.tgt_in, P.ref_in = self.tgt32[0].data_ptr(), self.ref[0].data_ptr()
+        P.vr_scale4, P.valid_ratios, P.dim_t = self.vr_scale4.data_ptr(), self.vr.data_ptr(), self.dim_t.data_ptr()
+        P.query_pad = self.query_pad.data_ptr() if self.trk is not None else None
+        P.kbuf, P.vbuf, P.barrier = self.dec_kbuf.data_ptr(), self.dec_vbuf.data_ptr(), self.dec_barrier.data_ptr()
+        for l, (h, w) in enumerate(self.shapes):
+            P.shapes[2 * l], P.shapes[2 * l + 1], P.lsi[l] = h, w, self.lsi_host[l]
+        for lid, ly in enumerate(self.dec):
+            D = P.layers[lid]
+            D.qk_b, D.v_b, D.sao_b = ly["self"]["qk"].b.data_ptr(), ly["self"]["v"].b.data_ptr(), ly["self"]["out"].b.data_ptr()
+            D.ol_b, D.cao_b = ly["attn"]["ol"].b.data_ptr(), ly["attn"]["out"].b.data_ptr()
+            D.f1_b, D.f2_b = ly["lin1"].b.data_ptr(), ly["lin2"].b.data_ptr()
+            D.bb0_b, D.bb1_b, D.bb2_b = (ly["bbox"][j].b.data_ptr() for j in range(3))
+            D.cls_b, D.bb2_w, D.cls_w = ly["cls"].b.data_ptr(), ly["bbox"][2].w.data_ptr(), ly["cls"].w.data_ptr()
+            (D.n1_g, D.n1_b), (D.n2_g, D.n2_b), (D.n3_g, D.n3_b) = (
+                tuple(t.data_ptr() for t in ly[k]) for k in ("norm1", "norm2", "norm3"))
+            D.value = self.value_all.data_ptr() + lid * C * 2
+            D.tgt_out, D.ref_out = self.tgt32[lid + 1].data_ptr(), self.ref[lid + 1].data_ptr()
+            D.pred_box, D.pred_logit = self.pred_box[lid].data_ptr(), self.pred_logit[lid].data_ptr()
+        self.dec_params = P
+
+    def _decoder_fused(self):
+        import ctypes
+        self._ck(self.lib.memotr_decoder_forward(ctypes.byref(self.dec_params), self._st()), "decoder_forward")
+        self.launches += 1
+
     # ------------------------------------------------------------------------------------------------ launch helpers
     def _st(self):
         return _lib.stream_ptr(self.dev)
@@ -384,7 +451,9 @@ class FrameEngine:
         # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
         self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
         Kd = self.cfg["n_dec_points"]
-        for lid, ly in enumerate(self.dec):
+        if self.dec_fused:
+            self._decoder_fused()
+        for lid, ly in enumerate(() if self.dec_fused else self.dec):
             out, ref = self.tgt[lid], self.ref[lid]
             n = nq if lid >= self.merge else nd              # det/track split before the merge layer (:292-297)
             # DAB positional query (deformable_decoder.py:88-95)

@@ -154,6 +154,29 @@ def test_fused_mlp2_tensor_core(M, Hd, out_dtype, cluster, monkeypatch):
     assert rel_err(got, want) < (1e-3 if out_dtype == torch.float32 else 6e-3)
 
 
+@pytest.mark.parametrize("split", [0, 2, 4, 8, 16])
+@pytest.mark.parametrize("M,Hd", [(22323, 2048), (300, 2048), (700, 1024)])
+def test_fused_mlp2_split_hidden(M, Hd, split, monkeypatch):
+    """Split-K over the hidden dimension (CTA (tile, split) reduce-adds its partial product into the zeroed fp32 output
+    with a TMA reduce-store); split = 0 is the automatic choice.  Also into a strided view whose neighbours must stay."""
+    if split:
+        monkeypatch.setenv("MEMOTR_MLP_SPLIT", str(split))
+    g = _g(M + Hd + split)
+    x = torch.randn(M, 256, generator=g).bfloat16()
+    w1 = (torch.randn(Hd, 256, generator=g) / 16).bfloat16()
+    w2 = (torch.randn(256, Hd, generator=g) / math.sqrt(Hd)).bfloat16()
+    b1, b2 = torch.randn(Hd, generator=g), torch.randn(256, generator=g)
+    h = F.linear(x.double(), w1.double(), b1.double()).relu().float().bfloat16().double()
+    want = F.linear(h, w2.double(), b2.double())
+    wide = torch.full((M, 768), 7.0, device=DEV)
+    K().mlp2(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out=wide[:, 256:512])
+    assert rel_err(wide[:, 256:512].cpu(), want) < 1e-3
+    assert (wide[:, :256] == 7).all() and (wide[:, 512:] == 7).all()
+    again = torch.full((M, 256), float("nan"), device=DEV)          # whatever the buffer held before is overwritten
+    K().mlp2(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out=again)
+    assert rel_err(again.cpu(), want) < 1e-3
+
+
 def test_fused_mlp2_epilogues_and_views():
     g = _g(21)
     M, Hd = 333, 256
@@ -384,6 +407,35 @@ def test_engine_bf16_matches_reference_modules(tag):
         assert worst[k] < (1e-1 if deep else 1e-2), (k, worst[k])
     for k in ("outputs", "aux_queries", "pred_logits", "aux_logits", "upd_query_embed", "upd_long_memory", "upd_last_output"):
         assert worst[k] < (2.5e-1 if deep else 3e-2), (k, worst[k])
+
+
+@pytest.mark.parametrize("tag", ["small", "small_padded", "full"])
+def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, monkeypatch):
+    """bf16 engine, decoder + heads as ONE persistent kernel (csrc/decoder_fused.cu, the default) against the same
+    engine with one launch per op (MEMOTR_DEC_FUSED=0): same arithmetic classes (bf16 GEMM operands, fp32 everything
+    else; the fused kernel keeps q/k/p/v of the self-attention in fp16 instead of fp32), so the two must agree with each
+    other as well as each agrees with the reference modules, layer by layer (aux outputs)."""
+    monkeypatch.setenv("MEMOTR_DEC_FUSED", "0")
+    g, eng0, res0, _ = _run_engine(tag, "bf16")
+    assert not eng0.dec_fused
+    monkeypatch.setenv("MEMOTR_DEC_FUSED", "1")
+    _, eng1, res1, _ = _run_engine(tag, "bf16")
+    assert eng1.dec_fused and eng1.launches < eng0.launches
+    deep = tag == "full"
+    report = {}
+    for k in FRAME_KEYS:
+        a, b, ref = res1[k].cpu().numpy(), res0[k].cpu().numpy(), g[k]
+        report[k] = (rel_err(a, b), rel_err(a, ref), rel_err(b, ref))
+    print("fused vs per-op / fused vs ref / per-op vs ref:", {k: tuple(f"{x:.1e}" for x in v) for k, v in report.items()})
+    n_l = res0["aux_queries"].shape[0]
+    for l in range(n_l):        # first layers first: a structural error shows up at layer 0 with O(1) differences
+        d = rel_err(res1["aux_queries"][l].cpu().numpy(), res0["aux_queries"][l].cpu().numpy())
+        assert d < (2.5e-1 if deep else 3e-2), ("aux_queries layer", l, d)
+    for k in ("pred_bboxes", "aux_bboxes", "last_ref_pts"):
+        assert report[k][1] < (1e-1 if deep else 1e-2), (k, report[k])
+    for k in ("outputs", "aux_queries", "pred_logits", "aux_logits"):
+        assert report[k][1] < (2.5e-1 if deep else 3e-2), (k, report[k])
+    assert rel_err(res1["init_ref_pts"].cpu().numpy(), g["init_ref_pts"]) < 1e-5
 
 
 def test_engine_memory_matches_oracle_encoder_only():
