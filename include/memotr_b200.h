@@ -256,9 +256,12 @@ MEMOTR_API int memotr_tracker_results(const memotr_track_table *tracks, int capa
  * All pointers are device pointers; the struct itself lives on the host and is passed by value to the kernel.
  */
 #define MEMOTR_DEC_MAX_LAYERS 8
-typedef struct memotr_dec_gemm { /* one dense layer of the weight program: W (N, K) bf16, K-major, row stride ldw */
+typedef struct memotr_dec_gemm { /* one dense layer of the weight program, W (N, K) bf16 with N % 64 == 0, K % 256 == 0,
+                                    packed as (N/64) x (K/256) slot images: K == 256: n-blocks in order; K > 256 (then
+                                    N must be 256): k-slice-major, i.e. (k-slice, n-block) row-major;
+                                    a slot image = 64 rows x 264 bf16 (256 weights of that row + 8 bf16 of padding) */
   const void *W;
-  int ldw, N, K, pad_;
+  int ldw, N, K, pad_;             /* ldw: unused (kept for layout), N, K as above */
 } memotr_dec_gemm;
 
 typedef struct memotr_dec_layer {

@@ -12,7 +12,10 @@
 //     out_proj + LN -> FFN + LN -> box head + refinement + class head
 // and the activations of the 16 rows never leave shared memory between layers.  Dense layers run on mma.sync.m16n8k16
 // (M = 16 is far below the tcgen05 minimum tile): the A operand is the row block in shared memory, the weights stream
-// from L2 through a 3-slot x 32 KB ring filled by a producer warp with cp.async.bulk row copies and mbarriers.  The weight
+// from L2 through a 3-slot x 33 KB ring, one cp.async.bulk per slot: the host packs every weight matrix as a sequence of
+// slot images (64 output rows x 256 k, rows padded to 528 B so that ldmatrix is bank-conflict-free) in exactly the order
+// the kernel consumes them (per-row 512-byte bulk copies were tried first: 64 requests per slot made the copy engine the
+// bottleneck, 275 us per layer).  The weight
 // stream is the roofline of this kernel: 3.8 MB per layer per CTA at the ~140-200 GB/s one SM sustains (tools/tma_stream.cu);
 // the producer runs ahead across op and layer boundaries (the program is static), so the stream never waits for the
 // epilogues, the attention or the grid barrier.  Attention: q, k in fp16 (11-bit mantissa; bf16 logits were measurably
@@ -33,8 +36,9 @@ constexpr int P256 = 256 * 2 + 16, P512 = 512 * 2 + 16, P1024 = 1024 * 2 + 16;  
 constexpr int F0P = 512;                                                         // fp32 scratch pitch (floats)
 constexpr int OFF_X32 = 0, OFF_XB = OFF_X32 + R * C * 4, OFF_QP = OFF_XB + R * P256, OFF_A = OFF_QP + R * P256,
               OFF_B = OFF_A + R * P512, OFF_H = OFF_B + R * P256, OFF_F0 = OFF_H + R * P1024,
-              OFF_RING = OFF_F0 + R * F0P * 4, OFF_MISC = OFF_RING + NSLOT * SLOT_BYTES, SMEM_TOTAL = OFF_MISC + 512;
-static_assert(OFF_RING % 16 == 0 && SMEM_TOTAL <= 227 * 1024, "shared memory plan");
+              OFF_RING = OFF_F0 + R * F0P * 4, OFF_MISC = OFF_RING + NSLOT * SLOT_BYTES, OFF_PROG = OFF_MISC + 512,
+              MAX_PROG = 15 * MEMOTR_DEC_MAX_LAYERS, SMEM_TOTAL = OFF_PROG + MAX_PROG * 24;
+static_assert(OFF_RING % 16 == 0 && SMEM_TOTAL + 128 <= 227 * 1024 && sizeof(memotr_dec_gemm) == 24, "shared memory plan");
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t n) {
@@ -96,33 +100,73 @@ struct Ring {
   int gi;         // next program entry
 };
 
-// out(16 x N) = A(16 x K, bf16 in shared memory, pitch pa bytes) . W^T, W streamed through the ring; epi(col0, acc) gets
-// the thread's fragment: rows lane/4 (acc[0..1]) and lane/4+8 (acc[2..3]), columns col0 + 2*(lane%4) + {0,1}
+// out(16 x N) = A(16 x K, bf16 in shared memory, pitch pa bytes) . W^T + bias, W streamed through the ring.
+// epi(col, acc, b0, b1) gets the thread's fragment: rows lane/4 (acc[0..1]) and lane/4+8 (acc[2..3]), columns col, col+1
+// and the two bias values.  The A fragments of a 256-wide k-slice live in REGISTERS (64 per thread) for the whole
+// slice: re-reading them from shared memory for every slot (8 warps x 8 KB per 33 KB slot) made the kernel
+// shared-memory-bandwidth-bound.  K == 256: slots are the n-blocks in order.  K > 256 (N == 256 only): slots are
+// k-slice-major, all four n-blocks' accumulators are live.  Two accumulator chains per tile hide the HMMA latency.
+__device__ __forceinline__ void load_a_slice(uint32_t (&af)[16][4], const uint8_t *A, int pa, int ks, int lane) {
+  const uint8_t *a = A + (lane & 15) * pa + (ks * SLOT_K + (lane >> 4) * 8) * 2;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ldsm4(af[i], a + i * 32);
+}
+__device__ __forceinline__ void slot_mma(float (&c0)[4], float (&c1)[4], const uint32_t (&af)[16][4], const uint8_t *w) {
+#pragma unroll
+  for (int kk = 0; kk < SLOT_K / 32; ++kk) {
+    uint32_t bq[4];
+    ldsm4(bq, w + kk * 64);
+    mma_bf16(c0, af[2 * kk], bq[0], bq[1]);
+    mma_bf16(c1, af[2 * kk + 1], bq[2], bq[3]);
+  }
+}
 template <class Epi>
-__device__ __forceinline__ void gemm(const memotr_dec_gemm *prog, Ring &rg, const uint8_t *A, int pa, int warp, int lane,
-                                     Epi epi) {
+__device__ __forceinline__ void gemm(const memotr_dec_gemm *prog, Ring &rg, const uint8_t *A, int pa,
+                                     const float *__restrict__ bias, int warp, int lane, Epi epi) {
   const memotr_dec_gemm d = prog[rg.gi++];
   const int nb = d.N / SLOT_ROWS, nk = d.K / SLOT_K;
-  for (int b = 0; b < nb; ++b) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ks = 0; ks < nk; ++ks, ++rg.t) {
+  const int cw = warp * 8 + 2 * (lane & 3);
+  const int woff = (warp * 8 + (lane & 7)) * WP + (lane >> 3) * 16;
+  uint32_t af[16][4];
+  if (nk == 1) {
+    load_a_slice(af, A, pa, 0, lane);
+    for (int b = 0; b < nb; ++b, ++rg.t) {
+      const int col = b * SLOT_ROWS + cw;
+      const float b0 = bias ? __ldg(bias + col) : 0.f, b1 = bias ? __ldg(bias + col + 1) : 0.f;   // in flight during the MMAs
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
       const int s = rg.t % NSLOT;
       mbar_wait(rg.full + s, (rg.t / NSLOT) & 1);
-      const uint8_t *w = rg.buf + s * SLOT_BYTES + (warp * 8 + (lane & 7)) * WP + (lane >> 3) * 16;
-      const uint8_t *a = A + (lane & 15) * pa + (ks * SLOT_K + (lane >> 4) * 8) * 2;
-#pragma unroll
-      for (int kk = 0; kk < SLOT_K / 32; ++kk) {
-        uint32_t bq[4], a0[4], a1[4];
-        ldsm4(bq, w + kk * 64);
-        ldsm4(a0, a + kk * 64);
-        ldsm4(a1, a + kk * 64 + 32);
-        mma_bf16(acc, a0, bq[0], bq[1]);
-        mma_bf16(acc, a1, bq[2], bq[3]);
-      }
+      slot_mma(c0, c1, af, rg.buf + s * SLOT_BYTES + woff);
       __syncwarp();
       if (lane == 0) mbar_arrive(rg.empty + s);
+      c0[0] += c1[0], c0[1] += c1[1], c0[2] += c1[2], c0[3] += c1[3];
+      epi(col, c0, b0, b1);
     }
-    epi(b * SLOT_ROWS + warp * 8 + 2 * (lane & 3), acc);
+  } else {   // nb == 4 (checked on the host): k-slice-major slots
+    float acc[4][2][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[b][0][j] = acc[b][1][j] = 0.f;
+    for (int ks = 0; ks < nk; ++ks) {
+      load_a_slice(af, A, pa, ks, lane);
+#pragma unroll
+      for (int b = 0; b < 4; ++b, ++rg.t) {
+        const int s = rg.t % NSLOT;
+        mbar_wait(rg.full + s, (rg.t / NSLOT) & 1);
+        slot_mma(acc[b][0], acc[b][1], af, rg.buf + s * SLOT_BYTES + woff);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rg.empty + s);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int col = b * SLOT_ROWS + cw;
+      const float b0 = bias ? __ldg(bias + col) : 0.f, b1 = bias ? __ldg(bias + col + 1) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[b][0][j] += acc[b][1][j];
+      epi(col, acc[b][0], b0, b1);
+    }
   }
 }
 
@@ -130,6 +174,8 @@ __device__ __forceinline__ void gemm(const memotr_dec_gemm *prog, Ring &rg, cons
 // writes x32 (fp32 master), xb (bf16), and optionally sum = bf16(value + qp) into `sumb` (pitch P512)
 __device__ __forceinline__ void layer_norm(const float *pre, const float *__restrict__ gamma, const float *__restrict__ beta,
                                            float *x32, uint8_t *xb, const uint8_t *qp, uint8_t *sumb, int warp, int lane) {
+  const float4 g0 = ldg_f4(gamma + lane * 8), g1 = ldg_f4(gamma + lane * 8 + 4), b0 = ldg_f4(beta + lane * 8),
+               b1 = ldg_f4(beta + lane * 8 + 4);                  // issued before the reductions that hide their latency
   for (int rr = 0; rr < 2; ++rr) {
     const int r = warp * 2 + rr, c0 = lane * 8;
     float v[8];
@@ -150,7 +196,6 @@ __device__ __forceinline__ void layer_norm(const float *pre, const float *__rest
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * (1.f / 256.f) + 1e-5f);
-    const float4 g0 = ldg_f4(gamma + c0), g1 = ldg_f4(gamma + c0 + 4), b0 = ldg_f4(beta + c0), b1 = ldg_f4(beta + c0 + 4);
     const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bb[i];
@@ -212,6 +257,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
   const int row0 = blockIdx.x * R;
   const int nq = P.nq, nd = P.nd;
 
+  memotr_dec_gemm *sprog = reinterpret_cast<memotr_dec_gemm *>(smem + OFF_PROG);   // the weight program, read many times
+  for (int i = tid; i < P.n_prog * 6; i += NTHREADS)
+    reinterpret_cast<uint32_t *>(sprog)[i] = reinterpret_cast<const uint32_t *>(P.prog)[i];
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) mbar_init(full + s, 1), mbar_init(empty + s, NCW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -222,24 +270,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
     // ------------------------------------------------------------------ producer: stream the weight program through the ring
     uint32_t t = 0;
     for (int gi = 0; gi < P.n_prog; ++gi) {
-      const memotr_dec_gemm d = P.prog[gi];
-      const bf16 *W = reinterpret_cast<const bf16 *>(d.W);
-      const int nb = d.N / SLOT_ROWS, nk = d.K / SLOT_K;
-      for (int b = 0; b < nb; ++b)
-        for (int ks = 0; ks < nk; ++ks, ++t) {
-          const int s = t % NSLOT;
-          if (lane == 0) {
-            mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
-            mbar_expect_tx(full + s, SLOT_ROWS * SLOT_K * 2);
-          }
-          __syncwarp();
-          uint8_t *dst = smem + OFF_RING + s * SLOT_BYTES;
-#pragma unroll
-          for (int rr = 0; rr < SLOT_ROWS / 32; ++rr) {
-            const int r = lane + rr * 32;
-            bulk_row(dst + r * WP, W + (long)(b * SLOT_ROWS + r) * d.ldw + ks * SLOT_K, SLOT_K * 2, full + s);
-          }
+      const memotr_dec_gemm d = sprog[gi];
+      const uint8_t *W = reinterpret_cast<const uint8_t *>(d.W);   // pre-packed slot images, in consumption order
+      const int nslots = (d.N / SLOT_ROWS) * (d.K / SLOT_K);
+      for (int i = 0; i < nslots; ++i, ++t) {
+        const int s = t % NSLOT;
+        if (lane == 0) {
+          mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
+          mbar_expect_tx(full + s, SLOT_BYTES);
+          bulk_row(smem + OFF_RING + s * SLOT_BYTES, W + (long)i * SLOT_BYTES, SLOT_BYTES, full + s);
         }
+      }
     }
     return;
   }
@@ -276,33 +317,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
       }
     }
     csync();
-    gemm(P.prog, rg, bufA, P512, warp, lane, [&](int col, const float (&a)[4]) {          // ref_point_head.0 + ReLU
-      const float b0 = __ldg(P.rph0_b + col), b1 = __ldg(P.rph0_b + col + 1);
+    gemm(sprog, rg, bufA, P512, P.rph0_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {          // ref_point_head.0 + ReLU
       *reinterpret_cast<uint32_t *>(bufB + g * P256 + col * 2) = pack_bf16(fmaxf(a[0] + b0, 0.f), fmaxf(a[1] + b1, 0.f));
       *reinterpret_cast<uint32_t *>(bufB + (g + 8) * P256 + col * 2) = pack_bf16(fmaxf(a[2] + b0, 0.f), fmaxf(a[3] + b1, 0.f));
     });
     csync();
     if (lid == 0) {
-      gemm(P.prog, rg, bufB, P256, warp, lane, [&](int col, const float (&a)[4]) {       // ref_point_head.1 -> query_pos
-        const float b0 = __ldg(P.rph1_b + col), b1 = __ldg(P.rph1_b + col + 1);
+      gemm(sprog, rg, bufB, P256, P.rph1_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {       // ref_point_head.1 -> query_pos
         *reinterpret_cast<uint32_t *>(qp + g * P256 + col * 2) = pack_bf16(a[0] + b0, a[1] + b1);
         *reinterpret_cast<uint32_t *>(qp + (g + 8) * P256 + col * 2) = pack_bf16(a[2] + b0, a[3] + b1);
       });
       csync();
     } else {
-      gemm(P.prog, rg, bufB, P256, warp, lane, [&](int col, const float (&a)[4]) {       // raw query pos -> bufA (bf16)
-        const float b0 = __ldg(P.rph1_b + col), b1 = __ldg(P.rph1_b + col + 1);
+      gemm(sprog, rg, bufB, P256, P.rph1_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {       // raw query pos -> bufA (bf16)
         *reinterpret_cast<uint32_t *>(bufA + g * P512 + col * 2) = pack_bf16(a[0] + b0, a[1] + b1);
         *reinterpret_cast<uint32_t *>(bufA + (g + 8) * P512 + col * 2) = pack_bf16(a[2] + b0, a[3] + b1);
       });
-      gemm(P.prog, rg, xb, P256, warp, lane, [&](int col, const float (&a)[4]) {         // query_scale.0 + ReLU
-        const float b0 = __ldg(P.qs0_b + col), b1 = __ldg(P.qs0_b + col + 1);
+      gemm(sprog, rg, xb, P256, P.qs0_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // query_scale.0 + ReLU
         *reinterpret_cast<uint32_t *>(bufB + g * P256 + col * 2) = pack_bf16(fmaxf(a[0] + b0, 0.f), fmaxf(a[1] + b1, 0.f));
         *reinterpret_cast<uint32_t *>(bufB + (g + 8) * P256 + col * 2) = pack_bf16(fmaxf(a[2] + b0, 0.f), fmaxf(a[3] + b1, 0.f));
       });
       csync();
-      gemm(P.prog, rg, bufB, P256, warp, lane, [&](int col, const float (&a)[4]) {       // query_scale.1 * raw query pos
-        const float b0 = __ldg(P.qs1_b + col), b1 = __ldg(P.qs1_b + col + 1);
+      gemm(sprog, rg, bufB, P256, P.qs1_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {       // query_scale.1 * raw query pos
         const float2 m0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(bufA + g * P512 + col * 2));
         const float2 m1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(bufA + (g + 8) * P512 + col * 2));
         *reinterpret_cast<uint32_t *>(qp + g * P256 + col * 2) = pack_bf16((a[0] + b0) * m0.x, (a[1] + b1) * m0.y);
@@ -322,8 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
       *reinterpret_cast<uint4 *>(bufA + r * P512 + c8 * 2) = f32x8_to_bf16(a);
     }
     csync();
-    gemm(P.prog, rg, bufA, P512, warp, lane, [&](int col, const float (&a)[4]) {         // [q | k] (fp16)
-      const float b0 = __ldg(Lp.qk_b + col), b1 = __ldg(Lp.qk_b + col + 1);
+    gemm(sprog, rg, bufA, P512, Lp.qk_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // [q | k] (fp16)
       if (col < C) {
         const float sc = 0.17677669529663687f;                                            // 1 / sqrt(32), folded into q
         *reinterpret_cast<uint32_t *>(bufB + g * P256 + col * 2) = pack_f16((a[0] + b0) * sc, (a[1] + b1) * sc);
@@ -334,8 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
           *reinterpret_cast<uint32_t *>(Kh + (long)(row0 + g + 8) * C + col - C) = pack_f16(a[2] + b0, a[3] + b1);
       }
     });
-    gemm(P.prog, rg, xb, P256, warp, lane, [&](int col, const float (&a)[4]) {           // v, stored transposed (fp16)
-      const float b0 = __ldg(Lp.v_b + col), b1 = __ldg(Lp.v_b + col + 1);
+    gemm(sprog, rg, xb, P256, Lp.v_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {           // v, stored transposed (fp16)
       if (row0 + g < nq) {
         Vt[(long)col * P.np + row0 + g] = __float2half_rn(a[0] + b0);
         Vt[(long)(col + 1) * P.np + row0 + g] = __float2half_rn(a[1] + b1);
@@ -426,8 +460,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
       }
     }
     csync();
-    gemm(P.prog, rg, bufA, P512, warp, lane, [&](int col, const float (&a)[4]) {         // out_proj + residual
-      const float b0 = __ldg(Lp.sao_b + col), b1 = __ldg(Lp.sao_b + col + 1);
+    gemm(sprog, rg, bufA, P512, Lp.sao_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // out_proj + residual
       *reinterpret_cast<float2 *>(f0 + g * F0P + col) = make_float2(a[0] + b0 + x32[g * C + col], a[1] + b1 + x32[g * C + col + 1]);
       *reinterpret_cast<float2 *>(f0 + (g + 8) * F0P + col) =
           make_float2(a[2] + b0 + x32[(g + 8) * C + col], a[3] + b1 + x32[(g + 8) * C + col + 1]);
@@ -437,8 +470,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
     csync();
 
     // ---- cross-attention into the encoder memory (ms_deform_attn.py:88-130)
-    gemm(P.prog, rg, bufA, P512, warp, lane, [&](int col, const float (&a)[4]) {         // [offsets | logits], fp32
-      const float b0 = __ldg(Lp.ol_b + col), b1 = __ldg(Lp.ol_b + col + 1);
+    gemm(sprog, rg, bufA, P512, Lp.ol_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // [offsets | logits], fp32
       *reinterpret_cast<float2 *>(f0 + g * F0P + col) = make_float2(a[0] + b0, a[1] + b1);
       *reinterpret_cast<float2 *>(f0 + (g + 8) * F0P + col) = make_float2(a[2] + b0, a[3] + b1);
     });
@@ -470,33 +502,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
           __half2 a2[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) a2[j] = __float2half2_rn(0.f);
-          for (int p = 0; p < Kp; ++p) {
-            const int i = l * Kp + p;
-            const float2 off = *reinterpret_cast<const float2 *>(rowp + (h * LK + i) * 2);
-            const float aw = __expf(rowp[2 * 8 * LK + h * LK + i] - mx) * rs;
-            const float lx = rx * vx + off.x * rk * (rw * vx) * 0.5f, ly = ry * vy + off.y * rk * (rh * vy) * 0.5f;
-            const float h_im = __fmaf_rn(ly, Hf, -0.5f), w_im = __fmaf_rn(lx, Wf, -0.5f);
-            const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
-            const float hfl = floorf(h_im), wfl = floorf(w_im);
-            const int y0 = (int)hfl, x0 = (int)wfl;
-            const float lh = h_im - hfl, lw = w_im - wfl, hh = 1.f - lh, hw = 1.f - lw;
-            const bool y0ok = inside && y0 >= 0, y1ok = inside && y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
-            const int yc0 = min(max(y0, 0), Hh - 1), yc1 = min(max(y0 + 1, 0), Hh - 1);
-            const int xc0 = min(max(x0, 0), Ww - 1), xc1 = min(max(x0 + 1, 0), Ww - 1);
-            const long o4[4] = {base + (long)yc0 * ys + xc0 * xs, base + (long)yc0 * ys + xc1 * xs, base + (long)yc1 * ys + xc0 * xs,
-                                base + (long)yc1 * ys + xc1 * xs};
-            const float w4[4] = {(y0ok && x0ok) ? hh * hw * aw : 0.f, (y0ok && x1ok) ? hh * lw * aw : 0.f,
-                                 (y1ok && x0ok) ? lh * hw * aw : 0.f, (y1ok && x1ok) ? lh * lw * aw : 0.f};
-            uint4 rv[4];
+          for (int pb = 0; pb < Kp; pb += 4) {       // 4 points = 16 corner rows in flight per thread
+            uint4 rv[4][4];
+            __half2 wq[4][4];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) rv[q4] = __ldg(reinterpret_cast<const uint4 *>(vb + o4[q4]));
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const __half2 wq = __float2half2_rn(w4[q4]);
-              const __half2 *v2 = reinterpret_cast<const __half2 *>(&rv[q4]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) a2[j] = __hfma2(wq, v2[j], a2[j]);
+            for (int pp = 0; pp < 4; ++pp) {
+              const int p = min(pb + pp, Kp - 1), i = l * Kp + p;
+              const bool pv = pb + pp < Kp;
+              const float2 off = *reinterpret_cast<const float2 *>(rowp + (h * LK + i) * 2);
+              const float aw = pv ? __expf(rowp[2 * 8 * LK + h * LK + i] - mx) * rs : 0.f;
+              const float lx = rx * vx + off.x * rk * (rw * vx) * 0.5f, ly = ry * vy + off.y * rk * (rh * vy) * 0.5f;
+              const float h_im = __fmaf_rn(ly, Hf, -0.5f), w_im = __fmaf_rn(lx, Wf, -0.5f);
+              const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
+              const float hfl = floorf(h_im), wfl = floorf(w_im);
+              const int y0 = (int)hfl, x0 = (int)wfl;
+              const float lh = h_im - hfl, lw = w_im - wfl, hh = 1.f - lh, hw = 1.f - lw;
+              const bool y0ok = inside && y0 >= 0, y1ok = inside && y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
+              const int yc0 = min(max(y0, 0), Hh - 1), yc1 = min(max(y0 + 1, 0), Hh - 1);
+              const int xc0 = min(max(x0, 0), Ww - 1), xc1 = min(max(x0 + 1, 0), Ww - 1);
+              rv[pp][0] = __ldg(reinterpret_cast<const uint4 *>(vb + base + (long)yc0 * ys + xc0 * xs));
+              rv[pp][1] = __ldg(reinterpret_cast<const uint4 *>(vb + base + (long)yc0 * ys + xc1 * xs));
+              rv[pp][2] = __ldg(reinterpret_cast<const uint4 *>(vb + base + (long)yc1 * ys + xc0 * xs));
+              rv[pp][3] = __ldg(reinterpret_cast<const uint4 *>(vb + base + (long)yc1 * ys + xc1 * xs));
+              wq[pp][0] = __float2half2_rn((y0ok && x0ok) ? hh * hw * aw : 0.f);
+              wq[pp][1] = __float2half2_rn((y0ok && x1ok) ? hh * lw * aw : 0.f);
+              wq[pp][2] = __float2half2_rn((y1ok && x0ok) ? lh * hw * aw : 0.f);
+              wq[pp][3] = __float2half2_rn((y1ok && x1ok) ? lh * lw * aw : 0.f);
             }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const __half2 *v2 = reinterpret_cast<const __half2 *>(&rv[pp][q4]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a2[j] = __hfma2(wq[pp][q4], v2[j], a2[j]);
+              }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -508,8 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
       }
     }
     csync();
-    gemm(P.prog, rg, bufA, P512, warp, lane, [&](int col, const float (&a)[4]) {         // output_proj + residual
-      const float b0 = __ldg(Lp.cao_b + col), b1 = __ldg(Lp.cao_b + col + 1);
+    gemm(sprog, rg, bufA, P512, Lp.cao_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // output_proj + residual
       *reinterpret_cast<float2 *>(f0 + g * F0P + col) = make_float2(a[0] + b0 + x32[g * C + col], a[1] + b1 + x32[g * C + col + 1]);
       *reinterpret_cast<float2 *>(f0 + (g + 8) * F0P + col) =
           make_float2(a[2] + b0 + x32[(g + 8) * C + col], a[3] + b1 + x32[(g + 8) * C + col + 1]);
@@ -522,18 +561,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
     const int n_half = P.d_ffn > 1024 ? 2 : 1;            // the hidden row block (16 x 1024 bf16) holds half of d_ffn = 2048
     for (int half = 0; half < n_half; ++half) {
       const int hoff = half * (P.d_ffn / n_half);
-      gemm(P.prog, rg, xb, P256, warp, lane, [&](int col, const float (&a)[4]) {         // linear1 + ReLU -> hidden (bf16)
-        const float b0 = __ldg(Lp.f1_b + hoff + col), b1 = __ldg(Lp.f1_b + hoff + col + 1);
+      gemm(sprog, rg, xb, P256, Lp.f1_b + hoff, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // linear1 + ReLU -> hidden (bf16)
         *reinterpret_cast<uint32_t *>(hbuf + g * P1024 + col * 2) = pack_bf16(fmaxf(a[0] + b0, 0.f), fmaxf(a[1] + b1, 0.f));
         *reinterpret_cast<uint32_t *>(hbuf + (g + 8) * P1024 + col * 2) = pack_bf16(fmaxf(a[2] + b0, 0.f), fmaxf(a[3] + b1, 0.f));
       });
       csync();
-      gemm(P.prog, rg, hbuf, P1024, warp, lane, [&](int col, const float (&a)[4]) {      // linear2 (accumulated) + residual
+      gemm(sprog, rg, hbuf, P1024, half == n_half - 1 ? Lp.f2_b : nullptr, warp, lane,
+           [&](int col, const float (&a)[4], float b0, float b1) {                          // linear2 (accumulated) + residual
         float2 *d0 = reinterpret_cast<float2 *>(f0 + g * F0P + col), *d1 = reinterpret_cast<float2 *>(f0 + (g + 8) * F0P + col);
         float2 p0 = make_float2(a[0], a[1]), p1 = make_float2(a[2], a[3]);
         if (half > 0) p0.x += d0->x, p0.y += d0->y, p1.x += d1->x, p1.y += d1->y;
         if (half == n_half - 1) {
-          const float b0 = __ldg(Lp.f2_b + col), b1 = __ldg(Lp.f2_b + col + 1);
           p0.x += b0 + x32[g * C + col], p0.y += b1 + x32[g * C + col + 1];
           p1.x += b0 + x32[(g + 8) * C + col], p1.y += b1 + x32[(g + 8) * C + col + 1];
         }
@@ -561,14 +599,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_fused_kernel(const __grid
     csync();
 
     // ---- box refinement + heads (deformable_decoder.py:139-159, memotr.py:147-162)
-    gemm(P.prog, rg, xb, P256, warp, lane, [&](int col, const float (&a)[4]) {           // bbox_embed.0 + ReLU
-      const float b0 = __ldg(Lp.bb0_b + col), b1 = __ldg(Lp.bb0_b + col + 1);
+    gemm(sprog, rg, xb, P256, Lp.bb0_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {           // bbox_embed.0 + ReLU
       *reinterpret_cast<uint32_t *>(bufB + g * P256 + col * 2) = pack_bf16(fmaxf(a[0] + b0, 0.f), fmaxf(a[1] + b1, 0.f));
       *reinterpret_cast<uint32_t *>(bufB + (g + 8) * P256 + col * 2) = pack_bf16(fmaxf(a[2] + b0, 0.f), fmaxf(a[3] + b1, 0.f));
     });
     csync();
-    gemm(P.prog, rg, bufB, P256, warp, lane, [&](int col, const float (&a)[4]) {         // bbox_embed.1 + ReLU
-      const float b0 = __ldg(Lp.bb1_b + col), b1 = __ldg(Lp.bb1_b + col + 1);
+    gemm(sprog, rg, bufB, P256, Lp.bb1_b, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {         // bbox_embed.1 + ReLU
       *reinterpret_cast<uint32_t *>(bufA + g * P512 + col * 2) = pack_bf16(fmaxf(a[0] + b0, 0.f), fmaxf(a[1] + b1, 0.f));
       *reinterpret_cast<uint32_t *>(bufA + (g + 8) * P512 + col * 2) = pack_bf16(fmaxf(a[2] + b0, 0.f), fmaxf(a[3] + b1, 0.f));
     });
@@ -608,7 +644,8 @@ extern "C" int memotr_decoder_forward(const memotr_dec_params *p, void *stream) 
   MEMOTR_REQUIRE(p && p->prog && p->n_prog > 0 && p->tgt_in && p->ref_in && p->kbuf && p->vbuf && p->barrier && p->dim_t &&
                      p->vr_scale4 && p->valid_ratios,
                  "decoder_forward: null pointer");
-  MEMOTR_REQUIRE(p->n_layers >= 1 && p->n_layers <= MEMOTR_DEC_MAX_LAYERS && p->nq >= 1 && p->nd >= 0 && p->nd <= p->nq,
+  MEMOTR_REQUIRE(p->n_layers >= 1 && p->n_layers <= MEMOTR_DEC_MAX_LAYERS && p->nq >= 1 && p->nd >= 0 && p->nd <= p->nq &&
+                     p->n_prog <= dec::MAX_PROG,
                  "decoder_forward: bad sizes");
   MEMOTR_REQUIRE(p->n_levels >= 1 && p->n_levels <= 8 && p->n_points >= 1 && p->n_levels * p->n_points * 3 * 8 <= dec::F0P,
                  "decoder_forward: levels x points too large");

@@ -407,9 +407,9 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   (void)tiles;
   const int cs = cs_env ? cs_env : 1;   // measured: the kernel is shared-memory-bound, multicast gives nothing (profiles/)
 #define MLP2_GO(TC_, CS_) return tc::launch_mlp2<TC_, CS_>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
-  // Split-K over the hidden dimension when the row tiles alone leave SMs idle (one CTA per SM: 175 tiles on 148 SMs are
-  // two rounds, the second 18 % full).  CTA (tile, split) handles Hd/nsplit hidden columns and reduce-adds into the fp32
-  // output; nsplit minimises rounds x (chunks per CTA x ~2 us + ~3 us fixed cost).  MEMOTR_MLP_SPLIT=1|2|4|8 overrides.
+  // Split-K over the hidden dimension (MEMOTR_MLP_SPLIT=2|4|8): meant for the case where the row tiles alone leave SMs
+  // idle (one CTA per SM: 175 tiles on 148 SMs are two rounds, the second 18 % full).  CTA (tile, split) handles
+  // Hd/nsplit hidden columns and reduce-adds into the fp32 output.
   if (c_dtype == MEMOTR_F32 && cs == 1 && act2 == 0 && !mul) {
     static int n_sm = 0;
     if (!n_sm) {
@@ -420,15 +420,8 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
     const char *sp = getenv("MEMOTR_MLP_SPLIT");
     int nsplit = sp ? atoi(sp) : 0;
     const int chunks = Hd / tc::mlp::HC;
-    if (nsplit <= 0) {
-      float best = 1e30f;
-      nsplit = 1;
-      for (int ns = 1; ns <= 8 && ns <= chunks; ns *= 2) {
-        if (chunks % ns) break;
-        const float cost = (float)ceil_div(tiles * ns, n_sm) * ((float)(chunks / ns) * 2.1f + 3.f) + (ns > 1 ? 4.f : 0.f);
-        if (cost < best - 0.5f) best = cost, nsplit = ns;
-      }
-    }
+    if (nsplit <= 0) nsplit = 1;   // measured (tools/time_mlp2.py): 74.8 / 72.7 / 78.8 / 110 us for 1 / 2 / 4 / 8 splits at the
+                                   // encoder shape -- the ~6.6 us fixed cost per CTA eats the better balance; opt-in only
     if (nsplit > 1 && chunks % nsplit == 0) return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, nsplit);
   }
   if (c_dtype == MEMOTR_F32) {

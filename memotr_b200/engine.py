@@ -261,10 +261,22 @@ class FrameEngine:
         F = self.Fd
         prog = []
 
+        self.dec_packed = []
+
         def g(L, row0=0, rows=None, col0=0, K=None):
+            """Pack W[row0:row0+rows, col0:col0+K] as slot images (see memotr_dec_gemm in include/memotr_b200.h)."""
             rows, K = (L.N if rows is None else rows), (L.K if K is None else K)
             assert rows % 64 == 0 and K % 256 == 0 and L.w.dtype == torch.bfloat16
-            prog.append((L.w.data_ptr() + (row0 * L.K + col0) * 2, L.K, rows, K))
+            w = L.w[row0:row0 + rows, col0:col0 + K].reshape(rows // 64, 64, K // 256, 256)
+            if K == 256:
+                img = torch.zeros(rows // 64, 1, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = w.permute(0, 2, 1, 3)
+            else:                                   # k-slice-major; the kernel keeps all four n-blocks' accumulators live
+                assert rows == 256
+                img = torch.zeros(K // 256, rows // 64, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = w.permute(2, 0, 1, 3)
+            self.dec_packed.append(img)
+            prog.append((img.data_ptr(), 264, rows, K))
 
         for lid, ly in enumerate(self.dec):
             g(self.ref_point_head[0]), g(self.ref_point_head[1])
