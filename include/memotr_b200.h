@@ -282,11 +282,22 @@ typedef struct memotr_dec_params {
   const unsigned char *query_pad;               /* (nq) key-padding mask or NULL */
   void *kbuf, *vbuf;                            /* scratch: 2 x (np,256) fp16 keys, 2 x (256,np) fp16 values (transposed) */
   unsigned int *barrier;                        /* scratch: one counter */
+  long long *prof;                              /* NULL, or (blocks, n_layers, 16) clock64 phase stamps (measurement) */
   int shapes[16], lsi[8];                       /* (H, W) and first pixel of every level */
   memotr_dec_layer layers[MEMOTR_DEC_MAX_LAYERS];
 } memotr_dec_params;
 
 MEMOTR_API int memotr_decoder_forward(const memotr_dec_params *params, void *stream);
+
+/*
+ * The same decoder with a 4-CTA thread-block cluster per 16-row block (csrc/decoder_cluster.cu): dense layers split over
+ * output columns, attention / gather over heads, the FFN over the hidden dimension.  `prog` holds FOUR programs of
+ * n_prog entries each (rank-major); rank r's entries are, per layer: ref_point_head.0 rows [64r,64r+64), .1 likewise,
+ * [query_scale.0/.1 if layer > 0], q rows, k rows, v rows, self-attn out rows, sampling-offset rows [64r,+64), attention-
+ * logit rows [32r,+32) padded to 64, cross-attn out rows, linear1 rows [F/4 r, +F/4), linear2 columns [F/4 r, +F/4)
+ * (K padded to a multiple of 256), bbox_embed.0 / .1 rows.  Requires n_levels * n_points == 16.
+ */
+MEMOTR_API int memotr_decoder_forward_cluster(const memotr_dec_params *params, void *stream);
 
 /*
  * Interval timer for measurement (bench.py): n CUDA events; memotr_timer_record enqueues event `idx` on `stream`

@@ -55,7 +55,7 @@ class DecParams(ctypes.Structure):
                 [(k, ctypes.c_int) for k in ("n_prog", "n_layers", "nq", "nd", "merge", "ncls", "n_levels", "n_points",
                                              "d_ffn", "value_stride", "np", "pad_")] +
                 [(k, ctypes.c_void_p) for k in ("rph0_b", "rph1_b", "qs0_b", "qs1_b", "tgt_in", "ref_in", "vr_scale4",
-                                                "valid_ratios", "dim_t", "query_pad", "kbuf", "vbuf", "barrier")] +
+                                                "valid_ratios", "dim_t", "query_pad", "kbuf", "vbuf", "barrier", "prof")] +
                 [("shapes", ctypes.c_int * 16), ("lsi", ctypes.c_int * 8),
                  ("layers", DecLayer * MEMOTR_DEC_MAX_LAYERS)])
 
@@ -85,6 +85,7 @@ _SIGNATURES = {
     "memotr_tracker_update": ([_vp, _i, _i, _i, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "memotr_tracker_results": ([_vp, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "memotr_decoder_forward": ([_vp, _vp], _i),
+    "memotr_decoder_forward_cluster": ([_vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),
     "memotr_timer_destroy": ([_vp], None),
     "memotr_timer_record": ([_vp, _i, _vp], _i),

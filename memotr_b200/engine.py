@@ -82,8 +82,14 @@ class FrameEngine:
                           and cfg["n_levels"] * cfg["n_dec_points"] * 24 <= 512)
         self._pack(state_dict)
         self._alloc()
+        # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
+        self.dec_cluster = (self.dec_fused and os.environ.get("MEMOTR_DEC_FUSED", "2") == "2"
+                            and cfg["n_levels"] * cfg["n_dec_points"] == 16 and cfg["d_ffn"] % 256 == 0
+                            and cfg["d_ffn"] <= 2048 and (self.nq + 15) // 16 * 4 <= 132)
         if self.dec_fused:
             self._build_decoder_program()
+        if self.dec_cluster:
+            self._build_decoder_program_cluster()
         self.graph = None
         self.timer = None
 
@@ -320,9 +326,62 @@ class FrameEngine:
             D.pred_box, D.pred_logit = self.pred_box[lid].data_ptr(), self.pred_logit[lid].data_ptr()
         self.dec_params = P
 
+    def _build_decoder_program_cluster(self):
+        """Per-rank weight programs of memotr_decoder_forward_cluster (include/memotr_b200.h)."""
+        import copy
+        import ctypes
+        dev, F, CS = self.dev, self.Fd, 4
+        hw = F // CS
+        self.dec_packed_cl = []
+
+        def pack(w):
+            """(rows, K) bf16 -> slot images; rows padded to 64, K to 256 with zeros."""
+            rows, K = w.shape
+            rp, Kp = (rows + 63) // 64 * 64, (K + 255) // 256 * 256
+            z = torch.zeros(rp, Kp, dtype=torch.bfloat16, device=dev)
+            z[:rows, :K] = w
+            v = z.reshape(rp // 64, 64, Kp // 256, 256)
+            if Kp == 256:
+                img = torch.zeros(rp // 64, 1, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = v.permute(0, 2, 1, 3)
+            else:
+                assert rp // 64 <= 4
+                img = torch.zeros(Kp // 256, rp // 64, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = v.permute(2, 0, 1, 3)
+            self.dec_packed_cl.append(img)
+            return (img.data_ptr(), 264, rp, Kp)
+
+        progs = []
+        for r in range(CS):
+            pr, rows = [], slice(64 * r, 64 * r + 64)
+            for lid, ly in enumerate(self.dec):
+                pr.append(pack(self.ref_point_head[0].w[rows])), pr.append(pack(self.ref_point_head[1].w[rows]))
+                if lid > 0:
+                    pr.append(pack(self.query_scale[0].w[rows])), pr.append(pack(self.query_scale[1].w[rows]))
+                qk, ol = ly["self"]["qk"].w, ly["attn"]["ol"].w
+                pr.append(pack(qk[rows])), pr.append(pack(qk[256 + 64 * r:256 + 64 * r + 64]))
+                pr.append(pack(ly["self"]["v"].w[rows])), pr.append(pack(ly["self"]["out"].w[rows]))
+                pr.append(pack(ol[rows])), pr.append(pack(ol[256 + 32 * r:256 + 32 * r + 32]))
+                pr.append(pack(ly["attn"]["out"].w[rows]))
+                pr.append(pack(ly["lin1"].w[hw * r:hw * r + hw])), pr.append(pack(ly["lin2"].w[:, hw * r:hw * r + hw]))
+                pr.append(pack(ly["bbox"][0].w[rows])), pr.append(pack(ly["bbox"][1].w[rows]))
+            progs.append(pr)
+        n_prog = len(progs[0])
+        flat = [e for pr in progs for e in pr]
+        arr = (_lib.DecGemm * len(flat))(*[_lib.DecGemm(w, ldw, n, k, 0) for (w, ldw, n, k) in flat])
+        self.dec_prog_cl = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        P = _lib.DecParams()
+        ctypes.memmove(ctypes.byref(P), ctypes.byref(self.dec_params), ctypes.sizeof(P))
+        P.prog, P.n_prog = self.dec_prog_cl.data_ptr(), n_prog
+        self.dec_params_cl = P
+
     def _decoder_fused(self):
         import ctypes
-        self._ck(self.lib.memotr_decoder_forward(ctypes.byref(self.dec_params), self._st()), "decoder_forward")
+        if self.dec_cluster:
+            self._ck(self.lib.memotr_decoder_forward_cluster(ctypes.byref(self.dec_params_cl), self._st()),
+                     "decoder_forward_cluster")
+        else:
+            self._ck(self.lib.memotr_decoder_forward(ctypes.byref(self.dec_params), self._st()), "decoder_forward")
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------------ launch helpers

@@ -409,8 +409,9 @@ def test_engine_bf16_matches_reference_modules(tag):
         assert worst[k] < (2.5e-1 if deep else 3e-2), (k, worst[k])
 
 
+@pytest.mark.parametrize("fused", ["1", "2"])          # 1: one CTA per 16-row block, 2: a 4-CTA cluster per block (default)
 @pytest.mark.parametrize("tag", ["small", "small_padded", "full"])
-def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, monkeypatch):
+def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monkeypatch):
     """bf16 engine, decoder + heads as ONE persistent kernel (csrc/decoder_fused.cu, the default) against the same
     engine with one launch per op (MEMOTR_DEC_FUSED=0): same arithmetic classes (bf16 GEMM operands, fp32 everything
     else; the fused kernel keeps q/k/p/v of the self-attention in fp16 instead of fp32), so the two must agree with each
@@ -418,9 +419,9 @@ def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, monkeypatch
     monkeypatch.setenv("MEMOTR_DEC_FUSED", "0")
     g, eng0, res0, _ = _run_engine(tag, "bf16")
     assert not eng0.dec_fused
-    monkeypatch.setenv("MEMOTR_DEC_FUSED", "1")
+    monkeypatch.setenv("MEMOTR_DEC_FUSED", fused)
     _, eng1, res1, _ = _run_engine(tag, "bf16")
-    assert eng1.dec_fused and eng1.launches < eng0.launches
+    assert eng1.dec_fused and eng1.dec_cluster == (fused == "2") and eng1.launches < eng0.launches
     deep = tag == "full"
     report = {}
     for k in FRAME_KEYS:
