@@ -230,12 +230,19 @@ bool linear_tc_supported(int lda, int ldw, int ldc, int c_dtype, int M, int N, i
          aligned16(W) && aligned16(C) && tc::encode_fn() != nullptr;
 }
 
+bool linear_tc_persist_wanted(int M, int N, int *n_sm_out);
+int linear_tc_persist_bf16(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int c_dtype, int M, int N,
+                           int K, const Epilogue &ep, int n_sm, cudaStream_t st);
+
 int linear_tc_bf16(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int c_dtype, int M, int N, int K,
                    const Epilogue &ep, cudaStream_t st) {
   if (ep.mul && (ep.ldmul % 8 != 0 || !aligned16(ep.mul))) return fail(MEMOTR_EINVAL, "linear(tc): mul misaligned");
   if (ep.add && (ep.ldadd % 8 != 0 || !aligned16(ep.add))) return fail(MEMOTR_EINVAL, "linear(tc): add misaligned");
   if (ep.bias && !aligned16(ep.bias)) return fail(MEMOTR_EINVAL, "linear(tc): bias misaligned");
   const bool wide = N % 128 == 0;
+  int n_sm = 0;
+  if (linear_tc_persist_wanted(M, N, &n_sm))      // more tiles than SMs: persistent CTAs, double-buffered accumulators
+    return linear_tc_persist_bf16(A, lda, W, ldw, C, ldc, c_dtype, M, N, K, ep, n_sm, st);
   if (c_dtype == MEMOTR_F16)
     return wide ? tc::launch<128, __half>(A, lda, W, ldw, C, ldc, M, N, K, ep, st)
                 : tc::launch<64, __half>(A, lda, W, ldw, C, ldc, M, N, K, ep, st);

@@ -1,0 +1,253 @@
+// gemm_tc_persist.cu -- persistent variant of gemm_tc.cu for GEMMs with more output tiles than SMs.
+//
+// The one-tile-per-CTA kernel is a latency chain per tile (TMA load ~1 us -> 16 MMAs 0.5 us -> commit -> TMEM read,
+// epilogue math, staging, TMA store ~2 us) that only co-residency of 2-3 CTAs per SM overlaps: the encoder projections
+// (350-525 tiles of 128 x 128 x 256) run at 160-190 TFLOP/s, 18-22 us each, with the tensor pipe busy < 15 % of the time.
+// Here one CTA per SM walks its tiles (tile = blockIdx.x + i * gridDim.x, n fastest so that neighbours share the A tile
+// in L2): the producer warp streams the k-blocks of consecutive tiles through a 4-stage ring without ever draining, the
+// MMA warp alternates between TWO TMEM accumulators, and the epilogue warps drain accumulator (i & 1) -- bias / activation
+// / multiplier / residual / padding mask, swizzled staging panels in their own shared-memory region, TMA store -- while
+// the MMAs of tile i + 1 run.  Same contract and epilogue as gemm_tc.cu (models/ops/modules/ms_deform_attn.py:104-129
+// projections and the other large-M nn.Linear call sites).
+#include <type_traits>
+
+#include "tc_common.cuh"
+
+namespace memotr {
+namespace tc {
+namespace persist {
+
+constexpr int NST = 4, BN = 128;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+constexpr int OFF_OUT = NST * STAGE_BYTES;                                                   // 128 KB
+constexpr int OUT_BYTES = 4 * BM * 128;                                                      // up to 4 panels (fp32)
+constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
+constexpr int TOTAL = OFF_BAR + 256 + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + OFF_BAR), *empty = full + NST, *acc_full = empty + NST,
+           *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  uint8_t *stage_out = smem + OFF_OUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = K / BK, n_nblk = N / BN, n_tiles = n_nblk * ceil_div(M, BM);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    for (int s = 0; s < NST; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+    for (int b = 0; b < 2; ++b) mbar_init(acc_full + b, 1), mbar_init(acc_empty + b, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m_blk = t / n_nblk, n_blk = t % n_nblk;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % NST;
+          mbar_wait(empty + s, ((it / NST) & 1) ^ 1);
+          mbar_expect_tx(full + s, STAGE_BYTES);
+          uint8_t *sa = smem + s * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full + s, kb * BK, m_blk * BM);
+          tma_load_2d(sa + A_BYTES, &tmW, full + s, kb * BK, n_blk * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN);
+      uint32_t it = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(acc_empty + buf, ((i >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator (tile i - 2)
+        tcgen05_fence_after();
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % NST;
+          mbar_wait(full + s, (it / NST) & 1);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_base + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty + s);
+        }
+        umma_commit(acc_full + buf);
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----
+    int i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int m_blk = t / n_nblk, n_blk = t % n_nblk, buf = i & 1;
+      // the previous tile's TMA store must have finished READING the staging panels before they are overwritten
+      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(acc_full + buf, (i >> 1) & 1);
+      tcgen05_fence_after();
+        const int quarter = warp & 3;
+        const int r_in = quarter * 32 + lane;  // row inside the tile == TMEM lane
+        const int row = m_blk * BM + r_in;
+        const bool row_ok = row < M;
+        const bool zero_row = row_ok && ep.rowzero && ep.rowzero[row];
+        const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
+        const __nv_bfloat16 *addp = (const __nv_bfloat16 *)ep.add + (long)row * ep.ldadd;
+        constexpr int PANEL_COLS = 128 / (int)sizeof(TC);       // columns per 128-byte panel row: 32 (fp32) or 64 (bf16)
+        constexpr int N_PANELS = BN / PANEL_COLS;
+    #pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+          if (c0 + 32 == BN) {            // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp
+            tcgen05_fence_before();
+            mbar_arrive(acc_empty + buf);
+          }
+          const int col0 = n_blk * BN + c0;
+          float v[32];
+    #pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+    #pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.bias + col0 + j));
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+          if (ep.act == ACT_RELU) {
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (ep.act == ACT_SIGMOID) {
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+          }
+          if (ep.mul && row_ok) {
+    #pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float t[8];
+              bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(mulp + col0 + j)), t);
+    #pragma unroll
+              for (int i = 0; i < 8; ++i) v[j + i] *= t[i];
+            }
+          }
+          if (ep.add && row_ok) {
+    #pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float t[8];
+              bf16x8_to_f32(__ldg(reinterpret_cast<const uint4 *>(addp + col0 + j)), t);
+    #pragma unroll
+              for (int i = 0; i < 8; ++i) v[j + i] += t[i];
+            }
+          }
+          if (zero_row) {
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          // stage: panel p holds PANEL_COLS columns; row r_in occupies 128 bytes; 16-byte chunk k sits at k ^ (r_in & 7)
+          const int panel = c0 / PANEL_COLS;
+          uint8_t *prow = stage_out + panel * (BM * 128) + r_in * 128;
+          if constexpr (sizeof(TC) == 4) {
+    #pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4 *>(prow + ((k ^ (r_in & 7)) << 4)) =
+                  make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          } else {
+            const int kbase = (c0 % PANEL_COLS) / 8;  // 0 or 4: which half of the 64-column panel row
+    #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float t[8];
+    #pragma unroll
+              for (int i = 0; i < 8; ++i) t[i] = v[8 * k + i];
+              *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = pack8<TC>(t);
+            }
+          }
+        }
+
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+#pragma unroll 1
+        for (int p = 0; p < N_PANELS; ++p)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                       "r"(smem_u32(stage_out + p * (BM * 128))), "r"(n_blk * BN + p * PANEL_COLS), "r"(m_blk * BM)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+template <typename TC>
+static int launch(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
+                  const Epilogue &ep, int n_sm, cudaStream_t st) {
+  CUtensorMap tmA, tmW, tmC;
+  if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN) ||
+      !make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4, std::is_same<TC, __half>::value))
+    return fail(MEMOTR_ECUDA, "linear(tc, persistent): cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
+  auto kern = gemm_tc_persist_kernel<TC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL);
+    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "linear(tc, persistent): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = (N / BN) * ceil_div(M, BM);
+  MEMOTR_LAUNCH((kern), tiles < n_sm ? tiles : n_sm, 192, TOTAL, st, tmA, tmW, tmC, M, N, K, ep);
+  return check_launch("gemm_tc_persist");
+}
+
+}  // namespace persist
+}  // namespace tc
+
+// used by linear_tc_bf16 (gemm_tc.cu) when there are more 128 x 128 tiles than SMs; MEMOTR_GEMM_PERSIST=0 switches it off
+bool linear_tc_persist_wanted(int M, int N, int *n_sm_out) {
+  static int n_sm = 0, enabled = -1;
+  if (enabled < 0) {
+    const char *e = getenv("MEMOTR_GEMM_PERSIST");
+    enabled = !(e && e[0] == '0');
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  *n_sm_out = n_sm;
+  return enabled && N % tc::persist::BN == 0 && (long)(N / tc::persist::BN) * ceil_div(M, tc::BM) > n_sm;
+}
+
+int linear_tc_persist_bf16(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int c_dtype, int M, int N,
+                           int K, const Epilogue &ep, int n_sm, cudaStream_t st) {
+  if (c_dtype == MEMOTR_F16) return tc::persist::launch<__half>(A, lda, W, ldw, C, ldc, M, N, K, ep, n_sm, st);
+  if (c_dtype == MEMOTR_F32) return tc::persist::launch<float>(A, lda, W, ldw, C, ldc, M, N, K, ep, n_sm, st);
+  return tc::persist::launch<__nv_bfloat16>(A, lda, W, ldw, C, ldc, M, N, K, ep, n_sm, st);
+}
+
+}  // namespace memotr

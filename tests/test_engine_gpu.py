@@ -64,9 +64,12 @@ def test_linear_fp32_epilogues():
 
 
 @pytest.mark.parametrize("M,N,K_", [(128, 64, 64), (1, 128, 256), (300, 384, 256), (400, 256, 512), (4000, 2048, 256),
-                                    (1025, 256, 2048), (22323, 256, 256), (22323, 1536, 256)])
+                                    (1025, 256, 2048), (22323, 256, 256), (22323, 1536, 256), (22323, 384, 256),
+                                    (19001, 128, 2048)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32, torch.float16])
 def test_linear_bf16_tensor_core(M, N, K_, out_dtype):
+    """Shapes with more 128 x 128 tiles than SMs run the persistent kernel (csrc/gemm_tc_persist.cu), the others one
+    tile per CTA (csrc/gemm_tc.cu)."""
     g = _g(M + N + 1)
     x = torch.randn(M, K_, generator=g).bfloat16()
     w = (torch.randn(N, K_, generator=g) / math.sqrt(K_)).bfloat16()
@@ -107,9 +110,10 @@ def test_linear_bf16_few_rows_mma(M, N, K_, out_dtype):
     assert torch.count_nonzero(wide_out[:, :N]) == 0 and torch.count_nonzero(wide_out[:, 2 * N:]) == 0
 
 
-def test_linear_bf16_tensor_core_epilogues_and_views():
+@pytest.mark.parametrize("M", [700, 20001])          # 20001 rows: the persistent kernel (314 tiles)
+def test_linear_bf16_tensor_core_epilogues_and_views(M):
     g = _g(11)
-    M, N, K_ = 700, 256, 256
+    N, K_ = 256, 256
     x = torch.randn(M, K_, generator=g).bfloat16()
     w = (torch.randn(N, K_, generator=g) / 16).bfloat16()
     b = torch.randn(N, generator=g)
