@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec at 1333x800, 300 det+100 track queries"
 N_TRACKS = 100
-N_ROT = 4   # distinct resident frames rotating through the input buffers (4 x 45.8 MB > 126 MB L2)
+N_ROT = 6            # resident frames rotating through the input buffers: 6 x 22.9 MB (45.8 MB with position maps) > L2
 
 
 def peaks():
@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / gpu_reference legs")
+    ap.add_argument("--upload-pos", action="store_true",
+                    help="upload the position maps with every frame (A/B; default: rebuilt on the device from the masks)")
     ap.add_argument("--no-tracker", action="store_true",
                     help="leave the RuntimeTracker glue out of the step (A/B; default: on the device, inside the graph)")
     args = ap.parse_args()
@@ -227,19 +229,23 @@ def main():
     # the 100 loaded tracks stay live and nothing is born: the step keeps BASELINE.json's 300 det + 100 track queries.
     tracker = None if args.no_tracker else dict(det_score_thresh=2.0, track_score_thresh=0.0, miss_tolerance=30,
                                                 result_score_thresh=0.5)
+    # Position maps: a function of the padding masks alone (PositionEmbeddingSine), rebuilt on the device every frame
+    # instead of crossing PCIe (the box's pinned H2D rate, ~26 GB/s, would cap e2e at 564 frames/s with them).
+    pos_embed = None if args.upload_pos else dict(temperature=20)
     eng = FrameEngine(sd, cfg, synth.DANCETRACK_SHAPES, N_TRACKS, dev, mode=args.mode, tracker=tracker,
-                      ori_size=(1920, 1080))
+                      ori_size=(1920, 1080), pos_embed=pos_embed)
     eng.enable_msda_timer()
     L, C, K = eng.L, eng.C, args.steps
 
     # resident copies of the rotating frames + pinned host copies for the e2e leg
     res_src = [[f["srcs"][l].reshape(C, -1).to(dev) for l in range(L)] for f in frames]
-    res_pos = [[f["pos"][l].reshape(C, -1).to(dev) for l in range(L)] for f in frames]
+    res_pos = [[f["pos"][l].reshape(C, -1).to(dev) for l in range(L)] for f in frames] if args.upload_pos else None
     pin = lambda t: t.contiguous().pin_memory()                                      # noqa: E731
     host = [{"srcs": [pin(t) for t in f["srcs"]], "pos": [pin(t) for t in f["pos"]],
              "masks": [pin(t.to(torch.uint8)) for t in f["masks"]]} for f in frames]
     x0 = frames[0]
-    eng.load_frame(x0["srcs"], x0["masks"], x0["pos"], x0["tracks"]["ref_pts"], x0["tracks"]["query_embed"])
+    eng.load_frame(x0["srcs"], x0["masks"], x0["pos"] if args.upload_pos else None, x0["tracks"]["ref_pts"],
+                   x0["tracks"]["query_embed"])
     eng.load_tracks(x0["tracks"])
     if eng.trk is not None:
         eng.trk.reset(x0["tracks"])
@@ -248,7 +254,8 @@ def main():
     def feed_resident(i):
         for l in range(L):
             eng.in_src[l].copy_(res_src[i % N_ROT][l], non_blocking=True)
-            eng.in_pos[l].copy_(res_pos[i % N_ROT][l], non_blocking=True)
+            if res_pos is not None:
+                eng.in_pos[l].copy_(res_pos[i % N_ROT][l], non_blocking=True)
 
     def reset_clip():
         eng.in_track_ref.copy_(x0["tracks"]["ref_pts"])
@@ -305,7 +312,7 @@ def main():
     from memotr_b200.engine import ClipRunner
     runner = ClipRunner(eng)
     h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
-    hf = [(h["srcs"], h["pos"], h["masks"]) for h in host]
+    hf = [(h["srcs"], h["pos"] if args.upload_pos else None, h["masks"]) for h in host]
 
     def e2e_clip(n):
         runner.prefetch(0, *hf[0])
@@ -353,8 +360,10 @@ def main():
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload, "clip": f"{K} chained frames per GPU; N>1: one NCCL all-gather of the packed "
-                   "track-query memory per clip", "l2": f"inputs larger than L2: {N_ROT} resident frames x 45.8 MB rotate "
+                   "track-query memory per clip", "l2": f"inputs larger than L2: {N_ROT} resident frames x {h2d / 1e6:.1f} MB rotate "
                    "through the input buffers and a step touches ~0.5 GB of workspace (L2 = 126 MB)",
+                   "position_maps": "uploaded with every frame (--upload-pos)" if args.upload_pos else
+                   "PositionEmbeddingSine rebuilt on the device from the padding masks inside the captured step",
                    "tracker": ("RuntimeTracker.update + select_active_tracks + result filter on the device inside the "
                                f"captured step; thresholds pinned so that {tracks_live} tracks stay live and none is born")
                    if eng.trk is not None else "off (--no-tracker)",

@@ -173,8 +173,23 @@ MEMOTR_API int memotr_tokens_from_nchw(const float *src, const float *pos, const
                                        void *pos_tok, void *q_tok, float *src_tok32, int C, int HW, int row0, int ld,
                                        int dtype, void *stream);
 
+/* memotr_tokens_from_nchw with the position map evaluated in place: pos = PositionEmbeddingSine(mask) of this level
+ * (models/position_embedding.py:23-49, see memotr_pos_embed_sine for dim_i / scale / scratch), never materialised */
+MEMOTR_API int memotr_tokens_from_nchw_pe(const float *src, const unsigned char *mask, int H, int W, const float *dim_i,
+                                          float scale, float *scratch, const float *level_embed, void *src_tok,
+                                          void *pos_tok, void *q_tok, float *src_tok32, int C, int row0, int ld, int dtype,
+                                          void *stream);
+
 /* valid ratio (w,h) of one level's (H,W) uint8 padding mask -- models/deformable_transformer.py:175-190 */
 MEMOTR_API int memotr_valid_ratio(const unsigned char *mask, int H, int W, float *out2, void *stream);
+
+/* PositionEmbeddingSine(normalize=True) of one level from its padding mask (models/position_embedding.py:23-43, as built by
+ * :46-49 with num_pos_feats = hidden_dim / 2, temperature 20, scale 2 pi): out (2 * num_pos_feats, H * W) fp32, channels
+ * [y features | x features]; dim_i (num_pos_feats) = temperature ** (2 * (i // 2) / num_pos_feats) from the host;
+ * scratch (2 * H * W) fp32.  The reference runs this inside the backbone and, for the extra level, inside
+ * MeMOTR.forward (models/memotr.py:121). */
+MEMOTR_API int memotr_pos_embed_sine(const unsigned char *mask, int H, int W, const float *dim_i, int num_pos_feats,
+                                     float scale, float *scratch, float *out, void *stream);
 
 /* sine embedding of (N,4) boxes -> (N,512): models/utils.py:78-85; optional sigmoid first (query_updater.py:102) and
  * per-coordinate scale (deformable_decoder.py:82-91); dim_t = the 128 divisors 10000^(2*(i//2)/128). */

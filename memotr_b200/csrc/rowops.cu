@@ -217,7 +217,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, const float *__restrict__ lvl_embed,
               T *__restrict__ src_tok, T *__restrict__ pos_tok, T *__restrict__ q_tok, float *__restrict__ src_tok32,
-              int C, int HW, int row0, int ld) {
+              int C, int HW, int row0, int ld, const float *__restrict__ emb, const float *__restrict__ dim_i) {
+  // emb != nullptr: the position map is not an input but PositionEmbeddingSine evaluated in place from the normalised
+  // cumulative counts `emb` (2, HW) of pos_cumsum_kernel: channel c < C/2 from the y count, else from the x count
   pdl_grid_sync();
   __shared__ float ts[32][33], tp[32][33];
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -226,14 +228,20 @@ tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, cons
     const int c = c0 + i, p = p0 + tx;
     const bool ok = c < C && p < HW;
     ts[i][tx] = ok ? src[(long)c * HW + p] : 0.f;
-    tp[i][tx] = ok ? pos[(long)c * HW + p] : 0.f;
+    tp[i][tx] = (ok && !emb) ? pos[(long)c * HW + p] : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
     if (p < HW && c < C) {
       const float s = ts[tx][i];
-      const float pe = tp[tx][i] + lvl_embed[c];
+      float pv = tp[tx][i];
+      if (emb) {
+        const int npf = C >> 1, j = c >= npf ? c - npf : c;
+        const float e = __fdiv_rn(emb[(long)(c >= npf) * HW + p], __ldg(dim_i + j));
+        pv = (j & 1) ? cosf(e) : sinf(e);
+      }
+      const float pe = pv + lvl_embed[c];
       const long o = (long)(row0 + p) * ld + c;
       src_tok[o] = from_f32<T>(s);
       if (src_tok32) src_tok32[o] = s;
@@ -259,6 +267,49 @@ __global__ void valid_ratio_kernel(const unsigned char *__restrict__ mask, int H
     out2[0] = (float)cnt[0] / (float)Ww;
     out2[1] = (float)cnt[1] / (float)Hh;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PositionEmbeddingSine of one level (models/position_embedding.py:23-43, normalize=True): the position map is a function
+// of the padding mask alone, so it is rebuilt on the device instead of crossing PCIe with every frame (22.9 MB per
+// 1333x800 frame).  Step 1: normalised cumulative counts of valid pixels down the columns (y) and along the rows (x):
+//   emb = (cumsum(~mask) - 0.5) / (last + 1e-6) * scale      -> scratch (2, H, W)
+__global__ void __launch_bounds__(1024)
+pos_cumsum_kernel(const unsigned char *__restrict__ mask, int Hh, int Ww, float scale, float *__restrict__ emb) {
+  pdl_grid_sync();
+  extern __shared__ unsigned char sm_mask[];      // the level's mask: the serial counting loops below run out of shared memory
+  const int HW = Hh * Ww;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) sm_mask[i] = mask[i];
+  __syncthreads();
+  for (int t = threadIdx.x; t < Ww + Hh; t += blockDim.x) {
+    const bool col = t < Ww;                      // column t: y embedding; row t - W: x embedding
+    const int n = col ? Hh : Ww, base = col ? t : (t - Ww) * Ww, step = col ? Ww : 1;
+    float cnt = 0.f;
+    for (int i = 0; i < n; ++i) cnt += sm_mask[base + i * step] ? 0.f : 1.f;
+    const float den = cnt + 1e-6f;
+    float run = 0.f;
+    float *o = emb + (col ? 0 : HW);
+    for (int i = 0; i < n; ++i) {
+      run += sm_mask[base + i * step] ? 0.f : 1.f;
+      o[base + i * step] = __fmul_rn(__fdiv_rn(run - 0.5f, den), scale);
+    }
+  }
+}
+// Step 2: out[c, p] = sin / cos (emb / dim_i): channels [0, npf) from y, [npf, 2 npf) from x; even feature sin, odd cos.
+// dim_i[2k] == dim_i[2k+1], so one thread produces the (sin, cos) pair of features 2k, 2k+1 of one pixel;
+// blockIdx.y = (y|x half) * npf/2 + k, so no integer division is needed.
+__global__ void __launch_bounds__(256)
+pos_sine_kernel(const float *__restrict__ emb, const float *__restrict__ dim_i, int npf, int HW, float *__restrict__ out) {
+  pdl_grid_sync();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int half = blockIdx.y / (npf / 2), k = blockIdx.y % (npf / 2);
+  const float e = __fdiv_rn(emb[(long)half * HW + p], __ldg(dim_i + 2 * k));
+  float sv, cv;
+  sincosf(e, &sv, &cv);
+  float *o = out + ((long)half * npf + 2 * k) * HW + p;
+  o[0] = sv;
+  o[HW] = cv;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -443,18 +494,54 @@ extern "C" int memotr_tokens_from_nchw(const float *src, const float *pos, const
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MEMOTR_F32)
     MEMOTR_LAUNCH((tokens_kernel<float>), grid, 256, 0, st, src, pos, level_embed, (float *)src_tok, (float *)pos_tok,
-                                               (float *)q_tok, src_tok32, C, HW, row0, ld);
+                                               (float *)q_tok, src_tok32, C, HW, row0, ld, (const float *)nullptr,
+                                               (const float *)nullptr);
   else
     MEMOTR_LAUNCH((tokens_kernel<__nv_bfloat16>), grid, 256, 0, st, src, pos, level_embed, (__nv_bfloat16 *)src_tok,
                                                        (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, HW,
-                                                       row0, ld);
+                                                       row0, ld, (const float *)nullptr, (const float *)nullptr);
   return check_launch("tokens_from_nchw");
+}
+
+extern "C" int memotr_tokens_from_nchw_pe(const float *src, const unsigned char *mask, int Hh, int Ww, const float *dim_i,
+                                          float scale, float *scratch, const float *level_embed, void *src_tok,
+                                          void *pos_tok, void *q_tok, float *src_tok32, int C, int row0, int ld, int dtype,
+                                          void *stream) {
+  MEMOTR_REQUIRE(src && mask && dim_i && scratch && level_embed && src_tok && pos_tok && q_tok && C > 0 && C % 4 == 0 &&
+                     Hh > 0 && Ww > 0 && ld >= C,
+                 "tokens_from_nchw_pe: bad arguments");
+  MEMOTR_REQUIRE(Hh * Ww <= 48 * 1024, "tokens_from_nchw_pe: level larger than 48K pixels");
+  MEMOTR_DTYPE_AB(dtype);
+  const int HW = Hh * Ww;
+  cudaStream_t st = (cudaStream_t)stream;
+  MEMOTR_LAUNCH((pos_cumsum_kernel), 1, 1024, (size_t)HW, st, mask, Hh, Ww, scale, scratch);
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32));
+  if (dtype == MEMOTR_F32)
+    MEMOTR_LAUNCH((tokens_kernel<float>), grid, 256, 0, st, src, (const float *)nullptr, level_embed, (float *)src_tok,
+                  (float *)pos_tok, (float *)q_tok, src_tok32, C, HW, row0, ld, (const float *)scratch, dim_i);
+  else
+    MEMOTR_LAUNCH((tokens_kernel<__nv_bfloat16>), grid, 256, 0, st, src, (const float *)nullptr, level_embed,
+                  (__nv_bfloat16 *)src_tok, (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, HW, row0, ld,
+                  (const float *)scratch, dim_i);
+  return check_launch("tokens_from_nchw_pe");
 }
 
 extern "C" int memotr_valid_ratio(const unsigned char *mask, int Hh, int Ww, float *out2, void *stream) {
   MEMOTR_REQUIRE(mask && out2 && Hh > 0 && Ww > 0, "valid_ratio: bad arguments");
   MEMOTR_LAUNCH((valid_ratio_kernel), 1, 256, 0, (cudaStream_t)stream, mask, Hh, Ww, out2);
   return check_launch("valid_ratio");
+}
+
+extern "C" int memotr_pos_embed_sine(const unsigned char *mask, int Hh, int Ww, const float *dim_i, int num_pos_feats,
+                                     float scale, float *scratch, float *out, void *stream) {
+  MEMOTR_REQUIRE(mask && dim_i && scratch && out && Hh > 0 && Ww > 0 && num_pos_feats > 0, "pos_embed_sine: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  MEMOTR_REQUIRE(Hh * Ww <= 48 * 1024, "pos_embed_sine: level larger than 48K pixels");
+  MEMOTR_LAUNCH((pos_cumsum_kernel), 1, 1024, (size_t)Hh * Ww, st, mask, Hh, Ww, scale, scratch);
+  MEMOTR_REQUIRE(num_pos_feats % 2 == 0, "pos_embed_sine: num_pos_feats must be even");
+  MEMOTR_LAUNCH((pos_sine_kernel), dim3(ceil_div(Hh * Ww, 256), num_pos_feats), 256, 0, st, (const float *)scratch, dim_i,
+                num_pos_feats, Hh * Ww, out);
+  return check_launch("pos_embed_sine");
 }
 
 extern "C" int memotr_sine_embed(const float *pts, int ldp, const float *scale4, int apply_sigmoid, const float *dim_t,

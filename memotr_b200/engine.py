@@ -39,12 +39,15 @@ class _Lin:
 
 class FrameEngine:
     def __init__(self, state_dict, cfg, shapes, n_tracks, device="cuda", mode="fp32", tracker=None,
-                 ori_size=(1920, 1080)):
+                 ori_size=(1920, 1080), pos_embed=None):
         """`n_tracks` is the number of track-query rows (= the capacity of the track table).  `tracker=None`: the
         caller owns the track bookkeeping and every row is live (the reference's model + query-updater path only).
         `tracker=dict(det_score_thresh=, track_score_thresh=, miss_tolerance=, result_score_thresh=)`: the
         RuntimeTracker glue runs on the device inside step() (memotr_b200/tracker.py) with a variable number of live
         rows; `ori_size` = (width, height) of the original image for the result boxes (submit_engine.py:89-98)."""
+        # pos_embed=dict(temperature=20, scale=2*pi): the position maps are rebuilt on the device from the padding masks
+        # (PositionEmbeddingSine, models/position_embedding.py:23-49) instead of being an input (None)
+        self.pos_cfg = dict(pos_embed) if pos_embed is not None else None
         assert mode in ("fp32", "bf16")
         self.tracker_cfg, self.ori_size = (dict(tracker) if tracker is not None else None), tuple(ori_size)
         self.cfg, self.mode = dict(cfg), mode
@@ -192,9 +195,16 @@ class FrameEngine:
         self.lsi_host = [sum(sizes[:i]) for i in range(self.L)]
         self.lsi_t = torch.as_tensor(self.lsi_host, dtype=torch.long, device=dev)
         # static inputs (filled by load_frame; fixed addresses so a captured graph can be replayed)
-        self.in_src = [f(C, h * w) for h, w in self.shapes]
-        self.in_pos = [f(C, h * w) for h, w in self.shapes]
-        self.in_mask = [torch.zeros(h * w, dtype=torch.uint8, device=dev) for h, w in self.shapes]
+        # one flat buffer [src (fp32) per level | pos (fp32) per level, if it is an input | masks (u8) per level] so that a
+        # staged frame arrives with ONE device-to-device copy (ClipRunner); in_src / in_pos / in_mask are views
+        self.in_layout = self.input_layout(self.shapes, C, with_pos=self.pos_cfg is None)
+        self.in_flat = torch.zeros(self.in_layout["bytes"], dtype=torch.uint8, device=dev)
+        self.in_src, self.in_pos, self.in_mask = self.input_views(self.in_flat, self.in_layout, self.shapes, C)
+        if self.pos_cfg is not None:
+            self.pos_scratch = f(2 * max(h * w for h, w in self.shapes))
+            i = torch.arange(C // 2, dtype=torch.float32)                              # models/position_embedding.py:33-34
+            self.pos_dim_i = (float(self.pos_cfg.get("temperature", 20)) **
+                              (2 * torch.div(i, 2, rounding_mode="trunc") / (C // 2))).to(dev)
         self.in_track_ref = torch.zeros(nt, 4, dtype=torch.float32, device=dev)
         self.in_track_embed = torch.zeros(nt, C, dtype=torch.float32, device=dev)
         # encoder
@@ -466,11 +476,33 @@ class FrameEngine:
                                             self.dt, self._st()), "sine_embed")
 
     # ------------------------------------------------------------------------------------------------ inputs
+    @staticmethod
+    def input_layout(shapes, C, with_pos=True):
+        off, lay = 0, {"src": [], "pos": [], "mask": []}
+        for key in (("src", "pos") if with_pos else ("src",)):
+            for h, w in shapes:
+                lay[key].append(off)
+                off += C * h * w * 4
+        for h, w in shapes:
+            lay["mask"].append(off)
+            off += h * w
+        lay["bytes"] = (off + 15) // 16 * 16
+        return lay
+
+    @staticmethod
+    def input_views(flat, lay, shapes, C):
+        f32 = lambda o, h, w: flat[o:o + C * h * w * 4].view(torch.float32).view(C, h * w)   # noqa: E731
+        src = [f32(o, h, w) for o, (h, w) in zip(lay["src"], shapes)]
+        pos = [f32(o, h, w) for o, (h, w) in zip(lay["pos"], shapes)] if lay["pos"] else None
+        mask = [flat[o:o + h * w] for o, (h, w) in zip(lay["mask"], shapes)]
+        return src, pos, mask
+
     def load_frame(self, srcs, masks, pos, track_ref_pts, track_query_embed, non_blocking=True):
         """Copy one frame's inputs (host or device tensors, fp32 NCHW with batch 1) into the static input buffers."""
         for l in range(self.L):
             self.in_src[l].copy_(srcs[l].reshape(self.C, -1), non_blocking=non_blocking)
-            self.in_pos[l].copy_(pos[l].reshape(self.C, -1), non_blocking=non_blocking)
+            if self.pos_cfg is None:
+                self.in_pos[l].copy_(pos[l].reshape(self.C, -1), non_blocking=non_blocking)
             self.in_mask[l].copy_(masks[l].reshape(-1).to(torch.uint8), non_blocking=non_blocking)
         self.in_track_ref.copy_(track_ref_pts, non_blocking=non_blocking)
         self.in_track_embed.copy_(track_query_embed, non_blocking=non_blocking)
@@ -487,10 +519,18 @@ class FrameEngine:
         self._mark(0)
         # -- level flattening, level embedding, valid ratios (deformable_transformer.py:196-220)
         for l, (h, w) in enumerate(self.shapes):
-            self._ck(self.lib.memotr_tokens_from_nchw(_p(self.in_src[l]), _p(self.in_pos[l]), _p(self.level_embed[l]),
-                                                      _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
-                                                      _p(None if self.mode == "fp32" else self.src32), C, h * w,
-                                                      self.lsi_host[l], C, dt, st()), "tokens")
+            if self.pos_cfg is not None:      # position map of this level evaluated inside the token kernel (2 launches)
+                self._ck(self.lib.memotr_tokens_from_nchw_pe(
+                    _p(self.in_src[l]), _p(self.in_mask[l]), h, w, _p(self.pos_dim_i),
+                    float(self.pos_cfg.get("scale", 2 * math.pi)), _p(self.pos_scratch), _p(self.level_embed[l]),
+                    _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok), _p(None if self.mode == "fp32" else self.src32), C,
+                    self.lsi_host[l], C, dt, st()), "tokens_pe")
+                self.launches += 1
+            else:
+                self._ck(self.lib.memotr_tokens_from_nchw(_p(self.in_src[l]), _p(self.in_pos[l]), _p(self.level_embed[l]),
+                                                          _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
+                                                          _p(None if self.mode == "fp32" else self.src32), C, h * w,
+                                                          self.lsi_host[l], C, dt, st()), "tokens")
             self._ck(self.lib.memotr_valid_ratio(_p(self.in_mask[l]), h, w, _p(self.vr[l]), st()), "valid_ratio")
             self.convert_u8(self.in_mask[l], self.mask_flat[self.lsi_host[l]:], h * w)
         # -- encoder (deformable_encoder.py:109-131)
@@ -697,37 +737,40 @@ class ClipRunner:
         if eng.graph is None:
             eng.capture()
         self.copy_stream = torch.cuda.Stream(dev)
-        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)              # noqa: E731
-        self.stage = [{"src": [f(eng.C, h * w) for h, w in eng.shapes], "pos": [f(eng.C, h * w) for h, w in eng.shapes],
-                       "mask": [torch.zeros(h * w, dtype=torch.uint8, device=dev) for h, w in eng.shapes]}
-                      for _ in range(2)]
+        lay = eng.in_layout
+        self.stage = []
+        for _ in range(2):          # two staging slots with the engine's own input layout: one D2D copy hands a frame over
+            flat = torch.zeros(lay["bytes"], dtype=torch.uint8, device=dev)
+            src, pos, mask = eng.input_views(flat, lay, eng.shapes, eng.C)
+            self.stage.append({"flat": flat, "src": src, "pos": pos, "mask": mask})
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.free = [torch.cuda.Event(), torch.cuda.Event()]
         for e in self.free:
             e.record(torch.cuda.current_stream(dev))
-        self.host_out = {
-            "pred_logits": torch.empty(eng.nq, eng.ncls).pin_memory(), "pred_bboxes": torch.empty(eng.nq, 4).pin_memory(),
-        }
-        if eng.trk is None:     # the caller keeps the tracks: hand the updated track queries back
-            self.host_out["track_query_embed"] = torch.empty(eng.nt, eng.C).pin_memory()
-            self.host_out["track_ref_pts"] = torch.empty(eng.nt, 4).pin_memory()
-        else:                   # tracks live on the device: only the frame's result rows travel (submit_engine.py:99-102)
-            self.host_out["ids"] = torch.empty(eng.nt, dtype=torch.long).pin_memory()
-            self.host_out["boxes_xyxy"] = torch.empty(eng.nt, 4).pin_memory()
-            self.host_out["scores"] = torch.empty(eng.nt).pin_memory()
-            self.host_out["keep"] = torch.empty(eng.nt, dtype=torch.uint8).pin_memory()
-            self.host_out["n_active"] = torch.empty(1, dtype=torch.int32).pin_memory()
-        self.h2d_bytes = sum(t.numel() * t.element_size() for k in ("src", "pos", "mask") for t in self.stage[0][k])
+        self.raw_outputs = eng.trk is None
+        self.host_out = {}
+        if self.raw_outputs:     # the caller keeps the tracks: raw frame outputs + the updated track queries
+            self.host_out = {"pred_logits": torch.empty(eng.nq, eng.ncls).pin_memory(),
+                             "pred_bboxes": torch.empty(eng.nq, 4).pin_memory(),
+                             "track_query_embed": torch.empty(eng.nt, eng.C).pin_memory(),
+                             "track_ref_pts": torch.empty(eng.nt, 4).pin_memory()}
+        else:                    # tracks live on the device: only the frame's result rows travel (submit_engine.py:99-102)
+            self.host_out = {"results": torch.empty(eng.trk.res_flat.numel(), dtype=torch.uint8).pin_memory(),
+                             "n_active": torch.empty(1, dtype=torch.int32).pin_memory()}
+        n_in = ("src", "pos", "mask") if eng.pos_cfg is None else ("src", "mask")
+        self.h2d_bytes = sum(t.numel() * t.element_size() for k in n_in for t in self.stage[0][k])
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.host_out.values())
 
     def prefetch(self, slot, srcs, pos, masks):
-        """Enqueue the H2D copy of one frame (pinned host tensors: per level (1,C,H,W) fp32 x2 and (1,H,W) uint8/bool)."""
+        """Enqueue the H2D copy of one frame (pinned host tensors: per level (1,C,H,W) fp32 and (1,H,W) uint8/bool; `pos`
+        is None when the engine rebuilds the position maps on the device)."""
         eng, st = self.eng, self.stage[slot]
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.free[slot])
             for l in range(eng.L):
                 st["src"][l].copy_(srcs[l].reshape(eng.C, -1), non_blocking=True)
-                st["pos"][l].copy_(pos[l].reshape(eng.C, -1), non_blocking=True)
+                if eng.pos_cfg is None:
+                    st["pos"][l].copy_(pos[l].reshape(eng.C, -1), non_blocking=True)
                 st["mask"][l].copy_(masks[l].reshape(-1), non_blocking=True)
             self.ready[slot].record(self.copy_stream)
 
@@ -736,26 +779,25 @@ class ClipRunner:
         eng, st = self.eng, self.stage[slot]
         cur = torch.cuda.current_stream(eng.dev)
         cur.wait_event(self.ready[slot])
-        for l in range(eng.L):
-            eng.in_src[l].copy_(st["src"][l], non_blocking=True)
-            eng.in_pos[l].copy_(st["pos"][l], non_blocking=True)
-            eng.in_mask[l].copy_(st["mask"][l], non_blocking=True)
+        eng.in_flat.copy_(st["flat"], non_blocking=True)
         self.free[slot].record(cur)
         eng.replay()
-        n = eng.n_dec
-        self.host_out["pred_logits"].copy_(eng.pred_logit[n - 1], non_blocking=True)
-        self.host_out["pred_bboxes"].copy_(eng.pred_box[n - 1], non_blocking=True)
-        if eng.trk is None:
+        if self.raw_outputs:
+            n = eng.n_dec
+            self.host_out["pred_logits"].copy_(eng.pred_logit[n - 1], non_blocking=True)
+            self.host_out["pred_bboxes"].copy_(eng.pred_box[n - 1], non_blocking=True)
             self.host_out["track_query_embed"].copy_(eng.st["query_embed"], non_blocking=True)
             self.host_out["track_ref_pts"].copy_(eng.st["ref_pts"], non_blocking=True)
         else:
-            t = eng.trk
-            self.host_out["ids"].copy_(t.res_ids, non_blocking=True)
-            self.host_out["boxes_xyxy"].copy_(t.res_boxes, non_blocking=True)
-            self.host_out["scores"].copy_(t.res_scores, non_blocking=True)
-            self.host_out["keep"].copy_(t.res_keep, non_blocking=True)
+            self.host_out["results"].copy_(eng.trk.res_flat, non_blocking=True)
             self.host_out["n_active"].copy_(eng.table.n_active, non_blocking=True)
         return self.host_out
+
+    def results(self):
+        """Tracker mode, after a synchronize: the frame's result rows (ids, xyxy boxes in pixels, scores) of the kept tracks."""
+        ids, boxes, scores, keep = self.eng.trk.split_results(self.host_out["results"])
+        k = keep.bool()
+        return ids[k], boxes[k], scores[k]
 
     def run_clip(self, frames):
         """frames: iterable of (srcs, pos, masks) pinned host tensors.  Returns the last frame's host outputs."""

@@ -119,6 +119,23 @@ def sine_embed(pts, dim_t, scale4=None, apply_sigmoid=False, out_dtype=torch.flo
     return out
 
 
+def pos_embed_sine(mask, num_pos_feats=128, temperature=20, scale=6.283185307179586):
+    """PositionEmbeddingSine(normalize=True) of one (H, W) padding mask (bool / uint8, device) -> (2*num_pos_feats, H, W) fp32
+    (models/position_embedding.py:23-49)."""
+    _lib.require_cuda(mask=mask)
+    H, W = mask.shape
+    m = mask.to(torch.uint8).contiguous()
+    i = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_i = (float(temperature) ** (2 * torch.div(i, 2, rounding_mode="trunc") / num_pos_feats)).to(mask.device)
+    scratch = torch.empty(2 * H * W, dtype=torch.float32, device=mask.device)
+    out = torch.empty(2 * num_pos_feats, H, W, dtype=torch.float32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        rc = _lib.lib().memotr_pos_embed_sine(_lib.ptr(m), H, W, _lib.ptr(dim_i), num_pos_feats, float(scale),
+                                              _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "memotr_pos_embed_sine")
+    return out
+
+
 def box_refine(delta, ref, n_take):
     new_ref, ref_next = torch.empty_like(ref), torch.empty_like(ref)
     with torch.cuda.device(ref.device):

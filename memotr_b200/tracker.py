@@ -92,11 +92,17 @@ class DeviceTracker:
         self.src_index = torch.full((cap,), -1, dtype=torch.int32, device=dev)
         self.track_pad = torch.ones(cap, dtype=torch.uint8, device=dev)              # empty table: every row is padding
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.res_ids = torch.full((cap,), -1, dtype=torch.long, device=dev)
-        self.res_boxes = torch.zeros(cap, 4, dtype=torch.float32, device=dev)
-        self.res_scores = torch.zeros(cap, dtype=torch.float32, device=dev)
-        self.res_keep = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        # result rows in ONE buffer [ids int64 | boxes 4 x fp32 | scores fp32 | keep u8] so that they leave with one copy
+        self.res_flat = torch.zeros(cap * (8 + 16 + 4 + 1), dtype=torch.uint8, device=dev)
+        self.res_ids, self.res_boxes, self.res_scores, self.res_keep = self.split_results(self.res_flat)
+        self.res_ids.fill_(-1)
         self.lib = _lib.lib()
+
+    def split_results(self, flat):
+        """Views of a flat result buffer (device or host copy): ids (cap) int64, boxes (cap, 4), scores (cap), keep (cap)."""
+        cap = self.table.capacity
+        return (flat[:cap * 8].view(torch.long), flat[cap * 8:cap * 24].view(torch.float32).view(cap, 4),
+                flat[cap * 24:cap * 28].view(torch.float32), flat[cap * 28:cap * 29])
 
     def reset(self, tracks=None, max_obj_id=0):
         """Start of a clip (submit_engine.py:60-62): empty table, identities from 0 -- or a given state."""

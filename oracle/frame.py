@@ -321,3 +321,21 @@ def to_reference_config(cfg):
         "UPDATE_THRESH": cfg["update_thresh"], "LONG_MEMORY_LAMBDA": cfg["long_memory_lambda"],
         "TP_DROP_RATE": 0.0, "FP_INSERT_RATE": 0.0,
     }
+
+
+def position_embedding_sine(mask, num_pos_feats=128, temperature=20, scale=2 * math.pi):
+    """PositionEmbeddingSine.forward with normalize=True (models/position_embedding.py:23-43; built with
+    num_pos_feats = hidden_dim / 2, temperature 20, scale 2 pi at :46-49).  mask (B, H, W) bool -> (B, 2*npf, H, W)."""
+    not_mask = ~mask
+    y = not_mask.cumsum(dim=1, dtype=torch.float32)
+    x = not_mask.cumsum(dim=2, dtype=torch.float32)
+    eps = 1e-6
+    y = (y - 0.5) / (y[:, -1:, :] + eps) * scale
+    x = (x - 0.5) / (x[:, :, -1:] + eps) * scale
+    dim_i = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_i = temperature ** (2 * torch.div(dim_i, 2, rounding_mode="trunc") / num_pos_feats)
+    pos_x = x[:, :, :, None] / dim_i
+    pos_y = y[:, :, :, None] / dim_i
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)

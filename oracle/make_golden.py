@@ -182,6 +182,21 @@ def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
     print(f"frame_{tag}.npz:", {k: v.shape for k, v in arrays.items()})
 
 
+def golden_pos_embed():
+    """The reference's PositionEmbeddingSine (as built by models/position_embedding.py:46-49) on two padded masks."""
+    from models.position_embedding import build as build_pe
+    from utils.nested_tensor import NestedTensor
+    pe = build_pe({"HIDDEN_DIM": 256})
+    arrays = {}
+    for i, (h, w, vh, vw) in enumerate([(12, 20, 10, 17), (7, 5, 7, 5)]):
+        m = torch.ones(1, h, w, dtype=torch.bool)
+        m[:, :vh, :vw] = False
+        arrays[f"mask{i}"] = m.numpy()
+        arrays[f"pos{i}"] = pe(NestedTensor(torch.zeros(1, 3, h, w), m)).numpy()
+    np.savez_compressed(os.path.join(OUT, "pos_embed.npz"), **arrays)
+    print("pos_embed.npz:", {k: v.shape for k, v in arrays.items()})
+
+
 def golden_tracker():
     """The reference's own RuntimeTracker / TrackInstances / QueryUpdater.select_active_tracks (eval) / result filter
     driven for several frames with synthetic model outputs; inputs and outputs of every frame are stored."""
@@ -243,6 +258,7 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     func = import_reference()
     golden_tracker()
+    golden_pos_embed()
     if "--tracker-only" in sys.argv:
         sys.exit(0)
     golden_msda(func)

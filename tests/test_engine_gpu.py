@@ -351,6 +351,75 @@ def test_sine_embed_and_box_refine():
     assert torch.equal(nxt[:30].cpu(), new[:30].cpu()) and torch.equal(nxt[30:].cpu(), ref[30:])
 
 
+@pytest.mark.parametrize("h,w,vh,vw", [(100, 168, 100, 168), (100, 168, 88, 167), (50, 84, 44, 84), (13, 21, 12, 20), (1, 1, 1, 1)])
+def test_pos_embed_sine_matches_oracle_and_reference_golden(h, w, vh, vw):
+    m = torch.ones(1, h, w, dtype=torch.bool)
+    m[:, :vh, :vw] = False
+    want = oframe.position_embedding_sine(m)[0]
+    got = K().pos_embed_sine(m[0].to(DEV)).cpu()
+    assert got.shape == want.shape and (got - want).abs().max() <= 2e-6
+    g = np.load(os.path.join(GOLDEN, "pos_embed.npz"))            # outputs of the reference's own class
+    for i in (0, 1):
+        got = K().pos_embed_sine(torch.from_numpy(g[f"mask{i}"][0]).to(DEV)).cpu().numpy()
+        assert np.abs(got - g[f"pos{i}"][0]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_engine_position_maps_on_device_equal_uploaded_maps(mode):
+    """pos_embed=dict(...): the engine rebuilds the position maps from the padding masks; same outputs as uploading them."""
+    from memotr_b200.engine import FrameEngine
+    g, cfg, sd, x, shapes, nt = _case("small_padded")
+    pos = [oframe.position_embedding_sine(m) for m in x["masks"]]
+    outs = []
+    for on_device in (False, True):
+        eng = FrameEngine(sd, cfg, shapes, nt, DEV, mode=mode, pos_embed=dict(temperature=20) if on_device else None)
+        eng.load_frame(x["srcs"], x["masks"], None if on_device else pos, x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
+        eng.forward()
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in eng.results().items()})
+    for k in ("pred_logits", "pred_bboxes", "outputs", "memory"):
+        assert rel_err(outs[1][k].cpu().numpy(), outs[0][k].cpu().numpy()) <= (1e-5 if mode == "fp32" else 2e-2), k
+
+
+def test_clip_runner_host_api_tracker_mode():
+    """ClipRunner with the tracker on the device and the position maps rebuilt on the device: pinned host frames in, packed
+    result rows out; same identities / boxes as stepping the engine by hand on device-resident inputs."""
+    from memotr_b200.engine import ClipRunner, FrameEngine
+    cfg = synth.small_cfg()
+    sd = synth.hot_path_state_dict(cfg, seed=5)
+    thr = dict(det_score_thresh=0.66, track_score_thresh=0.6, miss_tolerance=2, result_score_thresh=0.62)
+    frames = [synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10 + t) for t in range(4)]
+    kw = dict(mode="fp32", tracker=thr, pos_embed=dict(temperature=20))
+    ref = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 10, DEV, **kw)
+    want = []
+    for fr in frames:
+        ref.load_frame(fr["srcs"], fr["masks"], None, ref.in_track_ref, ref.in_track_embed)
+        ref.step()
+        torch.cuda.synchronize()
+        keep = ref.trk.res_keep.cpu().bool()
+        want.append((ref.trk.res_ids.cpu()[keep].tolist(), ref.trk.res_boxes.cpu()[keep].clone()))
+    eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 10, DEV, **kw)
+    fr0 = frames[0]
+    eng.load_frame(fr0["srcs"], fr0["masks"], None, eng.in_track_ref, eng.in_track_embed)
+    eng.capture()
+    eng.trk.reset()
+    eng.in_track_ref.zero_(), eng.in_track_embed.zero_()
+    runner = ClipRunner(eng)
+    pin = lambda t: t.contiguous().pin_memory()                                       # noqa: E731
+    host = [([pin(t) for t in fr["srcs"]], None, [pin(t.to(torch.uint8)) for t in fr["masks"]]) for fr in frames]
+    runner.prefetch(0, *host[0])
+    for i in range(len(host)):
+        if i + 1 < len(host):
+            runner.prefetch((i + 1) % 2, *host[i + 1])
+        runner.run(i % 2)
+        torch.cuda.synchronize()
+        ids, boxes, scores = runner.results()
+        assert ids.tolist() == want[i][0], i
+        assert torch.equal(boxes, want[i][1]), i
+    assert runner.h2d_bytes == sum(t.numel() * 4 for t in fr0["srcs"]) + sum(t.numel() for t in fr0["masks"])
+    assert runner.d2h_bytes == 10 * 29 + 4
+
+
 # ------------------------------------------------------------------------------------------------ engine
 def _case(tag):
     g = np.load(os.path.join(GOLDEN, f"frame_{tag}.npz"))
