@@ -315,6 +315,32 @@ MEMOTR_API int memotr_decoder_forward(const memotr_dec_params *params, void *str
 MEMOTR_API int memotr_decoder_forward_cluster(const memotr_dec_params *params, void *stream);
 
 /*
+ * QueryUpdater.update_tracks_embedding (models/query_updater.py:82-166, DAB branch) on a device-resident track table as one
+ * persistent kernel (csrc/updater_cluster.cu; a 4-CTA cluster per 16 track rows, bf16 engine).  `prog`: FOUR programs of
+ * n_prog = 14 entries (rank-major, slot images as in memotr_dec_gemm); rank r: confidence_weight_net.0/.1 rows [64r,+64),
+ * short_memory_fusion.0 rows [128r,+128) (K = 512), .1 rows [64r,+64) (K = 512), query_pos_head.0 rows (K = 512), .1 rows,
+ * memory_attn q / k / v / out_proj rows [64r,+64), memory_ffn.linear1 rows [F/4 r,+F/4), linear2 columns [F/4 r,+F/4),
+ * query_feat_ffn.linear1 / linear2 likewise.  The table fields are updated in place; `feedback_*` (optional) receive the
+ * next frame's track queries (ref_pts, query_embed).
+ */
+typedef struct memotr_upd_params {
+  const memotr_dec_gemm *prog;
+  int n_prog, nt, ncls, d_ffn, np, pad_;
+  float update_thresh, long_memory_lambda;
+  const float *conf0_b, *conf1_b, *fus0_b, *fus1_b, *ph0_b, *ph1_b, *q_b, *k_b, *v_b, *out_b, *mf1_b, *mf2_b, *ff1_b, *ff2_b;
+  const float *mn_g, *mn_b, *mfn_g, *mfn_b, *fn_g, *fn_b, *ffn_g, *ffn_b; /* memory_norm, memory_ffn.norm, query_feat_norm, query_feat_ffn.norm */
+  const float *dim_t;                  /* (128) sine temperatures, as memotr_sine_embed */
+  const unsigned char *track_pad;      /* (nt) key-padding mask of the table rows, or NULL */
+  const float *logits, *boxes, *output_embed;                  /* (nt,ncls), (nt,4), (nt,256): this frame's values */
+  float *ref_pts, *query_embed, *long_memory, *last_output;    /* (nt,4), (nt,256) x3: updated in place */
+  float *feedback_ref, *feedback_embed;                        /* NULL or (nt,4), (nt,256) */
+  void *kbuf, *vbuf;                   /* scratch: (np,256) fp16, (256,np) fp16 */
+  unsigned int *barrier;               /* scratch: one counter */
+} memotr_upd_params;
+
+MEMOTR_API int memotr_updater_forward_cluster(const memotr_upd_params *params, void *stream);
+
+/*
  * Interval timer for measurement (bench.py): n CUDA events; memotr_timer_record enqueues event `idx` on `stream`
  * (as an external event-record node when the stream is being captured into a CUDA graph), memotr_timer_elapsed_ms
  * reads the time between two recorded events after the work has completed.  No reference counterpart (the reference

@@ -60,6 +60,18 @@ class DecParams(ctypes.Structure):
                  ("layers", DecLayer * MEMOTR_DEC_MAX_LAYERS)])
 
 
+class UpdParams(ctypes.Structure):
+    """memotr_upd_params (include/memotr_b200.h)."""
+    _fields_ = ([("prog", ctypes.c_void_p)] +
+                [(k, ctypes.c_int) for k in ("n_prog", "nt", "ncls", "d_ffn", "np", "pad_")] +
+                [("update_thresh", ctypes.c_float), ("long_memory_lambda", ctypes.c_float)] +
+                [(k, ctypes.c_void_p) for k in (
+                    "conf0_b", "conf1_b", "fus0_b", "fus1_b", "ph0_b", "ph1_b", "q_b", "k_b", "v_b", "out_b", "mf1_b", "mf2_b",
+                    "ff1_b", "ff2_b", "mn_g", "mn_b", "mfn_g", "mfn_b", "fn_g", "fn_b", "ffn_g", "ffn_b", "dim_t", "track_pad",
+                    "logits", "boxes", "output_embed", "ref_pts", "query_embed", "long_memory", "last_output",
+                    "feedback_ref", "feedback_embed", "kbuf", "vbuf", "barrier")])
+
+
 _SIGNATURES = {
     "memotr_abi_version": ([], _i),
     "memotr_last_error": ([], ctypes.c_char_p),
@@ -88,6 +100,7 @@ _SIGNATURES = {
     "memotr_tracker_results": ([_vp, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "memotr_decoder_forward": ([_vp, _vp], _i),
     "memotr_decoder_forward_cluster": ([_vp, _vp], _i),
+    "memotr_updater_forward_cluster": ([_vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),
     "memotr_timer_destroy": ([_vp], None),
     "memotr_timer_record": ([_vp, _i, _vp], _i),

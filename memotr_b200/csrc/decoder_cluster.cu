@@ -20,49 +20,12 @@ namespace memotr {
 namespace dec {
 namespace cl {
 
-constexpr int CS = 4;                              // CTAs per row block
 constexpr int HP = 512 * 2 + 16;                   // hidden slice pitch (<= 512 hidden columns per CTA)
 constexpr int OFF_X32 = 0, OFF_XB = OFF_X32 + R * C * 4, OFF_QP = OFF_XB + R * P256, OFF_A = OFF_QP + R * P256,
               OFF_B = OFF_A + R * P512, OFF_H = OFF_B + R * P256, OFF_F0 = OFF_H + R * HP, OFF_RED = OFF_F0 + R * F0P * 4,
               OFF_RING = OFF_RED + CS * R * 64 * 4, OFF_MISC = OFF_RING + NSLOT * SLOT_BYTES, OFF_PROG = OFF_MISC + 512,
               MAX_PROG = 15 * MEMOTR_DEC_MAX_LAYERS, SMEM_TOTAL = OFF_PROG + MAX_PROG * 24;
 static_assert(OFF_RING % 16 == 0 && SMEM_TOTAL + 128 <= 227 * 1024, "shared memory plan");
-
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_cl_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_cl_f32x2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-struct Xchg {                 // one hand-off between the four CTAs of a cluster (consumer warps only)
-  uint32_t bar_remote[CS];    // shared::cluster addresses of every CTA's exchange barrier
-  uint64_t *bar;              // the local one
-  uint32_t phase;
-  __device__ __forceinline__ void sync(int lane) {
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int p = 0; p < CS; ++p)
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_remote[p]) : "memory");
-    }
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tX_LOOP:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@p bra X_DONE;\n\tbra X_LOOP;\n\tX_DONE:\n\t}" ::"r"(
-            s32(bar)),
-        "r"(phase & 1)
-        : "memory");
-    ++phase;
-  }
-};
 
 __global__ void __launch_bounds__(NTHREADS, 1) decoder_cluster_kernel(const __grid_constant__ memotr_dec_params P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -224,102 +187,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_cluster_kernel(const __gr
       STAMP(2)
       grid_barrier(P.barrier, (unsigned int)(lid + 1) * gridDim.x);
       STAMP(3)
-      // ---- attention: heads 2*rk, 2*rk+1; warp = (head, quarter of the key blocks); partials combined through f0
-      {
-        const int hl = warp >> 2, part = warp & 3, h = 2 * (int)rk + hl;
-        const uint4 qv0 = *reinterpret_cast<const uint4 *>(bufB + g * P256 + (hl * 32 + 8 * c) * 2);
-        const uint4 qv1 = *reinterpret_cast<const uint4 *>(bufB + (g + 8) * P256 + (hl * 32 + 8 * c) * 2);
-        float o[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-        const int nblk = (n + 63) / 64;
-        for (int blk = part; blk < nblk; blk += 4) {
-          const int kb = blk * 64;
-          uint4 kr[8], vr[4][2];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int key = kb + 16 * (g >> 1) + 4 * (j >> 1) + 2 * (j & 1) + (g & 1);
-            kr[j] = __ldcg(reinterpret_cast<const uint4 *>(Kh + (long)key * C + h * 32 + 8 * c));
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half *vp = Vt + (long)(h * 32 + 8 * i + g) * P.np + kb + 16 * c;
-            vr[i][0] = __ldcg(reinterpret_cast<const uint4 *>(vp));
-            vr[i][1] = __ldcg(reinterpret_cast<const uint4 *>(vp + 8));
-          }
-          float s[8][4];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-            mma_f16(s[j], qv0.x, qv1.x, qv0.y, qv1.y, kr[j].x, kr[j].y);
-            mma_f16(s[j], qv0.z, qv1.z, qv0.w, qv1.w, kr[j].z, kr[j].w);
-          }
-          float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int key = kb + 16 * c + 4 * (j >> 1) + 2 * (j & 1) + e;
-              const bool dead = key >= n || (P.query_pad && P.query_pad[key]);
-              if (dead) s[j][e] = -INFINITY, s[j][2 + e] = -INFINITY;
-              bm0 = fmaxf(bm0, s[j][e]), bm1 = fmaxf(bm1, s[j][2 + e]);
-            }
-          bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)), bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-          bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)), bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-          const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
-          const float u0 = n0 == -INFINITY ? 0.f : n0, u1 = n1 == -INFINITY ? 0.f : n1;
-          const float f0s = __expf(m0 - u0), f1s = __expf(m1 - u1);
-          m0 = n0, m1 = n1;
-          l0 *= f0s, l1 *= f1s;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o[i][0] *= f0s, o[i][1] *= f0s, o[i][2] *= f1s, o[i][3] *= f1s;
-          uint32_t pa[8][2];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float p0 = __expf(s[j][0] - u0), p1 = __expf(s[j][1] - u0), p2 = __expf(s[j][2] - u1), p3 = __expf(s[j][3] - u1);
-            l0 += p0 + p1, l1 += p2 + p3;
-            pa[j][0] = pack_f16(p0, p1), pa[j][1] = pack_f16(p2, p3);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t vv[8] = {vr[i][0].x, vr[i][0].y, vr[i][0].z, vr[i][0].w, vr[i][1].x, vr[i][1].y, vr[i][1].z, vr[i][1].w};
-#pragma unroll
-            for (int st = 0; st < 4; ++st)
-              mma_f16(o[i], pa[2 * st][0], pa[2 * st][1], pa[2 * st + 1][0], pa[2 * st + 1][1], vv[2 * st], vv[2 * st + 1]);
-          }
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1), l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        // partial (m, l, O) of this warp -> f0 scratch: [warp][row][36] floats (32 O columns, m, l)
-        float *sc = f0 + warp * (R * 36);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<float2 *>(sc + g * 36 + 8 * i + 2 * c) = make_float2(o[i][0], o[i][1]);
-          *reinterpret_cast<float2 *>(sc + (g + 8) * 36 + 8 * i + 2 * c) = make_float2(o[i][2], o[i][3]);
-        }
-        if (c == 0) sc[g * 36 + 32] = m0, sc[g * 36 + 33] = l0, sc[(g + 8) * 36 + 32] = m1, sc[(g + 8) * 36 + 33] = l1;
-        csync();
-        // combine the four key quarters: 2 heads x 16 rows x 32 columns = 1024 outputs, two adjacent columns per thread
-        for (int oi = tid; oi < 2 * R * 16; oi += 256) {
-          const int hh = oi / (R * 16), r = (oi / 16) % R, d2 = (oi % 16) * 2;
-          float M = -INFINITY;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) M = fmaxf(M, f0[(hh * 4 + p) * (R * 36) + r * 36 + 32]);
-          const float U = M == -INFINITY ? 0.f : M;
-          float num0 = 0.f, num1 = 0.f, den = 0.f;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float *pp = f0 + (hh * 4 + p) * (R * 36) + r * 36;
-            const float w = __expf(pp[32] - U);
-            num0 += w * pp[d2], num1 += w * pp[d2 + 1], den += w * pp[33];
-          }
-          const float inv = den > 0.f ? 1.f / den : 0.f;
-          bc_bf16(OFF_A, P512, r, cb + hh * 32 + d2, num0 * inv, num1 * inv);
-        }
-      }
+      // ---- attention: heads 2*rk, 2*rk+1 (decoder_common.cuh); the result is broadcast into bufA of all four CTAs
+      attention_2heads(bufB, Kh, Vt, P.np, n, P.query_pad, (int)rk, f0, peer, OFF_A, P512, warp, lane, tid);
       xc.sync(lane);
       STAMP(4)
       gemm(sprog, rg, bufA, P512, Lp.sao_b + cb, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {   // out_proj

@@ -93,6 +93,11 @@ class FrameEngine:
             self._build_decoder_program()
         if self.dec_cluster:
             self._build_decoder_program_cluster()
+        # the query updater as one persistent cluster kernel (csrc/updater_cluster.cu); A/B switch MEMOTR_UPD_FUSED=0
+        self.upd_fused = (self.dec_cluster and os.environ.get("MEMOTR_UPD_FUSED", "1") != "0"
+                          and (self.nt + 15) // 16 * 4 <= 132)
+        if self.upd_fused:
+            self._build_updater_program()
         self.graph = None
         self.timer = None
 
@@ -385,6 +390,68 @@ class FrameEngine:
         P.prog, P.n_prog = self.dec_prog_cl.data_ptr(), n_prog
         self.dec_params_cl = P
 
+    def _build_updater_program(self):
+        """Per-rank weight programs + parameter block of memotr_updater_forward_cluster (include/memotr_b200.h)."""
+        dev, F, C, nt, u, CS = self.dev, self.Fd, self.C, self.nt, self.upd, 4
+        hw = F // CS
+        self.upd_packed = []
+
+        def pack(w):
+            rows, K = w.shape
+            rp, Kp = (rows + 63) // 64 * 64, (K + 255) // 256 * 256
+            z = torch.zeros(rp, Kp, dtype=torch.bfloat16, device=dev)
+            z[:rows, :K] = w
+            v = z.reshape(rp // 64, 64, Kp // 256, 256)
+            if Kp == 256:
+                img = torch.zeros(rp // 64, 1, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = v.permute(0, 2, 1, 3)
+            else:
+                assert rp // 64 <= 4
+                img = torch.zeros(Kp // 256, rp // 64, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = v.permute(2, 0, 1, 3)
+            self.upd_packed.append(img)
+            return (img.data_ptr(), 264, rp, Kp)
+
+        progs = []
+        for r in range(CS):
+            rows = slice(64 * r, 64 * r + 64)
+            ma = u["attn"]
+            pr = [pack(u["conf"][0].w[rows]), pack(u["conf"][1].w[rows]),
+                  pack(u["fusion"][0].w[128 * r:128 * r + 128]), pack(u["fusion"][1].w[rows]),
+                  pack(u["pos_head"][0].w[rows]), pack(u["pos_head"][1].w[rows]),
+                  pack(ma["q"].w[rows]), pack(ma["k"].w[rows]), pack(ma["v"].w[rows]), pack(ma["out"].w[rows])]
+            for key in ("mffn", "fffn"):
+                l1, l2, _ = u[key]
+                pr.append(pack(l1.w[hw * r:hw * r + hw])), pr.append(pack(l2.w[:, hw * r:hw * r + hw]))
+            progs.append(pr)
+        flat = [e for pr in progs for e in pr]
+        arr = (_lib.DecGemm * len(flat))(*[_lib.DecGemm(w, ldw, n, k, 0) for (w, ldw, n, k) in flat])
+        self.upd_prog = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.upd_np = (nt + 63) // 64 * 64
+        self.upd_kbuf = torch.zeros(self.upd_np, C, dtype=torch.float16, device=dev)
+        self.upd_vbuf = torch.zeros(C, self.upd_np, dtype=torch.float16, device=dev)
+        self.upd_barrier = torch.zeros(1, dtype=torch.int32, device=dev)
+        P = _lib.UpdParams()
+        P.prog, P.n_prog, P.nt, P.ncls, P.d_ffn, P.np = self.upd_prog.data_ptr(), len(progs[0]), nt, self.ncls, F, self.upd_np
+        P.update_thresh, P.long_memory_lambda = float(self.cfg["update_thresh"]), float(self.cfg["long_memory_lambda"])
+        ma = u["attn"]
+        for name, L in (("conf0_b", u["conf"][0]), ("conf1_b", u["conf"][1]), ("fus0_b", u["fusion"][0]),
+                        ("fus1_b", u["fusion"][1]), ("ph0_b", u["pos_head"][0]), ("ph1_b", u["pos_head"][1]),
+                        ("q_b", ma["q"]), ("k_b", ma["k"]), ("v_b", ma["v"]), ("out_b", ma["out"]),
+                        ("mf1_b", u["mffn"][0]), ("mf2_b", u["mffn"][1]), ("ff1_b", u["fffn"][0]), ("ff2_b", u["fffn"][1])):
+            setattr(P, name, L.b.data_ptr())
+        for pre, (gam, bet) in (("mn", u["memory_norm"]), ("mfn", u["mffn"][2]), ("fn", u["feat_norm"]), ("ffn", u["fffn"][2])):
+            setattr(P, pre + "_g", gam.data_ptr()), setattr(P, pre + "_b", bet.data_ptr())
+        P.dim_t = self.dim_t.data_ptr()
+        P.track_pad = self.trk.track_pad.data_ptr() if self.trk is not None else None
+        st = self.st
+        P.logits, P.boxes, P.output_embed = st["logits"].data_ptr(), st["boxes"].data_ptr(), st["output_embed"].data_ptr()
+        P.ref_pts, P.query_embed = st["ref_pts"].data_ptr(), st["query_embed"].data_ptr()
+        P.long_memory, P.last_output = st["long_memory"].data_ptr(), st["last_output"].data_ptr()
+        P.feedback_ref, P.feedback_embed = self.in_track_ref.data_ptr(), self.in_track_embed.data_ptr()
+        P.kbuf, P.vbuf, P.barrier = self.upd_kbuf.data_ptr(), self.upd_vbuf.data_ptr(), self.upd_barrier.data_ptr()
+        self.upd_params = P
+
     def _decoder_fused(self):
         import ctypes
         if self.dec_cluster:
@@ -639,6 +706,11 @@ class FrameEngine:
     def update_tracks(self):
         """QueryUpdater.update_tracks_embedding on the fp32 track state in self.st (query_updater.py:82-166)."""
         C, nt, dt, st, u = self.C, self.nt, self.dt, self.st, self.upd
+        if self.upd_fused:      # one persistent kernel; it also writes the fed-back track queries (in_track_ref / _embed)
+            import ctypes
+            self._ck(self.lib.memotr_updater_forward_cluster(ctypes.byref(self.upd_params), self._st()), "updater_forward")
+            self.launches += 1
+            return
         self._ck(self.lib.memotr_upd_prepare(_p(st["logits"]), self.ncls, _p(st["boxes"]), _p(st["ref_pts"]),
                                              float(self.cfg["update_thresh"]), _p(self.is_pos), _p(self.u_ref), nt,
                                              self._st()), "upd_prepare")
@@ -698,8 +770,9 @@ class FrameEngine:
         if self.trk is not None:
             self.trk.results(*self.ori_size)
             self.launches += 1
-        self.convert(self.st["ref_pts"], F32, 4, self.in_track_ref, F32, 4, self.nt, 4)
-        self.convert(self.st["query_embed"], F32, self.C, self.in_track_embed, F32, self.C, self.nt, self.C)
+        if not self.upd_fused:      # (the fused updater kernel writes the fed-back track queries itself)
+            self.convert(self.st["ref_pts"], F32, 4, self.in_track_ref, F32, 4, self.nt, 4)
+            self.convert(self.st["query_embed"], F32, self.C, self.in_track_embed, F32, self.C, self.nt, self.C)
         self._mark(4)
 
     def capture(self, fn=None):

@@ -490,11 +490,12 @@ def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monk
     else; the fused kernel keeps q/k/p/v of the self-attention in fp16 instead of fp32), so the two must agree with each
     other as well as each agrees with the reference modules, layer by layer (aux outputs)."""
     monkeypatch.setenv("MEMOTR_DEC_FUSED", "0")
-    g, eng0, res0, _ = _run_engine(tag, "bf16")
-    assert not eng0.dec_fused
+    g, eng0, res0, st0 = _run_engine(tag, "bf16")
+    assert not eng0.dec_fused and not eng0.upd_fused
     monkeypatch.setenv("MEMOTR_DEC_FUSED", fused)
-    _, eng1, res1, _ = _run_engine(tag, "bf16")
+    _, eng1, res1, st1 = _run_engine(tag, "bf16")
     assert eng1.dec_fused and eng1.dec_cluster == (fused == "2") and eng1.launches < eng0.launches
+    assert eng1.upd_fused == (fused == "2")      # the fused query updater rides on the cluster machinery
     deep = tag == "full"
     report = {}
     for k in FRAME_KEYS:
@@ -510,6 +511,14 @@ def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monk
     for k in ("outputs", "aux_queries", "pred_logits", "aux_logits"):
         assert report[k][1] < (2.5e-1 if deep else 3e-2), (k, report[k])
     assert rel_err(res1["init_ref_pts"].cpu().numpy(), g["init_ref_pts"]) < 1e-5
+    # query updater (fused into one cluster kernel when fused == "2"): same inputs (the golden track state), so it is
+    # compared directly -- against the launch-per-op updater and against the reference module's outputs
+    upd = {k: (rel_err(st1[k].cpu().numpy(), st0[k].cpu().numpy()), rel_err(st1[k].cpu().numpy(), g["upd_" + k]),
+               rel_err(st0[k].cpu().numpy(), g["upd_" + k])) for k in UPD_KEYS}
+    print("updater fused vs per-op / vs ref / per-op vs ref:", {k: tuple(f"{x:.1e}" for x in v) for k, v in upd.items()})
+    assert upd["ref_pts"][1] < 1e-5                                   # geometry of the updater is fp32 in both
+    for k in ("query_embed", "long_memory", "last_output"):
+        assert upd[k][1] < (2.5e-1 if deep else 3e-2), (k, upd[k])
 
 
 def test_engine_memory_matches_oracle_encoder_only():
