@@ -555,4 +555,4 @@ def test_engine_cuda_graph_replay_equals_eager_and_chains_frames(mode):
         assert torch.equal(eager.results()[k], graph.results()[k]), k
     for k in UPD_KEYS:
         assert torch.equal(eager.st[k], graph.st[k]), k
-    assert graph.graph_launches > 50
+    assert graph.graph_launches > 20
