@@ -91,6 +91,20 @@ MEMOTR_API int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
                                       const float *attn_weight, void *output, int B, int S, int H, int L, int Lq,
                                       int K, int dtype, void *stream);
 
+/* memotr_msda_forward_ex for an fp16 value map (bf16 output) with strided sampling locations / attention weights */
+MEMOTR_API int memotr_msda_forward_strided(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                           const int64_t *level_start_idx, const float *sampling_loc, int ld_loc,
+                                           const float *attn_weight, int ld_attn, void *output, int B, int S, int H, int L,
+                                           int Lq, int K, void *stream);
+
+/* The offsets / attention-logits projection of MSDeformAttn with memotr_msda_prep (encoder mode) fused into the GEMM
+ * epilogue (ms_deform_attn.py:104-120): out (M, 3*H*L*K) fp32 rows = [sampling locations (H, L*K, 2) | softmax weights
+ * (H, L*K)]; A (M,K), W (3*H*L*K, K) bf16; shapes_hw (2L) / level_start (L) host arrays, valid_ratios (L,2) device.
+ * Needs L*K == 16 and more 128 x 128 output tiles than SMs (the persistent tcgen05 kernel). */
+MEMOTR_API int memotr_linear_msda_prep(const void *A, int lda, const void *W, int ldw, const float *bias, float *out, int ldo,
+                                       int M, int K, int n_heads, int n_levels, int n_points, const int *shapes_hw,
+                                       const int *level_start, const float *valid_ratios, void *stream);
+
 /*
  * Encoder-shaped bf16 fast path of the forward op on a re-laid-out value map.
  * memotr_msda_pairs_layout: value (S, >=H*32 per pixel, bf16) -> pairs (H, S, 2, 32) bf16: entry s = pixel (y,x) holds the

@@ -158,6 +158,12 @@ struct Epilogue {
   const void *add;               // (M,N) activation dtype or null: result += add  (residual)
   const unsigned char *rowzero;  // (M) or null: rows with rowzero[m] != 0 are written as 0 (padding mask)
   int ldmul, ldadd, act;
+  // MSDA "prep" epilogue of the offsets / attention-logits projection (gemm_tc_persist.cu only; prep = 0: off): the raw
+  // row [offsets (H, L*K, 2) | logits (H, L*K)] is turned in place into [sampling locations | softmax weights]
+  // (ms_deform_attn.py:108-120, encoder reference points of deformable_encoder.py:29-40); needs L*K == 16
+  int prep, prep_L, prep_K, prep_nh;
+  int prep_hw[16], prep_lsi[8];   // (H_l, W_l) and first row of every level
+  const float *prep_vr;           // device (L, 2) valid ratios
 };
 
 }  // namespace memotr

@@ -29,7 +29,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 template <typename TC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -47,7 +47,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < NST; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
-    for (int b = 0; b < 2; ++b) mbar_init(acc_full + b, 1), mbar_init(acc_empty + b, 128);
+    for (int b = 0; b < 2; ++b) mbar_init(acc_full + b, 1), mbar_init(acc_empty + b, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -100,29 +100,42 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----
+    // ---- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 (the epilogue is the pace-maker
+    //      of this kernel: with four warps the tile rate was bound by 128 threads x 128 values each) ----
+    const int chalf = (warp - 2) >> 2;
     int i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int m_blk = t / n_nblk, n_blk = t % n_nblk, buf = i & 1;
       // the previous tile's TMA store must have finished READING the staging panels before they are overwritten
       if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(acc_full + buf, (i >> 1) & 1);
       tcgen05_fence_after();
         const int quarter = warp & 3;
         const int r_in = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const int row = m_blk * BM + r_in;
         const bool row_ok = row < M;
+        float prep_bx = 0.f, prep_by = 0.f;         // encoder reference point of this row (pixel centre / valid extent)
+        if (ep.prep) {
+          const int rr = row_ok ? row : 0;
+          int lq = 0;
+          for (int t2 = 1; t2 < ep.prep_L; ++t2)
+            if (rr >= ep.prep_lsi[t2]) lq = t2;
+          const int Wq = ep.prep_hw[2 * lq + 1], Hq = ep.prep_hw[2 * lq], pp = rr - ep.prep_lsi[lq];
+          const int yy = (int)(((float)pp + 0.5f) * __frcp_rn((float)Wq)), xx = pp - yy * Wq;
+          prep_bx = ((float)xx + 0.5f) * __frcp_rn(__ldg(ep.prep_vr + 2 * lq) * (float)Wq);
+          prep_by = ((float)yy + 0.5f) * __frcp_rn(__ldg(ep.prep_vr + 2 * lq + 1) * (float)Hq);
+        }
         const bool zero_row = row_ok && ep.rowzero && ep.rowzero[row];
         const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
         const __nv_bfloat16 *addp = (const __nv_bfloat16 *)ep.add + (long)row * ep.ldadd;
         constexpr int PANEL_COLS = 128 / (int)sizeof(TC);       // columns per 128-byte panel row: 32 (fp32) or 64 (bf16)
         constexpr int N_PANELS = BN / PANEL_COLS;
     #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), r);
-          if (c0 + 32 == BN) {            // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp
+          if (c0 + 32 == (chalf + 1) * (BN / 2)) {   // this warp's half of the accumulator has been read: hand it back
             tcgen05_fence_before();
             mbar_arrive(acc_empty + buf);
           }
@@ -135,6 +148,29 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.bias + col0 + j));
               v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+          if (ep.prep) {
+            if (col0 < ep.prep_nh * 32) {             // 16 (x, y) offsets of one head -> sampling locations
+#pragma unroll
+              for (int i2 = 0; i2 < 16; ++i2) {
+                const int l = i2 / ep.prep_K;
+                v[2 * i2] = prep_bx * __ldg(ep.prep_vr + 2 * l) + v[2 * i2] * __frcp_rn((float)ep.prep_hw[2 * l + 1]);
+                v[2 * i2 + 1] = prep_by * __ldg(ep.prep_vr + 2 * l + 1) + v[2 * i2 + 1] * __frcp_rn((float)ep.prep_hw[2 * l]);
+              }
+            } else {                                  // the logits of two heads -> softmax over each head's 16 points
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float mx = v[16 * hh];
+#pragma unroll
+                for (int i2 = 1; i2 < 16; ++i2) mx = fmaxf(mx, v[16 * hh + i2]);
+                float sum = 0.f;
+#pragma unroll
+                for (int i2 = 0; i2 < 16; ++i2) v[16 * hh + i2] = __expf(v[16 * hh + i2] - mx), sum += v[16 * hh + i2];
+                const float rs = __frcp_rn(sum);
+#pragma unroll
+                for (int i2 = 0; i2 < 16; ++i2) v[16 * hh + i2] *= rs;
+              }
             }
           }
           if (ep.act == ACT_RELU) {
@@ -187,7 +223,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) {
 #pragma unroll 1
         for (int p = 0; p < N_PANELS; ++p)
@@ -222,7 +258,7 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
     attr_set = true;
   }
   const int tiles = (N / BN) * ceil_div(M, BM);
-  MEMOTR_LAUNCH((kern), tiles < n_sm ? tiles : n_sm, 192, TOTAL, st, tmA, tmW, tmC, M, N, K, ep);
+  MEMOTR_LAUNCH((kern), tiles < n_sm ? tiles : n_sm, 320, TOTAL, st, tmA, tmW, tmC, M, N, K, ep);
   return check_launch("gemm_tc_persist");
 }
 
@@ -251,3 +287,25 @@ int linear_tc_persist_bf16(const void *A, int lda, const void *W, int ldw, void 
 }
 
 }  // namespace memotr
+
+using namespace memotr;
+
+extern "C" int memotr_linear_msda_prep(const void *A, int lda, const void *W, int ldw, const float *bias, float *out, int ldo,
+                                       int M, int K, int n_heads, int n_levels, int n_points, const int *shapes_hw,
+                                       const int *level_start, const float *valid_ratios, void *stream) {
+  MEMOTR_REQUIRE(A && W && out && shapes_hw && level_start && valid_ratios && M > 0, "linear_msda_prep: bad arguments");
+  MEMOTR_REQUIRE(n_levels >= 1 && n_levels <= 8 && n_levels * n_points == 16 && n_heads % 2 == 0,
+                 "linear_msda_prep: needs levels x points == 16 and an even head count");
+  const int N = n_heads * 48;
+  int n_sm = 0;
+  MEMOTR_REQUIRE(K % tc::BK == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0 && aligned16(A) && aligned16(W) && aligned16(out) &&
+                     (!bias || aligned16(bias)) && tc::encode_fn() != nullptr,
+                 "linear_msda_prep: misaligned buffer");
+  MEMOTR_REQUIRE(linear_tc_persist_wanted(M, N, &n_sm),
+                 "linear_msda_prep: needs N %% 128 == 0 and more 128 x 128 tiles than SMs (M = %d, N = %d)", M, N);
+  Epilogue ep{bias, nullptr, nullptr, nullptr, 0, 0, ACT_NONE};
+  ep.prep = 1, ep.prep_L = n_levels, ep.prep_K = n_points, ep.prep_nh = n_heads, ep.prep_vr = valid_ratios;
+  for (int l = 0; l < n_levels; ++l)
+    ep.prep_hw[2 * l] = shapes_hw[2 * l], ep.prep_hw[2 * l + 1] = shapes_hw[2 * l + 1], ep.prep_lsi[l] = level_start[l];
+  return linear_tc_persist_bf16(A, lda, W, ldw, out, ldo, MEMOTR_F32, M, N, K, ep, n_sm, (cudaStream_t)stream);
+}

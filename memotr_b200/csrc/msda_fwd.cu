@@ -540,7 +540,8 @@ static int launch_v2(const void *value, const int64_t *shapes, const int64_t *ls
 
 namespace memotr {
 static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
-                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st);
+                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, int ld_loc = 0,
+                      int ld_attn = 0);
 }
 using namespace memotr;
 
@@ -586,6 +587,25 @@ extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
     return launch_vec<__nv_bfloat16, float>(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output,
                                             B, S, H, L, Lq, K, value_pixel_stride, st);
   return fail(MEMOTR_EINVAL, "msda_forward_ex: dtype must be f32 or bf16");
+}
+
+// fp16-value-map gather with strided sampling locations / attention weights (both fp32): the rows written by
+// memotr_linear_msda_prep hold [locations (H, L*K, 2) | weights (H, L*K)], ld_loc = ld_attn = 3*H*L*K.
+extern "C" int memotr_msda_forward_strided(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                           const int64_t *level_start_idx, const float *sampling_loc, int ld_loc,
+                                           const float *attn_weight, int ld_attn, void *output, int B, int S, int H, int L,
+                                           int Lq, int K, void *stream) {
+  MEMOTR_REQUIRE(B >= 0 && S > 0 && H > 0 && L > 0 && Lq >= 0 && K > 0, "msda_forward_strided: bad sizes");
+  MEMOTR_REQUIRE(value_pixel_stride >= H * 32 && value_pixel_stride % 8 == 0, "msda_forward_strided: bad pixel stride");
+  MEMOTR_REQUIRE((long)B * S * value_pixel_stride < (1L << 31), "msda_forward_strided: value spans >= 2^31 elements");
+  if ((long)B * Lq == 0) return MEMOTR_OK;
+  MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && sampling_loc && attn_weight && output,
+                 "msda_forward_strided: null pointer");
+  MEMOTR_REQUIRE(ld_loc >= H * L * K * 2 && ld_loc % 2 == 0 && ld_attn >= H * L * K && aligned16(value) && aligned16(output) &&
+                     ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
+                 "msda_forward_strided: bad stride / alignment");
+  return launch_h16(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L, Lq, K,
+                    value_pixel_stride, (cudaStream_t)stream, ld_loc, ld_attn);
 }
 
 // =====================================================================================================================
@@ -746,7 +766,9 @@ template <int KT, int SPLIT>
 __global__ void __launch_bounds__(256)
 msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
-             int L, int Lq, int Kr, int xs, long n_qh) {
+             int L, int Lq, int Kr, int xs, long n_qh, int ld_loc, int ld_attn) {
+  // ld_loc / ld_attn: floats between consecutive queries of `loc` / `attn` (dense: H*L*K*2 and H*L*K; 3*H*L*K each when
+  // both live in the [locations | weights] rows written by the prep epilogue of the projection GEMM)
   pdl_grid_sync();
   constexpr int D = 32, G = 4 * SPLIT;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -758,7 +780,8 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
   const int m = (int)(qh % H);
   const int b = (int)((qh / H) / Lq);
   const int K = KT ? KT : Kr;
-  const long pbase = qh * L * K;
+  const float2 *locq = reinterpret_cast<const float2 *>(loc + (qh / H) * (long)ld_loc) + m * L * K;
+  const float *attq = attn + (qh / H) * (long)ld_attn + m * L * K;
   const __half *vb = value + (long)b * S * xs + m * D + sub * 8;
   float acc[8];
 #pragma unroll
@@ -773,8 +796,8 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
     for (int j = 0; j < 4; ++j) a[j] = __float2half2_rn(0.f);
 
     auto point = [&](int p, __half2 (&w)[4], int (&o)[4]) {
-      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + pbase + l * K + p);
-      const float aw = __ldg(attn + pbase + l * K + p);
+      const float2 xy = __ldg(locq + l * K + p);
+      const float aw = __ldg(attq + l * K + p);
       const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
       const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
       const float hfl = floorf(h_im), wfl = floorf(w_im);
@@ -842,17 +865,20 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
 }
 
 static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
-                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st) {
+                      void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, int ld_loc,
+                      int ld_attn) {
+  if (!ld_loc) ld_loc = H * L * K * 2;
+  if (!ld_attn) ld_attn = H * L * K;
   const long n_qh = (long)B * Lq * H;
   const bool split = n_qh * 4 < (long)kNumSMs * 256 * 2;   // too few groups to fill the GPU: spread the levels over lanes
   const int grid = (int)((n_qh * (split ? 16 : 4) + 255) / 256);
 #define H16_LAUNCH(KT_)                                                                                               \
   if (split)                                                                                                          \
     MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh);                                                    \
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn);                                   \
   else                                                                                                                \
     MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh)
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn)
   switch (K) {
     case 1: H16_LAUNCH(1); break;
     case 2: H16_LAUNCH(2); break;

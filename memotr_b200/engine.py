@@ -83,6 +83,13 @@ class FrameEngine:
                           and self.nq <= 16 * 132
                           and (cfg["d_ffn"] % 256 == 0 if cfg["d_ffn"] <= 1024 else cfg["d_ffn"] in (1536, 2048))
                           and cfg["n_levels"] * cfg["n_dec_points"] * 24 <= 512)
+        # encoder: sampling locations / softmax weights computed in the epilogue of the offsets+logits GEMM.  Opt-in
+        # (MEMOTR_FUSE_PREP=1): measured 7.5 us per layer SLOWER than the separate prep kernel -- the persistent GEMM is
+        # epilogue-bound, and the extra ~50 instructions per element land exactly there
+        n_sm = torch.cuda.get_device_properties(self.dev).multi_processor_count if self.dev.type == "cuda" else 0
+        self.fuse_prep = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_FUSE_PREP", "0") == "1"
+                          and cfg["n_levels"] * cfg["n_enc_points"] == 16 and self.H % 2 == 0
+                          and 3 * ((self.S + 127) // 128) > n_sm > 0 and self.H * 48 % 128 == 0)
         self._pack(state_dict)
         self._alloc()
         # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
@@ -532,6 +539,28 @@ class FrameEngine:
         if timed:
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
 
+    def _encoder_ol_and_gather(self, a, K):
+        """offsets/logits GEMM with the location + softmax epilogue, then the gather straight from its output rows."""
+        import ctypes
+        L, S, H, N = self.L, self.S, self.H, a["ol"].N
+        if not hasattr(self, "_prep_hw"):
+            self._prep_hw = (ctypes.c_int * (2 * L))(*[v for hw in self.shapes for v in hw])
+            self._prep_lsi = (ctypes.c_int * L)(*self.lsi_host)
+        self._ck(self.lib.memotr_linear_msda_prep(_p(self.q_tok), self.C, _p(a["ol"].w), a["ol"].K, _p(a["ol"].b), _p(self.ol),
+                                                  N, S, self.C, H, L, K, self._prep_hw, self._prep_lsi, _p(self.vr),
+                                                  self._st()), "linear_msda_prep")
+        timed = self.timer is not None
+        if timed:
+            slot = self._timer_slot % self.n_enc
+            self._timer_slot += 1
+            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
+        attw = self.ol.view(-1)[H * L * K * 2:]                    # the weights start after the locations in every row
+        self._ck(self.lib.memotr_msda_forward_strided(_p(self.value), self.C, _p(self.shapes_t), _p(self.lsi_t), _p(self.ol),
+                                                      N, _p(attw), N, _p(self.att), 1, S, H, L, S, K, self._st()),
+                 "msda_forward_strided")
+        if timed:
+            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
+
     def mha(self, q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, kpm=None):
         """q/k/v are the fp32 projections (kept in fp32 in both modes: rounding them to bf16 perturbs the attention
         logits by ~1e-2); the output is an activation (GEMM operand) in the engine dtype."""
@@ -606,8 +635,11 @@ class FrameEngine:
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
             self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
-            self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
-            self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
+            if self.fuse_prep:
+                self._encoder_ol_and_gather(a, Ke)
+            else:
+                self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
+                self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
             self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
             self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
             self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)

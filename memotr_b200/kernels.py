@@ -109,6 +109,36 @@ def msda_forward_ex(value, spatial_shapes, level_start_index, loc, attn, n_heads
     return out
 
 
+def linear_msda_prep(x, w, b, shapes, level_start, valid_ratios, n_heads, n_levels, n_points):
+    """Offsets / logits projection with the location + softmax epilogue (encoder mode): x (M,K), w (3*H*L*K, K) bf16 ->
+    (M, 3*H*L*K) fp32 rows [sampling locations (H, L*K, 2) | attention weights (H, L*K)].  shapes / level_start: python ints."""
+    import ctypes
+    M, K = x.shape
+    N = n_heads * n_levels * n_points * 3
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    hw = (ctypes.c_int * (2 * n_levels))(*[int(v) for s_ in shapes for v in s_])
+    lsi = (ctypes.c_int * n_levels)(*[int(v) for v in level_start])
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_linear_msda_prep(_lib.ptr(x), _ld(x), _lib.ptr(w), _ld(w), _lib.ptr(b), _lib.ptr(out), N, M, K,
+                                                n_heads, n_levels, n_points, hw, lsi, _lib.ptr(valid_ratios),
+                                                _lib.stream_ptr())
+    _lib.check(rc, "memotr_linear_msda_prep")
+    return out
+
+
+def msda_forward_strided(value, spatial_shapes, level_start_index, rows, n_heads, n_levels, n_points):
+    """Gather from an fp16 value map with locations / weights taken from the (Lq, 3*H*L*K) rows of linear_msda_prep."""
+    S, Lq, N = value.shape[0], rows.shape[0], rows.shape[1]
+    out = torch.empty((Lq, n_heads * 32), dtype=torch.bfloat16, device=value.device)
+    attw = rows.view(-1)[n_heads * n_levels * n_points * 2:]
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().memotr_msda_forward_strided(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
+                                                    _lib.ptr(level_start_index), _lib.ptr(rows), N, _lib.ptr(attw), N,
+                                                    _lib.ptr(out), 1, S, n_heads, n_levels, Lq, n_points, _lib.stream_ptr())
+    _lib.check(rc, "memotr_msda_forward_strided")
+    return out
+
+
 def sine_embed(pts, dim_t, scale4=None, apply_sigmoid=False, out_dtype=torch.float32):
     N = pts.shape[0]
     out = torch.empty((N, 512), dtype=out_dtype, device=pts.device)

@@ -351,6 +351,31 @@ def test_sine_embed_and_box_refine():
     assert torch.equal(nxt[:30].cpu(), new[:30].cpu()) and torch.equal(nxt[30:].cpu(), ref[30:])
 
 
+def test_linear_with_msda_prep_epilogue_and_strided_gather():
+    """memotr_linear_msda_prep (persistent tcgen05 GEMM whose epilogue turns the raw offsets / logits into sampling locations
+    and softmax weights) == linear followed by memotr_msda_prep; the strided gather on its rows == the dense gather."""
+    g = _g(77)
+    shapes = [(100, 168), (50, 84), (25, 42), (13, 21)]
+    lsi = [0, 16800, 21000, 22050]
+    S, H, L, Kp = 22323, 8, 4, 4
+    x = torch.randn(S, 256, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(384, 256, generator=g) / 16).bfloat16().to(DEV)
+    b = torch.randn(384, generator=g).to(DEV)
+    vr = (0.8 + 0.2 * torch.rand(L, 2, generator=g)).to(DEV)
+    shapes_t, lsi_t = torch.tensor(shapes, device=DEV), torch.tensor(lsi, device=DEV)
+    raw = K().linear(x, w, b, out_dtype=torch.float32, path="tc")
+    loc, attn = K().msda_prep(raw, shapes_t, lsi_t, vr, H, L, Kp)
+    rows = K().linear_msda_prep(x, w, b, shapes, lsi, vr, H, L, Kp)
+    assert rel_err(rows[:, :256].cpu().numpy(), loc.reshape(S, 256).cpu().numpy()) < 2e-6
+    assert rel_err(rows[:, 256:].cpu().numpy(), attn.reshape(S, 128).cpu().numpy()) < 2e-6
+    value = torch.randn(S, 256, generator=g).half().to(DEV)
+    dense = K().msda_forward_ex(value, shapes_t, lsi_t, loc, attn, H)
+    strided = K().msda_forward_strided(value, shapes_t, lsi_t, rows, H, L, Kp)
+    assert rel_err(strided.float().cpu().numpy(), dense.float().cpu().numpy()) < 1e-2     # bf16 outputs of ~equal inputs
+    strided2 = K().msda_forward_strided(value, shapes_t, lsi_t, torch.cat((loc.reshape(S, 256), attn.reshape(S, 128)), 1).contiguous(), H, L, Kp)
+    assert torch.equal(strided2, dense)                                                       # same inputs: bit-equal
+
+
 @pytest.mark.parametrize("h,w,vh,vw", [(100, 168, 100, 168), (100, 168, 88, 167), (50, 84, 44, 84), (13, 21, 12, 20), (1, 1, 1, 1)])
 def test_pos_embed_sine_matches_oracle_and_reference_golden(h, w, vh, vw):
     m = torch.ones(1, h, w, dtype=torch.bool)
