@@ -194,6 +194,15 @@ MEMOTR_API int memotr_tokens_from_nchw_pe(const float *src, const unsigned char 
                                           void *pos_tok, void *q_tok, float *src_tok32, int C, int row0, int ld, int dtype,
                                           void *stream);
 
+/* The two steps of memotr_tokens_from_nchw_pe separately: the normalised cumulative counts of ALL levels in one launch
+ * (mask: the levels' masks concatenated, level l at level_start[l]; emb + 2 * level_start[l] receives its (2, H_l W_l) planes;
+ * shapes_hw / level_start are host arrays), then one token kernel per level reading its planes. */
+MEMOTR_API int memotr_pos_cumsum_levels(const unsigned char *mask, const int *shapes_hw, const int *level_start, int n_levels,
+                                        float scale, float *emb, void *stream);
+MEMOTR_API int memotr_tokens_from_nchw_emb(const float *src, const float *emb, const float *dim_i, const float *level_embed,
+                                           void *src_tok, void *pos_tok, void *q_tok, float *src_tok32, int C, int HW,
+                                           int row0, int ld, int dtype, void *stream);
+
 /* valid ratio (w,h) of one level's (H,W) uint8 padding mask -- models/deformable_transformer.py:175-190 */
 MEMOTR_API int memotr_valid_ratio(const unsigned char *mask, int H, int W, float *out2, void *stream);
 

@@ -295,6 +295,33 @@ pos_cumsum_kernel(const unsigned char *__restrict__ mask, int Hh, int Ww, float 
     }
   }
 }
+struct PosLevels {
+  int n, hw[16], off[8];   // (H, W) and first pixel of every level in the concatenated mask / scratch
+};
+// all levels in one launch (block = level): emb + 2 * off[l] is level l's (2, H_l * W_l) plane pair
+__global__ void __launch_bounds__(1024)
+pos_cumsum_levels_kernel(const unsigned char *__restrict__ mask, PosLevels lv, float scale, float *__restrict__ emb) {
+  pdl_grid_sync();
+  extern __shared__ unsigned char sm_mask[];
+  const int l = blockIdx.x, Hh = lv.hw[2 * l], Ww = lv.hw[2 * l + 1], HW = Hh * Ww;
+  const unsigned char *m = mask + lv.off[l];
+  float *e = emb + 2L * lv.off[l];
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) sm_mask[i] = m[i];
+  __syncthreads();
+  for (int t = threadIdx.x; t < Ww + Hh; t += blockDim.x) {
+    const bool col = t < Ww;
+    const int n = col ? Hh : Ww, base = col ? t : (t - Ww) * Ww, step = col ? Ww : 1;
+    float cnt = 0.f;
+    for (int i = 0; i < n; ++i) cnt += sm_mask[base + i * step] ? 0.f : 1.f;
+    const float den = cnt + 1e-6f;
+    float run = 0.f;
+    float *o = e + (col ? 0 : HW);
+    for (int i = 0; i < n; ++i) {
+      run += sm_mask[base + i * step] ? 0.f : 1.f;
+      o[base + i * step] = __fmul_rn(__fdiv_rn(run - 0.5f, den), scale);
+    }
+  }
+}
 // Step 2: out[c, p] = sin / cos (emb / dim_i): channels [0, npf) from y, [npf, 2 npf) from x; even feature sin, odd cos.
 // dim_i[2k] == dim_i[2k+1], so one thread produces the (sin, cos) pair of features 2k, 2k+1 of one pixel;
 // blockIdx.y = (y|x half) * npf/2 + k, so no integer division is needed.
@@ -524,6 +551,40 @@ extern "C" int memotr_tokens_from_nchw_pe(const float *src, const unsigned char 
                   (__nv_bfloat16 *)src_tok, (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, HW, row0, ld,
                   (const float *)scratch, dim_i);
   return check_launch("tokens_from_nchw_pe");
+}
+
+extern "C" int memotr_pos_cumsum_levels(const unsigned char *mask, const int *shapes_hw, const int *level_start, int n_levels,
+                                        float scale, float *emb, void *stream) {
+  MEMOTR_REQUIRE(mask && shapes_hw && level_start && emb && n_levels >= 1 && n_levels <= 8, "pos_cumsum_levels: bad arguments");
+  PosLevels lv;
+  lv.n = n_levels;
+  int mx = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    lv.hw[2 * l] = shapes_hw[2 * l], lv.hw[2 * l + 1] = shapes_hw[2 * l + 1], lv.off[l] = level_start[l];
+    MEMOTR_REQUIRE(shapes_hw[2 * l] > 0 && shapes_hw[2 * l + 1] > 0, "pos_cumsum_levels: bad level shape");
+    mx = shapes_hw[2 * l] * shapes_hw[2 * l + 1] > mx ? shapes_hw[2 * l] * shapes_hw[2 * l + 1] : mx;
+  }
+  MEMOTR_REQUIRE(mx <= 48 * 1024, "pos_cumsum_levels: level larger than 48K pixels");
+  MEMOTR_LAUNCH((pos_cumsum_levels_kernel), n_levels, 1024, (size_t)mx, (cudaStream_t)stream, mask, lv, scale, emb);
+  return check_launch("pos_cumsum_levels");
+}
+
+extern "C" int memotr_tokens_from_nchw_emb(const float *src, const float *emb, const float *dim_i, const float *level_embed,
+                                           void *src_tok, void *pos_tok, void *q_tok, float *src_tok32, int C, int HW,
+                                           int row0, int ld, int dtype, void *stream) {
+  MEMOTR_REQUIRE(src && emb && dim_i && level_embed && src_tok && pos_tok && q_tok && C > 0 && C % 4 == 0 && HW > 0 && ld >= C,
+                 "tokens_from_nchw_emb: bad arguments");
+  MEMOTR_DTYPE_AB(dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32));
+  if (dtype == MEMOTR_F32)
+    MEMOTR_LAUNCH((tokens_kernel<float>), grid, 256, 0, st, src, (const float *)nullptr, level_embed, (float *)src_tok,
+                  (float *)pos_tok, (float *)q_tok, src_tok32, C, HW, row0, ld, emb, dim_i);
+  else
+    MEMOTR_LAUNCH((tokens_kernel<__nv_bfloat16>), grid, 256, 0, st, src, (const float *)nullptr, level_embed,
+                  (__nv_bfloat16 *)src_tok, (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, HW, row0, ld, emb,
+                  dim_i);
+  return check_launch("tokens_from_nchw_emb");
 }
 
 extern "C" int memotr_valid_ratio(const unsigned char *mask, int Hh, int Ww, float *out2, void *stream) {

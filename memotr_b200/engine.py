@@ -83,11 +83,11 @@ class FrameEngine:
                           and self.nq <= 16 * 132
                           and (cfg["d_ffn"] % 256 == 0 if cfg["d_ffn"] <= 1024 else cfg["d_ffn"] in (1536, 2048))
                           and cfg["n_levels"] * cfg["n_dec_points"] * 24 <= 512)
-        # encoder: sampling locations / softmax weights computed in the epilogue of the offsets+logits GEMM.  Opt-in
-        # (MEMOTR_FUSE_PREP=1): measured 7.5 us per layer SLOWER than the separate prep kernel -- the persistent GEMM is
-        # epilogue-bound, and the extra ~50 instructions per element land exactly there
+        # encoder: sampling locations / softmax weights computed in the epilogue of the offsets+logits GEMM (A/B switch
+        # MEMOTR_FUSE_PREP=0).  With four epilogue warps in the persistent GEMM this was 7.5 us per layer SLOWER than the
+        # separate prep kernel (the kernel is epilogue-bound); with eight it is 9.5 us per layer faster
         n_sm = torch.cuda.get_device_properties(self.dev).multi_processor_count if self.dev.type == "cuda" else 0
-        self.fuse_prep = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_FUSE_PREP", "0") == "1"
+        self.fuse_prep = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_FUSE_PREP", "1") != "0"
                           and cfg["n_levels"] * cfg["n_enc_points"] == 16 and self.H % 2 == 0
                           and 3 * ((self.S + 127) // 128) > n_sm > 0 and self.H * 48 % 128 == 0)
         self._pack(state_dict)
@@ -213,7 +213,7 @@ class FrameEngine:
         self.in_flat = torch.zeros(self.in_layout["bytes"], dtype=torch.uint8, device=dev)
         self.in_src, self.in_pos, self.in_mask = self.input_views(self.in_flat, self.in_layout, self.shapes, C)
         if self.pos_cfg is not None:
-            self.pos_scratch = f(2 * max(h * w for h, w in self.shapes))
+            self.pos_scratch = f(2 * self.S)
             i = torch.arange(C // 2, dtype=torch.float32)                              # models/position_embedding.py:33-34
             self.pos_dim_i = (float(self.pos_cfg.get("temperature", 20)) **
                               (2 * torch.div(i, 2, rounding_mode="trunc") / (C // 2))).to(dev)
@@ -615,13 +615,19 @@ class FrameEngine:
         self._mark(0)
         # -- level flattening, level embedding, valid ratios (deformable_transformer.py:196-220)
         for l, (h, w) in enumerate(self.shapes):
-            if self.pos_cfg is not None:      # position map of this level evaluated inside the token kernel (2 launches)
-                self._ck(self.lib.memotr_tokens_from_nchw_pe(
-                    _p(self.in_src[l]), _p(self.in_mask[l]), h, w, _p(self.pos_dim_i),
-                    float(self.pos_cfg.get("scale", 2 * math.pi)), _p(self.pos_scratch), _p(self.level_embed[l]),
-                    _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok), _p(None if self.mode == "fp32" else self.src32), C,
-                    self.lsi_host[l], C, dt, st()), "tokens_pe")
-                self.launches += 1
+            if self.pos_cfg is not None:      # position map of this level evaluated inside the token kernel
+                if l == 0:                    # normalised cumulative counts of all levels: one launch
+                    import ctypes
+                    if not hasattr(self, "_pos_hw"):
+                        self._pos_hw = (ctypes.c_int * (2 * self.L))(*[v for hw in self.shapes for v in hw])
+                        self._pos_lsi = (ctypes.c_int * self.L)(*self.lsi_host)
+                    self._ck(self.lib.memotr_pos_cumsum_levels(_p(self.in_mask[0]), self._pos_hw, self._pos_lsi, self.L,
+                                                               float(self.pos_cfg.get("scale", 2 * math.pi)),
+                                                               _p(self.pos_scratch), st()), "pos_cumsum_levels")
+                self._ck(self.lib.memotr_tokens_from_nchw_emb(
+                    _p(self.in_src[l]), _p(self.pos_scratch[2 * self.lsi_host[l]:]), _p(self.pos_dim_i),
+                    _p(self.level_embed[l]), _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
+                    _p(None if self.mode == "fp32" else self.src32), C, h * w, self.lsi_host[l], C, dt, st()), "tokens_emb")
             else:
                 self._ck(self.lib.memotr_tokens_from_nchw(_p(self.in_src[l]), _p(self.in_pos[l]), _p(self.level_embed[l]),
                                                           _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
