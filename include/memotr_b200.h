@@ -198,7 +198,8 @@ MEMOTR_API int memotr_tokens_from_nchw_pe(const float *src, const unsigned char 
  * (mask: the levels' masks concatenated, level l at level_start[l]; emb + 2 * level_start[l] receives its (2, H_l W_l) planes;
  * shapes_hw / level_start are host arrays), then one token kernel per level reading its planes. */
 MEMOTR_API int memotr_pos_cumsum_levels(const unsigned char *mask, const int *shapes_hw, const int *level_start, int n_levels,
-                                        float scale, float *emb, void *stream);
+                                        float scale, float *emb, float *valid_ratios /* NULL or (L,2): as memotr_valid_ratio */,
+                                        void *stream);
 MEMOTR_API int memotr_tokens_from_nchw_emb(const float *src, const float *emb, const float *dim_i, const float *level_embed,
                                            void *src_tok, void *pos_tok, void *q_tok, float *src_tok32, int C, int HW,
                                            int row0, int ld, int dtype, void *stream);

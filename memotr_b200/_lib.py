@@ -89,7 +89,7 @@ _SIGNATURES = {
     "memotr_mha": ([_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 6 + [_vp], _i),
     "memotr_tokens_from_nchw": ([_vp] * 7 + [_i] * 5 + [_vp], _i),
     "memotr_tokens_from_nchw_pe": ([_vp, _vp, _i, _i, _vp, _f, _vp] + [_vp] * 5 + [_i] * 4 + [_vp], _i),
-    "memotr_pos_cumsum_levels": ([_vp, _vp, _vp, _i, _f, _vp, _vp], _i),
+    "memotr_pos_cumsum_levels": ([_vp, _vp, _vp, _i, _f, _vp, _vp, _vp], _i),
     "memotr_tokens_from_nchw_emb": ([_vp] * 8 + [_i] * 5 + [_vp], _i),
     "memotr_valid_ratio": ([_vp, _i, _i, _vp, _vp], _i),
     "memotr_pos_embed_sine": ([_vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp], _i),

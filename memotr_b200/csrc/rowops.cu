@@ -300,7 +300,8 @@ struct PosLevels {
 };
 // all levels in one launch (block = level): emb + 2 * off[l] is level l's (2, H_l * W_l) plane pair
 __global__ void __launch_bounds__(1024)
-pos_cumsum_levels_kernel(const unsigned char *__restrict__ mask, PosLevels lv, float scale, float *__restrict__ emb) {
+pos_cumsum_levels_kernel(const unsigned char *__restrict__ mask, PosLevels lv, float scale, float *__restrict__ emb,
+                         float *__restrict__ valid_ratios) {
   pdl_grid_sync();
   extern __shared__ unsigned char sm_mask[];
   const int l = blockIdx.x, Hh = lv.hw[2 * l], Ww = lv.hw[2 * l + 1], HW = Hh * Ww;
@@ -313,6 +314,9 @@ pos_cumsum_levels_kernel(const unsigned char *__restrict__ mask, PosLevels lv, f
     const int n = col ? Hh : Ww, base = col ? t : (t - Ww) * Ww, step = col ? Ww : 1;
     float cnt = 0.f;
     for (int i = 0; i < n; ++i) cnt += sm_mask[base + i * step] ? 0.f : 1.f;
+    // valid ratios of the level (deformable_transformer.py:175-190): (#valid in row 0) / W, (#valid in column 0) / H
+    if (valid_ratios && t == Ww) valid_ratios[2 * l] = cnt / (float)Ww;
+    if (valid_ratios && t == 0) valid_ratios[2 * l + 1] = cnt / (float)Hh;
     const float den = cnt + 1e-6f;
     float run = 0.f;
     float *o = e + (col ? 0 : HW);
@@ -554,7 +558,7 @@ extern "C" int memotr_tokens_from_nchw_pe(const float *src, const unsigned char 
 }
 
 extern "C" int memotr_pos_cumsum_levels(const unsigned char *mask, const int *shapes_hw, const int *level_start, int n_levels,
-                                        float scale, float *emb, void *stream) {
+                                        float scale, float *emb, float *valid_ratios, void *stream) {
   MEMOTR_REQUIRE(mask && shapes_hw && level_start && emb && n_levels >= 1 && n_levels <= 8, "pos_cumsum_levels: bad arguments");
   PosLevels lv;
   lv.n = n_levels;
@@ -565,7 +569,7 @@ extern "C" int memotr_pos_cumsum_levels(const unsigned char *mask, const int *sh
     mx = shapes_hw[2 * l] * shapes_hw[2 * l + 1] > mx ? shapes_hw[2 * l] * shapes_hw[2 * l + 1] : mx;
   }
   MEMOTR_REQUIRE(mx <= 48 * 1024, "pos_cumsum_levels: level larger than 48K pixels");
-  MEMOTR_LAUNCH((pos_cumsum_levels_kernel), n_levels, 1024, (size_t)mx, (cudaStream_t)stream, mask, lv, scale, emb);
+  MEMOTR_LAUNCH((pos_cumsum_levels_kernel), n_levels, 1024, (size_t)mx, (cudaStream_t)stream, mask, lv, scale, emb, valid_ratios);
   return check_launch("pos_cumsum_levels");
 }
 

@@ -220,7 +220,8 @@ class FrameEngine:
         self.in_track_ref = torch.zeros(nt, 4, dtype=torch.float32, device=dev)
         self.in_track_embed = torch.zeros(nt, C, dtype=torch.float32, device=dev)
         # encoder
-        self.mask_flat = torch.zeros(S, dtype=torch.uint8, device=dev)
+        m0 = self.in_layout["mask"][0]
+        self.mask_flat = self.in_flat[m0:m0 + S]        # the levels' masks are consecutive in the input buffer: a view
         self.vr = f(self.L, 2)
         self.src_tok, self.pos_tok, self.q_tok = e(S, C), e(S, C), e(S, C)
         self.value = e(S, C, dtype=self.tv)
@@ -623,7 +624,8 @@ class FrameEngine:
                         self._pos_lsi = (ctypes.c_int * self.L)(*self.lsi_host)
                     self._ck(self.lib.memotr_pos_cumsum_levels(_p(self.in_mask[0]), self._pos_hw, self._pos_lsi, self.L,
                                                                float(self.pos_cfg.get("scale", 2 * math.pi)),
-                                                               _p(self.pos_scratch), st()), "pos_cumsum_levels")
+                                                               _p(self.pos_scratch), _p(self.vr), st()),
+                             "pos_cumsum_levels")                      # (also writes the valid ratios of all levels)
                 self._ck(self.lib.memotr_tokens_from_nchw_emb(
                     _p(self.in_src[l]), _p(self.pos_scratch[2 * self.lsi_host[l]:]), _p(self.pos_dim_i),
                     _p(self.level_embed[l]), _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
@@ -633,8 +635,8 @@ class FrameEngine:
                                                           _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),
                                                           _p(None if self.mode == "fp32" else self.src32), C, h * w,
                                                           self.lsi_host[l], C, dt, st()), "tokens")
-            self._ck(self.lib.memotr_valid_ratio(_p(self.in_mask[l]), h, w, _p(self.vr[l]), st()), "valid_ratio")
-            self.convert_u8(self.in_mask[l], self.mask_flat[self.lsi_host[l]:], h * w)
+            if self.pos_cfg is None:
+                self._ck(self.lib.memotr_valid_ratio(_p(self.in_mask[l]), h, w, _p(self.vr[l]), st()), "valid_ratio")
         # -- encoder (deformable_encoder.py:109-131)
         self._mark(1)
         Ke = self.cfg["n_enc_points"]
