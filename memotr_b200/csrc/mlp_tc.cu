@@ -76,7 +76,8 @@ template <typename TC, int CS>
 __global__ void __launch_bounds__(320, 1)
 mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
-               const float *__restrict__ b1, int M, int Hd, Epilogue ep) {
+               const float *__restrict__ b1, int M, int Hd, Epilogue ep, int tile0) {
+  // tile0: first row tile of this launch (the tail tiles of a GEMM are launched separately with a hidden-dimension split)
   // gridDim.y > 1: split-K over the hidden dimension -- CTA (x, y) handles hidden chunks [y*NC, (y+1)*NC) of row tile x
   // and ADDS its partial product into the (zero-initialised, fp32) output with a TMA reduce-store; bias from split 0.
   using namespace mlp;
@@ -88,7 +89,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc2_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x;
+  const int m_blk = blockIdx.x + tile0;
   const int NC = Hd / HC / (int)gridDim.y;          // hidden chunks of this CTA
   const int c_off = (int)blockIdx.y * NC;           // first hidden chunk of this CTA
   const bool split = gridDim.y > 1;
@@ -349,7 +350,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 template <typename TC, int CS>
 static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
-                       int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1) {
+                       int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1, int tile0 = 0, int ntiles = -1) {
   using namespace mlp;
   CUtensorMap tmX, tmW1, tmW2, tmC;
   constexpr int W1_BOX = CS == 1 ? HC : (256 / CS < 128 ? 256 / CS : 128), W2_BOX = 256 / CS;
@@ -364,17 +365,19 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
     if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = ceil_div(M, BM);
+  const int tiles = ntiles < 0 ? ceil_div(M, BM) - tile0 : ntiles;
   if constexpr (CS == 1) {
     if (nsplit > 1) {   // partial products are reduce-added: start from zero (a memset node when captured into a graph)
-      const cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(TC), 0, (size_t)N2 * sizeof(TC), M, st);
+      const int r0 = tile0 * BM, nr = (M - r0 < tiles * BM) ? M - r0 : tiles * BM;
+      const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<TC *>(C) + (size_t)r0 * ldc, (size_t)ldc * sizeof(TC), 0,
+                                              (size_t)N2 * sizeof(TC), nr, st);
       if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
     }
-    MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep);
+    MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep, tile0);
   } else {
     // CTAs beyond the last tile (grid rounded up to a whole cluster) see zero-filled X and have their stores clipped
     launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(320), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
-                          M, Hd, ep);
+                          M, Hd, ep, 0);
   }
   return check_launch("mlp2_tc");
 }
@@ -423,6 +426,20 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
     if (nsplit <= 0) nsplit = 1;   // measured (tools/time_mlp2.py): 74.8 / 72.7 / 78.8 / 110 us for 1 / 2 / 4 / 8 splits at the
                                    // encoder shape -- the ~6.6 us fixed cost per CTA eats the better balance; opt-in only
     if (nsplit > 1 && chunks % nsplit == 0) return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, nsplit);
+    // Tail split (MEMOTR_MLP_TAIL=0 switches it off): with one CTA per SM, 175 row tiles on 148 SMs are two rounds of
+    // 33 us, the second 18 % full.  The first n_sm tiles run as usual; the remaining ones are launched with the hidden
+    // dimension split over as many CTAs as fit on the GPU (27 tiles x 4), so the second round costs 6.6 + 4 x 1.65 us.
+    const char *tl = getenv("MEMOTR_MLP_TAIL");
+    const int tail = tiles - n_sm;
+    if (!(tl && tl[0] == '0') && !sp && tail > 0 && tail * 2 <= n_sm) {
+      int ns = 2;
+      while (ns * 2 <= 8 && tail * ns * 2 <= n_sm && chunks % (ns * 2) == 0) ns *= 2;
+      if (chunks % ns == 0) {
+        const int rc = tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, n_sm);
+        if (rc != MEMOTR_OK) return rc;
+        return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail);
+      }
+    }
   }
   if (c_dtype == MEMOTR_F32) {
     if (cs == 4) MLP2_GO(float, 4);

@@ -159,7 +159,7 @@ def test_fused_mlp2_tensor_core(M, Hd, out_dtype, cluster, monkeypatch):
 
 
 @pytest.mark.parametrize("split", [0, 2, 4, 8, 16])
-@pytest.mark.parametrize("M,Hd", [(22323, 2048), (300, 2048), (700, 1024)])
+@pytest.mark.parametrize("M,Hd", [(22323, 2048), (300, 2048), (700, 1024), (128 * 148 + 1, 512), (128 * 221, 256)])
 def test_fused_mlp2_split_hidden(M, Hd, split, monkeypatch):
     """Split-K over the hidden dimension (CTA (tile, split) reduce-adds its partial product into the zeroed fp32 output
     with a TMA reduce-store); split = 0 is the automatic choice.  Also into a strided view whose neighbours must stay."""
