@@ -305,6 +305,13 @@ def main():
     if eng.trk is not None:
         eng.trk.check_overflow()
         assert tracks_live == N_TRACKS, f"the bench workload drifted: {tracks_live} live tracks instead of {N_TRACKS}"
+    # CPU cost of launching one step with an empty queue (the in-loop figure above includes back-pressure from the GPU)
+    torch.cuda.synchronize(dev)
+    h0 = time.perf_counter()
+    for _ in range(4):
+        eng.replay()
+    host_launch_ms = (time.perf_counter() - h0) * 1e3 / 4
+    torch.cuda.synchronize(dev)
     msda_us = eng.msda_times_us()                       # the 6 encoder MSDA launches of the last timed step
     sections = eng.section_times_us()
 
@@ -374,6 +381,7 @@ def main():
         "gpu_launches": eng.graph_launches * K,
         "sections_us": {k: round(v, 1) for k, v in sections.items()},
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
+        "host_graph_launch_ms": round(host_launch_ms, 3),
         "roofline": {"kernel": ("msda_fwd_h16 (fp16 value map)" if eng.value_f16 else "msda_fwd_vec") +
                                " -- encoder-shaped launch, Lq = S = 22323", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
