@@ -161,6 +161,13 @@ MEMOTR_API int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
                            const void *mul, int ldmul, void *C, int ldc, int M, int K1, int Hd, int N2, int c_dtype,
                            int act2, void *stream);
 
+/* memotr_mlp2 with a LayerNorm prologue, fp32 output: C = relu(X W1^T + b1) W2^T + b2 with X = LayerNorm(pre + res) (256
+ * columns) computed inside the kernel; out32 (optional) receives X in fp32 -- the pair LayerNorm + FFN of an encoder layer
+ * (models/deformable_encoder.py:92-107) without X ever being written to / read from global memory as a GEMM operand. */
+MEMOTR_API int memotr_mlp2_ln(const float *pre, int ldpre, const float *res, int ldres, const float *gamma, const float *beta,
+                              float eps, float *out32, int ld32, const void *W1, const float *b1, const void *W2,
+                              const float *b2, float *C, int ldc, int M, int Hd, void *stream);
+
 /*
  * y = LayerNorm(x [+ x2]) (C == 256, eps as given, affine fp32); optional ypos = y + pos and fp32 copy y32.
  * models/deformable_encoder.py:124-130, models/deformable_decoder.py:251-252,313-318, models/ffn.py:23-24,

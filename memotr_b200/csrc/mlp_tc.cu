@@ -72,11 +72,21 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
+// Optional LayerNorm prologue: X = LayerNorm(pre + res) computed by the (otherwise idle) epilogue warps straight into the
+// shared-memory A tile, instead of a separate LayerNorm kernel writing X to global memory and a TMA load reading it back
+// (deformable_encoder.py:92-95 followed by :97-107).  out32 receives the fp32 result (the residual of the next LayerNorm).
+struct LnIn {
+  const float *pre, *res, *gamma, *beta;   // pre == nullptr: off (X comes from tmX)
+  float *out32;
+  int ldpre, ldres, ld32;
+  float eps;
+};
+
 template <typename TC, int CS>
 __global__ void __launch_bounds__(320, 1)
 mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
-               const float *__restrict__ b1, int M, int Hd, Epilogue ep, int tile0) {
+               const float *__restrict__ b1, int M, int Hd, Epilogue ep, int tile0, LnIn ln) {
   // tile0: first row tile of this launch (the tail tiles of a GEMM are launched separately with a hidden-dimension split)
   // gridDim.y > 1: split-K over the hidden dimension -- CTA (x, y) handles hidden chunks [y*NC, (y+1)*NC) of row tile x
   // and ADDS its partial product into the (zero-initialised, fp32) output with a TMA reduce-store; bias from split 0.
@@ -101,7 +111,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    mbar_init(x_full, 1);
+    mbar_init(x_full, ln.pre ? 256 : 1);   // LayerNorm prologue: the 8 epilogue warps arrive instead of the TMA
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, CS);   // released by the MMA warps of all CTAs of the cluster
@@ -133,8 +143,10 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer: X once, then W1(0), [W1(c+1), W2(c)] ... in exactly the order the MMA warp consumes ----
-      mbar_expect_tx(x_full, X_BYTES);
-      for (int p = 0; p < XP; ++p) tma_load_2d(smem + p * PANEL, &tmX, x_full, p * BK, m_blk * BM);
+      if (!ln.pre) {
+        mbar_expect_tx(x_full, X_BYTES);
+        for (int p = 0; p < XP; ++p) tma_load_2d(smem + p * PANEL, &tmX, x_full, p * BK, m_blk * BM);
+      }
       int t = 0;
       // a ring slot is 256 row-units of 128 B; this CTA loads units [crank*UNITS, (crank+1)*UNITS) and multicasts them
       constexpr int UNITS = 256 / CS;
@@ -229,6 +241,61 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int quarter = warp & 3, chalf = (warp - 2) >> 2;
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    if (ln.pre) {
+      // ---- LayerNorm prologue: warp w - 2 normalises rows 16 (w - 2) .. +15 of the tile, four rows in flight; lane = 8
+      //      columns; the bf16 result goes into the 128B-swizzled K-major panels the TMA load would have produced ----
+      const int c0 = lane * 8, wr0 = (warp - 2) * 16;
+      const float4 g0 = ldg_f4(ln.gamma + c0), g1 = ldg_f4(ln.gamma + c0 + 4), be0 = ldg_f4(ln.beta + c0), be1 = ldg_f4(ln.beta + c0 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll 1
+      for (int rb = 0; rb < 16; rb += 4) {
+        float v[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = m_blk * BM + wr0 + rb + j;
+          if (row < M) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(ln.pre + (long)row * ln.ldpre + c0);
+            const float4 a1 = *reinterpret_cast<const float4 *>(ln.pre + (long)row * ln.ldpre + c0 + 4);
+            const float4 r0 = *reinterpret_cast<const float4 *>(ln.res + (long)row * ln.ldres + c0);
+            const float4 r1 = *reinterpret_cast<const float4 *>(ln.res + (long)row * ln.ldres + c0 + 4);
+            v[j][0] = a0.x + r0.x, v[j][1] = a0.y + r0.y, v[j][2] = a0.z + r0.z, v[j][3] = a0.w + r0.w;
+            v[j][4] = a1.x + r1.x, v[j][5] = a1.y + r1.y, v[j][6] = a1.z + r1.z, v[j][7] = a1.w + r1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rt = wr0 + rb + j, row = m_blk * BM + rt;
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum += v[j][i];
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float mean = sum * (1.f / 256.f);
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = v[j][i] - mean;
+            q += d * d;
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          const float rstd = rsqrtf(q * (1.f / 256.f) + ln.eps);
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = row < M ? (v[j][i] - mean) * rstd * g[i] + be[i] : 0.f;
+          *reinterpret_cast<uint4 *>(smem + (lane >> 3) * PANEL + rt * 128 + (((lane & 7) ^ (rt & 7)) << 4)) = f32x8_to_bf16(y);
+          if (row < M && blockIdx.y == 0 && ln.out32) {
+            *reinterpret_cast<float4 *>(ln.out32 + (long)row * ln.ld32 + c0) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4 *>(ln.out32 + (long)row * ln.ld32 + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the UMMA (async proxy)
+      mbar_arrive(x_full);
+    }
     for (int c = 0; c < NC; ++c) {
       const int b = c & 1;
       mbar_wait(acc1_full + b, (c >> 1) & 1);
@@ -350,11 +417,13 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 template <typename TC, int CS>
 static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
-                       int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1, int tile0 = 0, int ntiles = -1) {
+                       int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1, int tile0 = 0, int ntiles = -1,
+                       const LnIn &ln = LnIn{}) {
   using namespace mlp;
   CUtensorMap tmX, tmW1, tmW2, tmC;
   constexpr int W1_BOX = CS == 1 ? HC : (256 / CS < 128 ? 256 / CS : 128), W2_BOX = 256 / CS;
-  if (!make_map(&tmX, X, M, K1, ldx, BM) || !make_map(&tmW1, W1, Hd, K1, K1, W1_BOX) ||
+  // (with the LayerNorm prologue there is no X in global memory; the descriptor is then a placeholder that is never used)
+  if (!make_map(&tmX, X ? X : W1, X ? M : Hd, K1, X ? ldx : K1, BM) || !make_map(&tmW1, W1, Hd, K1, K1, W1_BOX) ||
       !make_map(&tmW2, W2, N2, Hd, Hd, W2_BOX) ||
       !make_map(&tmC, C, M, N2, ldc, BM, sizeof(TC) == 4))
     return fail(MEMOTR_ECUDA, "mlp2(tc): cuTensorMapEncodeTiled failed (M=%d Hd=%d)", M, Hd);
@@ -373,11 +442,11 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
                                               (size_t)N2 * sizeof(TC), nr, st);
       if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
     }
-    MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep, tile0);
+    MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep, tile0, ln);
   } else {
     // CTAs beyond the last tile (grid rounded up to a whole cluster) see zero-filled X and have their stores clipped
     launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(320), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
-                          M, Hd, ep, 0);
+                          M, Hd, ep, 0, LnIn{});
   }
   return check_launch("mlp2_tc");
 }
@@ -386,6 +455,39 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
 }  // namespace memotr
 
 using namespace memotr;
+
+// fp32-output FFN without activation / multiplier: env-forced uniform split, else the tail split, else one launch
+static int mlp2_f32_balanced(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
+                             int Hd, const Epilogue &ep, cudaStream_t st, const tc::LnIn &ln) {
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = ceil_div(M, tc::BM), chunks = Hd / tc::mlp::HC;
+  // Split-K over the hidden dimension (MEMOTR_MLP_SPLIT=2|4|8): CTA (tile, split) handles Hd/nsplit hidden columns and
+  // reduce-adds into the fp32 output.  Measured (tools/time_mlp2.py): 74.8 / 72.7 / 78.8 / 110 us for 1 / 2 / 4 / 8 splits
+  // at the encoder shape -- the ~6.6 us fixed cost per CTA eats the better balance; opt-in only.
+  const char *sp = getenv("MEMOTR_MLP_SPLIT");
+  const int nsplit = sp ? atoi(sp) : 1;
+  if (nsplit > 1 && chunks % nsplit == 0) return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, nsplit, 0, -1, ln);
+  // Tail split (MEMOTR_MLP_TAIL=0 switches it off): with one CTA per SM, 175 row tiles on 148 SMs are two rounds of
+  // 33 us, the second 18 % full.  The first n_sm tiles run as usual; the remaining ones are launched with the hidden
+  // dimension split over as many CTAs as fit on the GPU (27 tiles x 4), so the second round costs 6.6 + 4 x 1.65 us.
+  const char *tl = getenv("MEMOTR_MLP_TAIL");
+  const int tail = tiles - n_sm;
+  if (!(tl && tl[0] == '0') && !sp && tail > 0 && tail * 2 <= n_sm) {
+    int ns = 2;
+    while (ns * 2 <= 8 && tail * ns * 2 <= n_sm && chunks % (ns * 2) == 0) ns *= 2;
+    if (chunks % ns == 0) {
+      const int rc = tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, n_sm, ln);
+      if (rc != MEMOTR_OK) return rc;
+      return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail, ln);
+    }
+  }
+  return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, -1, ln);
+}
 
 extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, const float *b2,
                            const void *mul, int ldmul, void *C, int ldc, int M, int K1, int Hd, int N2, int c_dtype,
@@ -413,34 +515,8 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   // Split-K over the hidden dimension (MEMOTR_MLP_SPLIT=2|4|8): meant for the case where the row tiles alone leave SMs
   // idle (one CTA per SM: 175 tiles on 148 SMs are two rounds, the second 18 % full).  CTA (tile, split) handles
   // Hd/nsplit hidden columns and reduce-adds into the fp32 output.
-  if (c_dtype == MEMOTR_F32 && cs == 1 && act2 == 0 && !mul) {
-    static int n_sm = 0;
-    if (!n_sm) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const char *sp = getenv("MEMOTR_MLP_SPLIT");
-    int nsplit = sp ? atoi(sp) : 0;
-    const int chunks = Hd / tc::mlp::HC;
-    if (nsplit <= 0) nsplit = 1;   // measured (tools/time_mlp2.py): 74.8 / 72.7 / 78.8 / 110 us for 1 / 2 / 4 / 8 splits at the
-                                   // encoder shape -- the ~6.6 us fixed cost per CTA eats the better balance; opt-in only
-    if (nsplit > 1 && chunks % nsplit == 0) return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, nsplit);
-    // Tail split (MEMOTR_MLP_TAIL=0 switches it off): with one CTA per SM, 175 row tiles on 148 SMs are two rounds of
-    // 33 us, the second 18 % full.  The first n_sm tiles run as usual; the remaining ones are launched with the hidden
-    // dimension split over as many CTAs as fit on the GPU (27 tiles x 4), so the second round costs 6.6 + 4 x 1.65 us.
-    const char *tl = getenv("MEMOTR_MLP_TAIL");
-    const int tail = tiles - n_sm;
-    if (!(tl && tl[0] == '0') && !sp && tail > 0 && tail * 2 <= n_sm) {
-      int ns = 2;
-      while (ns * 2 <= 8 && tail * ns * 2 <= n_sm && chunks % (ns * 2) == 0) ns *= 2;
-      if (chunks % ns == 0) {
-        const int rc = tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, n_sm);
-        if (rc != MEMOTR_OK) return rc;
-        return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail);
-      }
-    }
-  }
+  if (c_dtype == MEMOTR_F32 && cs == 1 && act2 == 0 && !mul)
+    return mlp2_f32_balanced(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, tc::LnIn{});
   if (c_dtype == MEMOTR_F32) {
     if (cs == 4) MLP2_GO(float, 4);
     if (cs == 2) MLP2_GO(float, 2);
@@ -450,4 +526,21 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   if (cs == 2) MLP2_GO(__nv_bfloat16, 2);
   MLP2_GO(__nv_bfloat16, 1);
 #undef MLP2_GO
+}
+
+extern "C" int memotr_mlp2_ln(const float *pre, int ldpre, const float *res, int ldres, const float *gamma, const float *beta,
+                              float eps, float *out32, int ld32, const void *W1, const float *b1, const void *W2,
+                              const float *b2, float *C, int ldc, int M, int Hd, void *stream) {
+  MEMOTR_REQUIRE(M >= 0 && pre && res && gamma && beta && W1 && b1 && W2 && C, "mlp2_ln: bad arguments");
+  MEMOTR_REQUIRE(Hd > 0 && Hd % 128 == 0, "mlp2_ln: hidden %% 128 != 0 (got %d)", Hd);
+  MEMOTR_REQUIRE(ldpre % 4 == 0 && ldres % 4 == 0 && ldc % 4 == 0 && (!out32 || ld32 % 4 == 0) && aligned16(pre) && aligned16(res) &&
+                     aligned16(gamma) && aligned16(beta) && aligned16(W1) && aligned16(W2) && aligned16(C) && aligned16(b1) &&
+                     (!b2 || aligned16(b2)) && (!out32 || aligned16(out32)),
+                 "mlp2_ln: misaligned buffer");
+  MEMOTR_REQUIRE((const void *)pre != (const void *)C, "mlp2_ln: the output must not alias the LayerNorm input");
+  MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "mlp2_ln: cuTensorMapEncodeTiled unavailable");
+  if (M == 0) return MEMOTR_OK;
+  Epilogue ep{b2, nullptr, nullptr, nullptr, 0, 0, ACT_NONE};
+  const tc::LnIn ln{pre, res, gamma, beta, out32, ldpre, ldres, ld32, eps};
+  return mlp2_f32_balanced(nullptr, 0, W1, b1, W2, C, ldc, M, Hd, ep, (cudaStream_t)stream, ln);
 }

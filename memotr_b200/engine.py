@@ -90,6 +90,12 @@ class FrameEngine:
         self.fuse_prep = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_FUSE_PREP", "1") != "0"
                           and cfg["n_levels"] * cfg["n_enc_points"] == 16 and self.H % 2 == 0
                           and 3 * ((self.S + 127) // 128) > n_sm > 0 and self.H * 48 % 128 == 0)
+        # encoder: LayerNorm(norm1) computed inside the FFN kernel's prologue (memotr_mlp2_ln).  Opt-in (MEMOTR_FUSE_LN1=1):
+        # measured 8.7 us per layer SLOWER than the separate LayerNorm kernel -- the prologue (16 rows per warp, four in
+        # flight) sits on the critical path of every CTA (and is repeated by the tail-split CTAs), while the stand-alone
+        # kernel runs at 4.2 TB/s
+        self.fuse_ln1 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN1", "0") == "1" and self.fused_mlp
+                         and self.Fd % 128 == 0 and self.S >= 2048)
         self._pack(state_dict)
         self._alloc()
         # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
@@ -231,6 +237,7 @@ class FrameEngine:
         self.attw = f(S, self.H, LK)
         self.att = e(S, C)
         self.pre = f(S, C)                                           # pre-LayerNorm GEMM output, always fp32
+        self.pre2 = f(S, C) if self.fuse_ln1 else None               # FFN output when LayerNorm 1 runs inside the FFN kernel
         self.src1 = e(S, C)
         # fp32 residual stream: in fp32 mode the activation buffers are their own masters
         fp32 = self.mode == "fp32"
@@ -649,9 +656,17 @@ class FrameEngine:
                 self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
                 self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
             self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
-            self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
-            self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)
-            self.ln(self.pre, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
+            if self.fuse_ln1:        # norm1 inside the FFN kernel: no LayerNorm launch, no bf16 X round trip
+                g1, b1 = ly["norm1"]
+                self._ck(self.lib.memotr_mlp2_ln(_p(self.pre), C, _p(self.src32), C, _p(g1), _p(b1), 1e-5, _p(self.src1_32),
+                                                 C, _p(ly["lin1"].w), _p(ly["lin1"].b), _p(ly["lin2"].w), _p(ly["lin2"].b),
+                                                 _p(self.pre2), C, S, self.Fd, st()), "mlp2_ln")
+                ffn_out = self.pre2
+            else:
+                self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
+                self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)
+                ffn_out = self.pre
+            self.ln(ffn_out, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
                     ypos=self.q_tok)
         memory = self.src_tok
         self._mark(2)

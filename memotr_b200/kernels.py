@@ -149,6 +149,20 @@ def sine_embed(pts, dim_t, scale4=None, apply_sigmoid=False, out_dtype=torch.flo
     return out
 
 
+def mlp2_ln(pre, res, gamma, beta, w1, b1, w2, b2, eps=1e-5, want_x32=True):
+    """relu(X W1^T + b1) W2^T + b2 with X = LayerNorm(pre + res) computed inside the kernel (fp32 pre / res (M,256), bf16
+    weights).  -> (out fp32 (M,256), X fp32 or None)."""
+    M, Hd = pre.shape[0], w1.shape[0]
+    out = torch.empty((M, 256), dtype=torch.float32, device=pre.device)
+    x32 = torch.empty((M, 256), dtype=torch.float32, device=pre.device) if want_x32 else None
+    with torch.cuda.device(pre.device):
+        rc = _lib.lib().memotr_mlp2_ln(_lib.ptr(pre), _ld(pre), _lib.ptr(res), _ld(res), _lib.ptr(gamma), _lib.ptr(beta),
+                                       float(eps), _lib.ptr(x32), 256, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2),
+                                       _lib.ptr(b2), _lib.ptr(out), 256, M, Hd, _lib.stream_ptr())
+    _lib.check(rc, "memotr_mlp2_ln")
+    return out, x32
+
+
 def pos_embed_sine(mask, num_pos_feats=128, temperature=20, scale=6.283185307179586):
     """PositionEmbeddingSine(normalize=True) of one (H, W) padding mask (bool / uint8, device) -> (2*num_pos_feats, H, W) fp32
     (models/position_embedding.py:23-49)."""

@@ -181,6 +181,28 @@ def test_fused_mlp2_split_hidden(M, Hd, split, monkeypatch):
     assert rel_err(again.cpu(), want) < 1e-3
 
 
+@pytest.mark.parametrize("M", [300, 22323, 128 * 148 + 77])
+def test_fused_mlp2_with_layernorm_prologue(M):
+    """memotr_mlp2_ln == memotr_layernorm followed by memotr_mlp2 (the LayerNorm runs in the FFN kernel's prologue, its
+    bf16 result goes straight into the tensor-core operand tile); also against fp64."""
+    g = _g(M)
+    Hd = 2048
+    pre, res = torch.randn(M, 256, generator=g), torch.randn(M, 256, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    w1 = (torch.randn(Hd, 256, generator=g) / 16).bfloat16()
+    w2 = (torch.randn(256, Hd, generator=g) / math.sqrt(Hd)).bfloat16()
+    b1, b2 = torch.randn(Hd, generator=g), torch.randn(256, generator=g)
+    d = lambda t: t.to(DEV)                                                                 # noqa: E731
+    out, x32 = K().mlp2_ln(d(pre), d(res), d(gamma), d(beta), d(w1), d(b1), d(w2), d(b2))
+    y, y32 = K().layernorm(d(pre), d(gamma), d(beta), x2=d(res), out_dtype=torch.bfloat16, want_f32=True)
+    two = K().mlp2(y, d(w1), d(b1), d(w2), d(b2), out_dtype=torch.float32)
+    assert torch.equal(x32, y32)                                       # the same LayerNorm arithmetic
+    assert rel_err(out.cpu().numpy(), two.cpu().numpy()) < 2e-6        # same operands, different summation split at most
+    x = F.layer_norm(pre.double() + res.double(), (256,), gamma.double(), beta.double(), 1e-5)
+    h = F.linear(x.float().bfloat16().double(), w1.double(), b1.double()).relu().float().bfloat16().double()
+    assert rel_err(out.cpu().numpy(), F.linear(h, w2.double(), b2.double()).numpy()) < 2e-3
+
+
 def test_fused_mlp2_epilogues_and_views():
     g = _g(21)
     M, Hd = 333, 256
