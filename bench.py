@@ -176,7 +176,7 @@ def gpu_reference_fps(dev, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=256)   # ~0.5 s timed region: several nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
