@@ -391,7 +391,7 @@ def main():
                                 "recorded inside the captured graph",
                      "ceiling_note": "on-chip gather traffic (S*H*L*K*4 corners*32 ch) is ~18x the algorithmic bytes; see DESIGN.md"},
     }
-    if not args.no_baselines:
+    if not args.no_baselines and world == 1:      # the CPU / reference-GPU legs are timed at N = 1 only
         cpu_fps, cores = cpu_reference_fps(3, 1)
         out["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": "3 full frames after 1 warm-up (oracle/frame.py on the host cores, torch fp32; "
