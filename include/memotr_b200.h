@@ -95,7 +95,14 @@ MEMOTR_API int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
 MEMOTR_API int memotr_msda_forward_strided(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
                                            const int64_t *level_start_idx, const float *sampling_loc, int ld_loc,
                                            const float *attn_weight, int ld_attn, void *output, int B, int S, int H, int L,
-                                           int Lq, int K, void *stream);
+                                           int Lq, int K, int head_major /* value is (H, S, 32), pixel stride 32 */,
+                                           void *stream);
+
+/* value projection written HEAD-MAJOR: out (N/32, M, 32) fp16 = (A W^T + bias) with rows of padded pixels zeroed
+ * (ms_deform_attn.py:104-106); in this layout the two x-corners of a bilinear footprint are adjacent 64-byte blocks
+ * (3 instead of 4 L1 lines per sampling point).  bf16 A (M,K), W (N,K); persistent tcgen05 kernel only. */
+MEMOTR_API int memotr_linear_headmajor(const void *A, int lda, const void *W, int ldw, const float *bias,
+                                       const unsigned char *rowzero, void *out, int M, int N, int K, void *stream);
 
 /* The offsets / attention-logits projection of MSDeformAttn with memotr_msda_prep (encoder mode) fused into the GEMM
  * epilogue (ms_deform_attn.py:104-120): out (M, 3*H*L*K) fp32 rows = [sampling locations (H, L*K, 2) | softmax weights

@@ -541,7 +541,7 @@ static int launch_v2(const void *value, const int64_t *shapes, const int64_t *ls
 namespace memotr {
 static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                       void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, int ld_loc = 0,
-                      int ld_attn = 0);
+                      int ld_attn = 0, long head_stride = 32);
 }
 using namespace memotr;
 
@@ -594,9 +594,10 @@ extern "C" int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
 extern "C" int memotr_msda_forward_strided(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
                                            const int64_t *level_start_idx, const float *sampling_loc, int ld_loc,
                                            const float *attn_weight, int ld_attn, void *output, int B, int S, int H, int L,
-                                           int Lq, int K, void *stream) {
+                                           int Lq, int K, int head_major, void *stream) {
   MEMOTR_REQUIRE(B >= 0 && S > 0 && H > 0 && L > 0 && Lq >= 0 && K > 0, "msda_forward_strided: bad sizes");
-  MEMOTR_REQUIRE(value_pixel_stride >= H * 32 && value_pixel_stride % 8 == 0, "msda_forward_strided: bad pixel stride");
+  MEMOTR_REQUIRE(head_major ? (value_pixel_stride == 32 && B == 1) : (value_pixel_stride >= H * 32 && value_pixel_stride % 8 == 0),
+                 "msda_forward_strided: bad pixel stride (head-major maps: 32, batch 1)");
   MEMOTR_REQUIRE((long)B * S * value_pixel_stride < (1L << 31), "msda_forward_strided: value spans >= 2^31 elements");
   if ((long)B * Lq == 0) return MEMOTR_OK;
   MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && sampling_loc && attn_weight && output,
@@ -605,7 +606,7 @@ extern "C" int memotr_msda_forward_strided(const void *value, int value_pixel_st
                      ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0),
                  "msda_forward_strided: bad stride / alignment");
   return launch_h16(value, spatial_shapes, level_start_idx, sampling_loc, attn_weight, output, B, S, H, L, Lq, K,
-                    value_pixel_stride, (cudaStream_t)stream, ld_loc, ld_attn);
+                    value_pixel_stride, (cudaStream_t)stream, ld_loc, ld_attn, head_major ? (long)S * 32 : 32L);
 }
 
 // =====================================================================================================================
@@ -766,7 +767,8 @@ template <int KT, int SPLIT>
 __global__ void __launch_bounds__(256)
 msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
-             int L, int Lq, int Kr, int xs, long n_qh, int ld_loc, int ld_attn) {
+             int L, int Lq, int Kr, int xs, long n_qh, int ld_loc, int ld_attn, long head_stride) {
+  // head_stride: elements between the heads of one pixel (32 in the pixel-major map; S * 32 with xs = 32 in the head-major map)
   // ld_loc / ld_attn: floats between consecutive queries of `loc` / `attn` (dense: H*L*K*2 and H*L*K; 3*H*L*K each when
   // both live in the [locations | weights] rows written by the prep epilogue of the projection GEMM)
   pdl_grid_sync();
@@ -782,7 +784,7 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
   const int K = KT ? KT : Kr;
   const float2 *locq = reinterpret_cast<const float2 *>(loc + (qh / H) * (long)ld_loc) + m * L * K;
   const float *attq = attn + (qh / H) * (long)ld_attn + m * L * K;
-  const __half *vb = value + (long)b * S * xs + m * D + sub * 8;
+  const __half *vb = value + (head_stride == D ? (long)b * S * xs : 0L) + m * head_stride + sub * 8;
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
@@ -866,7 +868,7 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
 
 static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                       void *out, int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, int ld_loc,
-                      int ld_attn) {
+                      int ld_attn, long head_stride) {
   if (!ld_loc) ld_loc = H * L * K * 2;
   if (!ld_attn) ld_attn = H * L * K;
   const long n_qh = (long)B * Lq * H;
@@ -875,10 +877,10 @@ static int launch_h16(const void *value, const int64_t *shapes, const int64_t *l
 #define H16_LAUNCH(KT_)                                                                                               \
   if (split)                                                                                                          \
     MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn);                                   \
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride);                      \
   else                                                                                                                \
     MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn)
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride)
   switch (K) {
     case 1: H16_LAUNCH(1); break;
     case 2: H16_LAUNCH(2); break;

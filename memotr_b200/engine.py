@@ -96,6 +96,9 @@ class FrameEngine:
         # kernel runs at 4.2 TB/s
         self.fuse_ln1 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN1", "0") == "1" and self.fused_mlp
                          and self.Fd % 128 == 0 and self.S >= 2048)
+        # encoder value maps head-major (H, S, 32): the x-corners of a footprint are adjacent 64-byte blocks (A/B switch)
+        self.value_hm = (self.fuse_prep and os.environ.get("MEMOTR_VALUE_HM", "0") == "1"
+                         and 2 * ((self.S + 127) // 128) > n_sm)
         self._pack(state_dict)
         self._alloc()
         # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
@@ -563,9 +566,9 @@ class FrameEngine:
             self._timer_slot += 1
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
         attw = self.ol.view(-1)[H * L * K * 2:]                    # the weights start after the locations in every row
-        self._ck(self.lib.memotr_msda_forward_strided(_p(self.value), self.C, _p(self.shapes_t), _p(self.lsi_t), _p(self.ol),
-                                                      N, _p(attw), N, _p(self.att), 1, S, H, L, S, K, self._st()),
-                 "msda_forward_strided")
+        self._ck(self.lib.memotr_msda_forward_strided(_p(self.value), 32 if self.value_hm else self.C, _p(self.shapes_t),
+                                                      _p(self.lsi_t), _p(self.ol), N, _p(attw), N, _p(self.att), 1, S, H, L, S, K,
+                                                      int(self.value_hm), self._st()), "msda_forward_strided")
         if timed:
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
 
@@ -649,7 +652,11 @@ class FrameEngine:
         Ke = self.cfg["n_enc_points"]
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
-            self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
+            if self.value_hm:
+                self._ck(self.lib.memotr_linear_headmajor(_p(self.src_tok), C, _p(a["value"].w), a["value"].K, _p(a["value"].b),
+                                                          _p(self.mask_flat), _p(self.value), S, C, C, st()), "linear_headmajor")
+            else:
+                self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
             if self.fuse_prep:
                 self._encoder_ol_and_gather(a, Ke)
             else:

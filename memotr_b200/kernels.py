@@ -126,15 +126,30 @@ def linear_msda_prep(x, w, b, shapes, level_start, valid_ratios, n_heads, n_leve
     return out
 
 
-def msda_forward_strided(value, spatial_shapes, level_start_index, rows, n_heads, n_levels, n_points):
-    """Gather from an fp16 value map with locations / weights taken from the (Lq, 3*H*L*K) rows of linear_msda_prep."""
-    S, Lq, N = value.shape[0], rows.shape[0], rows.shape[1]
+def linear_headmajor(x, w, b, rowzero=None):
+    """x (M,K) bf16, w (N,K) bf16 -> (N/32, M, 32) fp16: the projection written head-major (value maps of the encoder)."""
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((N // 32, M, 32), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_linear_headmajor(_lib.ptr(x), _ld(x), _lib.ptr(w), _ld(w), _lib.ptr(b), _lib.ptr(rowzero),
+                                                _lib.ptr(out), M, N, K, _lib.stream_ptr())
+    _lib.check(rc, "memotr_linear_headmajor")
+    return out
+
+
+def msda_forward_strided(value, spatial_shapes, level_start_index, rows, n_heads, n_levels, n_points, head_major=False):
+    """Gather from an fp16 value map with locations / weights taken from the (Lq, 3*H*L*K) rows of linear_msda_prep.
+    head_major: value is (H, S, 32) instead of (S, >= H*32)."""
+    S = value.shape[1] if head_major else value.shape[0]
+    Lq, N = rows.shape[0], rows.shape[1]
     out = torch.empty((Lq, n_heads * 32), dtype=torch.bfloat16, device=value.device)
     attw = rows.view(-1)[n_heads * n_levels * n_points * 2:]
     with torch.cuda.device(value.device):
-        rc = _lib.lib().memotr_msda_forward_strided(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
-                                                    _lib.ptr(level_start_index), _lib.ptr(rows), N, _lib.ptr(attw), N,
-                                                    _lib.ptr(out), 1, S, n_heads, n_levels, Lq, n_points, _lib.stream_ptr())
+        rc = _lib.lib().memotr_msda_forward_strided(_lib.ptr(value), 32 if head_major else _ld(value),
+                                                    _lib.ptr(spatial_shapes), _lib.ptr(level_start_index), _lib.ptr(rows), N,
+                                                    _lib.ptr(attw), N, _lib.ptr(out), 1, S, n_heads, n_levels, Lq, n_points,
+                                                    int(head_major), _lib.stream_ptr())
     _lib.check(rc, "memotr_msda_forward_strided")
     return out
 

@@ -394,8 +394,19 @@ def test_linear_with_msda_prep_epilogue_and_strided_gather():
     dense = K().msda_forward_ex(value, shapes_t, lsi_t, loc, attn, H)
     strided = K().msda_forward_strided(value, shapes_t, lsi_t, rows, H, L, Kp)
     assert rel_err(strided.float().cpu().numpy(), dense.float().cpu().numpy()) < 1e-2     # bf16 outputs of ~equal inputs
-    strided2 = K().msda_forward_strided(value, shapes_t, lsi_t, torch.cat((loc.reshape(S, 256), attn.reshape(S, 128)), 1).contiguous(), H, L, Kp)
+    cat = torch.cat((loc.reshape(S, 256), attn.reshape(S, 128)), 1).contiguous()
+    strided2 = K().msda_forward_strided(value, shapes_t, lsi_t, cat, H, L, Kp)
     assert torch.equal(strided2, dense)                                                       # same inputs: bit-equal
+    # head-major value map (H, S, 32): same numbers in another layout -> bit-equal gather
+    hm = value.reshape(S, H, 32).permute(1, 0, 2).contiguous()
+    assert torch.equal(K().msda_forward_strided(hm, shapes_t, lsi_t, cat, H, L, Kp, head_major=True), dense)
+    # ... and the projection that writes it: (x W^T + b) with padded rows zeroed, head-major, against the plain tc GEMM
+    rz = (torch.rand(S, generator=g) < 0.1).to(torch.uint8).to(DEV)
+    wv = (torch.randn(256, 256, generator=g) / 16).bfloat16().to(DEV)
+    bv = torch.randn(256, generator=g).to(DEV)
+    plain = K().linear(x, wv, bv, rowzero=rz, out_dtype=torch.float16, path="tc")
+    got = K().linear_headmajor(x, wv, bv, rowzero=rz)
+    assert got.shape == (H, S, 32) and torch.equal(got.permute(1, 0, 2).reshape(S, 256), plain)
 
 
 @pytest.mark.parametrize("h,w,vh,vw", [(100, 168, 100, 168), (100, 168, 88, 167), (50, 84, 44, 84), (13, 21, 12, 20), (1, 1, 1, 1)])
