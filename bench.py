@@ -314,6 +314,7 @@ def main():
     torch.cuda.synchronize(dev)
     msda_us = eng.msda_times_us()                       # the 6 encoder MSDA launches of the last timed step
     sections = eng.section_times_us()
+    ffn_us = eng.ffn_times_us() if (eng.fused_mlp and not eng.fuse_ln1) else None
 
     # ---- end to end through the public API with host buffers ("e2e") ----------------------------------------------
     from memotr_b200.engine import ClipRunner
@@ -391,6 +392,17 @@ def main():
                                 "recorded inside the captured graph",
                      "ceiling_note": "on-chip gather traffic (S*H*L*K*4 corners*32 ch) is ~18x the algorithmic bytes; see DESIGN.md"},
     }
+    if ffn_us:      # second roofline object: the largest kernel by time is tensor-bound (fused encoder FFN)
+        fdur = sum(ffn_us) / len(ffn_us)
+        flops = 2.0 * 2.0 * eng.S * eng.C * eng.Fd
+        tpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", None) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+        tpeak = float(tpeak) if tpeak else 1430.2
+        out["roofline_tensor"] = {"kernel": "mlp2_tc_kernel -- fused encoder FFN (22323 x 256 -> 2048 -> 256), main launch + tail-split launch",
+                                  "bound": "tensor", "achieved": flops / fdur / 1e6, "peak": tpeak, "unit": "TFLOP/s",
+                                  "frac": flops / fdur / 1e6 / tpeak, "flop": flops, "duration_us": fdur,
+                                  "peak_source": "MEASURED_PEAKS.json bf16 dense, sustained (kernel timed inside a long step)",
+                                  "note": "shared-memory-bandwidth-bound in its cta_group::1 form, see profiles/r01_mlp2_ncu.md"}
     if not args.no_baselines and world == 1:      # the CPU / reference-GPU legs are timed at N = 1 only
         cpu_fps, cores = cpu_reference_fps(3, 1)
         out["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",

@@ -121,7 +121,7 @@ class FrameEngine:
     def enable_msda_timer(self):
         """Bracket every encoder-layer MSDA forward launch with a pair of (graph-capturable) CUDA events, and mark the
         section boundaries of a step (prep | encoder | decoder | updater) with five more."""
-        self.timer = self.lib.memotr_timer_create(2 * self.n_enc + 5)
+        self.timer = self.lib.memotr_timer_create(4 * self.n_enc + 5)     # [msda pairs | 5 section marks | ffn pairs]
         self._timer_slot = 0
 
     def _mark(self, i):
@@ -135,6 +135,15 @@ class FrameEngine:
         for i, name in enumerate(("prep", "encoder", "decoder_heads", "updater")):
             _lib.check(self.lib.memotr_timer_elapsed_ms(self.timer, b + i, b + i + 1, ctypes.byref(ms)), "timer_elapsed")
             out[name] = ms.value * 1e3
+        return out
+
+    def ffn_times_us(self):
+        """Durations of the encoder FFN launches (fused mlp2, incl. its tail-split launch) of the most recent step."""
+        import ctypes
+        out, ms, b = [], ctypes.c_float(), 2 * self.n_enc + 5
+        for i in range(self.n_enc):
+            _lib.check(self.lib.memotr_timer_elapsed_ms(self.timer, b + 2 * i, b + 2 * i + 1, ctypes.byref(ms)), "timer_elapsed")
+            out.append(ms.value * 1e3)
         return out
 
     def msda_times_us(self):
@@ -671,7 +680,11 @@ class FrameEngine:
                 ffn_out = self.pre2
             else:
                 self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
+                if self.timer is not None:
+                    _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 5 + 2 * i, st()), "timer_record")
                 self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)
+                if self.timer is not None:
+                    _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 6 + 2 * i, st()), "timer_record")
                 ffn_out = self.pre
             self.ln(ffn_out, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
                     ypos=self.q_tok)
