@@ -763,7 +763,7 @@ namespace memotr {
 // SPLIT = 4: 16 lanes per (b,q,head), each 4-lane subgroup takes every 4th level and the partial sums are combined with
 //            two xor-shuffles per channel -- 4x the threads and a quarter of the dependent load->blend chain for the
 //            decoder-shaped launch (400 queries: 50 CTAs of serial work otherwise, 12.4 us measured).
-template <int KT, int SPLIT>
+template <int KT, int SPLIT, bool HM>
 __global__ void __launch_bounds__(256)
 msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
@@ -784,7 +784,8 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
   const int K = KT ? KT : Kr;
   const float2 *locq = reinterpret_cast<const float2 *>(loc + (qh / H) * (long)ld_loc) + m * L * K;
   const float *attq = attn + (qh / H) * (long)ld_attn + m * L * K;
-  const __half *vb = value + (head_stride == D ? (long)b * S * xs : 0L) + m * head_stride + sub * 8;
+  // HM: head-major map (head_stride = S * 32, xs = 32, batch 1); otherwise the pixel-major layout with compile-time head offset
+  const __half *vb = HM ? value + m * head_stride + sub * 8 : value + (long)b * S * xs + m * D + sub * 8;
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
@@ -874,12 +875,17 @@ static int launch_h16(const void *value, const int64_t *shapes, const int64_t *l
   const long n_qh = (long)B * Lq * H;
   const bool split = n_qh * 4 < (long)kNumSMs * 256 * 2;   // too few groups to fill the GPU: spread the levels over lanes
   const int grid = (int)((n_qh * (split ? 16 : 4) + 255) / 256);
+  const bool hm = head_stride != 32;
+  if (hm && split) return fail(MEMOTR_EINVAL, "msda_fwd_h16: head-major value maps need an encoder-sized launch");
 #define H16_LAUNCH(KT_)                                                                                               \
   if (split)                                                                                                          \
-    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
+    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4, false>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,    \
+                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride);                      \
+  else if (hm)                                                                                                        \
+    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, true>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,     \
                   (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride);                      \
   else                                                                                                                \
-    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,           \
+    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, false>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,    \
                   (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride)
   switch (K) {
     case 1: H16_LAUNCH(1); break;

@@ -680,10 +680,11 @@ class FrameEngine:
                 ffn_out = self.pre2
             else:
                 self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
-                if self.timer is not None:
+                tf = self.timer is not None and getattr(self, "time_ffn", False)   # (event nodes cost PDL overlap: opt-in)
+                if tf:
                     _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 5 + 2 * i, st()), "timer_record")
                 self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)
-                if self.timer is not None:
+                if tf:
                     _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 6 + 2 * i, st()), "timer_record")
                 ffn_out = self.pre
             self.ln(ffn_out, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
