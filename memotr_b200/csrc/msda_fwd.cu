@@ -763,27 +763,30 @@ namespace memotr {
 // SPLIT = 4: 16 lanes per (b,q,head), each 4-lane subgroup takes every 4th level and the partial sums are combined with
 //            two xor-shuffles per channel -- 4x the threads and a quarter of the dependent load->blend chain for the
 //            decoder-shaped launch (400 queries: 50 CTAs of serial work otherwise, 12.4 us measured).
-template <int KT, int SPLIT, bool HM>
+template <int KT, int SPLIT, bool HM, bool H8>
 __global__ void __launch_bounds__(256)
 msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
-             int L, int Lq, int Kr, int xs, long n_qh, int ld_loc, int ld_attn, long head_stride) {
+             int L, int Lq, int Kr, int xs, int n_qh, int ld_loc, int ld_attn, long head_stride, int B) {
+  // H8: eight heads (shifts instead of integer divisions -- this kernel is issue-sensitive: a runtime head stride alone
+  // cost 9 %); all index arithmetic is 32-bit (the launcher checks n_qh * 16 < 2^31)
   // head_stride: elements between the heads of one pixel (32 in the pixel-major map; S * 32 with xs = 32 in the head-major map)
   // ld_loc / ld_attn: floats between consecutive queries of `loc` / `attn` (dense: H*L*K*2 and H*L*K; 3*H*L*K each when
   // both live in the [locations | weights] rows written by the prep epilogue of the projection GEMM)
   pdl_grid_sync();
   constexpr int D = 32, G = 4 * SPLIT;
-  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long qh_raw = tid / G;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int qh_raw = tid / G;
   const bool live = qh_raw < n_qh;
   if (SPLIT == 1 && !live) return;
-  const long qh = live ? qh_raw : n_qh - 1;     // SPLIT > 1: tail lanes shadow a valid group (shuffles stay full-warp)
-  const int sub = (int)(tid % 4), lvl0 = (int)((tid % G) / 4);
-  const int m = (int)(qh % H);
-  const int b = (int)((qh / H) / Lq);
+  const int qh = live ? qh_raw : n_qh - 1;      // SPLIT > 1: tail lanes shadow a valid group (shuffles stay full-warp)
+  const int sub = tid % 4, lvl0 = (tid % G) / 4;
+  const int m = H8 ? (qh & 7) : qh % H;
+  const int ql = H8 ? (qh >> 3) : qh / H;       // linear query index b * Lq + q
+  const int b = B == 1 ? 0 : ql / Lq;
   const int K = KT ? KT : Kr;
-  const float2 *locq = reinterpret_cast<const float2 *>(loc + (qh / H) * (long)ld_loc) + m * L * K;
-  const float *attq = attn + (qh / H) * (long)ld_attn + m * L * K;
+  const float2 *locq = reinterpret_cast<const float2 *>(loc + (long)ql * ld_loc) + m * L * K;
+  const float *attq = attn + (long)ql * ld_attn + m * L * K;
   // HM: head-major map (head_stride = S * 32, xs = 32, batch 1); otherwise the pixel-major layout with compile-time head offset
   const __half *vb = HM ? value + m * head_stride + sub * 8 : value + (long)b * S * xs + m * D + sub * 8;
   float acc[8];
@@ -864,7 +867,7 @@ msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shape
     }
     if (!live || lvl0 != 0) return;
   }
-  *reinterpret_cast<uint4 *>(out + qh * D + sub * 8) = f32x8_to_bf16(acc);
+  *reinterpret_cast<uint4 *>(out + (long)qh * D + sub * 8) = f32x8_to_bf16(acc);
 }
 
 static int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
@@ -875,18 +878,17 @@ static int launch_h16(const void *value, const int64_t *shapes, const int64_t *l
   const long n_qh = (long)B * Lq * H;
   const bool split = n_qh * 4 < (long)kNumSMs * 256 * 2;   // too few groups to fill the GPU: spread the levels over lanes
   const int grid = (int)((n_qh * (split ? 16 : 4) + 255) / 256);
-  const bool hm = head_stride != 32;
+  const bool hm = head_stride != 32, h8 = H == 8 && !hm;
   if (hm && split) return fail(MEMOTR_EINVAL, "msda_fwd_h16: head-major value maps need an encoder-sized launch");
-#define H16_LAUNCH(KT_)                                                                                               \
-  if (split)                                                                                                          \
-    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4, false>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,    \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride);                      \
-  else if (hm)                                                                                                        \
-    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, true>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,     \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride);                      \
-  else                                                                                                                \
-    MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, false>), grid, 256, 0, st, (const __half *)value, shapes, lsi, loc, attn,    \
-                  (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, n_qh, ld_loc, ld_attn, head_stride)
+  if (n_qh * 16 >= (1L << 31)) return fail(MEMOTR_EINVAL, "msda_fwd_h16: more than 2^27 (query, head) pairs");
+#define H16_ARGS (const __half *)value, shapes, lsi, loc, attn, (__nv_bfloat16 *)out, S, H, L, Lq, K, xs, (int)n_qh, ld_loc, \
+                 ld_attn, head_stride, B
+#define H16_LAUNCH(KT_)                                                                       \
+  if (split && h8) MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4, false, true>), grid, 256, 0, st, H16_ARGS);      \
+  else if (split) MEMOTR_LAUNCH((msda_fwd_h16<KT_, 4, false, false>), grid, 256, 0, st, H16_ARGS);      \
+  else if (hm) MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, true, false>), grid, 256, 0, st, H16_ARGS);          \
+  else if (h8) MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, false, true>), grid, 256, 0, st, H16_ARGS);          \
+  else MEMOTR_LAUNCH((msda_fwd_h16<KT_, 1, false, false>), grid, 256, 0, st, H16_ARGS)
   switch (K) {
     case 1: H16_LAUNCH(1); break;
     case 2: H16_LAUNCH(2); break;
@@ -895,6 +897,7 @@ static int launch_h16(const void *value, const int64_t *shapes, const int64_t *l
     default: H16_LAUNCH(0); break;
   }
 #undef H16_LAUNCH
+#undef H16_ARGS
   return check_launch("msda_fwd_h16");
 }
 
