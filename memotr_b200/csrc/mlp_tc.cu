@@ -418,7 +418,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 template <typename TC, int CS>
 static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
                        int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1, int tile0 = 0, int ntiles = -1,
-                       const LnIn &ln = LnIn{}) {
+                       const LnIn &ln = LnIn{}, bool zero_first = true) {
   using namespace mlp;
   CUtensorMap tmX, tmW1, tmW2, tmC;
   constexpr int W1_BOX = CS == 1 ? HC : (256 / CS < 128 ? 256 / CS : 128), W2_BOX = 256 / CS;
@@ -436,7 +436,7 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
   }
   const int tiles = ntiles < 0 ? ceil_div(M, BM) - tile0 : ntiles;
   if constexpr (CS == 1) {
-    if (nsplit > 1) {   // partial products are reduce-added: start from zero (a memset node when captured into a graph)
+    if (nsplit > 1 && zero_first) {   // partial products are reduce-added: start from zero (a memset node in a graph)
       const int r0 = tile0 * BM, nr = (M - r0 < tiles * BM) ? M - r0 : tiles * BM;
       const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<TC *>(C) + (size_t)r0 * ldc, (size_t)ldc * sizeof(TC), 0,
                                               (size_t)N2 * sizeof(TC), nr, st);
@@ -481,9 +481,14 @@ static int mlp2_f32_balanced(const void *X, int ldx, const void *W1, const float
     int ns = 2;
     while (ns * 2 <= 8 && tail * ns * 2 <= n_sm && chunks % (ns * 2) == 0) ns *= 2;
     if (chunks % ns == 0) {
+      // zero the tail rows BEFORE the main launch: the two kernels then follow each other directly (programmatic launch)
+      const int r0 = n_sm * tc::BM;
+      const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<float *>(C) + (size_t)r0 * ldc, (size_t)ldc * sizeof(float), 0,
+                                              (size_t)tc::mlp::N2 * sizeof(float), M - r0, st);
+      if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
       const int rc = tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, n_sm, ln);
       if (rc != MEMOTR_OK) return rc;
-      return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail, ln);
+      return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail, ln, false);
     }
   }
   return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, -1, ln);
