@@ -579,6 +579,41 @@ def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monk
         assert upd[k][1] < (2.5e-1 if deep else 3e-2), (k, upd[k])
 
 
+@pytest.mark.parametrize("ncls,nd,nt", [(3, 20, 7), (8, 33, 16)])
+def test_engine_bf16_multiclass_fused_paths_match_oracle(ncls, nd, nt, monkeypatch):
+    """Configurations the golden files do not cover (several classes, detect-query counts that are not a multiple of the
+    16-row blocks, a track count that fills whole blocks): the bf16 engine with every fused kernel (cluster decoder, fused
+    updater) against the functional oracle on the same seeded inputs, and against the launch-per-op engine."""
+    from memotr_b200.engine import FrameEngine
+    cfg = dict(synth.small_cfg(), num_classes=ncls, n_det_queries=nd)
+    sd = synth.hot_path_state_dict(cfg, seed=11)
+    x = synth.frame_inputs(cfg, synth.SMALL_SHAPES, nt, seed=12)
+    with torch.no_grad():
+        want = oframe.frame_forward(sd, x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"], cfg)
+        wupd = oframe.update_tracks(sd, x["tracks"], cfg)
+    res = {}
+    for fused in ("0", "2"):
+        monkeypatch.setenv("MEMOTR_DEC_FUSED", fused)
+        eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, nt, DEV, mode="bf16")
+        assert eng.dec_cluster == (fused == "2") and eng.upd_fused == (fused == "2")
+        eng.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
+        eng.forward()
+        eng.load_tracks(x["tracks"])
+        eng.update_tracks()
+        torch.cuda.synchronize()
+        res[fused] = ({k: v.clone() for k, v in eng.results().items()}, eng.track_state())
+    for fused in ("0", "2"):
+        out, st = res[fused]
+        assert out["pred_logits"].shape == (1, nd + nt, ncls)
+        for k in ("pred_bboxes", "last_ref_pts"):
+            assert rel_err(out[k].cpu().numpy(), want[k].numpy()) < 1e-2, (fused, k)
+        for k in ("pred_logits", "outputs", "aux_queries"):
+            assert rel_err(out[k].cpu().numpy(), want[k].numpy()) < 3e-2, (fused, k)
+        assert rel_err(st["ref_pts"].cpu().numpy(), wupd["ref_pts"].numpy()) < 1e-5
+        for k in ("query_embed", "long_memory", "last_output"):
+            assert rel_err(st[k].cpu().numpy(), wupd[k].numpy()) < 3e-2, (fused, k)
+
+
 def test_engine_memory_matches_oracle_encoder_only():
     """Encoder output (the memory) of the fp32 engine vs the functional oracle, padded masks (valid ratios < 1)."""
     g, cfg, sd, x, shapes, nt = _case("small_padded")
