@@ -331,11 +331,13 @@ typedef struct memotr_dec_params {
   int n_prog, n_layers, nq, nd, merge, ncls, n_levels, n_points, d_ffn, value_stride, np, pad_;
   const float *rph0_b, *rph1_b, *qs0_b, *qs1_b; /* biases of the shared ref_point_head / query_scale MLPs */
   const float *tgt_in, *ref_in;                 /* (nq,256) decoder input, (nq,4) initial reference boxes (sigmoid space) */
-  const float *vr_scale4, *valid_ratios, *dim_t; /* (4) level-0 ratios x2, (n_levels,2), (128) sine temperatures */
+  const float *vr_scale4, *valid_ratios, *dim_t; /* unused, (n_levels,2), (128) sine temperatures */
   const unsigned char *query_pad;               /* (nq) key-padding mask or NULL */
   void *kbuf, *vbuf;                            /* scratch: 2 x (np,256) fp16 keys, 2 x (256,np) fp16 values (transposed) */
   unsigned int *barrier;                        /* scratch: one counter */
   long long *prof;                              /* NULL, or (blocks, n_layers, 16) clock64 phase stamps (measurement) */
+  float *init_ref_out, *last_ref_out;           /* NULL or (nq,4): inverse_sigmoid of the references entering the first /
+                                                   the last layer (memotr.py:183-187); cluster kernel only */
   int shapes[16], lsi[8];                       /* (H, W) and first pixel of every level */
   memotr_dec_layer layers[MEMOTR_DEC_MAX_LAYERS];
 } memotr_dec_params;

@@ -55,7 +55,8 @@ class DecParams(ctypes.Structure):
                 [(k, ctypes.c_int) for k in ("n_prog", "n_layers", "nq", "nd", "merge", "ncls", "n_levels", "n_points",
                                              "d_ffn", "value_stride", "np", "pad_")] +
                 [(k, ctypes.c_void_p) for k in ("rph0_b", "rph1_b", "qs0_b", "qs1_b", "tgt_in", "ref_in", "vr_scale4",
-                                                "valid_ratios", "dim_t", "query_pad", "kbuf", "vbuf", "barrier", "prof")] +
+                                                "valid_ratios", "dim_t", "query_pad", "kbuf", "vbuf", "barrier", "prof",
+                                                "init_ref_out", "last_ref_out")] +
                 [("shapes", ctypes.c_int * 16), ("lsi", ctypes.c_int * 8),
                  ("layers", DecLayer * MEMOTR_DEC_MAX_LAYERS)])
 

@@ -111,12 +111,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_cluster_kernel(const __gr
       __half *Kh = reinterpret_cast<__half *>(P.kbuf) + (long)par * P.np * C;
       __half *Vt = reinterpret_cast<__half *>(P.vbuf) + (long)par * C * P.np;
       STAMP(0)
+      // init_ref_pts / last_ref_pts of the output dict (memotr.py:183-187): inverse_sigmoid of the references that enter
+      // the first / the last layer
+      if (rk == 0 && tid < R * 4 && row0 + (tid >> 2) < nq) {
+        const long o = (long)(row0 + (tid >> 2)) * 4 + (tid & 3);
+        if (lid == 0 && P.init_ref_out) P.init_ref_out[o] = inv_sigm(refs[tid]);
+        if (lid == P.n_layers - 1 && P.last_ref_out) P.last_ref_out[o] = inv_sigm(refs[tid]);
+      }
       // ---- DAB positional query: sine embedding (every CTA, it is the A operand of a split GEMM)
       {
         // e = p * 2pi / dim_t with the correctly rounded reciprocal; |e| <= 2pi, where __sinf / __cosf are good to ~1e-6
         // absolute -- the result is rounded to bf16 (4e-3) anyway; sinf / cosf cost ~100 instructions each on 8 warps
-        const float4 sc = ldg_f4(P.vr_scale4);
-        const float scl[4] = {sc.x, sc.y, sc.z, sc.w};
+        const float vr0x = __ldg(P.valid_ratios), vr0y = __ldg(P.valid_ratios + 1);   // level-0 ratios (deformable_decoder.py:82-91)
+        const float scl[4] = {vr0x, vr0y, vr0x, vr0y};
         for (int i = tid; i < R * 256; i += 256) {
           const int r = i >> 8, cc = (i >> 6) & 3, j = i & 63;
           const float e = refs[r * 4 + cc] * scl[cc] * 6.283185307179586f * __frcp_rn(__ldg(P.dim_t + 2 * j));
@@ -397,7 +404,7 @@ using namespace memotr;
 
 extern "C" int memotr_decoder_forward_cluster(const memotr_dec_params *p, void *stream) {
   MEMOTR_REQUIRE(p && p->prog && p->n_prog > 0 && p->tgt_in && p->ref_in && p->kbuf && p->vbuf && p->barrier && p->dim_t &&
-                     p->vr_scale4 && p->valid_ratios,
+                     p->valid_ratios,
                  "decoder_forward_cluster: null pointer");
   MEMOTR_REQUIRE(p->n_layers >= 1 && p->n_layers <= MEMOTR_DEC_MAX_LAYERS && p->nq >= 1 && p->nd >= 0 && p->nd <= p->nq &&
                      p->n_prog <= dec::cl::MAX_PROG,

@@ -415,6 +415,7 @@ class FrameEngine:
         P = _lib.DecParams()
         ctypes.memmove(ctypes.byref(P), ctypes.byref(self.dec_params), ctypes.sizeof(P))
         P.prog, P.n_prog = self.dec_prog_cl.data_ptr(), n_prog
+        P.init_ref_out, P.last_ref_out = self.init_ref_pts.data_ptr(), self.last_ref_pts.data_ptr()
         self.dec_params_cl = P
 
     def _build_updater_program(self):
@@ -693,15 +694,20 @@ class FrameEngine:
         self._mark(2)
         # -- decoder inputs (memotr.py:209-278, deformable_transformer.py:239-242)
         nd, nt, nq = self.nd, self.nt, self.nq
-        self.convert(self.det_anchor, F32, 4, self.ref_raw, F32, 4, nd, 4)
+        if not self.dec_cluster or not getattr(self, "_det_rows_ready", False):
+            # the detect-query rows are constants: with the fused decoder (which never touches these buffers' detect rows)
+            # they are written once -- capture() always runs one eager warm-up step first
+            self.convert(self.det_anchor, F32, 4, self.ref_raw, F32, 4, nd, 4)
+            self.convert(self.det_query_embed, F32, C, self.tgt32[0], F32, C, nd, C)
+            self._det_rows_ready = True
         self.convert(self.in_track_ref, F32, 4, self.ref_raw[nd:], F32, 4, nt, 4)
         self._ck(self.lib.memotr_unary(_p(self.ref_raw), _p(self.ref[0]), nq * 4, 0, st()), "sigmoid")
-        self.convert(self.det_query_embed, F32, C, self.tgt32[0], F32, C, nd, C)
         self.convert(self.in_track_embed, F32, C, self.tgt32[0][nd:], F32, C, nt, C)
-        if self.mode != "fp32":
-            self.convert(self.tgt32[0], F32, C, self.tgt[0], dt, C, nq, C)
-        self.convert(self.vr, F32, 2, self.vr_scale4, F32, 2, 1, 2)          # (vr0.w, vr0.h, vr0.w, vr0.h)
-        self.convert(self.vr, F32, 2, self.vr_scale4[2:], F32, 2, 1, 2)
+        if not self.dec_fused:
+            if self.mode != "fp32":
+                self.convert(self.tgt32[0], F32, C, self.tgt[0], dt, C, nq, C)
+            self.convert(self.vr, F32, 2, self.vr_scale4, F32, 2, 1, 2)          # (vr0.w, vr0.h, vr0.w, vr0.h)
+            self.convert(self.vr, F32, 2, self.vr_scale4[2:], F32, 2, 1, 2)
         # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
         self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
         Kd = self.cfg["n_dec_points"]
@@ -750,8 +756,9 @@ class FrameEngine:
             self._ck(self.lib.memotr_box_refine(_p(self.delta), _p(ref), _p(self.pred_box[lid]), _p(self.ref[lid + 1]),
                                                 nq, nq if lid >= self.merge else nd, st()), "box_refine")
             self.lin(new, C, ly["cls"], self.pred_logit[lid], self.ncls, nq, c_dtype=F32)
-        self._ck(self.lib.memotr_unary(_p(self.ref[self.n_dec - 1]), _p(self.last_ref_pts), nq * 4, 1, st()), "inv_sig")
-        self._ck(self.lib.memotr_unary(_p(self.ref[0]), _p(self.init_ref_pts), nq * 4, 1, st()), "inv_sig")
+        if not self.dec_cluster:        # (the cluster decoder kernel writes both itself)
+            self._ck(self.lib.memotr_unary(_p(self.ref[self.n_dec - 1]), _p(self.last_ref_pts), nq * 4, 1, st()), "inv_sig")
+            self._ck(self.lib.memotr_unary(_p(self.ref[0]), _p(self.init_ref_pts), nq * 4, 1, st()), "inv_sig")
         self._mark(3)
 
     def convert_u8(self, src, dst, n):
