@@ -763,8 +763,11 @@ namespace memotr {
 // SPLIT = 4: 16 lanes per (b,q,head), each 4-lane subgroup takes every 4th level and the partial sums are combined with
 //            two xor-shuffles per channel -- 4x the threads and a quarter of the dependent load->blend chain for the
 //            decoder-shaped launch (400 queries: 50 CTAs of serial work otherwise, 12.4 us measured).
+#ifndef MEMOTR_H16_MINB
+#define MEMOTR_H16_MINB 1   // (5 -> 48 registers, five CTAs per SM: measured neutral)
+#endif
 template <int KT, int SPLIT, bool HM, bool H8>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MEMOTR_H16_MINB)
 msda_fwd_h16(const __half *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
              const float *__restrict__ loc, const float *__restrict__ attn, __nv_bfloat16 *__restrict__ out, int S, int H,
              int L, int Lq, int Kr, int xs, int n_qh, int ld_loc, int ld_attn, long head_stride, int B) {
