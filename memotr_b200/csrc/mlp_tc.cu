@@ -20,10 +20,16 @@
 // 512 columns.  Shared memory: X 64 KB + ring 96 KB + H 64 KB = 224 KB (one CTA per SM).  Final epilogue as in
 // gemm_tc.cu: bias / activation / multiplier -> swizzled panels in the (dead) X+ring memory -> TMA store.
 //
-// Thread-block clusters (CS = 2 or 4 CTAs on neighbouring SMs, different row tiles): every CTA needs the SAME W1/W2
-// chunks, and with one CTA per SM the kernel is bound by the per-SM L2->SM bandwidth (2 MB of weights per 128-row tile;
-// measured 82 us per encoder FFN vs a ~17 us MMA bound).  Each CTA of a cluster therefore loads 1/CS of every ring slot
-// and TMA-multicasts it into the shared memory of all CS CTAs (cp.async.bulk.tensor ... .multicast::cluster); the slot's
+// What bounds it (profiles/r01_mlp2_ncu.md): the 128 B/clk shared-memory pipe -- per 128-wide hidden chunk 224 KB of MMA
+// operand reads + 128 KB of TMA writes + 32 KB of epilogue stores = ~3000 clk against 2048 clk of tcgen05 work; a tile
+// costs 6.6 us fixed + 16 x 1.65 us.  One CTA per SM (224 KB), so 175 encoder row tiles on 148 SMs are two rounds: the
+// host launches the tiles beyond the first round separately with the hidden dimension split 4-ways (gridDim.y, TMA
+// reduce-add stores into the zeroed fp32 output): 73 -> 59 us per encoder FFN.  An optional LayerNorm prologue (LnIn)
+// computes X in the kernel; it is correct but slower than the stand-alone LayerNorm kernel and therefore opt-in.
+//
+// Thread-block clusters (CS = 2 or 4 CTAs on neighbouring SMs, different row tiles; opt-in, measured neutral because the
+// L2 -> SM stream is not the limit): every CTA needs the SAME W1/W2 chunks, so each CTA of a cluster loads 1/CS of every
+// ring slot and TMA-multicasts it into the shared memory of all CS CTAs (cp.async.bulk.tensor ... .multicast::cluster); the slot's
 // `full` mbarrier in every CTA counts the bytes arriving from all issuers, and a slot is re-filled only after the MMA
 // warps of ALL CTAs released it (tcgen05.commit ... multicast::cluster onto every CTA's `empty` barrier, count CS).
 #include "tc_common.cuh"
