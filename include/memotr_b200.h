@@ -112,6 +112,15 @@ MEMOTR_API int memotr_linear_msda_prep(const void *A, int lda, const void *W, in
                                        int M, int K, int n_heads, int n_levels, int n_points, const int *shapes_hw,
                                        const int *level_start, const float *valid_ratios, void *stream);
 
+/* EXPERIMENT (csrc/msda_window.cu): encoder-shaped gather with TMA-staged value-map windows in shared memory for tiles of
+ * 8 x 8 level-0 queries (global-memory fallback for samples that leave the window; the coarser levels' queries go through
+ * memotr_msda_forward_strided).  fp16 pixel-major value map, 4 levels, strided locations / weights, bf16 output.
+ * shapes_hw (2L) / level_start (L): host copies of spatial_shapes / level_start_idx; valid_ratios (L,2) device. */
+MEMOTR_API int memotr_msda_forward_window(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
+                                          const int64_t *level_start_idx, const int *shapes_hw, const int *level_start,
+                                          const float *sampling_loc, int ld_loc, const float *attn_weight, int ld_attn,
+                                          const float *valid_ratios, void *output, int S, int H, int L, int K, void *stream);
+
 /*
  * Encoder-shaped bf16 fast path of the forward op on a re-laid-out value map.
  * memotr_msda_pairs_layout: value (S, >=H*32 per pixel, bf16) -> pairs (H, S, 2, 32) bf16: entry s = pixel (y,x) holds the

@@ -99,6 +99,9 @@ class FrameEngine:
         # encoder value maps head-major (H, S, 32): the x-corners of a footprint are adjacent 64-byte blocks (A/B switch)
         self.value_hm = (self.fuse_prep and os.environ.get("MEMOTR_VALUE_HM", "0") == "1"
                          and 2 * ((self.S + 127) // 128) > n_sm)
+        # experimental: TMA-staged value-map windows in shared memory for the encoder gather (csrc/msda_window.cu)
+        self.msda_window = (self.fuse_prep and not self.value_hm and self.L == 4 and self.H % 2 == 0
+                            and os.environ.get("MEMOTR_MSDA_WINDOW", "0") == "1")
         self._pack(state_dict)
         self._alloc()
         # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
@@ -576,11 +579,20 @@ class FrameEngine:
             self._timer_slot += 1
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
         attw = self.ol.view(-1)[H * L * K * 2:]                    # the weights start after the locations in every row
+        if self.msda_window:
+            self._ck(self.lib.memotr_msda_forward_window(_p(self.value), self.C, _p(self.shapes_t), _p(self.lsi_t), self._prep_hw,
+                                                         self._prep_lsi, _p(self.ol), N, _p(attw), N, _p(self.vr), _p(self.att),
+                                                         S, H, L, K, self._st()), "msda_forward_window")
+            self.launches += 1
+        else:
+            self._encoder_gather_strided(N, attw, S, H, L, K)
+        if timed:
+            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
+
+    def _encoder_gather_strided(self, N, attw, S, H, L, K):
         self._ck(self.lib.memotr_msda_forward_strided(_p(self.value), 32 if self.value_hm else self.C, _p(self.shapes_t),
                                                       _p(self.lsi_t), _p(self.ol), N, _p(attw), N, _p(self.att), 1, S, H, L, S, K,
                                                       int(self.value_hm), self._st()), "msda_forward_strided")
-        if timed:
-            _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
 
     def mha(self, q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, kpm=None):
         """q/k/v are the fp32 projections (kept in fp32 in both modes: rounding them to bf16 perturbs the attention

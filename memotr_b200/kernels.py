@@ -154,6 +154,24 @@ def msda_forward_strided(value, spatial_shapes, level_start_index, rows, n_heads
     return out
 
 
+def msda_forward_window(value, spatial_shapes, level_start_index, shapes, level_start, rows, valid_ratios, n_heads, n_levels,
+                        n_points):
+    """Experimental windowed gather (csrc/msda_window.cu): value (S, >=H*32) fp16 pixel-major, rows as linear_msda_prep."""
+    import ctypes
+    S, N = rows.shape
+    out = torch.empty((S, n_heads * 32), dtype=torch.bfloat16, device=value.device)
+    attw = rows.view(-1)[n_heads * n_levels * n_points * 2:]
+    hw = (ctypes.c_int * (2 * n_levels))(*[int(v) for s_ in shapes for v in s_])
+    lsi = (ctypes.c_int * n_levels)(*[int(v) for v in level_start])
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().memotr_msda_forward_window(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
+                                                   _lib.ptr(level_start_index), hw, lsi, _lib.ptr(rows), N, _lib.ptr(attw), N,
+                                                   _lib.ptr(valid_ratios), _lib.ptr(out), S, n_heads, n_levels, n_points,
+                                                   _lib.stream_ptr())
+    _lib.check(rc, "memotr_msda_forward_window")
+    return out
+
+
 def sine_embed(pts, dim_t, scale4=None, apply_sigmoid=False, out_dtype=torch.float32):
     N = pts.shape[0]
     out = torch.empty((N, 512), dtype=out_dtype, device=pts.device)

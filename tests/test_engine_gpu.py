@@ -397,6 +397,13 @@ def test_linear_with_msda_prep_epilogue_and_strided_gather():
     cat = torch.cat((loc.reshape(S, 256), attn.reshape(S, 128)), 1).contiguous()
     strided2 = K().msda_forward_strided(value, shapes_t, lsi_t, cat, H, L, Kp)
     assert torch.equal(strided2, dense)                                                       # same inputs: bit-equal
+    # experimental windowed gather (TMA-staged windows in shared memory + global fallback): same taps, same order
+    win = K().msda_forward_window(value, shapes_t, lsi_t, shapes, lsi, rows, vr, H, L, Kp)
+    assert torch.equal(win, strided)
+    far = rows.clone()                      # offsets far beyond the halo: every sample takes the global fallback
+    far[:, :256] += 0.3 * torch.randn(S, 256, generator=g).to(DEV)
+    assert torch.equal(K().msda_forward_window(value, shapes_t, lsi_t, shapes, lsi, far, vr, H, L, Kp),
+                       K().msda_forward_strided(value, shapes_t, lsi_t, far, H, L, Kp))
     # head-major value map (H, S, 32): same numbers in another layout -> bit-equal gather
     hm = value.reshape(S, H, 32).permute(1, 0, 2).contiguous()
     assert torch.equal(K().msda_forward_strided(hm, shapes_t, lsi_t, cat, H, L, Kp, head_major=True), dense)
