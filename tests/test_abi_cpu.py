@@ -62,3 +62,50 @@ def test_module_state_dict_keys_match_reference_table():
             if k.startswith("transformer.encoder.layers.0.self_attn.")}
     have = {k: tuple(v.shape) for k, v in MSDeformAttn(256, 4, 8, 4).state_dict().items()}
     assert have == want
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The parameter blocks passed by value / by pointer across the C ABI: sizes and a few field offsets as a C compiler
+    sees include/memotr_b200.h must equal the ctypes mirrors in memotr_b200/_lib.py (a silent drift would corrupt pointers)."""
+    import subprocess
+    from memotr_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "memotr_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(memotr_track_table), sizeof(memotr_frame_outputs), sizeof(memotr_dec_gemm),
+         sizeof(memotr_dec_layer), sizeof(memotr_dec_params), sizeof(memotr_upd_params));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(memotr_dec_params, rph0_b), offsetof(memotr_dec_params, shapes),
+         offsetof(memotr_dec_params, layers), offsetof(memotr_upd_params, update_thresh), offsetof(memotr_upd_params, kbuf));
+  return 0;
+}
+''')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes, offs = (tuple(int(v) for v in line.split()) for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    mirrors = (_lib.TrackTable, _lib.FrameOutputs, _lib.DecGemm, _lib.DecLayer, _lib.DecParams, _lib.UpdParams)
+    assert sizes == tuple(ctypes.sizeof(m) for m in mirrors)
+    assert offs == (_lib.DecParams.rph0_b.offset, _lib.DecParams.shapes.offset, _lib.DecParams.layers.offset,
+                    _lib.UpdParams.update_thresh.offset, _lib.UpdParams.kbuf.offset)
+
+
+def test_engine_input_layout_is_one_contiguous_buffer():
+    """FrameEngine.input_layout / input_views (the flat staging buffer of ClipRunner): views tile the buffer without overlap,
+    masks are consecutive (the engine reads them as one (S,) padding mask), with and without uploaded position maps."""
+    from memotr_b200.engine import FrameEngine
+    shapes, C = [(5, 7), (3, 4), (2, 2)], 8
+    for with_pos in (True, False):
+        lay = FrameEngine.input_layout(shapes, C, with_pos=with_pos)
+        flat = torch.zeros(lay["bytes"], dtype=torch.uint8)
+        src, pos, mask = FrameEngine.input_views(flat, lay, shapes, C)
+        assert (pos is None) == (not with_pos) and len(src) == len(mask) == 3
+        for i, t in enumerate(src + (pos or []) + mask):
+            t.reshape(-1).view(torch.uint8).fill_(i + 1)        # tag every BYTE of the view
+        used = sum(t.numel() * t.element_size() for t in src + (pos or []) + mask)
+        assert used <= lay["bytes"] < used + 16 and int((flat != 0).sum()) == used      # no overlap, no gaps but the tail pad
+        S = sum(h * w for h, w in shapes)
+        m0 = lay["mask"][0]
+        assert [int(v) for v in flat[m0:m0 + S].unique()] == sorted({int(m[0]) for m in mask})
+        assert all(int(flat[lay["mask"][l]]) == int(mask[l][0]) for l in range(3))
