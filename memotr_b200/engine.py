@@ -114,7 +114,7 @@ class FrameEngine:
             self._build_decoder_program_cluster()
         # the query updater as one persistent cluster kernel (csrc/updater_cluster.cu); A/B switch MEMOTR_UPD_FUSED=0
         self.upd_fused = (self.dec_cluster and os.environ.get("MEMOTR_UPD_FUSED", "1") != "0"
-                          and (self.nt + 15) // 16 * 4 <= 132)
+                          and 1 <= self.nt and (self.nt + 15) // 16 * 4 <= 132)
         if self.upd_fused:
             self._build_updater_program()
         self.graph = None
@@ -801,6 +801,8 @@ class FrameEngine:
     def update_tracks(self):
         """QueryUpdater.update_tracks_embedding on the fp32 track state in self.st (query_updater.py:82-166)."""
         C, nt, dt, st, u = self.C, self.nt, self.dt, self.st, self.upd
+        if nt == 0:
+            return
         if self.upd_fused:      # one persistent kernel; it also writes the fed-back track queries (in_track_ref / _embed)
             import ctypes
             self._ck(self.lib.memotr_updater_forward_cluster(ctypes.byref(self.upd_params), self._st()), "updater_forward")
