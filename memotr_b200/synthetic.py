@@ -141,6 +141,69 @@ def hot_path_state_dict(cfg, seed=0):
     return sd
 
 
+def reference_init_state_dict(cfg, seed=0, zero_init_scale=0.1):
+    """Weights drawn from the reference's OWN initialisation distributions -- what SURVEY.md 8d names for the
+    single-frame configuration ("default init of the reference modules"), regenerated from a seed so that the GPU box
+    needs no checkpoint:
+      * every matrix of the transformer and the query updater: xavier_uniform (deformable_transformer.py:111-114,
+        query_updater.py:67-70); nn.Linear biases U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (torch default);
+        MultiheadAttention in_proj_bias / out_proj.bias 0; LayerNorm 1 / 0
+      * MSDeformAttn: sampling_offsets.bias = the ring pattern, value_proj / output_proj xavier with zero bias
+        (ms_deform_attn.py:72-86); level_embed, det_anchor, det_query_embed ~ N(0, 1) (memotr.py:59-60)
+      * class_embed: torch default weight, bias -log(99) (memotr.py:79-81); bbox_embed: torch default, last layer's bias
+        (0, 0, -2, -2) on layer 0 (memotr.py:82-91)
+    The four matrices the reference initialises to exactly ZERO (sampling_offsets.weight, attention_weights.weight/bias,
+    the last bbox_embed layer) get `zero_init_scale` x their xavier range instead, so that their GEMMs carry signal in
+    the parity tests (a zero matrix cannot expose a wrong kernel); zero_init_scale=0 reproduces the reference init."""
+    g = _gen(seed)
+    C, H, L = cfg["d_model"], cfg["n_heads"], cfg["n_levels"]
+    sd = {}
+
+    def uniform(shape, bound):
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+    def xavier(shape, gain=1.0):
+        return uniform(shape, gain * math.sqrt(6.0 / (shape[0] + shape[1])))
+
+    shapes = hot_path_param_shapes(cfg)
+    for key, shape in shapes.items():
+        parts = key.split(".")
+        leaf = parts[-1]
+        is_norm = len(parts) >= 2 and "norm" in parts[-2]
+        in_core = key.startswith("transformer.") or key.startswith("query_updater.")
+        if is_norm:
+            v = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+        elif key.endswith("sampling_offsets.bias"):
+            K = shape[0] // (H * L * 2)
+            th = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+            ring = torch.stack([th.cos(), th.sin()], -1)
+            ring = (ring / ring.abs().max(-1, keepdim=True)[0]).view(H, 1, 1, 2).repeat(1, L, K, 1)
+            v = (ring * torch.arange(1, K + 1, dtype=torch.float32).view(1, 1, K, 1)).reshape(-1)
+        elif key.endswith("sampling_offsets.weight") or key.endswith("attention_weights.weight"):
+            v = xavier(shape, zero_init_scale)
+        elif key.endswith("attention_weights.bias"):
+            v = uniform(shape, zero_init_scale / math.sqrt(C))
+        elif key.endswith("value_proj.bias") or key.endswith("output_proj.bias") or leaf == "in_proj_bias" \
+                or key.endswith("out_proj.bias"):
+            v = torch.zeros(shape)
+        elif key in ("det_anchor", "det_query_embed", "transformer.level_embed"):
+            v = torch.randn(shape, generator=g)
+        elif key.startswith("class_embed") and leaf == "bias":
+            v = torch.full(shape, -math.log(99.0))
+        elif key.startswith("bbox_embed") and parts[-2] == "2":          # last layer of the box MLP
+            if leaf == "weight":
+                v = xavier(shape, zero_init_scale)
+            else:
+                v = torch.tensor([0.0, 0.0, -2.0, -2.0]) if parts[1] == "0" else torch.zeros(shape)
+        elif leaf in ("weight", "in_proj_weight"):
+            v = xavier(shape) if in_core else uniform(shape, 1.0 / math.sqrt(shape[1]))
+        else:                                                             # nn.Linear bias, torch default
+            fan_in = shapes[key[:-len("bias")] + "weight"][1]
+            v = uniform(shape, 1.0 / math.sqrt(fan_in))
+        sd[key] = v.float()
+    return sd
+
+
 def frame_inputs(cfg, shapes=DANCETRACK_SHAPES, n_tracks=100, seed=1, padded=False):
     """One synthetic frame for batch size 1.  -> dict(srcs, masks, pos: lists per level;  tracks: dict)."""
     g = _gen(seed)

@@ -28,9 +28,90 @@ import torch.nn.functional as F
 LN_EPS = 1e-5
 
 
+# ----------------------------------------------------------------------------------------------- numerics model
+# The engine's arithmetic modes restated as ROUNDING POINTS on the fp32 graph (test infrastructure: this is how the
+# parity tests separate "the kernels compute what they claim" from "the network amplifies operand rounding"):
+#   gemm   None      fp32 operands (the reference's precision contract, main.py:96-97: TF32 off)
+#          "bf16"    both operands of every nn.Linear rounded to bf16, fp32 accumulation (engine mode "bf16")
+#          "bf16x3"  a = a_hi + a_lo (two bf16 terms each), products hi*hi + hi*lo + lo*hi, fp32 accumulation (~2^-16)
+#          "bf16x6"  three bf16 terms per operand, the six products down to 2^-24 (engine mode "fp32tc")
+#          "tf32x3"  two tf32 terms per operand, three products (~2^-21)
+#          "fp16x3"  two fp16 terms per operand (22 mantissa bits), three products (engine mode "fp32tc")
+#   value  None | "fp16" | "bf16"   storage type of the projected value maps the gather reads
+#   gather None | "bf16"            storage type of the gather's output rows (a GEMM operand)
+NUMERICS = {"gemm": None, "value": None, "gather": None, "fp16_weight_shift": 6}
+
+
+class numerics:
+    """with numerics(gemm="bf16", value="fp16", gather="bf16"): ... -- scoped switch of the rounding model."""
+
+    def __init__(self, **kw):
+        assert set(kw) <= set(NUMERICS), kw
+        self.kw = kw
+
+    def __enter__(self):
+        self.saved = dict(NUMERICS)
+        NUMERICS.update(self.kw)
+        return self
+
+    def __exit__(self, *exc):
+        NUMERICS.clear()
+        NUMERICS.update(self.saved)
+        return False
+
+
+def _tf32(x):
+    """Round fp32 to the nearest tf32 (10 explicit mantissa bits), ties to even."""
+    i = x.contiguous().view(torch.int32)
+    r = ((i >> 13) & 1) + 0xFFF
+    return ((i + r) & ~0x1FFF).view(torch.float32)
+
+
+def _split(x, n, rnd):
+    parts, rest = [], x
+    for _ in range(n):
+        p = rnd(rest)
+        parts.append(p)
+        rest = rest - p
+    return parts
+
+
+def _rounded_matmul(x, w, mode):
+    """x (…, K) @ w (N, K)^T under the operand-rounding model `mode`; fp32 accumulation."""
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)              # noqa: E731
+    if mode == "bf16":
+        return F.linear(bf(x), bf(w))
+    hf = lambda t: t.to(torch.float16).to(torch.float32)               # noqa: E731  (subnormals kept, like the MMA)
+    n, rnd = {"bf16x3": (2, bf), "bf16x6": (3, bf), "tf32x3": (2, _tf32), "fp16x3": (2, hf)}[mode]
+    sc = 1.0
+    if mode == "fp16x3":       # the packed weights carry an exact power-of-two scale so that their low halves stay normal
+        sc = 2.0 ** NUMERICS.get("fp16_weight_shift", 6)
+    xs, ws = _split(x, n, rnd), _split(w * sc, n, rnd)
+    out = None
+    for i in reversed(range(n)):                 # smallest terms first
+        for j in reversed(range(n)):
+            if i + j < n:
+                t = F.linear(xs[i], ws[j])
+                out = t if out is None else out + t
+    return out / sc if sc != 1.0 else out
+
+
+def _store(x, kind):
+    if kind is None:
+        return x
+    return x.to({"fp16": torch.float16, "bf16": torch.bfloat16}[kind]).to(x.dtype)
+
+
 # ----------------------------------------------------------------------------------------------- small pieces
 def linear(sd, key, x):
-    return F.linear(x, sd[key + ".weight"], sd[key + ".bias"])
+    w, b = sd[key + ".weight"], sd[key + ".bias"]
+    mode = NUMERICS["gemm"]
+    if isinstance(mode, dict):                   # per-region model: longest matching key prefix wins ("" = default)
+        hit = max((p for p in mode if key.startswith(p)), key=len, default=None)
+        mode = mode[hit] if hit is not None else None
+    if mode is None or x.dtype != torch.float32:
+        return F.linear(x, w, b)
+    return _rounded_matmul(x, w, mode) + b
 
 
 def layer_norm(sd, key, x):
@@ -75,9 +156,9 @@ def mha(sd, key, q, k, v, n_heads, key_padding_mask=None):
     Nk = k.shape[1]
     d = C // n_heads
     w, b = sd[key + ".in_proj_weight"], sd[key + ".in_proj_bias"]
-    qp = F.linear(q, w[:C], b[:C])
-    kp = F.linear(k, w[C:2 * C], b[C:2 * C])
-    vp = F.linear(v, w[2 * C:], b[2 * C:])
+    tmp = {"q.weight": w[:C], "q.bias": b[:C], "k.weight": w[C:2 * C], "k.bias": b[C:2 * C],
+           "v.weight": w[2 * C:], "v.bias": b[2 * C:]}
+    qp, kp, vp = linear(tmp, "q", q), linear(tmp, "k", k), linear(tmp, "v", v)
     qp = qp.view(B, Nq, n_heads, d).transpose(1, 2) * math.sqrt(1.0 / d)
     kp = kp.view(B, Nk, n_heads, d).transpose(1, 2)
     vp = vp.view(B, Nk, n_heads, d).transpose(1, 2)
@@ -117,7 +198,7 @@ def msda_module(sd, key, query, ref, src, shapes, lsi, padding_mask, n_heads, n_
     value = linear(sd, key + ".value_proj", src)
     if padding_mask is not None:
         value = value.masked_fill(padding_mask[..., None], 0.0)
-    value = value.view(B, S, n_heads, C // n_heads)
+    value = _store(value, NUMERICS["value"]).view(B, S, n_heads, C // n_heads)
     off = linear(sd, key + ".sampling_offsets", query).view(B, Lq, n_heads, n_levels, n_points, 2)
     aw = linear(sd, key + ".attention_weights", query).view(B, Lq, n_heads, n_levels * n_points)
     aw = torch.softmax(aw, -1).view(B, Lq, n_heads, n_levels, n_points)
@@ -131,7 +212,7 @@ def msda_module(sd, key, query, ref, src, shapes, lsi, padding_mask, n_heads, n_
         out = msda_core(value, shapes, loc, aw)
     else:
         out = core(value, shapes_t, lsi, loc, aw)
-    return linear(sd, key + ".output_proj", out)
+    return linear(sd, key + ".output_proj", _store(out, NUMERICS["gather"]))
 
 
 # ----------------------------------------------------------------------------------------------- encoder
@@ -182,27 +263,37 @@ def decoder_layer(sd, key, tgt, query_pos, ref_in, memory, shapes, lsi, query_ma
     return tgt
 
 
+def decoder_step(sd, lid, out, ref, memory, shapes, lsi, valid_ratios, query_mask, mem_mask, cfg, core=None,
+                 key="transformer.decoder", bbox_key="bbox_embed"):
+    """One iteration of DeformableDecoder.forward's layer loop (deformable_decoder.py:80-159, USE_DAB + box refinement):
+    (layer input `out` (B,Nq,C), sigmoid-space boxes `ref` (B,Nq,4)) -> (layer output, refined boxes).  Also the unit the
+    teacher-forced parity tests drive layer by layer."""
+    C = out.shape[-1]
+    nd, merge_layer = cfg["n_det_queries"], cfg["merge_det_track_layer"]
+    ref_in = ref[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
+    anchor = pos_to_pos_embed(ref_in[:, :, 0, :], num_pos_feats=C // 2)
+    raw_pos = mlp(sd, key + ".ref_point_head", anchor, 2)
+    scale = mlp(sd, key + ".query_scale", out, 2) if lid != 0 else 1
+    query_pos = scale * raw_pos
+    out = decoder_layer(sd, f"{key}.layers.{lid}", out, query_pos, ref_in, memory, shapes, lsi, query_mask,
+                        mem_mask, cfg, merge=(lid >= merge_layer), core=core)
+    new_ref = (mlp(sd, f"{bbox_key}.{lid}", out, 3) + inverse_sigmoid(ref)).sigmoid()
+    if lid < merge_layer:                  # refined points are detached (deformable_decoder.py:150-159)
+        ref = torch.cat((new_ref[:, :nd].detach(), ref[:, nd:]), dim=1)
+    else:
+        ref = new_ref.detach()
+    return out, ref
+
+
 def decoder(sd, key, bbox_key, tgt, ref, memory, shapes, lsi, valid_ratios, query_mask, mem_mask, cfg, core=None):
     """DeformableDecoder.forward, USE_DAB branch with iterative box refinement
     (deformable_decoder.py:56-171).  Returns (outputs[n,B,Nq,C], refs[n,B,Nq,4], queries[n,B,Nq,C])."""
-    C = tgt.shape[-1]
-    nd, merge_layer = cfg["n_det_queries"], cfg["merge_det_track_layer"]
     outs, refs, queries = [], [], []
     out = tgt
     for lid in range(cfg["n_dec_layers"]):
-        ref_in = ref[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
-        anchor = pos_to_pos_embed(ref_in[:, :, 0, :], num_pos_feats=C // 2)
-        raw_pos = mlp(sd, key + ".ref_point_head", anchor, 2)
-        scale = mlp(sd, key + ".query_scale", out, 2) if lid != 0 else 1
-        query_pos = scale * raw_pos
         queries.append(out)
-        out = decoder_layer(sd, f"{key}.layers.{lid}", out, query_pos, ref_in, memory, shapes, lsi, query_mask,
-                            mem_mask, cfg, merge=(lid >= merge_layer), core=core)
-        new_ref = (mlp(sd, f"{bbox_key}.{lid}", out, 3) + inverse_sigmoid(ref)).sigmoid()
-        if lid < merge_layer:                  # refined points are detached (deformable_decoder.py:150-159)
-            ref = torch.cat((new_ref[:, :nd].detach(), ref[:, nd:]), dim=1)
-        else:
-            ref = new_ref.detach()
+        out, ref = decoder_step(sd, lid, out, ref, memory, shapes, lsi, valid_ratios, query_mask, mem_mask, cfg, core,
+                                key, bbox_key)
         outs.append(out)
         refs.append(ref)
     return torch.stack(outs), torch.stack(refs), torch.stack(queries)

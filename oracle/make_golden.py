@@ -13,6 +13,10 @@ script is only ever run here and its products are committed under tests/golden/:
                     nn.Modules on oracle.synth's small configuration (weights/inputs regenerated from seeds, only
                     outputs stored).
   frame_full.npz    the same at the DanceTrack 1333x800 configuration (S=22323, 300+100 queries, 6+6 layers).
+  frame_full_refinit.npz   the same configuration with weights from the reference's own initialisation distributions
+                    (synth.reference_init_state_dict), right/bottom-padded masks and the reference's PositionEmbeddingSine
+                    maps: the well-conditioned case the bf16 engine is held to 1e-2 on (frame_full's white-noise weights
+                    amplify operand rounding 40x, tests/test_numerics_cpu.py).
 
 The compiled reference op cannot run on a CPU ("Not implemented on the CPU", src/ms_deform_attn.h:38), so --
 exactly as BASELINE.md section 3 prescribes -- MSDeformAttnFunction.apply is routed to the reference's own
@@ -116,7 +120,10 @@ class _Const(nn.Module):
         return self.t
 
 
-def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
+def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag, weights="synth", sine_pos=False):
+    """weights="refinit": the reference's own initialisation distributions (synth.reference_init_state_dict);
+    sine_pos: the position maps are the reference's PositionEmbeddingSine of the padding masks (instead of white noise),
+    i.e. exactly what BackboneWithPE hands MeMOTR.forward."""
     import models.memotr as memotr
     from models.deformable_transformer import build as build_tr
     from models.query_updater import build as build_qu
@@ -125,6 +132,10 @@ def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
 
     rc = oframe.to_reference_config(cfg)
     x = synth.frame_inputs(cfg, shapes, n_tracks, seed=seed_x, padded=padded)
+    if sine_pos:
+        from models.position_embedding import build as build_pe
+        pe = build_pe({"HIDDEN_DIM": cfg["d_model"]})
+        x["pos"] = [pe(NestedTensor(torch.zeros(1, 3, m.shape[1], m.shape[2]), m)) for m in x["masks"]]
     torch.manual_seed(0)
     model = memotr.MeMOTR(backbone=_FakeBackbone(x["srcs"], x["masks"], x["pos"]), transformer=build_tr(rc),
                           query_updater=build_qu(rc), num_classes=cfg["num_classes"],
@@ -141,7 +152,8 @@ def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
     have = {k: tuple(v.shape) for k, v in model.state_dict().items()
             if not k.startswith(("feature_projs", "transformer.decoder.bbox_embed"))}
     assert have == want, (set(have) ^ set(want), [k for k in have if k in want and have[k] != want[k]])
-    sd = synth.hot_path_state_dict(cfg, seed=seed_w)
+    sd = (synth.reference_init_state_dict(cfg, seed=seed_w) if weights == "refinit"
+          else synth.hot_path_state_dict(cfg, seed=seed_w))
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.startswith(("feature_projs", "transformer.decoder.bbox_embed"))
                                   for k in missing), (missing, unexpected)
@@ -176,7 +188,8 @@ def golden_frame(cfg, shapes, n_tracks, seed_w, seed_x, padded, tag):
         out["upd_" + k] = getattr(upd, k)
 
     arrays = {k: v.detach().numpy() for k, v in out.items()}
-    arrays["meta"] = np.asarray([n_tracks, seed_w, seed_x, int(padded)], dtype=np.int64)
+    arrays["meta"] = np.asarray([n_tracks, seed_w, seed_x, int(padded), int(weights == "refinit"), int(sine_pos)],
+                                dtype=np.int64)
     arrays["shapes"] = np.asarray(shapes, dtype=np.int64)
     np.savez_compressed(os.path.join(OUT, f"frame_{tag}.npz"), **arrays)
     print(f"frame_{tag}.npz:", {k: v.shape for k, v in arrays.items()})
@@ -257,6 +270,10 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     func = import_reference()
+    if "--refinit-only" in sys.argv:
+        golden_frame(oframe.dancetrack_cfg(), synth.DANCETRACK_SHAPES, n_tracks=100, seed_w=0, seed_x=1, padded=True,
+                     tag="full_refinit", weights="refinit", sine_pos=True)
+        sys.exit(0)
     golden_tracker()
     golden_pos_embed()
     if "--tracker-only" in sys.argv:
@@ -267,3 +284,5 @@ if __name__ == "__main__":
     if "--full" in sys.argv:
         cfg = oframe.dancetrack_cfg()
         golden_frame(cfg, synth.DANCETRACK_SHAPES, n_tracks=100, seed_w=0, seed_x=1, padded=False, tag="full")
+        golden_frame(cfg, synth.DANCETRACK_SHAPES, n_tracks=100, seed_w=0, seed_x=1, padded=True, tag="full_refinit",
+                     weights="refinit", sine_pos=True)
