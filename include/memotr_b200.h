@@ -95,14 +95,7 @@ MEMOTR_API int memotr_msda_forward_ex(const void *value, int value_pixel_stride,
 MEMOTR_API int memotr_msda_forward_strided(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
                                            const int64_t *level_start_idx, const float *sampling_loc, int ld_loc,
                                            const float *attn_weight, int ld_attn, void *output, int B, int S, int H, int L,
-                                           int Lq, int K, int head_major /* value is (H, S, 32), pixel stride 32 */,
-                                           void *stream);
-
-/* value projection written HEAD-MAJOR: out (N/32, M, 32) fp16 = (A W^T + bias) with rows of padded pixels zeroed
- * (ms_deform_attn.py:104-106); in this layout the two x-corners of a bilinear footprint are adjacent 64-byte blocks
- * (3 instead of 4 L1 lines per sampling point).  bf16 A (M,K), W (N,K); persistent tcgen05 kernel only. */
-MEMOTR_API int memotr_linear_headmajor(const void *A, int lda, const void *W, int ldw, const float *bias,
-                                       const unsigned char *rowzero, void *out, int M, int N, int K, void *stream);
+                                           int Lq, int K, void *stream);
 
 /* The offsets / attention-logits projection of MSDeformAttn with memotr_msda_prep (encoder mode) fused into the GEMM
  * epilogue (ms_deform_attn.py:104-120): out (M, 3*H*L*K) fp32 rows = [sampling locations (H, L*K, 2) | softmax weights
@@ -112,28 +105,33 @@ MEMOTR_API int memotr_linear_msda_prep(const void *A, int lda, const void *W, in
                                        int M, int K, int n_heads, int n_levels, int n_points, const int *shapes_hw,
                                        const int *level_start, const float *valid_ratios, void *stream);
 
-/* EXPERIMENT (csrc/msda_window.cu): encoder-shaped gather with TMA-staged value-map windows in shared memory for tiles of
- * 8 x 8 level-0 queries (global-memory fallback for samples that leave the window; the coarser levels' queries go through
- * memotr_msda_forward_strided).  fp16 pixel-major value map, 4 levels, strided locations / weights, bf16 output.
- * shapes_hw (2L) / level_start (L): host copies of spatial_shapes / level_start_idx; valid_ratios (L,2) device. */
-MEMOTR_API int memotr_msda_forward_window(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
-                                          const int64_t *level_start_idx, const int *shapes_hw, const int *level_start,
-                                          const float *sampling_loc, int ld_loc, const float *attn_weight, int ld_attn,
-                                          const float *valid_ratios, void *output, int S, int H, int L, int K, void *stream);
-
 /*
- * Encoder-shaped bf16 fast path of the forward op on a re-laid-out value map.
- * memotr_msda_pairs_layout: value (S, >=H*32 per pixel, bf16) -> pairs (H, S, 2, 32) bf16: entry s = pixel (y,x) holds the
- *   32 channels of head h of that pixel followed by those of its right neighbour (y,x+1) (zeros at the end of a row), so
- *   the two x-corners of a bilinear footprint are one aligned 128-byte line (the L1 serves one line per clock).
- * memotr_msda_forward_pairs: same arithmetic as memotr_msda_forward_ex (B = 1, D = 32, fp32 loc/attn, bf16 output
- *   (Lq, H*32)) reading that layout: 2 lines and 2 loads per sampling point instead of 4 and 4.  K in {1,2,4,8}.
+ * Encoder-shaped forward op (queries = the S pixels of the pyramid, models/deformable_encoder.py:124; batch 1) with
+ * TMA-staged value-map windows in shared memory (csrc/msda_window.cu): replaces ms_deformable_im2col_gpu_kernel
+ * (models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299) for an fp16 pixel-major value map (pixel stride >= H*32) and a
+ * bf16 output (S, H*32); sampling locations / attention weights fp32 with row strides ld_loc / ld_attn.  Bit-identical to
+ * memotr_msda_forward_strided on the same inputs.
+ *   shapes_hw (2L) / level_start (L): HOST copies of spatial_shapes / level_start_idx; valid_ratios (L,2) device.
+ *   window_shift: host (H, L, 2) floats or NULL -- expected sampling offset (x, y) of each head on each level in pixels of
+ *     that level (for MSDeformAttn: the mean over the K points of sampling_offsets.bias, ms_deform_attn.py:72-81);
+ *   window_radius: spread of the samples around it, pixels.  Both only steer WHAT is staged: a tap outside its window is
+ *     read from global memory with the same arithmetic.
+ *   max_classes: 0 = default; 1 = stage windows only for the queries of level 0; 2 = levels 0 and 1.
+ *   stats: device, 2 x uint64 or NULL -- profiling counters += {sampling points served from windows, points left to
+ *     global memory} over the window units of this launch.
+ * L <= 5, H <= 16, K even.
  */
-MEMOTR_API int memotr_msda_pairs_layout(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
-                                        const int64_t *level_start_idx, void *pairs, int S, int H, int L, void *stream);
-MEMOTR_API int memotr_msda_forward_pairs(const void *pairs, const int64_t *spatial_shapes, const int64_t *level_start_idx,
-                                         const float *sampling_loc, const float *attn_weight, void *output, int S, int H,
-                                         int L, int Lq, int K, void *stream);
+MEMOTR_API int memotr_msda_forward_window(const void *value, int value_pixel_stride, const int *shapes_hw, const int *level_start,
+                                          const float *sampling_loc, int ld_loc, const float *attn_weight, int ld_attn,
+                                          const float *valid_ratios, const float *window_shift, float window_radius,
+                                          int max_classes, unsigned long long *stats, void *output, int S, int H, int L, int K,
+                                          void *stream);
+/* The staging plan of memotr_msda_forward_window as integers (host only, no GPU needed): info[0..7] = {classes, window
+ * units (CTAs), global-memory CTAs, first global-memory query, dynamic shared memory bytes per CTA, 0, 0, 0}, then per
+ * class 18 ints {query level, tile w, tile h, tiles_x, tiles_y, units, TMA bytes per unit, record stride, ww[5], wh[5]}.
+ * `info` must hold 8 + 2 * 18 ints. */
+MEMOTR_API int memotr_msda_window_plan(const int *shapes_hw, const int *level_start, int S, int H, int L, int K, float radius,
+                                       int max_classes, int *info);
 
 /*
  * Sampling locations + attention weights from the raw projections -- models/ops/modules/ms_deform_attn.py:108-120.

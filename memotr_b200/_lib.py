@@ -79,12 +79,10 @@ _SIGNATURES = {
     "memotr_msda_forward": ([_vp] * 6 + [_i] * 8 + [_vp], _i),
     "memotr_msda_backward": ([_vp] * 9 + [_i] * 8 + [_vp], _i),
     "memotr_msda_forward_ex": ([_vp, _i] + [_vp] * 5 + [_i] * 7 + [_vp], _i),
-    "memotr_msda_forward_strided": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp] + [_i] * 7 + [_vp], _i),
-    "memotr_linear_headmajor": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "memotr_msda_forward_strided": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp] + [_i] * 6 + [_vp], _i),
     "memotr_linear_msda_prep": ([_vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 5 + [_vp, _vp, _vp, _vp], _i),
-    "memotr_msda_forward_window": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
-    "memotr_msda_pairs_layout": ([_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
-    "memotr_msda_forward_pairs": ([_vp] * 6 + [_i] * 5 + [_vp], _i),
+    "memotr_msda_forward_window": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "memotr_msda_window_plan": ([_vp, _vp, _i, _i, _i, _i, _f, _i, _vp], _i),
     "memotr_msda_prep": ([_vp, _i] + [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 4 + [_vp], _i),
     "memotr_linear": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 7 + [_vp], _i),
     "memotr_mlp2": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 6 + [_vp], _i),

@@ -164,9 +164,6 @@ struct Epilogue {
   int prep, prep_L, prep_K, prep_nh;
   int prep_hw[16], prep_lsi[8];   // (H_l, W_l) and first row of every level
   const float *prep_vr;           // device (L, 2) valid ratios
-  // head-major store (gemm_tc_persist.cu, fp16 output only): the (M, H*32) result is written as (H, M, 32) -- the layout in
-  // which the two x-corners of a bilinear footprint are adjacent 64-byte blocks (msda_fwd.cu)
-  int headmajor;
 };
 
 }  // namespace memotr

@@ -210,15 +210,6 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int k = 0; k < 8; ++k)
               *reinterpret_cast<float4 *>(prow + ((k ^ (r_in & 7)) << 4)) =
                   make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          } else if (ep.headmajor) {   // one head (32 columns) per chunk: its own (128 rows x 64 B) block, no swizzle
-            uint8_t *hrow = stage_out + (c0 / 32) * (BM * 64) + r_in * 64;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float t[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) t[i] = v[8 * k + i];
-              *reinterpret_cast<uint4 *>(hrow + (k << 4)) = pack8<TC>(t);
-            }
           } else {
             const int kbase = (c0 % PANEL_COLS) / 8;  // 0 or 4: which half of the 64-column panel row
     #pragma unroll
@@ -234,19 +225,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) {
-        if (ep.headmajor) {       // tmC is the 3-D (H, M, 32) map: one store per head of this 128-column tile
 #pragma unroll 1
-          for (int hh = 0; hh < BN / 32; ++hh)
-            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC),
-                         "r"(smem_u32(stage_out + hh * (BM * 64))), "r"(0), "r"(m_blk * BM), "r"(n_blk * (BN / 32) + hh)
-                         : "memory");
-        } else {
-#pragma unroll 1
-          for (int p = 0; p < N_PANELS; ++p)
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
-                         "r"(smem_u32(stage_out + p * (BM * 128))), "r"(n_blk * BN + p * PANEL_COLS), "r"(m_blk * BM)
-                         : "memory");
-        }
+        for (int p = 0; p < N_PANELS; ++p)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                       "r"(smem_u32(stage_out + p * (BM * 128))), "r"(n_blk * BN + p * PANEL_COLS), "r"(m_blk * BM)
+                       : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
@@ -264,10 +247,8 @@ template <typename TC>
 static int launch(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
                   const Epilogue &ep, int n_sm, cudaStream_t st) {
   CUtensorMap tmA, tmW, tmC;
-  const bool hm = ep.headmajor && std::is_same<TC, __half>::value;
   if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN) ||
-      !(hm ? make_map_headmajor(&tmC, C, N / 32, M)
-           : make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4, std::is_same<TC, __half>::value)))
+      !make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4, std::is_same<TC, __half>::value))
     return fail(MEMOTR_ECUDA, "linear(tc, persistent): cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   auto kern = gemm_tc_persist_kernel<TC>;
   static bool attr_set = false;
@@ -308,19 +289,6 @@ int linear_tc_persist_bf16(const void *A, int lda, const void *W, int ldw, void 
 }  // namespace memotr
 
 using namespace memotr;
-
-extern "C" int memotr_linear_headmajor(const void *A, int lda, const void *W, int ldw, const float *bias,
-                                       const unsigned char *rowzero, void *out, int M, int N, int K, void *stream) {
-  MEMOTR_REQUIRE(A && W && out && M > 0 && N % 128 == 0 && K % tc::BK == 0, "linear_headmajor: bad arguments");
-  MEMOTR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && aligned16(A) && aligned16(W) && aligned16(out) && (!bias || aligned16(bias)) &&
-                     tc::encode_fn() != nullptr,
-                 "linear_headmajor: misaligned buffer");
-  int n_sm = 0;
-  MEMOTR_REQUIRE(linear_tc_persist_wanted(M, N, &n_sm), "linear_headmajor: needs more 128 x 128 tiles than SMs (M = %d, N = %d)", M, N);
-  Epilogue ep{bias, nullptr, nullptr, rowzero, 0, 0, ACT_NONE};
-  ep.headmajor = 1;
-  return linear_tc_persist_bf16(A, lda, W, ldw, out, N, MEMOTR_F16, M, N, K, ep, n_sm, (cudaStream_t)stream);
-}
 
 extern "C" int memotr_linear_msda_prep(const void *A, int lda, const void *W, int ldw, const float *bias, float *out, int ldo,
                                        int M, int K, int n_heads, int n_levels, int n_points, const int *shapes_hw,

@@ -1,146 +1,256 @@
-// msda_window.cu -- EXPERIMENT (opt-in, MEMOTR_MSDA_WINDOW=1): encoder-shaped MSDA forward with TMA-staged value-map
-// windows in shared memory (the structure BASELINE.json's north star names).
+// msda_window.cu -- encoder-shaped multi-scale deformable attention forward with TMA-staged value-map windows in shared
+// memory (the structure BASELINE.json's north star names).  Replaces ms_deformable_im2col_gpu_kernel
+// (/root/reference/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299, bilinear taps :33-84) for the encoder's
+// self-attention (deformable_encoder.py:124: the queries ARE the pixels of the pyramid), fp16 value map, bf16 output.
+// Arithmetic: msda_h16.cuh -- bit-identical to the global-memory gather msda_fwd_h16.
 //
-// The global-memory gather (msda_fwd.cu, msda_fwd_h16) is bound on the SM by the L1 line rate: every bilinear corner is its
-// own 64-byte segment of a 128-byte line.  Encoder queries are pixels; the sampling points of a tile of neighbouring queries
-// fall, on every level, into a small window around the tile's footprint.  Here a CTA owns a tile of 8 x 8 level-0 queries
-// and a PAIR of heads, loads one window per level (footprint + halo, 64 channels = 128 B per pixel) with four 3-D TMA
-// copies (out-of-image pixels arrive as zeros, which is exactly the bilinear zero padding), and takes the taps from shared
-// memory; a sampling point whose 2 x 2 footprint leaves the window falls back to the global path of msda_fwd_h16 with its
-// validity masks.  Queries of the coarser levels (25 % of the rows) go through the global kernel.
-#include "tc_common.cuh"
+// Why: a gather over a pixel-major map from global memory pays one L1 tag cycle per 64-byte corner (the lane groups of a
+// warp touch different lines; measured 2 cycles per line inside one LDG), 24 cycles per 4 sampling points, 61 us per encoder
+// launch = 14 % of the HBM roofline with the DRAM pipe 7 % busy (profiles/r01_msda_fwd_h16_final_ncu.md).  Shared memory
+// has no line granularity, only banks.  So:
+//
+//   unit  = (tile of neighbouring queries of one level, one head); one CTA of 256 threads per unit, two CTAs per SM
+//   stage = per level one 3-D TMA copy of the window (32 channels x ww x wh pixels, 64 B per pixel, pixels outside the
+//           image arrive as zeros = the bilinear zero padding) around where the tile's reference points land on that
+//           level, shifted by the head's mean sampling offset (a host-side hint; correctness never depends on it)
+//   decode= every sampling point of the tile is decoded ONCE (one point per thread, coalesced reads of the locations /
+//           weights) into an 8-byte record per x-side: {shared-memory offset of (y0, x_side) | fallback pixel, w(y0), w(y1)}
+//   taps  = eight lanes per (query, head): lanes 0-3 own the x0 pixel, lanes 4-7 the x0+1 pixel, 16 bytes = 8 channels
+//           each, so the two x-corners of a footprint row are ONE contiguous 128-byte shared-memory read -- a single
+//           conflict-free wavefront -- and a point costs two LDS.128 per lane; packed-half FMAs; one xor-shuffle per
+//           channel at the end adds the two sides.  A point whose footprint leaves the window reads global memory instead
+//           (same arithmetic), so any sampling pattern is computed correctly.
+//   the queries of the coarse levels (6 % of the rows at 1333x800), whose windows would be larger than their taps, run
+//   in the same launch on CTAs that take the global-memory path.
+//
+// Floors per encoder launch (22 323 queries x 8 heads x 16 points x 4 corners x 64 B = 731 MB of taps): shared-memory
+// bandwidth 128 B/clk/SM x 148 SMs = 19.6 us at 1.965 GHz; algorithmic HBM bytes 57.1 MB = 8.7 us.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
 
-extern "C" int memotr_msda_forward_strided(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
-                                           const int64_t *level_start_idx, const float *sampling_loc, int ld_loc,
-                                           const float *attn_weight, int ld_attn, void *output, int B, int S, int H, int L,
-                                           int Lq, int K, int head_major, void *stream);
+#include "msda_h16.cuh"
+#include "tc_common.cuh"
 
 namespace memotr {
 namespace win {
 
-constexpr int TQ = 8, HALO = 3, NL = 4;
+constexpr int MAXL = 5, MAXC = 2, MAXH = 16, THREADS = 256;
+constexpr int SMEM_BUDGET = 112 * 1024;      // per CTA, so that two CTAs share one SM (227 KB)
 
-struct Levels {
-  int hw[2 * NL], lsi[NL];      // (H, W) and first pixel of every level
-  int ww[NL], wh[NL], off[NL];  // window width / height (pixels) and byte offset of the level's window in shared memory
-  int bytes;                    // sum of the window bytes
+struct ClassGeom {
+  int lq;                       // the level this class's queries live on
+  int tw, th, tiles_x, tiles_y; // tile of tw x th queries (powers of two, tw * th a multiple of 32); tiles over the level
+  int tw_shift;
+  int unit0, n_units;           // first unit of the class; units = tiles * heads (head fastest)
+  int q0, Wq, Hq;               // first query row of the level, its extent
+  int ww[MAXL], wh[MAXL];       // window extent in pixels per value level (0: no window, the level's taps read global memory)
+  int off[MAXL];                // byte offset of the window in dynamic shared memory
+  int win_bytes, rec_off, rec_stride;
 };
 
-__global__ void __launch_bounds__(256)
-msda_window_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                   const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3,
-                   const __half *__restrict__ value, int xs, Levels lv, const float *__restrict__ loc, int ld_loc,
-                   const float *__restrict__ attn, int ld_attn, const float *__restrict__ vr, __nv_bfloat16 *__restrict__ out,
-                   int H, int K) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+struct Params {
+  ClassGeom cls[MAXC];
+  int n_cls, n_glob_blocks, glob_q0;   // CTAs [0, n_glob_blocks) take the queries [glob_q0, S) from global memory
+  int hw[2 * MAXL], lsi[MAXL];
+  int L, K, H, S, xs, ld_loc, ld_attn;
+  float radius;
+  float shift[MAXH * MAXL * 2];        // per (head, level): expected sampling offset (x, y) in pixels of that level
+};
+
+struct Maps {
+  CUtensorMap m[MAXC * MAXL];
+};
+
+// record of one sampling point and x-side
+//   window tap:   off = byte offset of pixel (y0, x_side) in dynamic shared memory (the y1 row is ww_l * 64 B further)
+//   global tap:   off = 1 << 31 | (y1 row == y0 row) << 30 | pixel index of (yc0, xc_side) in the whole value map
+struct __align__(8) Rec {
+  uint32_t off;
+  __half2 w;                     // (w(y0, side), w(y1, side))
+};
+
+template <int KT>
+__global__ void __launch_bounds__(THREADS, 2)
+msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params P, const __half *__restrict__ value,
+                   const float *__restrict__ loc, const float *__restrict__ attn, const float *__restrict__ vr,
+                   unsigned long long *__restrict__ stats, __nv_bfloat16 *__restrict__ out) {
+  extern __shared__ __align__(128) uint8_t smem[];      // (declared alignment: the windows are TMA destinations)
   __shared__ uint64_t bar;
-  __shared__ int worg[2 * NL];                       // window origin (x, y) per level
+  __shared__ int worg[2 * MAXL];
   const int tid = threadIdx.x;
-  const int W0 = lv.hw[1], H0 = lv.hw[0];
-  const int tiles_x = (W0 + TQ - 1) / TQ;
-  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, hp = blockIdx.y;
-  pdl_grid_sync();
+  const int K = KT ? KT : P.K, L = P.L, H = P.H, LK = L * K;
+
+  // ------------------------------------------------------------------------------------------- global-memory role
+  if ((int)blockIdx.x < P.n_glob_blocks) {
+    pdl_grid_sync();
+    const int n_qh = (P.S - P.glob_q0) * H;
+    const int qh = (blockIdx.x * THREADS + tid) >> 2, sub = tid & 3;
+    if (qh >= n_qh) return;
+    const int q = P.glob_q0 + qh / H, m = qh % H;
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = 0.f;
+    h16::gather_global<0>(value + m * 32 + sub * 8, h16::ShapesI32{P.hw, P.lsi},
+                           reinterpret_cast<const float2 *>(loc + (long)q * P.ld_loc) + m * LK,
+                           attn + (long)q * P.ld_attn + m * LK, L, P.K, P.xs, 0, 1, acc0, acc1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc0[c] += acc1[c];
+    *reinterpret_cast<uint4 *>(out + ((long)q * H + m) * 32 + sub * 8) = f32x8_to_bf16(acc0);
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------------- window role
+  const int unit_all = blockIdx.x - P.n_glob_blocks;
+  const int c = (P.n_cls > 1 && unit_all >= P.cls[1].unit0) ? 1 : 0;
+  const ClassGeom &G = P.cls[c];
+  const int unit = unit_all - G.unit0;
+  const int h = unit % H, tile = unit / H;
+  const int tx = tile % G.tiles_x, ty = tile / G.tiles_x;
+  const int TQ = G.tw * G.th;
+
   if (tid == 0) {
     tc::mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // window origin per level: pixel coordinate of the tile's first query on that level, minus the halo
-    const float vx0 = __ldg(vr), vy0 = __ldg(vr + 1);
-    const float rx = ((float)(tx * TQ) + 0.5f) / (vx0 * (float)W0), ry = ((float)(ty * TQ) + 0.5f) / (vy0 * (float)H0);
-    tc::mbar_expect_tx(&bar, (uint32_t)lv.bytes);
-    for (int l = 0; l < NL; ++l) {
-      const float px = rx * __ldg(vr + 2 * l) * (float)lv.hw[2 * l + 1] - 0.5f, py = ry * __ldg(vr + 2 * l + 1) * (float)lv.hw[2 * l] - 0.5f;
-      const int ox = (int)floorf(px) - HALO, oy = (int)floorf(py) - HALO;
+  }
+  pdl_grid_sync();
+  if (tid == 0) {
+    // where the tile's first reference point lands on every level (deformable_encoder.py:29-40), plus the head's expected
+    // offset, minus the radius: the window origin.  Any origin is correct; a good one makes every tap a window tap.
+    const float rx = ((float)(tx * G.tw) + 0.5f) / (__ldg(vr + 2 * G.lq) * (float)G.Wq);
+    const float ry = ((float)(ty * G.th) + 0.5f) / (__ldg(vr + 2 * G.lq + 1) * (float)G.Hq);
+    if (G.win_bytes) tc::mbar_expect_tx(&bar, (uint32_t)G.win_bytes);
+    for (int l = 0; l < L; ++l) {
+      const float px = rx * __ldg(vr + 2 * l) * (float)P.hw[2 * l + 1] - 0.5f + P.shift[(h * MAXL + l) * 2];
+      const float py = ry * __ldg(vr + 2 * l + 1) * (float)P.hw[2 * l] - 0.5f + P.shift[(h * MAXL + l) * 2 + 1];
+      const int ox = (int)floorf(px - P.radius), oy = (int)floorf(py - P.radius);
       worg[2 * l] = ox, worg[2 * l + 1] = oy;
-      const CUtensorMap *tm = l == 0 ? &tm0 : l == 1 ? &tm1 : l == 2 ? &tm2 : &tm3;
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-              tc::smem_u32(smem + lv.off[l])),
-          "l"(tm), "r"(tc::smem_u32(&bar)), "r"(hp * 64), "r"(ox), "r"(oy)
-          : "memory");
+      if (G.ww[l]) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                tc::smem_u32(smem + G.off[l])),
+            "l"(&maps.m[c * MAXL + l]), "r"(tc::smem_u32(&bar)), "r"(h * 32), "r"(ox), "r"(oy)
+            : "memory");
+      }
     }
   }
   __syncthreads();
-  tc::mbar_wait(&bar, 0);
 
-  const int LK = NL * K;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int task = pass * 256 + tid;
-    const int ql = task >> 3, hl = (task >> 2) & 1, sub = task & 3;
-    const int x = tx * TQ + (ql & 7), y = ty * TQ + (ql >> 3);
-    if (x >= W0 || y >= H0) continue;                 // (whole 4-lane groups leave together)
-    const int q = y * W0 + x, h = hp * 2 + hl;
-    const float2 *locq = reinterpret_cast<const float2 *>(loc + (long)q * ld_loc) + h * LK;
-    const float *attq = attn + (long)q * ld_attn + h * LK;
-    const __half *vb = value + h * 32 + sub * 8;
-    float acc[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    for (int l = 0; l < NL; ++l) {
-      const int Hh = lv.hw[2 * l], Ww = lv.hw[2 * l + 1];
-      const float Hf = (float)Hh, Wf = (float)Ww;
-      const int ox = worg[2 * l], oy = worg[2 * l + 1], ww = lv.ww[l], wh = lv.wh[l];
-      const uint8_t *wbase = smem + lv.off[l] + hl * 64 + sub * 16;
-      const long gbase = (long)lv.lsi[l] * xs;
-      const int ys = Ww * xs;
-      __half2 a[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] = __float2half2_rn(0.f);
-      for (int p = 0; p < K; ++p) {
-        const float2 xy = __ldg(locq + l * K + p);
-        const float aw = __ldg(attq + l * K + p);
-        const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
-        const float hfl = floorf(h_im), wfl = floorf(w_im);
-        const int y0 = (int)hfl, x0 = (int)wfl;
-        const float lh = h_im - hfl, lw = w_im - wfl, hh = 1.f - lh, hw = 1.f - lw;
-        uint4 r[4];
-        __half2 w[4];
-        const int dx = x0 - ox, dy = y0 - oy;
-        if (dx >= 0 && dx + 1 < ww && dy >= 0 && dy + 1 < wh) {
-          // the 2 x 2 footprint lies inside the staged window: taps from shared memory, zero padding came with the TMA fill
-          const uint8_t *t0 = wbase + (dy * ww + dx) * 128;
-          r[0] = *reinterpret_cast<const uint4 *>(t0);
-          r[1] = *reinterpret_cast<const uint4 *>(t0 + 128);
-          r[2] = *reinterpret_cast<const uint4 *>(t0 + ww * 128);
-          r[3] = *reinterpret_cast<const uint4 *>(t0 + ww * 128 + 128);
-          w[0] = __float2half2_rn(hh * hw * aw), w[1] = __float2half2_rn(hh * lw * aw);
-          w[2] = __float2half2_rn(lh * hw * aw), w[3] = __float2half2_rn(lh * lw * aw);
-        } else {
-          const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
-          const bool y0ok = inside && y0 >= 0, y1ok = inside && y0 + 1 <= Hh - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= Ww - 1;
-          const int yc0 = min(max(y0, 0), Hh - 1), yc1 = min(max(y0 + 1, 0), Hh - 1);
-          const int xc0 = min(max(x0, 0), Ww - 1), xc1 = min(max(x0 + 1, 0), Ww - 1);
-          r[0] = __ldg(reinterpret_cast<const uint4 *>(vb + gbase + (long)yc0 * ys + xc0 * xs));
-          r[1] = __ldg(reinterpret_cast<const uint4 *>(vb + gbase + (long)yc0 * ys + xc1 * xs));
-          r[2] = __ldg(reinterpret_cast<const uint4 *>(vb + gbase + (long)yc1 * ys + xc0 * xs));
-          r[3] = __ldg(reinterpret_cast<const uint4 *>(vb + gbase + (long)yc1 * ys + xc1 * xs));
-          w[0] = __float2half2_rn((y0ok && x0ok) ? hh * hw * aw : 0.f), w[1] = __float2half2_rn((y0ok && x1ok) ? hh * lw * aw : 0.f);
-          w[2] = __float2half2_rn((y1ok && x0ok) ? lh * hw * aw : 0.f), w[3] = __float2half2_rn((y1ok && x1ok) ? lh * lw * aw : 0.f);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const __half2 *v = reinterpret_cast<const __half2 *>(&r[c]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = __hfma2(w[c], v[j], a[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(a[j]);
-        acc[2 * j] += f.x, acc[2 * j + 1] += f.y;
+  // ---- decode: one sampling point per thread and step --------------------------------------------------------------
+  uint8_t *recs = smem + G.rec_off;
+  int ql = tid / LK, j = tid - ql * LK;
+  const int dq = THREADS / LK, dj = THREADS - dq * LK;
+  int n_win = 0, n_glob = 0;                    // (profiling only: taps staged / taps left to global memory)
+  while (ql < TQ) {
+    const int l = KT ? j / KT : j / K;
+    const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
+    Rec r0, r1;
+    r0.off = r1.off = 0u;                       // a query outside the level: two zero-weight taps on the first bytes of the buffer
+    r0.w = r1.w = __float2half2_rn(0.f);
+    if (x < G.Wq && y < G.Hq) {
+      const long q = G.q0 + y * G.Wq + x;
+      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc + q * P.ld_loc) + h * LK + j);
+      const float aw = __ldg(attn + q * P.ld_attn + h * LK + j);
+      const int Hh = P.hw[2 * l], Ww = P.hw[2 * l + 1];
+      const h16::Point p = h16::decode(xy, aw, Hh, Ww);
+      const int ww = G.ww[l], dx = p.x0 - worg[2 * l], dy = p.y0 - worg[2 * l + 1];
+      r0.w = p.ws[0], r1.w = p.ws[1];
+      if (ww && dx >= 0 && dx + 1 < ww && dy >= 0 && dy + 1 < G.wh[l]) {
+        r0.off = (uint32_t)(G.off[l] + (dy * ww + dx) * 64);
+        r1.off = r0.off + 64u;
+        ++n_win;
+      } else {
+        ++n_glob;
+        const uint32_t flags = 0x80000000u | (p.yc[1] == p.yc[0] ? 0x40000000u : 0u);
+        const uint32_t row = (uint32_t)(P.lsi[l] + p.yc[0] * Ww);
+        r0.off = flags | (row + (uint32_t)p.xc[0]);
+        r1.off = flags | (row + (uint32_t)p.xc[1]);
       }
     }
-    *reinterpret_cast<uint4 *>(out + (long)q * (H * 32) + h * 32 + sub * 8) = f32x8_to_bf16(acc);
+    // records of a query: LK/2 blocks of 32 B = [side 0: points 2k, 2k+1 | side 1: points 2k, 2k+1]
+    uint8_t *dst = recs + ql * G.rec_stride + (j >> 1) * 32 + (j & 1) * 8;
+    *reinterpret_cast<Rec *>(dst) = r0;
+    *reinterpret_cast<Rec *>(dst + 16) = r1;
+    ql += dq, j += dj;
+    if (j >= LK) j -= LK, ++ql;
+  }
+  if (stats) atomicAdd(stats, (unsigned long long)n_win), atomicAdd(stats + 1, (unsigned long long)n_glob);
+  __syncthreads();
+  if (G.win_bytes) tc::mbar_wait(&bar, 0);
+
+  // ---- taps: eight lanes per (query, head) -----------------------------------------------------------------------
+  const int grp = tid >> 3, side = (tid >> 2) & 1, sub = tid & 3;
+  const uint32_t smem_base = tc::smem_u32(smem) + sub * 16;
+  const __half *vb = value + h * 32 + sub * 8;
+  const int xs = P.xs;
+  for (int ql = grp; ql < TQ; ql += THREADS / 8) {
+    const uint8_t *rq = recs + ql * G.rec_stride + side * 16;
+    float acc[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      __half2 a[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) a[jj] = __float2half2_rn(0.f);
+      const uint32_t rowb = (uint32_t)G.ww[l] * 64u;        // bytes between the y0 and y1 rows of this level's window
+      auto window_tap = [&](uint32_t off, uint32_t wbits, uint4 &r0, uint4 &r1) {
+        const uint32_t a0 = smem_base + off, a1 = a0 + rowb;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
+        (void)wbits;
+      };
+      auto any_tap = [&](uint32_t off, uint4 &r0, uint4 &r1) {
+        if (off & 0x80000000u) {
+          const __half *p0 = vb + (long)(off & 0x3FFFFFFFu) * xs;
+          const __half *p1 = (off & 0x40000000u) ? p0 : p0 + (long)P.hw[2 * l + 1] * xs;
+          r0 = __ldg(reinterpret_cast<const uint4 *>(p0));
+          r1 = __ldg(reinterpret_cast<const uint4 *>(p1));
+        } else {
+          window_tap(off, 0u, r0, r1);
+        }
+      };
+      if constexpr (KT == 4) {
+        const uint4 ra = *reinterpret_cast<const uint4 *>(rq + (l * 2) * 32);
+        const uint4 rb = *reinterpret_cast<const uint4 *>(rq + (l * 2 + 1) * 32);
+        uint4 v[4][2];
+        // warp-uniform choice per point: the plain shared-memory pair unless some lane of the warp has a global-memory tap
+        const bool g0 = __any_sync(0xffffffffu, ra.x & 0x80000000u), g1 = __any_sync(0xffffffffu, ra.z & 0x80000000u);
+        const bool g2 = __any_sync(0xffffffffu, rb.x & 0x80000000u), g3 = __any_sync(0xffffffffu, rb.z & 0x80000000u);
+        if (!g0) window_tap(ra.x, 0u, v[0][0], v[0][1]); else any_tap(ra.x, v[0][0], v[0][1]);
+        if (!g1) window_tap(ra.z, 0u, v[1][0], v[1][1]); else any_tap(ra.z, v[1][0], v[1][1]);
+        if (!g2) window_tap(rb.x, 0u, v[2][0], v[2][1]); else any_tap(rb.x, v[2][0], v[2][1]);
+        if (!g3) window_tap(rb.z, 0u, v[3][0], v[3][1]); else any_tap(rb.z, v[3][0], v[3][1]);
+        h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v[0][0], v[0][1]);
+        h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v[1][0], v[1][1]);
+        h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.y), v[2][0], v[2][1]);
+        h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.w), v[3][0], v[3][1]);
+      } else {
+        for (int pp = 0; pp < K / 2; ++pp) {
+          const uint4 ra = *reinterpret_cast<const uint4 *>(rq + (l * (K / 2) + pp) * 32);
+          uint4 v[2][2];
+          any_tap(ra.x, v[0][0], v[0][1]);
+          any_tap(ra.z, v[1][0], v[1][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v[0][0], v[0][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v[1][0], v[1][1]);
+        }
+      }
+      h16::widen_add(acc, a);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], 4);
+    const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
+    if (side == 0 && x < G.Wq && y < G.Hq)
+      *reinterpret_cast<uint4 *>(out + ((long)(G.q0 + y * G.Wq + x) * H + h) * 32 + sub * 8) = f32x8_to_bf16(acc);
   }
 }
 
-// 3-D fp16 map of one level of a pixel-major value map: dims (channels, W, H), box (64 channels, ww, wh), no swizzle
+// 3-D fp16 map of one level of a pixel-major value map: dims (channels, W, H), box (32 channels, ww, wh), no swizzle
 static bool make_level_map(CUtensorMap *map, const void *base, int C, int xs, int Hh, int Ww, int ww, int wh) {
   tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Ww, (cuuint64_t)Hh};
   cuuint64_t strides[2] = {(cuuint64_t)xs * 2, (cuuint64_t)Ww * xs * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)ww, (cuuint32_t)wh};
+  cuuint32_t box[3] = {32, (cuuint32_t)ww, (cuuint32_t)wh};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -148,59 +258,151 @@ static bool make_level_map(CUtensorMap *map, const void *base, int C, int xs, in
 }
 
 }  // namespace win
+
+int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn, void *out,
+               int B, int S, int H, int L, int Lq, int K, int xs, cudaStream_t st, int ld_loc, int ld_attn);
+
 }  // namespace memotr
 
 using namespace memotr;
 
-extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_stride, const int64_t *spatial_shapes,
-                                          const int64_t *level_start_idx, const int *shapes_hw, const int *level_start,
-                                          const float *sampling_loc, int ld_loc, const float *attn_weight, int ld_attn,
-                                          const float *valid_ratios, void *output, int S, int H, int L, int K, void *stream) {
-  MEMOTR_REQUIRE(value && spatial_shapes && level_start_idx && shapes_hw && level_start && sampling_loc && attn_weight &&
-                     valid_ratios && output,
-                 "msda_forward_window: null pointer");
-  MEMOTR_REQUIRE(L == win::NL && H % 2 == 0 && H * 32 <= value_pixel_stride && value_pixel_stride % 8 == 0 && K >= 1,
-                 "msda_forward_window: needs 4 levels, an even head count, pixel stride >= H*32");
-  MEMOTR_REQUIRE(aligned16(value) && aligned16(output) && ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) && ld_loc % 2 == 0,
-                 "msda_forward_window: misaligned buffer");
-  MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "msda_forward_window: cuTensorMapEncodeTiled unavailable");
-  win::Levels lv;
-  CUtensorMap tm[win::NL];
-  const int W0 = shapes_hw[1], H0 = shapes_hw[0];
-  int off = 0;
-  for (int l = 0; l < win::NL; ++l) {
-    const int Hh = shapes_hw[2 * l], Ww = shapes_hw[2 * l + 1];
-    lv.hw[2 * l] = Hh, lv.hw[2 * l + 1] = Ww, lv.lsi[l] = level_start[l];
-    // footprint of 8 level-0 pixels on this level (+5 % for differing valid ratios) + halo on both sides + bilinear + rounding
-    lv.ww[l] = (int)((win::TQ - 1) * 1.05f * Ww / W0) + 2 * win::HALO + 3;
-    lv.wh[l] = (int)((win::TQ - 1) * 1.05f * Hh / H0) + 2 * win::HALO + 3;
-    lv.off[l] = off;
-    off += lv.ww[l] * lv.wh[l] * 128;
-    MEMOTR_REQUIRE(lv.ww[l] <= 256 && lv.wh[l] <= 256, "msda_forward_window: window too large");
-    if (!win::make_level_map(&tm[l], reinterpret_cast<const __half *>(value) + (long)level_start[l] * value_pixel_stride, H * 32,
-                             value_pixel_stride, Hh, Ww, lv.ww[l], lv.wh[l]))
-      return fail(MEMOTR_ECUDA, "msda_forward_window: cuTensorMapEncodeTiled failed (level %d)", l);
+static int plan(win::Params &P, const int *shapes_hw, const int *level_start, int S, int H, int L, int K, int xs, int ld_loc,
+                int ld_attn, const float *shift, float radius, int max_classes) {
+  std::memset(&P, 0, sizeof(P));
+  P.L = L, P.K = K, P.H = H, P.S = S, P.xs = xs, P.ld_loc = ld_loc, P.ld_attn = ld_attn, P.radius = radius;
+  for (int l = 0; l < L; ++l) P.hw[2 * l] = shapes_hw[2 * l], P.hw[2 * l + 1] = shapes_hw[2 * l + 1], P.lsi[l] = level_start[l];
+  for (int h = 0; h < H; ++h)
+    for (int l = 0; l < L; ++l)
+      for (int d = 0; d < 2; ++d) P.shift[(h * win::MAXL + l) * 2 + d] = shift ? shift[(h * L + l) * 2 + d] : 0.f;
+  const int LK = L * K;
+  int units = 0, q_end = 0;
+  for (int c = 0; c < std::min(std::min(max_classes, win::MAXC), L); ++c) {
+    win::ClassGeom &G = P.cls[c];
+    G.lq = c, G.Hq = shapes_hw[2 * c], G.Wq = shapes_hw[2 * c + 1], G.q0 = level_start[c];
+    if (level_start[c] != q_end) break;                       // levels must be consecutive rows of the query table
+    G.rec_stride = (LK / 2) * 32 + 32;                         // pad so that the four queries of a warp start in different banks
+    while (G.rec_stride % 128 != 32) G.rec_stride += 32;
+    // tile: 16 x 8 queries of level 0, 8 x 8 of level 1 (its reference points are twice as far apart), halved while the
+    // records of the tile (one per sampling point and x-side) would take more than 40 KB
+    G.tw = c == 0 ? 16 : 8, G.th = 8, G.tw_shift = c == 0 ? 4 : 3;
+    while (G.tw * G.th > 32 && G.tw * G.th * G.rec_stride > 40 * 1024) {
+      if (G.tw > G.th) G.tw >>= 1, --G.tw_shift; else G.th >>= 1;
+    }
+    if (G.tw * G.th * G.rec_stride > 64 * 1024) break;
+    G.tiles_x = ceil_div(G.Wq, G.tw), G.tiles_y = ceil_div(G.Hq, G.th);
+    const int rec_bytes = G.tw * G.th * G.rec_stride;
+    // window extents: footprint of the tile's reference points on the level (+5 % for differing valid ratios) + the radius
+    // on both sides + the second bilinear column / row + rounding
+    for (int l = 0; l < L; ++l) {
+      const float sx = (float)(G.tw - 1) * 1.05f * (float)shapes_hw[2 * l + 1] / (float)G.Wq;
+      const float sy = (float)(G.th - 1) * 1.05f * (float)shapes_hw[2 * l] / (float)G.Hq;
+      G.ww[l] = std::min(std::min(255, shapes_hw[2 * l + 1] + 2), (int)std::ceil(sx + 2.f * radius) + 2);
+      G.wh[l] = std::min(std::min(255, shapes_hw[2 * l] + 2), (int)std::ceil(sy + 2.f * radius) + 2);
+    }
+    // drop the largest windows until everything fits next to the records (their taps then come from global memory)
+    for (;;) {
+      int bytes = 0, big = -1;
+      for (int l = 0; l < L; ++l) {
+        if (!G.ww[l]) continue;
+        if (big < 0 || G.ww[l] * G.wh[l] > G.ww[big] * G.wh[big]) big = l;
+        bytes += (G.ww[l] * G.wh[l] * 64 + 127) / 128 * 128;
+      }
+      if (bytes + rec_bytes + 256 <= win::SMEM_BUDGET || big < 0) break;
+      G.ww[big] = G.wh[big] = 0;
+    }
+    int off = 0, any = 0;
+    for (int l = 0; l < L; ++l) {
+      G.off[l] = off;
+      if (G.ww[l]) off += (G.ww[l] * G.wh[l] * 64 + 127) / 128 * 128, G.win_bytes += G.ww[l] * G.wh[l] * 64, any = 1;
+    }
+    if (!any || off >= (1 << 20)) break;                       // nothing fits: leave this class to the global-memory role
+    G.rec_off = off;
+    G.unit0 = units, G.n_units = G.tiles_x * G.tiles_y * H;
+    units += G.n_units;
+    q_end = G.q0 + G.Hq * G.Wq;
+    P.n_cls = c + 1;
   }
-  lv.bytes = off;
-  MEMOTR_REQUIRE(off + 256 <= 200 * 1024, "msda_forward_window: windows do not fit in shared memory");
-  static int attr_bytes = 0;
-  if (attr_bytes < off + 256) {
-    const cudaError_t e = cudaFuncSetAttribute(win::msda_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off + 256);
-    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "msda_forward_window: smem attribute: %s", cudaGetErrorString(e));
-    attr_bytes = off + 256;
+  P.glob_q0 = q_end;
+  P.n_glob_blocks = ceil_div((S - q_end) * H * 4, win::THREADS);
+  return units;
+}
+
+// The staging plan memotr_msda_forward_window would use, as integers (host-only; tests and bench reporting):
+// info[0..7] = {classes, window units, global-role CTAs, first global-role query, dynamic shared memory bytes, 0, 0, 0};
+// then per class 8 + 2*MAXL ints: {query level, tw, th, tiles_x, tiles_y, units, window bytes, record stride, ww[5], wh[5]}.
+extern "C" int memotr_msda_window_plan(const int *shapes_hw, const int *level_start, int S, int H, int L, int K, float radius,
+                                       int max_classes, int *info) {
+  MEMOTR_REQUIRE(shapes_hw && level_start && info && L >= 1 && L <= win::MAXL && H >= 1 && H <= win::MAXH && K >= 2 && K % 2 == 0,
+                 "msda_window_plan: bad arguments");
+  win::Params P;
+  const int units = plan(P, shapes_hw, level_start, S, H, L, K, H * 32, 0, 0, nullptr, radius,
+                         max_classes <= 0 ? win::MAXC : max_classes);
+  size_t smem = 0;
+  for (int c = 0; c < P.n_cls; ++c)
+    smem = std::max(smem, (size_t)P.cls[c].rec_off + (size_t)P.cls[c].tw * P.cls[c].th * P.cls[c].rec_stride + 128);
+  std::memset(info, 0, sizeof(int) * (8 + win::MAXC * (8 + 2 * win::MAXL)));
+  info[0] = P.n_cls, info[1] = units, info[2] = P.n_glob_blocks, info[3] = P.glob_q0, info[4] = (int)smem;
+  for (int c = 0; c < P.n_cls; ++c) {
+    const win::ClassGeom &G = P.cls[c];
+    int *o = info + 8 + c * (8 + 2 * win::MAXL);
+    o[0] = G.lq, o[1] = G.tw, o[2] = G.th, o[3] = G.tiles_x, o[4] = G.tiles_y, o[5] = G.n_units, o[6] = G.win_bytes, o[7] = G.rec_stride;
+    for (int l = 0; l < L; ++l) o[8 + l] = G.ww[l], o[8 + win::MAXL + l] = G.wh[l];
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int tiles = ceil_div(W0, win::TQ) * ceil_div(H0, win::TQ);
-  MEMOTR_LAUNCH((win::msda_window_kernel), dim3(tiles, H / 2), 256, (size_t)off + 256, st, tm[0], tm[1], tm[2], tm[3],
-                (const __half *)value, value_pixel_stride, lv, sampling_loc, ld_loc, attn_weight, ld_attn, valid_ratios,
-                (__nv_bfloat16 *)output, H, K);
-  const int rc = check_launch("msda_window");
-  if (rc != MEMOTR_OK) return rc;
-  const int n0 = H0 * W0;                                   // the coarser levels' queries: global-memory gather
-  if (S > n0)
-    return memotr_msda_forward_strided(value, value_pixel_stride, spatial_shapes, level_start_idx,
-                                       sampling_loc + (long)n0 * ld_loc, ld_loc, attn_weight + (long)n0 * ld_attn, ld_attn,
-                                       reinterpret_cast<__nv_bfloat16 *>(output) + (long)n0 * H * 32, 1, S, H, L, S - n0, K, 0,
-                                       stream);
   return MEMOTR_OK;
+}
+
+// Encoder-shaped gather (queries = the S pixels of the pyramid, batch 1) from TMA-staged windows.  `window_shift` (host
+// memory, (H, L, 2) floats, may be null): expected sampling offset of each head on each level in pixels of that level --
+// for MSDeformAttn the mean over the K points of sampling_offsets.bias; `window_radius`: how far around it the samples
+// spread (pixels).  Both only steer what is staged: taps outside a window are read from global memory.  `stats` (device,
+// 2 x u64, may be null): profiling counters += {taps taken from windows, taps left to global memory} of the window units.
+extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_stride, const int *shapes_hw, const int *level_start,
+                                          const float *sampling_loc, int ld_loc, const float *attn_weight, int ld_attn,
+                                          const float *valid_ratios, const float *window_shift, float window_radius,
+                                          int max_classes, unsigned long long *stats, void *output, int S, int H, int L, int K,
+                                          void *stream) {
+  MEMOTR_REQUIRE(value && shapes_hw && level_start && sampling_loc && attn_weight && valid_ratios && output,
+                 "msda_forward_window: null pointer");
+  MEMOTR_REQUIRE(L >= 1 && L <= win::MAXL && H >= 1 && H <= win::MAXH && K >= 2 && K % 2 == 0 && K <= 64,
+                 "msda_forward_window: needs 1..5 levels, 1..16 heads, an even number of points per level");
+  MEMOTR_REQUIRE(H * 32 <= value_pixel_stride && value_pixel_stride % 8 == 0 && (long)S * value_pixel_stride < (1L << 30),
+                 "msda_forward_window: bad pixel stride");
+  MEMOTR_REQUIRE(aligned16(value) && aligned16(output) && ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) &&
+                     ld_loc % 2 == 0 && ld_loc >= H * L * K * 2 && ld_attn >= H * L * K,
+                 "msda_forward_window: misaligned buffer / bad row stride");
+  MEMOTR_REQUIRE(window_radius >= 0.f && window_radius <= 32.f, "msda_forward_window: radius out of range");
+  MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "msda_forward_window: cuTensorMapEncodeTiled unavailable");
+  int total = 0;
+  for (int l = 0; l < L; ++l) {
+    MEMOTR_REQUIRE(level_start[l] == total && shapes_hw[2 * l] > 0 && shapes_hw[2 * l + 1] > 0,
+                   "msda_forward_window: level_start must be the running sum of H_l * W_l");
+    total += shapes_hw[2 * l] * shapes_hw[2 * l + 1];
+  }
+  MEMOTR_REQUIRE(total == S, "msda_forward_window: S != sum of the level sizes");
+  win::Params P;
+  win::Maps M;
+  const int units = plan(P, shapes_hw, level_start, S, H, L, K, value_pixel_stride, ld_loc, ld_attn, window_shift, window_radius,
+                         max_classes <= 0 ? win::MAXC : max_classes);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = 0;
+  std::memset(&M, 0, sizeof(M));
+  for (int c = 0; c < P.n_cls; ++c) {
+    const win::ClassGeom &G = P.cls[c];
+    smem = std::max(smem, (size_t)G.rec_off + (size_t)G.tw * G.th * G.rec_stride + 128);
+    for (int l = 0; l < L; ++l)
+      if (G.ww[l] && !win::make_level_map(&M.m[c * win::MAXL + l],
+                                          reinterpret_cast<const __half *>(value) + (long)level_start[l] * value_pixel_stride, H * 32,
+                                          value_pixel_stride, shapes_hw[2 * l], shapes_hw[2 * l + 1], G.ww[l], G.wh[l]))
+        return fail(MEMOTR_ECUDA, "msda_forward_window: cuTensorMapEncodeTiled failed (class %d, level %d)", c, l);
+  }
+  auto kern = K == 4 ? win::msda_window_kernel<4> : win::msda_window_kernel<0>;
+  static size_t attr_bytes[2] = {0, 0};
+  if (attr_bytes[K == 4] < smem) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, win::SMEM_BUDGET);
+    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "msda_forward_window: smem attribute: %s", cudaGetErrorString(e));
+    attr_bytes[K == 4] = win::SMEM_BUDGET;
+  }
+  MEMOTR_LAUNCH((kern), P.n_glob_blocks + units, win::THREADS, smem, st, M, P, (const __half *)value, sampling_loc, attn_weight,
+                valid_ratios, stats, (__nv_bfloat16 *)output);
+  return check_launch("msda_window");
 }

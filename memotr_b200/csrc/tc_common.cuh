@@ -128,19 +128,5 @@ inline bool make_map(CUtensorMap *map, const void *base, long rows, long cols, l
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// 3-D fp16 map of a HEAD-MAJOR value map (H, S, 32): box = 128 pixels x 32 channels of one head, no swizzle.  Stores of
-// the last row tile are clipped at S per head (a 2-D (H*S, 32) view would spill into the next head's plane).
-inline bool make_map_headmajor(CUtensorMap *map, const void *base, long H, long S) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[3] = {32, (cuuint64_t)S, (cuuint64_t)H};
-  cuuint64_t strides[2] = {64, (cuuint64_t)S * 64};
-  cuuint32_t box[3] = {32, 128, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 }  // namespace tc
 }  // namespace memotr

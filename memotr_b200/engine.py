@@ -69,13 +69,9 @@ class FrameEngine:
         self.launches = 0
         import os
         self.fused_mlp = os.environ.get("MEMOTR_FUSED_MLP", "1") != "0"   # A/B switch for the on-chip FFN/MLP kernel
-        # encoder MSDA on the pair-duplicated head-major value map (bf16 mode, K in {1,2,4,8}); A/B switch
-        # (measured slower than the plain layout -- the gather is ALU-bound, not L1-bound -- so off by default)
-        self.use_pairs = (os.environ.get("MEMOTR_MSDA_PAIRS", "0") == "1" and mode == "bf16"
-                          and cfg["n_enc_points"] in (1, 2, 4, 8))
         # value maps in fp16 (bf16 mode): more mantissa than bf16 for this read-only intermediate, and the gather can
         # blend corners with packed HFMA2 instead of widening every bf16 element on the (binding) ALU pipe; A/B switch
-        self.value_f16 = mode == "bf16" and os.environ.get("MEMOTR_VALUE_F16", "1") != "0" and not self.use_pairs
+        self.value_f16 = mode == "bf16" and os.environ.get("MEMOTR_VALUE_F16", "1") != "0"
         self.vdt = F16 if self.value_f16 else self.dt
         self.tv = torch.float16 if self.value_f16 else self.ta
         # the whole decoder + heads as one persistent kernel (csrc/decoder_fused.cu); A/B switch
@@ -96,12 +92,12 @@ class FrameEngine:
         # kernel runs at 4.2 TB/s
         self.fuse_ln1 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN1", "0") == "1" and self.fused_mlp
                          and self.Fd % 128 == 0 and self.S >= 2048)
-        # encoder value maps head-major (H, S, 32): the x-corners of a footprint are adjacent 64-byte blocks (A/B switch)
-        self.value_hm = (self.fuse_prep and os.environ.get("MEMOTR_VALUE_HM", "0") == "1"
-                         and 2 * ((self.S + 127) // 128) > n_sm)
-        # experimental: TMA-staged value-map windows in shared memory for the encoder gather (csrc/msda_window.cu)
-        self.msda_window = (self.fuse_prep and not self.value_hm and self.L == 4 and self.H % 2 == 0
-                            and os.environ.get("MEMOTR_MSDA_WINDOW", "0") == "1")
+        # encoder gather from TMA-staged value-map windows in shared memory (csrc/msda_window.cu); MEMOTR_MSDA_WINDOW=0: the
+        # global-memory gather (bit-identical results)
+        self.msda_window = (self.fuse_prep and self.L <= 5 and self.H <= 16 and cfg["n_enc_points"] % 2 == 0
+                            and os.environ.get("MEMOTR_MSDA_WINDOW", "1") != "0")
+        self.window_classes = int(os.environ.get("MEMOTR_WINDOW_CLASSES", "0"))
+        self.window_stats = None             # device int64[2] when profiling: taps served from windows / from global memory
         self._pack(state_dict)
         self._alloc()
         # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
@@ -119,6 +115,7 @@ class FrameEngine:
             self._build_updater_program()
         self.graph = None
         self.timer = None
+        self.debug_enc = None        # tests: a list that forward() fills with the fp32 encoder state before / after every layer
 
     # ------------------------------------------------------------------------------------------------ measurement
     def enable_msda_timer(self):
@@ -160,6 +157,25 @@ class FrameEngine:
         return out
 
     # ------------------------------------------------------------------------------------------------ weights
+    def _window_hint(self, bias, weight):
+        """Where the windowed gather should stage value-map windows for one MSDeformAttn: per (head, level) the mean
+        sampling offset over the K points (pixels of that level: ms_deform_attn.py:115-117 divides the offsets by the
+        level's extent), and a radius around it = spread of the bias over the points (90th percentile) + two standard
+        deviations of the query-dependent part (row norms of sampling_offsets.weight x an r.m.s. query of 1.5) + 0.5.
+        Only a hint: taps outside a window are read from global memory with the same arithmetic."""
+        import ctypes
+        import os
+        H, L = self.H, self.L
+        b = bias.detach().float().cpu().view(H, L, -1, 2)
+        shift = b.mean(2)                                           # (H, L, 2)
+        dev = (b - shift[:, :, None]).abs().flatten()
+        spread = float(torch.quantile(dev, 0.9)) if dev.numel() > 1 else 0.0
+        wn = float(weight.detach().float().norm(dim=1).max())
+        radius = min(max(spread + 2.0 * wn * 1.5 + 0.5, 1.5), 6.0)
+        if os.environ.get("MEMOTR_WINDOW_RADIUS"):
+            radius = float(os.environ["MEMOTR_WINDOW_RADIUS"])
+        return (ctypes.c_float * (H * L * 2))(*[float(v) for v in shift.reshape(-1).tolist()]), radius
+
     def _pack(self, sd):
         dev, ta = self.dev, self.ta
         lin = lambda k: _Lin(sd[k + ".weight"], sd[k + ".bias"], ta, dev)          # noqa: E731
@@ -168,7 +184,10 @@ class FrameEngine:
         def msda(k):
             ol_w = torch.cat([sd[k + ".sampling_offsets.weight"], sd[k + ".attention_weights.weight"]], 0)
             ol_b = torch.cat([sd[k + ".sampling_offsets.bias"], sd[k + ".attention_weights.bias"]], 0)
-            return {"ol": _Lin(ol_w, ol_b, ta, dev), "value": lin(k + ".value_proj"), "out": lin(k + ".output_proj")}
+            d = {"ol": _Lin(ol_w, ol_b, ta, dev), "value": lin(k + ".value_proj"), "out": lin(k + ".output_proj")}
+            d["win_shift"], d["win_radius"] = self._window_hint(sd[k + ".sampling_offsets.bias"],
+                                                                sd[k + ".sampling_offsets.weight"])
+            return d
 
         def ln(k):
             return f32(k + ".weight"), f32(k + ".bias")
@@ -246,7 +265,6 @@ class FrameEngine:
         self.vr = f(self.L, 2)
         self.src_tok, self.pos_tok, self.q_tok = e(S, C), e(S, C), e(S, C)
         self.value = e(S, C, dtype=self.tv)
-        self.pairs = e(self.H, S, 2, 32) if self.use_pairs else None
         self.ol = f(S, 3 * self.H * LK)
         self.loc = f(S, self.H, LK, 2)
         self.attw = f(S, self.H, LK)
@@ -540,19 +558,6 @@ class FrameEngine:
         self._ck(self.lib.memotr_msda_prep(_p(ol), ldol, _p(self.shapes_t), _p(self.lsi_t), _p(self.vr), _p(ref4), mode,
                                            _p(self.loc), _p(self.attw), Lq, self.H, self.L, K, self._st()), "msda_prep")
         timed = self.timer is not None and mode == 0
-        if mode == 0 and self.use_pairs:
-            self._ck(self.lib.memotr_msda_pairs_layout(_p(value), stride, _p(self.shapes_t), _p(self.lsi_t),
-                                                       _p(self.pairs), self.S, self.H, self.L, self._st()), "pairs_layout")
-            if timed:
-                slot = self._timer_slot % self.n_enc
-                self._timer_slot += 1
-                _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
-            self._ck(self.lib.memotr_msda_forward_pairs(_p(self.pairs), _p(self.shapes_t), _p(self.lsi_t), _p(self.loc),
-                                                        _p(self.attw), _p(out), self.S, self.H, self.L, Lq, K,
-                                                        self._st()), "msda_forward_pairs")
-            if timed:
-                _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
-            return
         if timed:
             slot = self._timer_slot % self.n_enc
             self._timer_slot += 1
@@ -580,19 +585,16 @@ class FrameEngine:
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot, self._st()), "timer_record")
         attw = self.ol.view(-1)[H * L * K * 2:]                    # the weights start after the locations in every row
         if self.msda_window:
-            self._ck(self.lib.memotr_msda_forward_window(_p(self.value), self.C, _p(self.shapes_t), _p(self.lsi_t), self._prep_hw,
-                                                         self._prep_lsi, _p(self.ol), N, _p(attw), N, _p(self.vr), _p(self.att),
+            self._ck(self.lib.memotr_msda_forward_window(_p(self.value), self.C, self._prep_hw, self._prep_lsi, _p(self.ol), N,
+                                                         _p(attw), N, _p(self.vr), a["win_shift"], a["win_radius"],
+                                                         self.window_classes, _p(self.window_stats), _p(self.att),
                                                          S, H, L, K, self._st()), "msda_forward_window")
-            self.launches += 1
         else:
-            self._encoder_gather_strided(N, attw, S, H, L, K)
+            self._ck(self.lib.memotr_msda_forward_strided(_p(self.value), self.C, _p(self.shapes_t), _p(self.lsi_t), _p(self.ol),
+                                                          N, _p(attw), N, _p(self.att), 1, S, H, L, S, K, self._st()),
+                     "msda_forward_strided")
         if timed:
             _lib.check(self.lib.memotr_timer_record(self.timer, 2 * slot + 1, self._st()), "timer_record")
-
-    def _encoder_gather_strided(self, N, attw, S, H, L, K):
-        self._ck(self.lib.memotr_msda_forward_strided(_p(self.value), 32 if self.value_hm else self.C, _p(self.shapes_t),
-                                                      _p(self.lsi_t), _p(self.ol), N, _p(attw), N, _p(self.att), 1, S, H, L, S, K,
-                                                      int(self.value_hm), self._st()), "msda_forward_strided")
 
     def mha(self, q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, kpm=None):
         """q/k/v are the fp32 projections (kept in fp32 in both modes: rounding them to bf16 perturbs the attention
@@ -674,11 +676,9 @@ class FrameEngine:
         Ke = self.cfg["n_enc_points"]
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
-            if self.value_hm:
-                self._ck(self.lib.memotr_linear_headmajor(_p(self.src_tok), C, _p(a["value"].w), a["value"].K, _p(a["value"].b),
-                                                          _p(self.mask_flat), _p(self.value), S, C, C, st()), "linear_headmajor")
-            else:
-                self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
+            if self.debug_enc is not None:
+                self.debug_enc.append(self.src32.float().clone())
+            self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
             if self.fuse_prep:
                 self._encoder_ol_and_gather(a, Ke)
             else:
@@ -703,6 +703,8 @@ class FrameEngine:
             self.ln(ffn_out, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
                     ypos=self.q_tok)
         memory = self.src_tok
+        if self.debug_enc is not None:
+            self.debug_enc.append(self.src32.float().clone())
         self._mark(2)
         # -- decoder inputs (memotr.py:209-278, deformable_transformer.py:239-242)
         nd, nt, nq = self.nd, self.nt, self.nq

@@ -126,48 +126,68 @@ def linear_msda_prep(x, w, b, shapes, level_start, valid_ratios, n_heads, n_leve
     return out
 
 
-def linear_headmajor(x, w, b, rowzero=None):
-    """x (M,K) bf16, w (N,K) bf16 -> (N/32, M, 32) fp16: the projection written head-major (value maps of the encoder)."""
-    M, K = x.shape
-    N = w.shape[0]
-    out = torch.empty((N // 32, M, 32), dtype=torch.float16, device=x.device)
-    with torch.cuda.device(x.device):
-        rc = _lib.lib().memotr_linear_headmajor(_lib.ptr(x), _ld(x), _lib.ptr(w), _ld(w), _lib.ptr(b), _lib.ptr(rowzero),
-                                                _lib.ptr(out), M, N, K, _lib.stream_ptr())
-    _lib.check(rc, "memotr_linear_headmajor")
-    return out
-
-
-def msda_forward_strided(value, spatial_shapes, level_start_index, rows, n_heads, n_levels, n_points, head_major=False):
-    """Gather from an fp16 value map with locations / weights taken from the (Lq, 3*H*L*K) rows of linear_msda_prep.
-    head_major: value is (H, S, 32) instead of (S, >= H*32)."""
-    S = value.shape[1] if head_major else value.shape[0]
-    Lq, N = rows.shape[0], rows.shape[1]
+def msda_forward_strided(value, spatial_shapes, level_start_index, rows=None, n_heads=8, n_levels=4, n_points=4, loc=None,
+                         attn=None):
+    """Global-memory gather from an fp16 value map (S, >= H*32): locations / weights either from the (Lq, 3*H*L*K) rows of
+    linear_msda_prep (`rows`) or from dense `loc` (Lq,H,L,K,2) / `attn` (Lq,H,L,K) fp32."""
+    S = value.shape[0]
+    if rows is not None:
+        Lq, N = rows.shape[0], rows.shape[1]
+        loc, attn, ld_loc, ld_attn = rows, rows.view(-1)[n_heads * n_levels * n_points * 2:], N, N
+    else:
+        Lq, ld_loc, ld_attn = loc.shape[0], n_heads * n_levels * n_points * 2, n_heads * n_levels * n_points
     out = torch.empty((Lq, n_heads * 32), dtype=torch.bfloat16, device=value.device)
-    attw = rows.view(-1)[n_heads * n_levels * n_points * 2:]
     with torch.cuda.device(value.device):
-        rc = _lib.lib().memotr_msda_forward_strided(_lib.ptr(value), 32 if head_major else _ld(value),
-                                                    _lib.ptr(spatial_shapes), _lib.ptr(level_start_index), _lib.ptr(rows), N,
-                                                    _lib.ptr(attw), N, _lib.ptr(out), 1, S, n_heads, n_levels, Lq, n_points,
-                                                    int(head_major), _lib.stream_ptr())
+        rc = _lib.lib().memotr_msda_forward_strided(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
+                                                    _lib.ptr(level_start_index), _lib.ptr(loc), ld_loc, _lib.ptr(attn), ld_attn,
+                                                    _lib.ptr(out), 1, S, n_heads, n_levels, Lq, n_points, _lib.stream_ptr())
     _lib.check(rc, "memotr_msda_forward_strided")
     return out
 
 
-def msda_forward_window(value, spatial_shapes, level_start_index, shapes, level_start, rows, valid_ratios, n_heads, n_levels,
-                        n_points):
-    """Experimental windowed gather (csrc/msda_window.cu): value (S, >=H*32) fp16 pixel-major, rows as linear_msda_prep."""
+def window_plan(shapes, n_heads=8, n_points=4, radius=2.5, max_classes=0):
+    """The staging plan of msda_forward_window (host only): dict(classes, units, global_ctas, global_q0, smem, cls=[...])."""
     import ctypes
-    S, N = rows.shape
+    L = len(shapes)
+    hw = (ctypes.c_int * (2 * L))(*[int(v) for s_ in shapes for v in s_])
+    sizes = [int(h) * int(w) for h, w in shapes]
+    lsi = (ctypes.c_int * L)(*[sum(sizes[:i]) for i in range(L)])
+    info = (ctypes.c_int * (8 + 2 * 18))()
+    _lib.check(_lib.lib().memotr_msda_window_plan(hw, lsi, sum(sizes), n_heads, L, n_points, float(radius), max_classes, info),
+               "memotr_msda_window_plan")
+    out = dict(classes=info[0], units=info[1], global_ctas=info[2], global_q0=info[3], smem=info[4], cls=[])
+    for c in range(info[0]):
+        o = info[8 + 18 * c: 8 + 18 * (c + 1)]
+        out["cls"].append(dict(level=o[0], tile=(o[1], o[2]), tiles=(o[3], o[4]), units=o[5], tma_bytes=o[6], rec_stride=o[7],
+                               ww=list(o[8:8 + L]), wh=list(o[13:13 + L])))
+    return out
+
+
+def msda_forward_window(value, shapes, valid_ratios, rows=None, n_heads=8, n_points=4, shift=None, radius=2.5, max_classes=0,
+                        loc=None, attn=None, stats=None):
+    """Encoder-shaped gather from TMA-staged windows (csrc/msda_window.cu): value (S, >= H*32) fp16 pixel-major; locations /
+    weights as for msda_forward_strided; `shift` (H, L, 2) host floats or None; `stats` device int64[2] or None."""
+    import ctypes
+    L = len(shapes)
+    S = value.shape[0]
+    if rows is not None:
+        N = rows.shape[1]
+        loc, attn, ld_loc, ld_attn = rows, rows.view(-1)[n_heads * L * n_points * 2:], N, N
+    else:
+        ld_loc, ld_attn = n_heads * L * n_points * 2, n_heads * L * n_points
     out = torch.empty((S, n_heads * 32), dtype=torch.bfloat16, device=value.device)
-    attw = rows.view(-1)[n_heads * n_levels * n_points * 2:]
-    hw = (ctypes.c_int * (2 * n_levels))(*[int(v) for s_ in shapes for v in s_])
-    lsi = (ctypes.c_int * n_levels)(*[int(v) for v in level_start])
+    hw = (ctypes.c_int * (2 * L))(*[int(v) for s_ in shapes for v in s_])
+    sizes = [int(h) * int(w) for h, w in shapes]
+    lsi = (ctypes.c_int * L)(*[sum(sizes[:i]) for i in range(L)])
+    sh = None
+    if shift is not None:
+        flat = [float(v) for v in torch.as_tensor(shift, dtype=torch.float32).reshape(-1).tolist()]
+        assert len(flat) == n_heads * L * 2
+        sh = (ctypes.c_float * len(flat))(*flat)
     with torch.cuda.device(value.device):
-        rc = _lib.lib().memotr_msda_forward_window(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
-                                                   _lib.ptr(level_start_index), hw, lsi, _lib.ptr(rows), N, _lib.ptr(attw), N,
-                                                   _lib.ptr(valid_ratios), _lib.ptr(out), S, n_heads, n_levels, n_points,
-                                                   _lib.stream_ptr())
+        rc = _lib.lib().memotr_msda_forward_window(_lib.ptr(value), _ld(value), hw, lsi, _lib.ptr(loc), ld_loc, _lib.ptr(attn),
+                                                   ld_attn, _lib.ptr(valid_ratios), sh, float(radius), int(max_classes),
+                                                   _lib.ptr(stats), _lib.ptr(out), S, n_heads, L, n_points, _lib.stream_ptr())
     _lib.check(rc, "memotr_msda_forward_window")
     return out
 
@@ -220,27 +240,3 @@ def box_refine(delta, ref, n_take):
                                           ref.shape[0], n_take, _lib.stream_ptr())
     _lib.check(rc, "memotr_box_refine")
     return new_ref, ref_next
-
-
-def msda_pairs_layout(value, spatial_shapes, level_start_index, n_heads):
-    """(S, >=H*32) bf16 pixel-major value map -> (H, S, 2, 32) pair-duplicated head-major map."""
-    S = value.shape[0]
-    pairs = torch.empty((n_heads, S, 2, 32), dtype=torch.bfloat16, device=value.device)
-    with torch.cuda.device(value.device):
-        rc = _lib.lib().memotr_msda_pairs_layout(_lib.ptr(value), _ld(value), _lib.ptr(spatial_shapes),
-                                                 _lib.ptr(level_start_index), _lib.ptr(pairs), S, n_heads,
-                                                 spatial_shapes.shape[0], _lib.stream_ptr())
-    _lib.check(rc, "memotr_msda_pairs_layout")
-    return pairs
-
-
-def msda_forward_pairs(pairs, spatial_shapes, level_start_index, loc, attn):
-    H, S = pairs.shape[0], pairs.shape[1]
-    Lq, _, L, K = attn.shape
-    out = torch.empty((Lq, H * 32), dtype=torch.bfloat16, device=pairs.device)
-    with torch.cuda.device(pairs.device):
-        rc = _lib.lib().memotr_msda_forward_pairs(_lib.ptr(pairs), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
-                                                  _lib.ptr(loc), _lib.ptr(attn), _lib.ptr(out), S, H, L, Lq, K,
-                                                  _lib.stream_ptr())
-    _lib.check(rc, "memotr_msda_forward_pairs")
-    return out

@@ -45,6 +45,38 @@ def msda_inputs(shapes, B=1, H=8, D=32, K=4, Lq=100, seed=3, border=False, dtype
     return value.to(dtype), shapes_t, lsi, loc.to(dtype), attn.to(dtype)
 
 
+def encoder_msda_inputs(shapes, H=8, K=4, seed=3, noise_px=0.5, valid=(1.0, 1.0), dtype=torch.float32):
+    """Inputs of an ENCODER-shaped MSDA call (the queries are the S pixels of the pyramid, deformable_encoder.py:124):
+    reference points = pixel centres over the valid extent (deformable_encoder.py:29-40), sampling offsets = the ring
+    pattern MSDeformAttn initialises its bias to (head direction x point index, ms_deform_attn.py:72-81) plus Gaussian
+    noise of `noise_px` pixels -- the distribution a (lightly) trained encoder produces.  `valid` = (w, h) valid ratio of
+    every level.  -> value (S, H*32), valid_ratios (L, 2), loc (S, H, L, K, 2), attn (S, H, L, K), shift (H, L, 2) [mean
+    offset per head and level in pixels: the staging hint of the windowed gather]."""
+    g = _gen(seed)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    vr = torch.tensor([[float(valid[0]), float(valid[1])]] * L)
+    refs = []
+    for l, (h, w) in enumerate(shapes):
+        ys = (torch.arange(h, dtype=torch.float32) + 0.5) / (vr[l, 1] * h)
+        xs = (torch.arange(w, dtype=torch.float32) + 0.5) / (vr[l, 0] * w)
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        refs.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
+    ref = torch.cat(refs, 0)                                                    # (S, 2), normalised by the valid extent
+    th = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+    ring = torch.stack([th.cos(), th.sin()], -1)
+    ring = (ring / ring.abs().max(-1, keepdim=True)[0]).view(1, H, 1, 1, 2)
+    off = ring * torch.arange(1, K + 1, dtype=torch.float32).view(1, 1, 1, K, 1)      # (1, H, 1, K, 2) pixels
+    off = off + noise_px * torch.randn(S, H, L, K, 2, generator=g)
+    wh = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32).view(1, 1, L, 1, 2)
+    loc = ref.view(S, 1, 1, 1, 2) * vr.view(1, 1, L, 1, 2) + off / wh
+    attn = torch.rand(S, H, L, K, generator=g) + 1e-5
+    attn = attn / attn.sum((-1, -2), keepdim=True)
+    value = torch.randn(S, H * 32, generator=g)
+    shift = (ring * (K + 1) / 2.0).view(H, 1, 2).repeat(1, L, 1)
+    return value.to(dtype), vr, loc.to(dtype).contiguous(), attn.to(dtype).contiguous(), shift
+
+
 def hot_path_param_shapes(cfg):
     """Key -> shape for every hot-path parameter, in the reference's state_dict naming.
     oracle/make_golden.py asserts this table against the instantiated reference modules."""

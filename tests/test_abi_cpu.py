@@ -109,3 +109,31 @@ def test_engine_input_layout_is_one_contiguous_buffer():
         m0 = lay["mask"][0]
         assert [int(v) for v in flat[m0:m0 + S].unique()] == sorted({int(m[0]) for m in mask})
         assert all(int(flat[lay["mask"][l]]) == int(mask[l][0]) for l in range(3))
+
+
+def test_window_plan_host_logic():
+    """The staging plan of the windowed encoder gather (host-only code of csrc/msda_window.cu): units cover every query of
+    the staged levels exactly once, the rest goes to the global-memory CTAs, shared memory stays within two CTAs per SM."""
+    from memotr_b200 import kernels
+    from memotr_b200 import synthetic as synth
+    for shapes, K, radius in ((synth.DANCETRACK_SHAPES, 4, 2.5), (synth.DANCETRACK_SHAPES, 4, 5.75), (synth.BDD_SHAPES_L5, 8, 3.0),
+                              (synth.BDD_SHAPES, 16, 2.0), (synth.SMALL_SHAPES, 4, 2.0)):
+        plan = kernels.window_plan(shapes, 8, K, radius)
+        sizes = [h * w for h, w in shapes]
+        assert 1 <= plan["classes"] <= 2 and plan["smem"] <= 112 * 1024
+        assert plan["global_q0"] == sum(sizes[:plan["classes"]])
+        assert plan["global_ctas"] == -(-(sum(sizes) - plan["global_q0"]) * 8 * 4 // 256)
+        units = 0
+        for c in plan["cls"]:
+            h, w = shapes[c["level"]]
+            assert c["tiles"] == (-(-w // c["tile"][0]), -(-h // c["tile"][1])) and c["units"] == c["tiles"][0] * c["tiles"][1] * 8
+            assert c["tile"][0] * c["tile"][1] % 32 == 0 and c["rec_stride"] % 128 == 32
+            assert c["tma_bytes"] == sum(a * b * 64 for a, b in zip(c["ww"], c["wh"])) > 0
+            for l, (a, b) in enumerate(zip(c["ww"], c["wh"])):
+                assert (a == 0) == (b == 0) and a <= shapes[l][1] + 2 and b <= shapes[l][0] + 2
+            units += c["units"]
+        assert units == plan["units"]
+    # a radius that does not fit drops the finest window first instead of failing
+    big = kernels.window_plan(synth.DANCETRACK_SHAPES, 8, 4, 6.0)
+    small = kernels.window_plan(synth.DANCETRACK_SHAPES, 8, 4, 2.5)
+    assert all(small["cls"][0]["ww"]) and big["cls"][0]["ww"][0] == 0 and all(big["cls"][0]["ww"][1:])

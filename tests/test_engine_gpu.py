@@ -296,31 +296,6 @@ def test_msda_forward_ex_fp16_value_map_is_tighter_than_bf16():
     assert err[torch.float16] <= err[torch.bfloat16] * 1.05 and err[torch.float16] < 5e-3, err
 
 
-@pytest.mark.parametrize("Kp,shapes,Lq", [(4, synth.DANCETRACK_SHAPES, 777), (8, synth.BDD_SHAPES, 100), (4, synth.BDD_SHAPES_L5, 64),
-                                          (2, synth.SMALL_SHAPES, 50), (1, ((1, 1), (2, 3)), 9)])
-def test_msda_pairs_layout_and_gather(Kp, shapes, Lq):
-    """Encoder fast path: pair-duplicated head-major value map + 2-loads-per-point gather, against the C oracle (border
-    samples included: x0 = -1, x1 = W, y out of range), reading the value map through a pixel stride."""
-    from oracle import msda as omsda
-    value, shp, lsi, loc, attn = synth.msda_inputs(shapes, B=1, H=8, D=32, K=Kp, Lq=Lq, seed=70 + Kp, border=True)
-    S = value.shape[1]
-    wide = torch.randn(S, 2 * 256, generator=_g(2)).bfloat16()
-    wide[:, 256:] = value.reshape(S, 256).bfloat16()
-    v_used = wide[:, 256:].float().reshape(1, S, 8, 32)
-    want = omsda.forward(v_used.numpy(), shp.numpy(), lsi.numpy(), loc.numpy(), attn.numpy(), fma=True)[0]
-    pairs = K().msda_pairs_layout(wide.to(DEV)[:, 256:], shp.to(DEV), lsi.to(DEV), 8)
-    # layout property: half 0 is the pixel itself, half 1 its right neighbour (zeros at row ends)
-    hm = v_used[0].permute(1, 0, 2)                                       # (H, S, 32)
-    assert torch.equal(pairs[:, :, 0].float().cpu(), hm)
-    x_idx = torch.cat([torch.arange(h * w) % w for h, w in shapes])
-    w_of = torch.cat([torch.full((h * w,), w) for h, w in shapes])
-    right = torch.roll(hm, -1, dims=1) * (x_idx + 1 < w_of)[None, :, None]
-    assert torch.equal(pairs[:, :, 1].float().cpu(), right)
-    got = K().msda_forward_pairs(pairs, shp.to(DEV), lsi.to(DEV), loc[0].contiguous().to(DEV),
-                                 attn[0].contiguous().to(DEV)).float().cpu().numpy()
-    assert rel_err(got, want) < 4e-3
-
-
 @pytest.mark.parametrize("mode,L,Kp", [("enc", 4, 4), ("dec", 4, 4), ("enc", 4, 8), ("dec", 4, 3), ("enc", 5, 4)])
 def test_msda_prep_matches_module_arithmetic(mode, L, Kp):
     """Sampling locations / attention weights against the torch expressions of ms_deform_attn.py:108-120 with the
@@ -397,23 +372,9 @@ def test_linear_with_msda_prep_epilogue_and_strided_gather():
     cat = torch.cat((loc.reshape(S, 256), attn.reshape(S, 128)), 1).contiguous()
     strided2 = K().msda_forward_strided(value, shapes_t, lsi_t, cat, H, L, Kp)
     assert torch.equal(strided2, dense)                                                       # same inputs: bit-equal
-    # experimental windowed gather (TMA-staged windows in shared memory + global fallback): same taps, same order
-    win = K().msda_forward_window(value, shapes_t, lsi_t, shapes, lsi, rows, vr, H, L, Kp)
+    # the windowed gather on the rows of the projection (tests/test_msda_window_gpu.py has the thorough cases)
+    win = K().msda_forward_window(value, shapes, vr, rows=rows, n_heads=H, n_points=Kp, radius=3.0)
     assert torch.equal(win, strided)
-    far = rows.clone()                      # offsets far beyond the halo: every sample takes the global fallback
-    far[:, :256] += 0.3 * torch.randn(S, 256, generator=g).to(DEV)
-    assert torch.equal(K().msda_forward_window(value, shapes_t, lsi_t, shapes, lsi, far, vr, H, L, Kp),
-                       K().msda_forward_strided(value, shapes_t, lsi_t, far, H, L, Kp))
-    # head-major value map (H, S, 32): same numbers in another layout -> bit-equal gather
-    hm = value.reshape(S, H, 32).permute(1, 0, 2).contiguous()
-    assert torch.equal(K().msda_forward_strided(hm, shapes_t, lsi_t, cat, H, L, Kp, head_major=True), dense)
-    # ... and the projection that writes it: (x W^T + b) with padded rows zeroed, head-major, against the plain tc GEMM
-    rz = (torch.rand(S, generator=g) < 0.1).to(torch.uint8).to(DEV)
-    wv = (torch.randn(256, 256, generator=g) / 16).bfloat16().to(DEV)
-    bv = torch.randn(256, generator=g).to(DEV)
-    plain = K().linear(x, wv, bv, rowzero=rz, out_dtype=torch.float16, path="tc")
-    got = K().linear_headmajor(x, wv, bv, rowzero=rz)
-    assert got.shape == (H, S, 32) and torch.equal(got.permute(1, 0, 2).reshape(S, 256), plain)
 
 
 @pytest.mark.parametrize("h,w,vh,vw", [(100, 168, 100, 168), (100, 168, 88, 167), (50, 84, 44, 84), (13, 21, 12, 20), (1, 1, 1, 1)])
@@ -488,18 +449,24 @@ def test_clip_runner_host_api_tracker_mode():
 # ------------------------------------------------------------------------------------------------ engine
 def _case(tag):
     g = np.load(os.path.join(GOLDEN, f"frame_{tag}.npz"))
-    n_tracks, seed_w, seed_x, padded = (int(v) for v in g["meta"])
+    meta = [int(v) for v in g["meta"]]
+    n_tracks, seed_w, seed_x, padded = meta[:4]
+    refinit, sine_pos = (meta[4], meta[5]) if len(meta) > 4 else (0, 0)
     shapes = [tuple(int(v) for v in r) for r in g["shapes"]]
-    cfg = oframe.dancetrack_cfg() if tag == "full" else synth.small_cfg()
-    sd = synth.hot_path_state_dict(cfg, seed=seed_w)
+    cfg = oframe.dancetrack_cfg() if tag.startswith("full") else synth.small_cfg()
+    sd = synth.reference_init_state_dict(cfg, seed=seed_w) if refinit else synth.hot_path_state_dict(cfg, seed=seed_w)
     x = synth.frame_inputs(cfg, shapes, n_tracks, seed=seed_x, padded=bool(padded))
+    if sine_pos:            # the golden was made with the reference's PositionEmbeddingSine maps: the engine rebuilds them
+        x["pos"] = None     # on the device from the padding masks (pos_embed=dict(...))
     return g, cfg, sd, x, shapes, n_tracks
 
 
-def _run_engine(tag, mode):
+def _run_engine(tag, mode, debug_enc=False):
     from memotr_b200.engine import FrameEngine
     g, cfg, sd, x, shapes, nt = _case(tag)
-    eng = FrameEngine(sd, cfg, shapes, nt, DEV, mode=mode)
+    eng = FrameEngine(sd, cfg, shapes, nt, DEV, mode=mode, pos_embed=dict(temperature=20) if x["pos"] is None else None)
+    if debug_enc:
+        eng.debug_enc = []
     eng.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
     eng.forward()
     eng.load_tracks(x["tracks"])
@@ -545,6 +512,76 @@ def test_engine_bf16_matches_reference_modules(tag):
         assert worst[k] < (1e-1 if deep else 1e-2), (k, worst[k])
     for k in ("outputs", "aux_queries", "pred_logits", "aux_logits", "upd_query_embed", "upd_long_memory", "upd_last_output"):
         assert worst[k] < (2.5e-1 if deep else 3e-2), (k, worst[k])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_engine_matches_reference_modules_on_reference_init_weights(mode):
+    """The benchmarked configuration (full DanceTrack sizes, 6+6 layers, 300+100 queries, padded frame, position maps rebuilt
+    on the device, every fused kernel) on weights drawn from the reference's OWN initialisation
+    (synth.reference_init_state_dict), against outputs of the reference nn.Modules (frame_full_refinit.npz): the north
+    star's bars on EVERY output -- fp32 <= 1e-4, bf16 <= 1e-2.  (tests/test_numerics_cpu.py: the rounding model of the bf16
+    mode predicts 7e-3 here, and shows why the white-noise weights of frame_full.npz amplify the same rounding 40x.)"""
+    g, eng, res, st = _run_engine("full_refinit", mode)
+    if mode == "bf16":
+        assert eng.dec_cluster and eng.upd_fused and eng.fuse_prep and eng.msda_window
+    worst = {k: rel_err(res[k].cpu().numpy(), g[k]) for k in FRAME_KEYS}
+    worst.update({"upd_" + k: rel_err(st[k].cpu().numpy(), g["upd_" + k]) for k in UPD_KEYS})
+    print(mode, "engine vs reference modules, reference-init weights:", {k: f"{v:.1e}" for k, v in worst.items()})
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    assert max(worst.values()) < tol, worst
+
+
+@pytest.mark.parametrize("tag", ["full", "full_refinit"])
+def test_engine_bf16_every_layer_teacher_forced_within_1e2(tag):
+    """Teacher forcing, layer by layer: the oracle's fp32 layer applied to the ENGINE's own input of that layer must agree
+    with the engine's output of that layer to 1e-2 -- encoder layers, decoder layers (hidden state and refined boxes) and the
+    query updater -- also on the white-noise weights whose end-to-end deviation is several 1e-2 (amplification, not kernels)."""
+    g, eng, res, st = _run_engine(tag, "bf16", debug_enc=True)
+    _, cfg, sd, x, shapes, nt = _case(tag)
+    pos = x["pos"] if x["pos"] is not None else [oframe.position_embedding_sine(m) for m in x["masks"]]
+    report = {}
+    with torch.no_grad():
+        src0, mask, posf, shp, lsi, vr = oframe.flatten_levels(sd, "transformer", x["srcs"], x["masks"], pos)
+        ref = oframe.encoder_reference_points(shp, vr, "cpu")
+        states = [t.cpu()[None] for t in eng.debug_enc]
+        assert len(states) == cfg["n_enc_layers"] + 1
+        assert rel_err(states[0].numpy(), src0.numpy()) < 1e-6
+        for i in range(cfg["n_enc_layers"]):
+            want = oframe.encoder_layer(sd, f"transformer.encoder.layers.{i}", states[i], posf, ref, shp, lsi, mask, cfg)
+            report[f"enc{i}"] = rel_err(states[i + 1].numpy(), want.numpy())
+        memory = states[-1]
+        qm = torch.zeros((1, eng.nq), dtype=torch.bool)
+        for lid in range(cfg["n_dec_layers"]):
+            tgt_in, ref_in = eng.tgt32[lid].float().cpu()[None], eng.ref[lid].cpu()[None]
+            want_t, want_r = oframe.decoder_step(sd, lid, tgt_in, ref_in, memory, shp, lsi, vr, qm, mask, cfg)
+            report[f"dec{lid}"] = rel_err(eng.tgt32[lid + 1].float().cpu().numpy(), want_t[0].numpy())
+            report[f"ref{lid}"] = rel_err(eng.ref[lid + 1].cpu().numpy(), want_r[0].numpy())
+        wupd = oframe.update_tracks(sd, x["tracks"], cfg)
+        for k in UPD_KEYS:
+            report["upd_" + k] = rel_err(st[k].cpu().numpy(), wupd[k].numpy())
+    print(tag, "teacher-forced per-layer rel err:", {k: f"{v:.1e}" for k, v in report.items()})
+    assert max(report.values()) < 1e-2, report
+
+
+def test_engine_bf16_white_noise_weights_vs_matched_rounding_oracle():
+    """frame_full.npz: the bf16 engine against the oracle evaluated under the SAME rounding model (bf16 GEMM operands, fp16
+    value maps, bf16 gather rows).  The network amplifies every rounding difference 40x (tests/test_numerics_cpu.py), so even
+    the matched model only agrees to the extent the individual rounding decisions coincide; the deviations are recorded, and
+    bounded by what the rounding model itself shows against fp32."""
+    g, eng, res, st = _run_engine("full", "bf16")
+    _, cfg, sd, x, shapes, nt = _case("full")
+    with torch.no_grad(), oframe.numerics(gemm="bf16", value="fp16", gather="bf16"):
+        want = oframe.frame_forward(sd, x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"], cfg)
+    rep = {k: (rel_err(res[k].cpu().numpy(), want[k].numpy()), rel_err(res[k].cpu().numpy(), g[k]),
+               rel_err(want[k].numpy(), g[k])) for k in ("pred_logits", "pred_bboxes", "outputs", "aux_queries")}
+    rep["memory"] = (rel_err(res["memory"].cpu().numpy(), want["memory"].numpy()), float("nan"), float("nan"))
+    print("engine vs matched oracle / engine vs fp32 reference / matched oracle vs fp32 reference:",
+          {k: tuple(f"{v:.1e}" for v in t) for k, t in rep.items()})
+    assert rep["memory"][0] < 1e-2
+    for k in ("pred_bboxes",):
+        assert rep[k][0] < 1e-1
+    for k in ("pred_logits", "outputs", "aux_queries"):
+        assert rep[k][0] < 2.5e-1
 
 
 @pytest.mark.parametrize("fused", ["1", "2"])          # 1: one CTA per 16-row block, 2: a 4-CTA cluster per block (default)

@@ -1,13 +1,12 @@
 #!/usr/bin/env python
-"""tools/micro_msda.py -- MSDA micro-benchmark on one B200 (development aid; bench.py is the contract).
+"""tools/micro_msda.py -- MSDA forward micro-benchmark on one B200 (development aid; bench.py is the contract).
 
-Times memotr_msda_forward/backward (fp32, bf16) and, when oracle/_ref travelled, the reference CUDA op on the same
-tensors: encoder-shaped (Lq = S = 22323) and decoder-shaped (Lq = 400) calls of the DanceTrack config, with
-  * "uniform" sampling locations (models/ops/test.py recipe: rand in [0,1) -- worst-case locality), and
-  * "encoder" locations (pixel-centre reference points + Gaussian offsets of a few pixels -- what a trained encoder
-    produces, ms_deform_attn.py:115-117).
-CUDA events on the current stream, L2 flushed between iterations, algorithmic bytes per BASELINE.md section 3.
-Writes gpurun_out/micro_msda.json.
+Encoder-shaped launches (Lq = S) of the fp16-value-map gathers on encoder-like sampling patterns (ring offsets + noise,
+memotr_b200/synthetic.py:encoder_msda_inputs): the windowed kernel (csrc/msda_window.cu) against the global-memory kernel
+(msda_fwd_h16), for the DanceTrack pyramid and the BDD100K sweep of BASELINE.json config 5 (K in {4,8,16} x L in {4,5}).
+CUDA events on the current stream, L2 flushed between iterations, algorithmic bytes = fp16 value map + fp32 locations /
+weights + bf16 output.  Writes gpurun_out/micro_msda.json.
+  --ncu : run each kernel of the DanceTrack case exactly once (profiling target), no timing
 """
 import json
 import os
@@ -17,8 +16,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import memotr_b200  # noqa: E402
-from oracle import synth  # noqa: E402
+from memotr_b200 import kernels, synthetic as synth  # noqa: E402
 
 DEV = "cuda"
 PEAK = 6567.4
@@ -26,7 +24,7 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
 
-def timeit(fn, iters=20, warmup=3, flush=None):
+def timeit(fn, iters=30, warmup=5, flush=None):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -44,79 +42,62 @@ def timeit(fn, iters=20, warmup=3, flush=None):
     return ts[len(ts) // 2], ts[0]
 
 
-def encoder_locs(shapes, H, K, sigma_px, seed):
-    g = torch.Generator().manual_seed(seed)
-    refs = []
-    for (h, w) in shapes:
-        ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h) / h, torch.linspace(0.5, w - 0.5, w) / w, indexing="ij")
-        refs.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), -1))
-    ref = torch.cat(refs, 0)                                  # (S, 2)
-    S, L = ref.shape[0], len(shapes)
-    off = torch.randn(1, S, H, L, K, 2, generator=g) * sigma_px
-    wh = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
-    return ref[None, :, None, None, None, :] + off / wh[None, None, None, :, None, :]
+def case(shapes, H, K, noise, radius=None, classes=0):
+    value, vr, loc, attn, shift = synth.encoder_msda_inputs(shapes, H=H, K=K, seed=7, noise_px=noise)
+    shp = torch.as_tensor(shapes, dtype=torch.long)
+    lsi = torch.cat((shp.new_zeros(1), shp.prod(1).cumsum(0)[:-1]))
+    d = dict(value=value.half().to(DEV), vr=vr.to(DEV), loc=loc.to(DEV), attn=attn.to(DEV), shift=shift, shp=shp.to(DEV),
+             lsi=lsi.to(DEV), shapes=shapes, H=H, K=K, L=len(shapes), S=value.shape[0],
+             radius=radius if radius is not None else min((K - 1) / 2 + 2.5 * noise + 0.5, 6.0), classes=classes)
+    d["bytes"] = d["S"] * H * 32 * 2 + d["S"] * H * d["L"] * K * 12 + d["S"] * H * 32 * 2
+    return d
+
+
+def run_window(c, stats=None):
+    return kernels.msda_forward_window(c["value"], c["shapes"], c["vr"], n_heads=c["H"], n_points=c["K"], loc=c["loc"],
+                                       attn=c["attn"], shift=c["shift"], radius=c["radius"], max_classes=c["classes"], stats=stats)
+
+
+def run_global(c):
+    return kernels.msda_forward_strided(c["value"], c["shp"], c["lsi"], n_heads=c["H"], n_levels=c["L"], n_points=c["K"],
+                                        loc=c["loc"], attn=c["attn"])
 
 
 def main():
-    shapes = synth.DANCETRACK_SHAPES
-    S = sum(h * w for h, w in shapes)
+    if "--ncu" in sys.argv:
+        c = case(synth.DANCETRACK_SHAPES, 8, 4, 0.15)
+        for _ in range(3):
+            run_window(c), run_global(c)
+        torch.cuda.synchronize()
+        return
     flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)   # 256 MB > 126 MB L2
-    ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    MSDA = None
-    if os.path.exists(os.path.join(ref_dir, "MultiScaleDeformableAttention.so")):
-        sys.path.insert(0, ref_dir)
-        import MultiScaleDeformableAttention as MSDA
     res = []
-    for tag, Lq, K in (("enc", S, 4), ("dec", 400, 4), ("enc_K8", S, 8), ("enc_K16", S, 16)):
-        value, shp, lsi, loc, attn = (x.to(DEV) for x in synth.msda_inputs(shapes, Lq=Lq, K=K, seed=1))
-        locs = {"uniform": loc}
-        if Lq == S:
-            locs["encoder"] = encoder_locs(shapes, 8, K, 2.0, 2).to(DEV).contiguous()
-        for lname, lc in locs.items():
-            nbytes = (S * 256 + Lq * 8 * 4 * K * 3 + Lq * 256) * 4
-            row = {"case": tag, "loc": lname, "Lq": Lq, "K": K, "fp32_bytes": nbytes}
-            if Lq == S:
-                os.environ["MEMOTR_MSDA_MAPPING"] = "linear"
-                row["ours_fwd_fp32_linear_us"], _ = timeit(
-                    lambda: memotr_b200.ms_deform_attn_forward(value, shp, lsi, lc, attn, 64), flush=flush)
-                os.environ["MEMOTR_MSDA_MAPPING"] = "tiled"
-            t, tmin = timeit(lambda: memotr_b200.ms_deform_attn_forward(value, shp, lsi, lc, attn, 64), flush=flush)
-            os.environ.pop("MEMOTR_MSDA_MAPPING", None)
-            row["ours_fwd_fp32_us"], row["ours_fwd_fp32_min_us"] = t, tmin
-            row["ours_fwd_fp32_gbs"] = nbytes / t / 1e3
-            row["ours_fwd_fp32_frac"] = row["ours_fwd_fp32_gbs"] / PEAK
-            vb, lb, ab = value.bfloat16(), lc.bfloat16(), attn.bfloat16()
-            t, tmin = timeit(lambda: memotr_b200.ms_deform_attn_forward(vb, shp, lsi, lb, ab, 64), flush=flush)
-            row["ours_fwd_bf16_us"] = t
-            row["ours_fwd_bf16_gbs"] = nbytes / 2 / t / 1e3
-            from memotr_b200 import kernels
-            for nm, vv in (("fp32", value.reshape(S, 256)), ("bf16", value.reshape(S, 256).bfloat16())):
-                for kern, U in (("v1", "2"), ("v2", "1"), ("v2", "2"), ("v2", "4")):
-                    os.environ["MEMOTR_MSDA_KERNEL"] = kern
-                    os.environ["MEMOTR_MSDA_U"] = U
-                    t, _ = timeit(lambda: kernels.msda_forward_ex(vv, shp, lsi, lc[0], attn[0], 8), flush=flush)
-                    row[f"ex_{kern}{'_U' + U if kern == 'v2' else ''}_{nm}_us"] = t
-            os.environ.pop("MEMOTR_MSDA_KERNEL", None)
-            os.environ.pop("MEMOTR_MSDA_U", None)
-            vh16 = value.reshape(S, 256).half()
-            row["ex_v4_fp16_us"], _ = timeit(lambda: kernels.msda_forward_ex(vh16, shp, lsi, lc[0], attn[0], 8), flush=flush)
-            if K in (4, 8):
-                vb16 = value.reshape(S, 256).bfloat16()
-                row["pairs_layout_us"], _ = timeit(lambda: kernels.msda_pairs_layout(vb16, shp, lsi, 8), flush=flush)
-                pr = kernels.msda_pairs_layout(vb16, shp, lsi, 8)
-                row["pairs_gather_us"], _ = timeit(lambda: kernels.msda_forward_pairs(pr, shp, lsi, lc[0], attn[0]), flush=flush)
-            if K == 4:
-                go = torch.randn(1, Lq, 256, device=DEV)
-                t, _ = timeit(lambda: memotr_b200.ms_deform_attn_backward(value, shp, lsi, lc, attn, go, 64), flush=flush)
-                row["ours_bwd_fp32_us"] = t
-            if MSDA is not None:
-                t, tmin = timeit(lambda: MSDA.ms_deform_attn_forward(value, shp, lsi, lc, attn, 64), flush=flush)
-                row["ref_fwd_fp32_us"], row["ref_fwd_fp32_gbs"] = t, nbytes / t / 1e3
-                if K == 4:
-                    t, _ = timeit(lambda: MSDA.ms_deform_attn_backward(value, shp, lsi, lc, attn, go, 64), flush=flush)
-                    row["ref_bwd_fp32_us"] = t
-            print(json.dumps(row), flush=True)
-            res.append(row)
+    cases = [("dancetrack_refinit_like", synth.DANCETRACK_SHAPES, 4, 0.15, None, 0),
+             ("dancetrack_refinit_like_c1", synth.DANCETRACK_SHAPES, 4, 0.15, None, 1),
+             ("dancetrack_noise0.5", synth.DANCETRACK_SHAPES, 4, 0.5, None, 0),
+             ("dancetrack_noise1.0", synth.DANCETRACK_SHAPES, 4, 1.0, None, 0),
+             ("dancetrack_noise1.0_r2.5", synth.DANCETRACK_SHAPES, 4, 1.0, 2.5, 0)]
+    for L, shapes in ((4, synth.BDD_SHAPES), (5, synth.BDD_SHAPES_L5)):
+        for K in (4, 8, 16):
+            cases.append((f"bdd_L{L}K{K}", shapes, K, 0.15, None, 0))
+    for name, shapes, K, noise, radius, classes in cases:
+        c = case(shapes, 8, K, noise, radius, classes)
+        stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+        a, b = run_window(c, stats), run_global(c)
+        torch.cuda.synchronize()
+        row = {"case": name, "S": c["S"], "L": c["L"], "K": K, "noise_px": noise, "radius": c["radius"], "bit_equal": bool(torch.equal(a, b)),
+               "plan": kernels.window_plan(shapes, 8, K, c["radius"], classes), "bytes": c["bytes"]}
+        nw, ng = (int(v) for v in stats.tolist())
+        row["staged_points"], row["global_points_in_staged_units"] = nw, ng
+        for tag, fn in (("window", lambda: run_window(c)), ("global", lambda: run_global(c))):
+            t, tmin = timeit(fn, flush=flush)
+            row[f"{tag}_us"], row[f"{tag}_min_us"] = t, tmin
+            row[f"{tag}_gbs"] = c["bytes"] / t / 1e3
+            row[f"{tag}_frac"] = row[f"{tag}_gbs"] / PEAK
+            t, _ = timeit(fn, flush=None)
+            row[f"{tag}_l2warm_us"] = t
+        print(json.dumps({k: v for k, v in row.items() if k != "plan"}), flush=True)
+        res.append(row)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "micro_msda.json"), "w"), indent=1)
 
