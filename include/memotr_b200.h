@@ -116,7 +116,8 @@ MEMOTR_API int memotr_linear_msda_prep(const void *A, int lda, const void *W, in
  *     that level (for MSDeformAttn: the mean over the K points of sampling_offsets.bias, ms_deform_attn.py:72-81);
  *   window_radius: spread of the samples around it, pixels.  Both only steer WHAT is staged: a tap outside its window is
  *     read from global memory with the same arithmetic.
- *   max_classes: 0 = default; 1 = stage windows only for the queries of level 0; 2 = levels 0 and 1.
+ *   max_classes: 0 = default (the queries of up to four levels); n = stage windows only for the queries of levels < n,
+ *     the rest reads global memory.
  *   stats: device, 2 x uint64 or NULL -- profiling counters += {sampling points served from windows, points left to
  *     global memory} over the window units of this launch.
  * L <= 5, H <= 16, K even.
@@ -129,7 +130,7 @@ MEMOTR_API int memotr_msda_forward_window(const void *value, int value_pixel_str
 /* The staging plan of memotr_msda_forward_window as integers (host only, no GPU needed): info[0..7] = {classes, window
  * units (CTAs), global-memory CTAs, first global-memory query, dynamic shared memory bytes per CTA, 0, 0, 0}, then per
  * class 18 ints {query level, tile w, tile h, tiles_x, tiles_y, units, TMA bytes per unit, record stride, ww[5], wh[5]}.
- * `info` must hold 8 + 2 * 18 ints. */
+ * `info` must hold 8 + 4 * 18 ints (up to four classes: the queries of levels 0 .. 3). */
 MEMOTR_API int memotr_msda_window_plan(const int *shapes_hw, const int *level_start, int S, int H, int L, int K, float radius,
                                        int max_classes, int *info);
 
@@ -349,10 +350,8 @@ typedef struct memotr_dec_params {
   memotr_dec_layer layers[MEMOTR_DEC_MAX_LAYERS];
 } memotr_dec_params;
 
-MEMOTR_API int memotr_decoder_forward(const memotr_dec_params *params, void *stream);
-
 /*
- * The same decoder with a 4-CTA thread-block cluster per 16-row block (csrc/decoder_cluster.cu): dense layers split over
+ * The fused decoder: a 4-CTA thread-block cluster per 16-row block (csrc/decoder_cluster.cu): dense layers split over
  * output columns, attention / gather over heads, the FFN over the hidden dimension.  `prog` holds FOUR programs of
  * n_prog entries each (rank-major); rank r's entries are, per layer: ref_point_head.0 rows [64r,64r+64), .1 likewise,
  * [query_scale.0/.1 if layer > 0], q rows, k rows, v rows, self-attn out rows, sampling-offset rows [64r,+64), attention-

@@ -104,7 +104,6 @@ _SIGNATURES = {
     "memotr_upd_finalize": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp], _i),
     "memotr_tracker_update": ([_vp, _i, _i, _i, _vp, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "memotr_tracker_results": ([_vp, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
-    "memotr_decoder_forward": ([_vp, _vp], _i),
     "memotr_decoder_forward_cluster": ([_vp, _vp], _i),
     "memotr_updater_forward_cluster": ([_vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),

@@ -181,14 +181,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_cluster_kernel(const __gr
         if (row0 + g + 8 < nq)
           *reinterpret_cast<uint32_t *>(Kh + (long)(row0 + g + 8) * C + cb + col) = pack_f16(a[2] + b0, a[3] + b1);
       });
+      // (V of a padded key is written as zero: its softmax weight is exactly 0, but 0 x a stale non-finite row would be NaN)
+      const bool keep0 = !(row0 + g < nq && P.query_pad && P.query_pad[row0 + g]);
+      const bool keep1 = !(row0 + g + 8 < nq && P.query_pad && P.query_pad[row0 + g + 8]);
       gemm(sprog, rg, xb, P256, Lp.v_b + cb, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {       // v^T
         if (row0 + g < nq) {
-          Vt[(long)(cb + col) * P.np + row0 + g] = __float2half_rn(a[0] + b0);
-          Vt[(long)(cb + col + 1) * P.np + row0 + g] = __float2half_rn(a[1] + b1);
+          Vt[(long)(cb + col) * P.np + row0 + g] = __float2half_rn(keep0 ? a[0] + b0 : 0.f);
+          Vt[(long)(cb + col + 1) * P.np + row0 + g] = __float2half_rn(keep0 ? a[1] + b1 : 0.f);
         }
         if (row0 + g + 8 < nq) {
-          Vt[(long)(cb + col) * P.np + row0 + g + 8] = __float2half_rn(a[2] + b0);
-          Vt[(long)(cb + col + 1) * P.np + row0 + g + 8] = __float2half_rn(a[3] + b1);
+          Vt[(long)(cb + col) * P.np + row0 + g + 8] = __float2half_rn(keep1 ? a[2] + b0 : 0.f);
+          Vt[(long)(cb + col + 1) * P.np + row0 + g + 8] = __float2half_rn(keep1 ? a[3] + b1 : 0.f);
         }
       });
       STAMP(2)

@@ -9,9 +9,10 @@
 //   per sampling point: (x, y) -> pixel coordinate as the reference does (h = fma(loc_y, H, -0.5), .cuh:285-286), the
 //   open-interval test of .cuh:288, floor, the four bilinear weights times the attention weight in fp32, each rounded
 //   to fp16 (0 for a corner outside the image, .cuh:56-78);
-//   per level and x-SIDE s in {x0, x0+1}:  a_s = sum over the level's points of  w(y0,s) v(y0,s) + w(y1,s) v(y1,s)  as
-//   packed-half FMAs in that order (two channels per instruction);
-//   acc_s += float(a_s) after every level (fp32);   out = bf16(acc_0 + acc_1).
+//   per PAIR of levels (2j, 2j+1) and x-SIDE s in {x0, x0+1}:  a_s = sum over the pair's points, level-major, of
+//   w(y0,s) v(y0,s) + w(y1,s) v(y1,s)  as packed-half FMAs in that order (two channels per instruction; 16 FMAs per
+//   accumulator at K = 4, the length round 1 validated against the oracle);
+//   acc_s += float(a_s) after every level pair (fp32);   out = bf16(acc_0 + acc_1).
 //
 // The split by x-side is what lets the shared-memory gather read both x-corners of a footprint row with ONE conflict-free
 // 128-byte wavefront (eight lanes: four on the x0 pixel, four on the x0+1 pixel).
@@ -33,8 +34,9 @@ __device__ __forceinline__ Point decode(float2 xy, float aw, int Hh, int Ww) {
   const bool inside = h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf;
   const float hfl = floorf(h_im), wfl = floorf(w_im);
   Point p;
-  // (int) of a huge / non-finite float is undefined: clamp first (such a point is not `inside` and contributes nothing)
-  p.y0 = (int)fminf(fmaxf(hfl, -4.f), Hf + 4.f), p.x0 = (int)fminf(fmaxf(wfl, -4.f), Wf + 4.f);
+  // (float -> int conversion saturates on the GPU, NaN -> 0: a far-away or non-finite location is not `inside`, contributes
+  //  nothing, and its clamped addresses below stay valid)
+  p.y0 = __float2int_rd(h_im), p.x0 = __float2int_rd(w_im);
   const float lh = h_im - hfl, lw = w_im - wfl, hh = 1.f - lh, hw = 1.f - lw;
   const bool y0ok = inside && p.y0 >= 0, y1ok = inside && p.y0 + 1 <= Hh - 1, x0ok = p.x0 >= 0, x1ok = p.x0 + 1 <= Ww - 1;
   p.yc[0] = min(max(p.y0, 0), Hh - 1), p.yc[1] = min(max(p.y0 + 1, 0), Hh - 1);
@@ -84,12 +86,13 @@ __device__ __forceinline__ void gather_global(const __half *__restrict__ vb, con
                                               const float *__restrict__ attq, int L, int Kr, int xs, int l0, int lstep,
                                               float (&acc0)[8], float (&acc1)[8]) {
   const int K = KT ? KT : Kr;
-  for (int l = l0; l < L; l += lstep) {
+  __half2 a0[4], a1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a0[j] = a1[j] = __float2half2_rn(0.f);
+  int it = 0;
+  for (int l = l0; l < L; l += lstep, ++it) {
     const int Hh = sh.H(l), Ww = sh.W(l);
     const int base = sh.start(l) * xs, ys = Ww * xs;
-    __half2 a0[4], a1[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a0[j] = a1[j] = __float2half2_rn(0.f);
     if constexpr (KT > 0) {
       Point p[KT];
       uint4 r[KT][4];
@@ -116,8 +119,12 @@ __device__ __forceinline__ void gather_global(const __half *__restrict__ vb, con
         blend(a1, p.ws[1], r[1], r[3]);
       }
     }
-    widen_add(acc0, a0);
-    widen_add(acc1, a1);
+    if ((it & 1) || l + lstep >= L) {        // end of a level pair (or of the levels): widen into the fp32 sums
+      widen_add(acc0, a0);
+      widen_add(acc1, a1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a0[j] = a1[j] = __float2half2_rn(0.f);
+    }
   }
 }
 

@@ -35,8 +35,9 @@
 namespace memotr {
 namespace win {
 
-constexpr int MAXL = 5, MAXC = 2, MAXH = 16, THREADS = 256;
-constexpr int SMEM_BUDGET = 112 * 1024;      // per CTA, so that two CTAs share one SM (227 KB)
+constexpr int MAXL = 5, MAXC = 4, MAXH = 16;
+constexpr int TAP_WARPS = 8, DEC_WARPS = 4, THREADS = (TAP_WARPS + DEC_WARPS) * 32;
+constexpr int SMEM_BUDGET = 112 * 1024;      // per stage (windows + records of one unit); a CTA holds two stages (227 KB per SM)
 
 struct ClassGeom {
   int lq;                       // the level this class's queries live on
@@ -54,6 +55,7 @@ struct Params {
   int n_cls, n_glob_blocks, glob_q0;   // CTAs [0, n_glob_blocks) take the queries [glob_q0, S) from global memory
   int hw[2 * MAXL], lsi[MAXL];
   int L, K, H, S, xs, ld_loc, ld_attn;
+  int stage_bytes;                     // bytes of one stage (windows + records); the CTA double-buffers stages
   float radius;
   float shift[MAXH * MAXL * 2];        // per (head, level): expected sampling offset (x, y) in pixels of that level
 };
@@ -70,14 +72,68 @@ struct __align__(8) Rec {
   __half2 w;                     // (w(y0, side), w(y1, side))
 };
 
+// window origin of level l for the tile whose first query has the normalised reference point (rx, ry): every thread that
+// needs it evaluates exactly this sequence (explicitly rounded operations: no context-dependent contraction), so the copy
+// the TMA issuer uses and the copies the decoding threads use are the same integers
+__device__ __forceinline__ int2 window_origin(const Params &P, const float *__restrict__ vr, float rx, float ry, int h, int l) {
+  const float px = __fadd_rn(__fmaf_rn(__fmul_rn(rx, __ldg(vr + 2 * l)), (float)P.hw[2 * l + 1], -0.5f), P.shift[(h * MAXL + l) * 2]);
+  const float py = __fadd_rn(__fmaf_rn(__fmul_rn(ry, __ldg(vr + 2 * l + 1)), (float)P.hw[2 * l], -0.5f), P.shift[(h * MAXL + l) * 2 + 1]);
+  return make_int2((int)floorf(__fsub_rn(px, P.radius)), (int)floorf(__fsub_rn(py, P.radius)));
+}
+
+struct Unit {
+  int c, h, tx, ty;
+};
+__device__ __forceinline__ Unit unit_of(const Params &P, int u) {
+  Unit t;
+  t.c = 0;
+  for (int c = 1; c < P.n_cls; ++c)
+    if (u >= P.cls[c].unit0) t.c = c;
+  const ClassGeom &G = P.cls[t.c];
+  const int v = u - G.unit0, tile = v / P.H;
+  t.h = v - tile * P.H;
+  t.ty = tile / G.tiles_x, t.tx = tile - t.ty * G.tiles_x;
+  return t;
+}
+
+// one sampling point -> its two records (x-side 0 / 1)
+__device__ __forceinline__ void make_records(const Params &P, const ClassGeom &G, int l, int2 org, uint32_t wbase, float2 xy,
+                                             float aw, Rec &r0, Rec &r1, int &n_win, int &n_glob) {
+  const int Hh = P.hw[2 * l], Ww = P.hw[2 * l + 1];
+  const h16::Point p = h16::decode(xy, aw, Hh, Ww);
+  const int ww = G.ww[l], dx = p.x0 - org.x, dy = p.y0 - org.y;
+  r0.w = p.ws[0], r1.w = p.ws[1];
+  // (unsigned compares: a saturated x0 / y0 of a far-away or non-finite location can never pass)
+  if (ww && (unsigned)dx < (unsigned)(ww - 1) && (unsigned)dy < (unsigned)(G.wh[l] - 1)) {
+    r0.off = wbase + (uint32_t)(G.off[l] + (dy * ww + dx) * 64);
+    r1.off = r0.off + 64u;
+    ++n_win;
+  } else {
+    const uint32_t flags = 0x80000000u | (p.yc[1] == p.yc[0] ? 0x40000000u : 0u);
+    const uint32_t row = (uint32_t)(P.lsi[l] + p.yc[0] * Ww);
+    r0.off = flags | (row + (uint32_t)p.xc[0]);
+    r1.off = flags | (row + (uint32_t)p.xc[1]);
+    ++n_glob;
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised: one CTA per SM walks units u = blockIdx, + stride, ...; the DECODE warps (4) stage unit n + 1
+// (TMA windows + records, two buffers of each) while the TAP warps (8) consume unit n, so the shared-memory pipe -- the
+// resource that bounds this kernel -- never waits for a decode phase.
+//   win_full[b]  TMA bytes of window buffer b have landed           (decode thread 0 arms it, the copy engine completes it)
+//   rec_full[b]  the records of buffer b are written                (one arrival per decode warp)
+//   buf_free[b]  the tap warps are done with buffers b               (one arrival per tap warp)
 template <int KT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1)
 msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params P, const __half *__restrict__ value,
                    const float *__restrict__ loc, const float *__restrict__ attn, const float *__restrict__ vr,
                    unsigned long long *__restrict__ stats, __nv_bfloat16 *__restrict__ out) {
   extern __shared__ __align__(128) uint8_t smem[];      // (declared alignment: the windows are TMA destinations)
-  __shared__ uint64_t bar;
-  __shared__ int worg[2 * MAXL];
+  __shared__ uint64_t win_full[2], rec_full[2], buf_free[2];
   const int tid = threadIdx.x;
   const int K = KT ? KT : P.K, L = P.L, H = P.H, LK = L * K;
 
@@ -100,147 +156,210 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
     return;
   }
 
-  // ------------------------------------------------------------------------------------------- window role
-  const int unit_all = blockIdx.x - P.n_glob_blocks;
-  const int c = (P.n_cls > 1 && unit_all >= P.cls[1].unit0) ? 1 : 0;
-  const ClassGeom &G = P.cls[c];
-  const int unit = unit_all - G.unit0;
-  const int h = unit % H, tile = unit / H;
-  const int tx = tile % G.tiles_x, ty = tile / G.tiles_x;
-  const int TQ = G.tw * G.th;
-
+  // ------------------------------------------------------------------------------------------- window role (persistent)
+  const int n_units = P.cls[P.n_cls - 1].unit0 + P.cls[P.n_cls - 1].n_units;
+  const int stride = gridDim.x - P.n_glob_blocks;
+  const int first = blockIdx.x - P.n_glob_blocks;
   if (tid == 0) {
-    tc::mbar_init(&bar, 1);
+    for (int b = 0; b < 2; ++b) tc::mbar_init(win_full + b, 1), tc::mbar_init(rec_full + b, DEC_WARPS), tc::mbar_init(buf_free + b, TAP_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
   pdl_grid_sync();
-  if (tid == 0) {
-    // where the tile's first reference point lands on every level (deformable_encoder.py:29-40), plus the head's expected
-    // offset, minus the radius: the window origin.  Any origin is correct; a good one makes every tap a window tap.
-    const float rx = ((float)(tx * G.tw) + 0.5f) / (__ldg(vr + 2 * G.lq) * (float)G.Wq);
-    const float ry = ((float)(ty * G.th) + 0.5f) / (__ldg(vr + 2 * G.lq + 1) * (float)G.Hq);
-    if (G.win_bytes) tc::mbar_expect_tx(&bar, (uint32_t)G.win_bytes);
-    for (int l = 0; l < L; ++l) {
-      const float px = rx * __ldg(vr + 2 * l) * (float)P.hw[2 * l + 1] - 0.5f + P.shift[(h * MAXL + l) * 2];
-      const float py = ry * __ldg(vr + 2 * l + 1) * (float)P.hw[2 * l] - 0.5f + P.shift[(h * MAXL + l) * 2 + 1];
-      const int ox = (int)floorf(px - P.radius), oy = (int)floorf(py - P.radius);
-      worg[2 * l] = ox, worg[2 * l + 1] = oy;
-      if (G.ww[l]) {
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                tc::smem_u32(smem + G.off[l])),
-            "l"(&maps.m[c * MAXL + l]), "r"(tc::smem_u32(&bar)), "r"(h * 32), "r"(ox), "r"(oy)
-            : "memory");
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- decode: one sampling point per thread and step --------------------------------------------------------------
-  uint8_t *recs = smem + G.rec_off;
-  int ql = tid / LK, j = tid - ql * LK;
-  const int dq = THREADS / LK, dj = THREADS - dq * LK;
-  int n_win = 0, n_glob = 0;                    // (profiling only: taps staged / taps left to global memory)
-  while (ql < TQ) {
-    const int l = KT ? j / KT : j / K;
-    const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
-    Rec r0, r1;
-    r0.off = r1.off = 0u;                       // a query outside the level: two zero-weight taps on the first bytes of the buffer
-    r0.w = r1.w = __float2half2_rn(0.f);
-    if (x < G.Wq && y < G.Hq) {
-      const long q = G.q0 + y * G.Wq + x;
-      const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc + q * P.ld_loc) + h * LK + j);
-      const float aw = __ldg(attn + q * P.ld_attn + h * LK + j);
-      const int Hh = P.hw[2 * l], Ww = P.hw[2 * l + 1];
-      const h16::Point p = h16::decode(xy, aw, Hh, Ww);
-      const int ww = G.ww[l], dx = p.x0 - worg[2 * l], dy = p.y0 - worg[2 * l + 1];
-      r0.w = p.ws[0], r1.w = p.ws[1];
-      if (ww && dx >= 0 && dx + 1 < ww && dy >= 0 && dy + 1 < G.wh[l]) {
-        r0.off = (uint32_t)(G.off[l] + (dy * ww + dx) * 64);
-        r1.off = r0.off + 64u;
-        ++n_win;
-      } else {
-        ++n_glob;
-        const uint32_t flags = 0x80000000u | (p.yc[1] == p.yc[0] ? 0x40000000u : 0u);
-        const uint32_t row = (uint32_t)(P.lsi[l] + p.yc[0] * Ww);
-        r0.off = flags | (row + (uint32_t)p.xc[0]);
-        r1.off = flags | (row + (uint32_t)p.xc[1]);
-      }
-    }
-    // records of a query: LK/2 blocks of 32 B = [side 0: points 2k, 2k+1 | side 1: points 2k, 2k+1]
-    uint8_t *dst = recs + ql * G.rec_stride + (j >> 1) * 32 + (j & 1) * 8;
-    *reinterpret_cast<Rec *>(dst) = r0;
-    *reinterpret_cast<Rec *>(dst + 16) = r1;
-    ql += dq, j += dj;
-    if (j >= LK) j -= LK, ++ql;
-  }
-  if (stats) atomicAdd(stats, (unsigned long long)n_win), atomicAdd(stats + 1, (unsigned long long)n_glob);
-  __syncthreads();
-  if (G.win_bytes) tc::mbar_wait(&bar, 0);
-
-  // ---- taps: eight lanes per (query, head) -----------------------------------------------------------------------
-  const int grp = tid >> 3, side = (tid >> 2) & 1, sub = tid & 3;
-  const uint32_t smem_base = tc::smem_u32(smem) + sub * 16;
-  const __half *vb = value + h * 32 + sub * 8;
   const int xs = P.xs;
-  for (int ql = grp; ql < TQ; ql += THREADS / 8) {
-    const uint8_t *rq = recs + ql * G.rec_stride + side * 16;
-    float acc[8];
+
+  if (tid >= TAP_WARPS * 32) {
+    // =========================================================================================== decode warps
+    const int dt = tid - TAP_WARPS * 32, lane = tid & 31;
+    int n_win = 0, n_glob = 0;                  // (profiling only: points staged / points left to global memory)
+    // KT == 4: a thread decodes the four points of (query, level) pairs -- pair p = dt + 128 i, query = p / L, level = p % L --
+    // from registers that were loaded one unit ahead (the global-memory latency hides behind the previous unit's decode)
+    constexpr int NPRE = KT == 4 ? 4 : 1;
+    float4 pre_xy[NPRE][2], pre_w[NPRE];
+    auto prefetch = [&](int u) {
+      if constexpr (KT == 4) {
+        const Unit t = unit_of(P, u);
+        const ClassGeom &G = P.cls[t.c];
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
-    for (int l = 0; l < L; ++l) {
+        for (int i = 0; i < NPRE; ++i) {
+          const int p = dt + i * DEC_WARPS * 32, ql = p / L, l = p - ql * L;
+          const int x = t.tx * G.tw + (ql & (G.tw - 1)), y = t.ty * G.th + (ql >> G.tw_shift);
+          pre_w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pre_xy[i][0] = pre_xy[i][1] = pre_w[i];
+          if (ql < G.tw * G.th && x < G.Wq && y < G.Hq) {
+            const long q = G.q0 + y * G.Wq + x;
+            const float4 *pl = reinterpret_cast<const float4 *>(loc + q * P.ld_loc + (t.h * LK + l * 4) * 2);
+            pre_xy[i][0] = __ldg(pl), pre_xy[i][1] = __ldg(pl + 1);
+            pre_w[i] = __ldg(reinterpret_cast<const float4 *>(attn + q * P.ld_attn + t.h * LK + l * 4));
+          }
+        }
+      }
+    };
+    if (first < n_units) prefetch(first);
+    int n = 0;
+    for (int unit = first; unit < n_units; unit += stride, ++n) {
+      const int b = n & 1;
+      const Unit t = unit_of(P, unit);
+      const int c = t.c, h = t.h, tx = t.tx, ty = t.ty;
+      const ClassGeom &G = P.cls[c];
+      const int TQ = G.tw * G.th;
+      const uint32_t wbase = (uint32_t)(b * P.stage_bytes);
+      uint8_t *recs = smem + wbase + G.rec_off;
+      const float rx = __fdiv_rn(__fadd_rn((float)(tx * G.tw), 0.5f), __fmul_rn(__ldg(vr + 2 * G.lq), (float)G.Wq));
+      const float ry = __fdiv_rn(__fadd_rn((float)(ty * G.th), 0.5f), __fmul_rn(__ldg(vr + 2 * G.lq + 1), (float)G.Hq));
+      if (n >= 2) tc::mbar_wait(buf_free + b, ((n >> 1) - 1) & 1);       // the tap warps have finished unit n - 2
+      if (dt == 0) {
+        // where the tile's first reference point lands on every level (deformable_encoder.py:29-40), plus the head's
+        // expected offset, minus the radius: the window origin.  Any origin is correct; a good one makes every tap a window tap.
+        tc::mbar_expect_tx(win_full + b, (uint32_t)G.win_bytes);
+        for (int l = 0; l < L; ++l) {
+          if (!G.ww[l]) continue;
+          const int2 org = window_origin(P, vr, rx, ry, h, l);
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                  tc::smem_u32(smem + wbase + G.off[l])),
+              "l"(&maps.m[c * MAXL + l]), "r"(tc::smem_u32(win_full + b)), "r"(h * 32), "r"(org.x), "r"(org.y)
+              : "memory");
+        }
+      }
+      // ---- every sampling point of the tile once, into the records ------------------------------------------------
+      if constexpr (KT == 4) {
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) {
+          const int p = dt + i * DEC_WARPS * 32, ql = p / L, l = p - ql * L;
+          if (ql >= TQ) continue;
+          const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
+          Rec r[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[j][0].off = r[j][1].off = wbase, r[j][0].w = r[j][1].w = __float2half2_rn(0.f);
+          if (x < G.Wq && y < G.Hq) {    // (a query outside the level: zero-weight taps on the first bytes of the buffer)
+            const int2 org = window_origin(P, vr, rx, ry, h, l);
+            const float4 a = pre_xy[i][0], bb = pre_xy[i][1], w = pre_w[i];
+            make_records(P, G, l, org, wbase, make_float2(a.x, a.y), w.x, r[0][0], r[0][1], n_win, n_glob);
+            make_records(P, G, l, org, wbase, make_float2(a.z, a.w), w.y, r[1][0], r[1][1], n_win, n_glob);
+            make_records(P, G, l, org, wbase, make_float2(bb.x, bb.y), w.z, r[2][0], r[2][1], n_win, n_glob);
+            make_records(P, G, l, org, wbase, make_float2(bb.z, bb.w), w.w, r[3][0], r[3][1], n_win, n_glob);
+          }
+          // records of a query: per pair of points a 32-byte block [side 0: point 2k, 2k+1 | side 1: point 2k, 2k+1]
+          uint4 *dst = reinterpret_cast<uint4 *>(recs + ql * G.rec_stride + l * 64);
+          dst[0] = make_uint4(r[0][0].off, *reinterpret_cast<uint32_t *>(&r[0][0].w), r[1][0].off, *reinterpret_cast<uint32_t *>(&r[1][0].w));
+          dst[1] = make_uint4(r[0][1].off, *reinterpret_cast<uint32_t *>(&r[0][1].w), r[1][1].off, *reinterpret_cast<uint32_t *>(&r[1][1].w));
+          dst[2] = make_uint4(r[2][0].off, *reinterpret_cast<uint32_t *>(&r[2][0].w), r[3][0].off, *reinterpret_cast<uint32_t *>(&r[3][0].w));
+          dst[3] = make_uint4(r[2][1].off, *reinterpret_cast<uint32_t *>(&r[2][1].w), r[3][1].off, *reinterpret_cast<uint32_t *>(&r[3][1].w));
+        }
+        if (unit + stride < n_units) prefetch(unit + stride);
+      } else {
+        int ql = dt / LK, j = dt - ql * LK;
+        const int dq = (DEC_WARPS * 32) / LK, dj = DEC_WARPS * 32 - dq * LK;
+        while (ql < TQ) {
+          const int l = j / K;
+          const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
+          Rec r0, r1;
+          r0.off = r1.off = wbase;
+          r0.w = r1.w = __float2half2_rn(0.f);
+          if (x < G.Wq && y < G.Hq) {
+            const long q = G.q0 + y * G.Wq + x;
+            const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc + q * P.ld_loc) + h * LK + j);
+            const float aw = __ldg(attn + q * P.ld_attn + h * LK + j);
+            make_records(P, G, l, window_origin(P, vr, rx, ry, h, l), wbase, xy, aw, r0, r1, n_win, n_glob);
+          }
+          uint8_t *dst = recs + ql * G.rec_stride + (j >> 1) * 32 + (j & 1) * 8;
+          *reinterpret_cast<Rec *>(dst) = r0;
+          *reinterpret_cast<Rec *>(dst + 16) = r1;
+          ql += dq, j += dj;
+          if (j >= LK) j -= LK, ++ql;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rec_full + b);     // (release: this warp's record stores are visible to the waiting tap warps)
+    }
+    if (stats) atomicAdd(stats, (unsigned long long)n_win), atomicAdd(stats + 1, (unsigned long long)n_glob);
+    return;
+  }
+
+  // ============================================================================================= tap warps
+  const int grp = tid >> 3, side = (tid >> 2) & 1, sub = tid & 3, lane = tid & 31;
+  const uint32_t smem_base = tc::smem_u32(smem) + sub * 16;
+  int n = 0;
+  for (int unit = first; unit < n_units; unit += stride, ++n) {
+    const int b = n & 1;
+    const Unit t = unit_of(P, unit);
+    const int h = t.h, tx = t.tx, ty = t.ty;
+    const ClassGeom &G = P.cls[t.c];
+    const int TQ = G.tw * G.th;
+    const uint8_t *recs = smem + b * P.stage_bytes + G.rec_off;
+    tc::mbar_wait(rec_full + b, (n >> 1) & 1);
+    tc::mbar_wait(win_full + b, (n >> 1) & 1);
+    const __half *vb = value + h * 32 + sub * 8;
+    for (int ql = grp; ql < TQ; ql += TAP_WARPS * 4) {
+      const uint8_t *rq = recs + ql * G.rec_stride + side * 16;
+      float acc[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
       __half2 a[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) a[jj] = __float2half2_rn(0.f);
-      const uint32_t rowb = (uint32_t)G.ww[l] * 64u;        // bytes between the y0 and y1 rows of this level's window
-      auto window_tap = [&](uint32_t off, uint32_t wbits, uint4 &r0, uint4 &r1) {
-        const uint32_t a0 = smem_base + off, a1 = a0 + rowb;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
-        (void)wbits;
-      };
-      auto any_tap = [&](uint32_t off, uint4 &r0, uint4 &r1) {
-        if (off & 0x80000000u) {
-          const __half *p0 = vb + (long)(off & 0x3FFFFFFFu) * xs;
-          const __half *p1 = (off & 0x40000000u) ? p0 : p0 + (long)P.hw[2 * l + 1] * xs;
-          r0 = __ldg(reinterpret_cast<const uint4 *>(p0));
-          r1 = __ldg(reinterpret_cast<const uint4 *>(p1));
-        } else {
-          window_tap(off, 0u, r0, r1);
-        }
-      };
-      if constexpr (KT == 4) {
-        const uint4 ra = *reinterpret_cast<const uint4 *>(rq + (l * 2) * 32);
-        const uint4 rb = *reinterpret_cast<const uint4 *>(rq + (l * 2 + 1) * 32);
-        uint4 v[4][2];
-        // warp-uniform choice per point: the plain shared-memory pair unless some lane of the warp has a global-memory tap
-        const bool g0 = __any_sync(0xffffffffu, ra.x & 0x80000000u), g1 = __any_sync(0xffffffffu, ra.z & 0x80000000u);
-        const bool g2 = __any_sync(0xffffffffu, rb.x & 0x80000000u), g3 = __any_sync(0xffffffffu, rb.z & 0x80000000u);
-        if (!g0) window_tap(ra.x, 0u, v[0][0], v[0][1]); else any_tap(ra.x, v[0][0], v[0][1]);
-        if (!g1) window_tap(ra.z, 0u, v[1][0], v[1][1]); else any_tap(ra.z, v[1][0], v[1][1]);
-        if (!g2) window_tap(rb.x, 0u, v[2][0], v[2][1]); else any_tap(rb.x, v[2][0], v[2][1]);
-        if (!g3) window_tap(rb.z, 0u, v[3][0], v[3][1]); else any_tap(rb.z, v[3][0], v[3][1]);
-        h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v[0][0], v[0][1]);
-        h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v[1][0], v[1][1]);
-        h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.y), v[2][0], v[2][1]);
-        h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.w), v[3][0], v[3][1]);
-      } else {
-        for (int pp = 0; pp < K / 2; ++pp) {
-          const uint4 ra = *reinterpret_cast<const uint4 *>(rq + (l * (K / 2) + pp) * 32);
-          uint4 v[2][2];
-          any_tap(ra.x, v[0][0], v[0][1]);
-          any_tap(ra.z, v[1][0], v[1][1]);
+      for (int l = 0; l < L; ++l) {
+        const uint32_t rowb = (uint32_t)G.ww[l] * 64u;        // bytes between the y0 and y1 rows of this level's window
+        auto window_tap = [&](uint32_t off, uint4 &r0, uint4 &r1) {
+          const uint32_t a0 = smem_base + off, a1 = a0 + rowb;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
+        };
+        auto any_tap = [&](uint32_t off, uint4 &r0, uint4 &r1) {
+          if (off & 0x80000000u) {
+            const __half *p0 = vb + (long)(off & 0x3FFFFFFFu) * xs;
+            const __half *p1 = (off & 0x40000000u) ? p0 : p0 + (long)P.hw[2 * l + 1] * xs;
+            r0 = __ldg(reinterpret_cast<const uint4 *>(p0));
+            r1 = __ldg(reinterpret_cast<const uint4 *>(p1));
+          } else {
+            window_tap(off, r0, r1);
+          }
+        };
+        if constexpr (KT == 4) {
+          const uint4 ra = *reinterpret_cast<const uint4 *>(rq + (l * 2) * 32);
+          const uint4 rb = *reinterpret_cast<const uint4 *>(rq + (l * 2 + 1) * 32);
+          uint4 v[4][2];
+          // warp-uniform choice: the plain shared-memory loads unless some lane of the warp has a global-memory tap
+          if (!__any_sync(0xffffffffu, (ra.x | ra.z | rb.x | rb.z) & 0x80000000u)) {
+            window_tap(ra.x, v[0][0], v[0][1]);
+            window_tap(ra.z, v[1][0], v[1][1]);
+            window_tap(rb.x, v[2][0], v[2][1]);
+            window_tap(rb.z, v[3][0], v[3][1]);
+          } else {
+            any_tap(ra.x, v[0][0], v[0][1]);
+            any_tap(ra.z, v[1][0], v[1][1]);
+            any_tap(rb.x, v[2][0], v[2][1]);
+            any_tap(rb.z, v[3][0], v[3][1]);
+          }
           h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v[0][0], v[0][1]);
           h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v[1][0], v[1][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.y), v[2][0], v[2][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.w), v[3][0], v[3][1]);
+        } else {
+          for (int pp = 0; pp < K / 2; ++pp) {
+            const uint4 ra = *reinterpret_cast<const uint4 *>(rq + (l * (K / 2) + pp) * 32);
+            uint4 v[2][2];
+            any_tap(ra.x, v[0][0], v[0][1]);
+            any_tap(ra.z, v[1][0], v[1][1]);
+            h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v[0][0], v[0][1]);
+            h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v[1][0], v[1][1]);
+          }
+        }
+        if ((l & 1) || l + 1 == L) {             // end of a level pair: widen into the fp32 sums (msda_h16.cuh)
+          h16::widen_add(acc, a);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) a[jj] = __float2half2_rn(0.f);
         }
       }
-      h16::widen_add(acc, a);
-    }
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], 4);
-    const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
-    if (side == 0 && x < G.Wq && y < G.Hq)
-      *reinterpret_cast<uint4 *>(out + ((long)(G.q0 + y * G.Wq + x) * H + h) * 32 + sub * 8) = f32x8_to_bf16(acc);
+      for (int cc = 0; cc < 8; ++cc) acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], 4);
+      const int x = tx * G.tw + (ql & (G.tw - 1)), y = ty * G.th + (ql >> G.tw_shift);
+      if (side == 0 && x < G.Wq && y < G.Hq)
+        *reinterpret_cast<uint4 *>(out + ((long)(G.q0 + y * G.Wq + x) * H + h) * 32 + sub * 8) = f32x8_to_bf16(acc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(buf_free + b);
   }
 }
 
@@ -282,10 +401,11 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
     if (level_start[c] != q_end) break;                       // levels must be consecutive rows of the query table
     G.rec_stride = (LK / 2) * 32 + 32;                         // pad so that the four queries of a warp start in different banks
     while (G.rec_stride % 128 != 32) G.rec_stride += 32;
-    // tile: 16 x 8 queries of level 0, 8 x 8 of level 1 (its reference points are twice as far apart), halved while the
-    // records of the tile (one per sampling point and x-side) would take more than 40 KB
-    G.tw = c == 0 ? 16 : 8, G.th = 8, G.tw_shift = c == 0 ? 4 : 3;
-    while (G.tw * G.th > 32 && G.tw * G.th * G.rec_stride > 40 * 1024) {
+    // tile: 16 x 8 queries of level 0, 8 x 8 of level 1, 8 x 4 of the coarser levels (their reference points are 2x, 4x, ...
+    // as far apart, so the windows of a tile grow with the level), halved while the records of the tile (one per sampling
+    // point and x-side) would take more than 40 KB
+    G.tw = c == 0 ? 16 : 8, G.th = c <= 1 ? 8 : 4, G.tw_shift = c == 0 ? 4 : 3;
+    while (G.tw * G.th > 32 && (G.tw * G.th * G.rec_stride > 40 * 1024 || (K == 4 && G.tw * G.th * L > 4 * win::DEC_WARPS * 32))) {
       if (G.tw > G.th) G.tw >>= 1, --G.tw_shift; else G.th >>= 1;
     }
     if (G.tw * G.th * G.rec_stride > 64 * 1024) break;
@@ -324,6 +444,9 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
   }
   P.glob_q0 = q_end;
   P.n_glob_blocks = ceil_div((S - q_end) * H * 4, win::THREADS);
+  P.stage_bytes = 0;
+  for (int c = 0; c < P.n_cls; ++c)
+    P.stage_bytes = std::max(P.stage_bytes, (P.cls[c].rec_off + P.cls[c].tw * P.cls[c].th * P.cls[c].rec_stride + 127) / 128 * 128);
   return units;
 }
 
@@ -337,9 +460,7 @@ extern "C" int memotr_msda_window_plan(const int *shapes_hw, const int *level_st
   win::Params P;
   const int units = plan(P, shapes_hw, level_start, S, H, L, K, H * 32, 0, 0, nullptr, radius,
                          max_classes <= 0 ? win::MAXC : max_classes);
-  size_t smem = 0;
-  for (int c = 0; c < P.n_cls; ++c)
-    smem = std::max(smem, (size_t)P.cls[c].rec_off + (size_t)P.cls[c].tw * P.cls[c].th * P.cls[c].rec_stride + 128);
+  const size_t smem = 2 * (size_t)P.stage_bytes;
   std::memset(info, 0, sizeof(int) * (8 + win::MAXC * (8 + 2 * win::MAXL)));
   info[0] = P.n_cls, info[1] = units, info[2] = P.n_glob_blocks, info[3] = P.glob_q0, info[4] = (int)smem;
   for (int c = 0; c < P.n_cls; ++c) {
@@ -370,6 +491,8 @@ extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_str
   MEMOTR_REQUIRE(aligned16(value) && aligned16(output) && ((reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) &&
                      ld_loc % 2 == 0 && ld_loc >= H * L * K * 2 && ld_attn >= H * L * K,
                  "msda_forward_window: misaligned buffer / bad row stride");
+  MEMOTR_REQUIRE(K != 4 || (aligned16(sampling_loc) && aligned16(attn_weight) && ld_loc % 4 == 0 && ld_attn % 4 == 0 && (H * L * K) % 4 == 0),
+                 "msda_forward_window: K == 4 needs 16-byte aligned location / weight rows");
   MEMOTR_REQUIRE(window_radius >= 0.f && window_radius <= 32.f, "msda_forward_window: radius out of range");
   MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "msda_forward_window: cuTensorMapEncodeTiled unavailable");
   int total = 0;
@@ -384,11 +507,10 @@ extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_str
   const int units = plan(P, shapes_hw, level_start, S, H, L, K, value_pixel_stride, ld_loc, ld_attn, window_shift, window_radius,
                          max_classes <= 0 ? win::MAXC : max_classes);
   cudaStream_t st = (cudaStream_t)stream;
-  size_t smem = 0;
+  const size_t smem = 2 * (size_t)P.stage_bytes;       // two stages: the decode warps fill one while the tap warps drain the other
   std::memset(&M, 0, sizeof(M));
   for (int c = 0; c < P.n_cls; ++c) {
     const win::ClassGeom &G = P.cls[c];
-    smem = std::max(smem, (size_t)G.rec_off + (size_t)G.tw * G.th * G.rec_stride + 128);
     for (int l = 0; l < L; ++l)
       if (G.ww[l] && !win::make_level_map(&M.m[c * win::MAXL + l],
                                           reinterpret_cast<const __half *>(value) + (long)level_start[l] * value_pixel_stride, H * 32,
@@ -396,13 +518,18 @@ extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_str
         return fail(MEMOTR_ECUDA, "msda_forward_window: cuTensorMapEncodeTiled failed (class %d, level %d)", c, l);
   }
   auto kern = K == 4 ? win::msda_window_kernel<4> : win::msda_window_kernel<0>;
-  static size_t attr_bytes[2] = {0, 0};
-  if (attr_bytes[K == 4] < smem) {
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, win::SMEM_BUDGET);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[K == 4]) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * win::SMEM_BUDGET);
     if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "msda_forward_window: smem attribute: %s", cudaGetErrorString(e));
-    attr_bytes[K == 4] = win::SMEM_BUDGET;
+    attr_set[K == 4] = true;
   }
-  MEMOTR_LAUNCH((kern), P.n_glob_blocks + units, win::THREADS, smem, st, M, P, (const __half *)value, sampling_loc, attn_weight,
-                valid_ratios, stats, (__nv_bfloat16 *)output);
+  // persistent window CTAs: one per SM (two stages of shared memory each)
+  int dev = 0, n_sm = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int win_ctas = std::min(units, n_sm);
+  MEMOTR_LAUNCH((kern), P.n_glob_blocks + win_ctas, win::THREADS, smem, st, M, P, (const __half *)value, sampling_loc,
+                attn_weight, valid_ratios, stats, (__nv_bfloat16 *)output);
   return check_launch("msda_window");
 }

@@ -177,14 +177,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) updater_cluster_kernel(const __gr
       if (row0 + g + 8 < nt)
         *reinterpret_cast<uint32_t *>(Kh + (long)(row0 + g + 8) * C + cb + col) = pack_f16(a[2] + b0, a[3] + b1);
     });
+    // (V of a padded key is written as zero: its softmax weight is exactly 0, but 0 x a stale non-finite row would be NaN)
+    const float keep0 = (row0 + g < nt && P.track_pad && P.track_pad[row0 + g]) ? 0.f : 1.f;
+    const float keep1 = (row0 + g + 8 < nt && P.track_pad && P.track_pad[row0 + g + 8]) ? 0.f : 1.f;
     gemm(sprog, rg, xb, P256, P.v_b + cb, warp, lane, [&](int col, const float (&a)[4], float b0, float b1) {
       if (row0 + g < nt) {
-        Vt[(long)(cb + col) * P.np + row0 + g] = __float2half_rn(a[0] + b0);
-        Vt[(long)(cb + col + 1) * P.np + row0 + g] = __float2half_rn(a[1] + b1);
+        Vt[(long)(cb + col) * P.np + row0 + g] = __float2half_rn(keep0 != 0.f ? a[0] + b0 : 0.f);
+        Vt[(long)(cb + col + 1) * P.np + row0 + g] = __float2half_rn(keep0 != 0.f ? a[1] + b1 : 0.f);
       }
       if (row0 + g + 8 < nt) {
-        Vt[(long)(cb + col) * P.np + row0 + g + 8] = __float2half_rn(a[2] + b0);
-        Vt[(long)(cb + col + 1) * P.np + row0 + g + 8] = __float2half_rn(a[3] + b1);
+        Vt[(long)(cb + col) * P.np + row0 + g + 8] = __float2half_rn(keep1 != 0.f ? a[2] + b0 : 0.f);
+        Vt[(long)(cb + col + 1) * P.np + row0 + g + 8] = __float2half_rn(keep1 != 0.f ? a[3] + b1 : 0.f);
       }
     });
     grid_barrier(P.barrier, gridDim.x);

@@ -74,11 +74,12 @@ class FrameEngine:
         self.value_f16 = mode == "bf16" and os.environ.get("MEMOTR_VALUE_F16", "1") != "0"
         self.vdt = F16 if self.value_f16 else self.dt
         self.tv = torch.float16 if self.value_f16 else self.ta
-        # the whole decoder + heads as one persistent kernel (csrc/decoder_fused.cu); A/B switch
+        # the whole decoder + heads as ONE persistent kernel, a 4-CTA cluster per block of 16 query rows
+        # (csrc/decoder_cluster.cu); MEMOTR_DEC_FUSED=0: one launch per op (A/B, and the path of the fp32 modes)
         self.dec_fused = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_DEC_FUSED", "1") != "0"
-                          and self.nq <= 16 * 132
-                          and (cfg["d_ffn"] % 256 == 0 if cfg["d_ffn"] <= 1024 else cfg["d_ffn"] in (1536, 2048))
-                          and cfg["n_levels"] * cfg["n_dec_points"] * 24 <= 512)
+                          and (self.nq + 15) // 16 * 4 <= 132 and cfg["d_ffn"] % 256 == 0 and cfg["d_ffn"] <= 2048
+                          and cfg["n_levels"] * cfg["n_dec_points"] == 16)
+        self.dec_cluster = self.dec_fused
         # encoder: sampling locations / softmax weights computed in the epilogue of the offsets+logits GEMM (A/B switch
         # MEMOTR_FUSE_PREP=0).  With four epilogue warps in the persistent GEMM this was 7.5 us per layer SLOWER than the
         # separate prep kernel (the kernel is epilogue-bound); with eight it is 9.5 us per layer faster
@@ -100,13 +101,8 @@ class FrameEngine:
         self.window_stats = None             # device int64[2] when profiling: taps served from windows / from global memory
         self._pack(state_dict)
         self._alloc()
-        # 2 = a 4-CTA cluster per row block (csrc/decoder_cluster.cu), 1 = one CTA per row block (csrc/decoder_fused.cu)
-        self.dec_cluster = (self.dec_fused and os.environ.get("MEMOTR_DEC_FUSED", "2") == "2"
-                            and cfg["n_levels"] * cfg["n_dec_points"] == 16 and cfg["d_ffn"] % 256 == 0
-                            and cfg["d_ffn"] <= 2048 and (self.nq + 15) // 16 * 4 <= 132)
         if self.dec_fused:
             self._build_decoder_program()
-        if self.dec_cluster:
             self._build_decoder_program_cluster()
         # the query updater as one persistent cluster kernel (csrc/updater_cluster.cu); A/B switch MEMOTR_UPD_FUSED=0
         self.upd_fused = (self.dec_cluster and os.environ.get("MEMOTR_UPD_FUSED", "1") != "0"
@@ -324,47 +320,16 @@ class FrameEngine:
 
     # ------------------------------------------------------------------------------------------------ fused decoder
     def _build_decoder_program(self):
-        """Weight program + parameter block of memotr_decoder_forward (include/memotr_b200.h, csrc/decoder_fused.cu)."""
+        """Parameter block shared by the fused decoder kernels (memotr_dec_params, include/memotr_b200.h)."""
         import ctypes
         C, nq, dev, nl = self.C, self.nq, self.dev, self.n_dec
         F = self.Fd
-        prog = []
-
-        self.dec_packed = []
-
-        def g(L, row0=0, rows=None, col0=0, K=None):
-            """Pack W[row0:row0+rows, col0:col0+K] as slot images (see memotr_dec_gemm in include/memotr_b200.h)."""
-            rows, K = (L.N if rows is None else rows), (L.K if K is None else K)
-            assert rows % 64 == 0 and K % 256 == 0 and L.w.dtype == torch.bfloat16
-            w = L.w[row0:row0 + rows, col0:col0 + K].reshape(rows // 64, 64, K // 256, 256)
-            if K == 256:
-                img = torch.zeros(rows // 64, 1, 64, 264, dtype=torch.bfloat16, device=dev)
-                img[..., :256] = w.permute(0, 2, 1, 3)
-            else:                                   # k-slice-major; the kernel keeps all four n-blocks' accumulators live
-                assert rows == 256
-                img = torch.zeros(K // 256, rows // 64, 64, 264, dtype=torch.bfloat16, device=dev)
-                img[..., :256] = w.permute(2, 0, 1, 3)
-            self.dec_packed.append(img)
-            prog.append((img.data_ptr(), 264, rows, K))
-
-        for lid, ly in enumerate(self.dec):
-            g(self.ref_point_head[0]), g(self.ref_point_head[1])
-            if lid > 0:
-                g(self.query_scale[0]), g(self.query_scale[1])
-            g(ly["self"]["qk"]), g(ly["self"]["v"]), g(ly["self"]["out"]), g(ly["attn"]["ol"]), g(ly["attn"]["out"])
-            nh = 2 if F > 1024 else 1
-            for half in range(nh):
-                g(ly["lin1"], row0=half * F // nh, rows=F // nh)
-                g(ly["lin2"], col0=half * F // nh, K=F // nh)
-            g(ly["bbox"][0]), g(ly["bbox"][1])
-        arr = (_lib.DecGemm * len(prog))(*[_lib.DecGemm(w, ldw, n, k, 0) for (w, ldw, n, k) in prog])
-        self.dec_prog = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.dec_np = (nq + 63) // 64 * 64
         self.dec_kbuf = torch.zeros(2, self.dec_np, C, dtype=torch.float16, device=dev)
         self.dec_vbuf = torch.zeros(2, C, self.dec_np, dtype=torch.float16, device=dev)
         self.dec_barrier = torch.zeros(1, dtype=torch.int32, device=dev)
         P = _lib.DecParams()
-        P.prog, P.n_prog, P.n_layers, P.nq, P.nd, P.merge = self.dec_prog.data_ptr(), len(prog), nl, nq, self.nd, self.merge
+        P.prog, P.n_prog, P.n_layers, P.nq, P.nd, P.merge = None, 0, nl, nq, self.nd, self.merge
         P.ncls, P.n_levels, P.n_points, P.d_ffn = self.ncls, self.L, self.cfg["n_dec_points"], F
         P.value_stride, P.np = nl * C, self.dec_np
         P.rph0_b, P.rph1_b = self.ref_point_head[0].b.data_ptr(), self.ref_point_head[1].b.data_ptr()
@@ -503,11 +468,8 @@ class FrameEngine:
 
     def _decoder_fused(self):
         import ctypes
-        if self.dec_cluster:
-            self._ck(self.lib.memotr_decoder_forward_cluster(ctypes.byref(self.dec_params_cl), self._st()),
-                     "decoder_forward_cluster")
-        else:
-            self._ck(self.lib.memotr_decoder_forward(ctypes.byref(self.dec_params), self._st()), "decoder_forward")
+        self._ck(self.lib.memotr_decoder_forward_cluster(ctypes.byref(self.dec_params_cl), self._st()),
+                 "decoder_forward_cluster")
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------------ launch helpers
@@ -645,6 +607,12 @@ class FrameEngine:
     # ------------------------------------------------------------------------------------------------ the frame
     def forward(self):
         """Transformer + heads on the loaded frame.  Results stay in the workspace; see results()."""
+        self.encode()
+        self.decode()
+
+    def encode(self):
+        """Everything that depends on the frame alone (phase 1 of an exact sharded clip, memotr_b200/clip.py): level
+        flattening, the encoder, and the stacked value projection of all decoder layers."""
         C, S, H, L, dt = self.C, self.S, self.H, self.L, self.dt
         st = self._st
         self._mark(0)
@@ -706,6 +674,14 @@ class FrameEngine:
         if self.debug_enc is not None:
             self.debug_enc.append(self.src32.float().clone())
         self._mark(2)
+        # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
+        self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
+
+    def decode(self):
+        """The recurrent part of a frame: the decoder and heads on the CURRENT track queries (in_track_ref / in_track_embed)
+        and the value maps / valid ratios encode() left in the workspace."""
+        C, S, H, L, dt = self.C, self.S, self.H, self.L, self.dt
+        st = self._st
         # -- decoder inputs (memotr.py:209-278, deformable_transformer.py:239-242)
         nd, nt, nq = self.nd, self.nt, self.nq
         if not self.dec_cluster or not getattr(self, "_det_rows_ready", False):
@@ -722,8 +698,6 @@ class FrameEngine:
                 self.convert(self.tgt32[0], F32, C, self.tgt[0], dt, C, nq, C)
             self.convert(self.vr, F32, 2, self.vr_scale4, F32, 2, 1, 2)          # (vr0.w, vr0.h, vr0.w, vr0.h)
             self.convert(self.vr, F32, 2, self.vr_scale4[2:], F32, 2, 1, 2)
-        # value maps of all decoder layers in one GEMM over the memory (ms_deform_attn.py:104-106, x6)
-        self.lin(memory, C, self.dec_value, self.value_all, self.n_dec * C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
         Kd = self.cfg["n_dec_points"]
         if self.dec_fused:
             self._decoder_fused()
@@ -857,7 +831,43 @@ class FrameEngine:
         """One hot-path step: frame forward, hand the track rows to the updater, update the track embeddings, and
         feed the updated (ref_pts, query_embed) back as the next frame's track queries (submit_engine.py:64-72 with
         the host-side RuntimeTracker glue reduced to the field hand-off of runtime_tracker.py:43-45)."""
-        self.forward()
+        self.encode()
+        self.step_tail()
+
+    # -- exact sharded clips (memotr_b200/clip.py:run_clip_two_phase): phase-1 token and the track memory hand-off ------
+    def frame_token(self):
+        """What decode() needs from encode(), detached from the workspace: the decoder value maps and the valid ratios."""
+        return self.value_all.clone(), self.vr.clone()
+
+    def load_token(self, token):
+        self.value_all.copy_(token[0], non_blocking=True)
+        self.vr.copy_(token[1], non_blocking=True)
+
+    def get_track_memory(self):
+        """The complete recurrent state as one packed uint8 tensor (clip.pack_track_state): every TrackInstances field of the
+        table, the live-row count and the tracker's id counter."""
+        from . import clip
+        if self.trk is None:
+            return clip.pack_track_state(self.st)
+        return clip.pack_track_state({k: self.table[k] for k in clip.FLOAT_FIELDS + clip.INT_FIELDS},
+                                     self.table.n_active, self.trk.max_obj_id)
+
+    def set_track_memory(self, packed):
+        """Adopt a packed track memory (from another rank): table, padding mask, id counter and the fed-back track queries."""
+        from . import clip
+        m = clip.unpack_track_state(packed, self.nt, self.C, self.ncls)
+        if self.trk is None:
+            for k in clip.FLOAT_FIELDS:
+                self.st[k].copy_(m[k])
+        else:
+            n = int(m["n_active"].item())
+            self.trk.reset({k: m[k][:n] for k in clip.FLOAT_FIELDS + clip.INT_FIELDS}, max_obj_id=int(m["max_obj_id"].item()))
+        self.in_track_ref.copy_(self.st["ref_pts"])
+        self.in_track_embed.copy_(self.st["query_embed"])
+
+    def step_tail(self):
+        """The recurrent tail of a step: decoder + heads, tracker glue, query updater, feedback."""
+        self.decode()
         if self.trk is None:
             self.tracks_from_frame()
         else:       # RuntimeTracker.update + select_active_tracks on the device (submit_engine.py:66-70)

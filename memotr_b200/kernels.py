@@ -152,7 +152,7 @@ def window_plan(shapes, n_heads=8, n_points=4, radius=2.5, max_classes=0):
     hw = (ctypes.c_int * (2 * L))(*[int(v) for s_ in shapes for v in s_])
     sizes = [int(h) * int(w) for h, w in shapes]
     lsi = (ctypes.c_int * L)(*[sum(sizes[:i]) for i in range(L)])
-    info = (ctypes.c_int * (8 + 2 * 18))()
+    info = (ctypes.c_int * (8 + 4 * 18))()
     _lib.check(_lib.lib().memotr_msda_window_plan(hw, lsi, sum(sizes), n_heads, L, n_points, float(radius), max_classes, info),
                "memotr_msda_window_plan")
     out = dict(classes=info[0], units=info[1], global_ctas=info[2], global_q0=info[3], smem=info[4], cls=[])

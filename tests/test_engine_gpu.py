@@ -584,10 +584,9 @@ def test_engine_bf16_white_noise_weights_vs_matched_rounding_oracle():
         assert rep[k][0] < 2.5e-1
 
 
-@pytest.mark.parametrize("fused", ["1", "2"])          # 1: one CTA per 16-row block, 2: a 4-CTA cluster per block (default)
 @pytest.mark.parametrize("tag", ["small", "small_padded", "full"])
-def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monkeypatch):
-    """bf16 engine, decoder + heads as ONE persistent kernel (csrc/decoder_fused.cu, the default) against the same
+def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, monkeypatch, fused="1"):
+    """bf16 engine, decoder + heads as ONE persistent cluster kernel (csrc/decoder_cluster.cu, the default) against the same
     engine with one launch per op (MEMOTR_DEC_FUSED=0): same arithmetic classes (bf16 GEMM operands, fp32 everything
     else; the fused kernel keeps q/k/p/v of the self-attention in fp16 instead of fp32), so the two must agree with each
     other as well as each agrees with the reference modules, layer by layer (aux outputs)."""
@@ -596,8 +595,8 @@ def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monk
     assert not eng0.dec_fused and not eng0.upd_fused
     monkeypatch.setenv("MEMOTR_DEC_FUSED", fused)
     _, eng1, res1, st1 = _run_engine(tag, "bf16")
-    assert eng1.dec_fused and eng1.dec_cluster == (fused == "2") and eng1.launches < eng0.launches
-    assert eng1.upd_fused == (fused == "2")      # the fused query updater rides on the cluster machinery
+    assert eng1.dec_fused and eng1.dec_cluster and eng1.launches < eng0.launches
+    assert eng1.upd_fused                        # the fused query updater rides on the cluster machinery
     deep = tag == "full"
     report = {}
     for k in FRAME_KEYS:
@@ -613,7 +612,7 @@ def test_engine_fused_decoder_agrees_with_launch_per_op_decoder(tag, fused, monk
     for k in ("outputs", "aux_queries", "pred_logits", "aux_logits"):
         assert report[k][1] < (2.5e-1 if deep else 3e-2), (k, report[k])
     assert rel_err(res1["init_ref_pts"].cpu().numpy(), g["init_ref_pts"]) < 1e-5
-    # query updater (fused into one cluster kernel when fused == "2"): same inputs (the golden track state), so it is
+    # query updater (fused into one cluster kernel): same inputs (the golden track state), so it is
     # compared directly -- against the launch-per-op updater and against the reference module's outputs
     upd = {k: (rel_err(st1[k].cpu().numpy(), st0[k].cpu().numpy()), rel_err(st1[k].cpu().numpy(), g["upd_" + k]),
                rel_err(st0[k].cpu().numpy(), g["upd_" + k])) for k in UPD_KEYS}
@@ -636,17 +635,17 @@ def test_engine_bf16_multiclass_fused_paths_match_oracle(ncls, nd, nt, monkeypat
         want = oframe.frame_forward(sd, x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"], cfg)
         wupd = oframe.update_tracks(sd, x["tracks"], cfg)
     res = {}
-    for fused in ("0", "2"):
+    for fused in ("0", "1"):
         monkeypatch.setenv("MEMOTR_DEC_FUSED", fused)
         eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, nt, DEV, mode="bf16")
-        assert eng.dec_cluster == (fused == "2") and eng.upd_fused == (fused == "2")
+        assert eng.dec_cluster == (fused == "1") and eng.upd_fused == (fused == "1")
         eng.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
         eng.forward()
         eng.load_tracks(x["tracks"])
         eng.update_tracks()
         torch.cuda.synchronize()
         res[fused] = ({k: v.clone() for k, v in eng.results().items()}, eng.track_state())
-    for fused in ("0", "2"):
+    for fused in ("0", "1"):
         out, st = res[fused]
         assert out["pred_logits"].shape == (1, nd + nt, ncls)
         for k in ("pred_bboxes", "last_ref_pts"):

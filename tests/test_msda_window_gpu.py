@@ -63,7 +63,7 @@ def test_window_gather_bit_equal_to_global_gather_and_close_to_oracle(shapes, H,
                        for c in plan["cls"])
         assert n_win + n_glob == staged_q * H * L * Kp, (kw, plan)
         if kw.get("shift") is not None and kw["radius"] >= full and plan["classes"] and all(all(c["ww"]) for c in plan["cls"]):
-            assert n_win >= 0.97 * (n_win + n_glob), (kw, n_win, n_glob)        # the hint does its job
+            assert n_win >= 0.9 * (n_win + n_glob), (kw, n_win, n_glob)         # the hint does its job
     v32, l32, a32 = cpu
     S = v32.shape[0]
     ref = omsda.forward(v32.half().float().reshape(1, S, H, 32).numpy(), shp.numpy(), lsi.numpy(), l32[None].numpy(),
