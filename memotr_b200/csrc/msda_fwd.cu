@@ -362,7 +362,12 @@ int launch_h16(const void *value, const int64_t *shapes, const int64_t *lsi, con
   if (!ld_loc) ld_loc = H * L * K * 2;
   if (!ld_attn) ld_attn = H * L * K;
   const long n_qh = (long)B * Lq * H;
-  const bool split = n_qh * 4 < (long)kNumSMs * 256 * 2;   // too few groups to fill the GPU: spread the levels over lanes
+  // too few groups to fill the GPU: spread the levels over lanes.  (The level-split sums round differently from the
+  // level-pair order of msda_h16.cuh -- both within the bf16 bar; MEMOTR_MSDA_NO_SPLIT=1 keeps the sequential order, which is
+  // what the bit-equality tests against the windowed gather use on small pyramids.)
+  const char *ns = getenv("MEMOTR_MSDA_NO_SPLIT");
+  const bool no_split = ns && ns[0] == '1';
+  const bool split = !no_split && n_qh * 4 < (long)kNumSMs * 256 * 2;
   const int grid = (int)((n_qh * (split ? 16 : 4) + 255) / 256);
   const bool h8 = H == 8;
   if (n_qh * 16 >= (1L << 31)) return fail(MEMOTR_EINVAL, "msda_fwd_h16: more than 2^27 (query, head) pairs");

@@ -89,8 +89,7 @@ __device__ __forceinline__ void gather_global(const __half *__restrict__ vb, con
   __half2 a0[4], a1[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) a0[j] = a1[j] = __float2half2_rn(0.f);
-  int it = 0;
-  for (int l = l0; l < L; l += lstep, ++it) {
+  auto level = [&](int l) {
     const int Hh = sh.H(l), Ww = sh.W(l);
     const int base = sh.start(l) * xs, ys = Ww * xs;
     if constexpr (KT > 0) {
@@ -119,11 +118,23 @@ __device__ __forceinline__ void gather_global(const __half *__restrict__ vb, con
         blend(a1, p.ws[1], r[1], r[3]);
       }
     }
-    if ((it & 1) || l + lstep >= L) {        // end of a level pair (or of the levels): widen into the fp32 sums
-      widen_add(acc0, a0);
-      widen_add(acc1, a1);
+  };
+  auto widen = [&]() {                        // end of a level pair: into the fp32 sums
+    widen_add(acc0, a0);
+    widen_add(acc1, a1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a0[j] = a1[j] = __float2half2_rn(0.f);
+    for (int j = 0; j < 4; ++j) a0[j] = a1[j] = __float2half2_rn(0.f);
+  };
+  if (lstep == 1) {
+    for (int l = l0; l < L; l += 2) {
+      level(l);
+      if (l + 1 < L) level(l + 1);
+      widen();
+    }
+  } else {                                     // (levels spread over lane subgroups: each subgroup's levels are 'pairs' of one)
+    for (int l = l0; l < L; l += lstep) {
+      level(l);
+      widen();
     }
   }
 }

@@ -36,7 +36,7 @@ namespace memotr {
 namespace win {
 
 constexpr int MAXL = 5, MAXC = 4, MAXH = 16;
-constexpr int TAP_WARPS = 8, DEC_WARPS = 4, THREADS = (TAP_WARPS + DEC_WARPS) * 32;
+constexpr int TAP_WARPS = 16, DEC_WARPS = 8, THREADS = (TAP_WARPS + DEC_WARPS) * 32;
 constexpr int SMEM_BUDGET = 112 * 1024;      // per stage (windows + records of one unit); a CTA holds two stages (227 KB per SM)
 
 struct ClassGeom {
@@ -48,6 +48,7 @@ struct ClassGeom {
   int ww[MAXL], wh[MAXL];       // window extent in pixels per value level (0: no window, the level's taps read global memory)
   int off[MAXL];                // byte offset of the window in dynamic shared memory
   int win_bytes, rec_off, rec_stride;
+  float tiles_x_rcp;
 };
 
 struct Params {
@@ -56,6 +57,7 @@ struct Params {
   int hw[2 * MAXL], lsi[MAXL];
   int L, K, H, S, xs, ld_loc, ld_attn;
   int stage_bytes;                     // bytes of one stage (windows + records); the CTA double-buffers stages
+  int h_shift;                         // log2(H) when H is a power of two, else -1
   float radius;
   float shift[MAXH * MAXL * 2];        // per (head, level): expected sampling offset (x, y) in pixels of that level
 };
@@ -90,39 +92,68 @@ __device__ __forceinline__ Unit unit_of(const Params &P, int u) {
   for (int c = 1; c < P.n_cls; ++c)
     if (u >= P.cls[c].unit0) t.c = c;
   const ClassGeom &G = P.cls[t.c];
-  const int v = u - G.unit0, tile = v / P.H;
-  t.h = v - tile * P.H;
-  t.ty = tile / G.tiles_x, t.tx = tile - t.ty * G.tiles_x;
+  const int v = u - G.unit0;
+  int tile;
+  if (P.h_shift >= 0) tile = v >> P.h_shift, t.h = v & (P.H - 1);
+  else tile = v / P.H, t.h = v - tile * P.H;
+  int ty = (int)(((float)tile + 0.5f) * G.tiles_x_rcp);       // tile / tiles_x (tile < 2^20: exact after the fix-up)
+  if (ty * G.tiles_x > tile) --ty;
+  t.ty = ty, t.tx = tile - ty * G.tiles_x;
   return t;
 }
 
-// one sampling point -> its two records (x-side 0 / 1)
+// one sampling point -> its two records (x-side 0 / 1).  Same numbers as h16::decode; a tap that lands in its window needs
+// neither clamped addresses nor zeroed weights (pixels outside the image arrive as zeros from the TMA fill).
 __device__ __forceinline__ void make_records(const Params &P, const ClassGeom &G, int l, int2 org, uint32_t wbase, float2 xy,
                                              float aw, Rec &r0, Rec &r1, int &n_win, int &n_glob) {
   const int Hh = P.hw[2 * l], Ww = P.hw[2 * l + 1];
-  const h16::Point p = h16::decode(xy, aw, Hh, Ww);
-  const int ww = G.ww[l], dx = p.x0 - org.x, dy = p.y0 - org.y;
-  r0.w = p.ws[0], r1.w = p.ws[1];
-  // (unsigned compares: a saturated x0 / y0 of a far-away or non-finite location can never pass)
+  const float Hf = (float)Hh, Wf = (float)Ww;
+  const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
+  r0.off = r1.off = wbase;
+  r0.w = r1.w = __float2half2_rn(0.f);
+  if (!(h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf)) return;        // contributes nothing (.cuh:288; NaN too)
+  const int y0 = __float2int_rd(h_im), x0 = __float2int_rd(w_im);
+  const int ww = G.ww[l], dx = x0 - org.x, dy = y0 - org.y;
   if (ww && (unsigned)dx < (unsigned)(ww - 1) && (unsigned)dy < (unsigned)(G.wh[l] - 1)) {
+    const float lh = h_im - floorf(h_im), lw = w_im - floorf(w_im), hh = 1.f - lh, hw = 1.f - lw;
+    r0.w = __floats2half2_rn(hh * hw * aw, lh * hw * aw);
+    r1.w = __floats2half2_rn(hh * lw * aw, lh * lw * aw);
     r0.off = wbase + (uint32_t)(G.off[l] + (dy * ww + dx) * 64);
     r1.off = r0.off + 64u;
     ++n_win;
   } else {
+    const h16::Point p = h16::decode(xy, aw, Hh, Ww);
     const uint32_t flags = 0x80000000u | (p.yc[1] == p.yc[0] ? 0x40000000u : 0u);
     const uint32_t row = (uint32_t)(P.lsi[l] + p.yc[0] * Ww);
+    r0.w = p.ws[0], r1.w = p.ws[1];
     r0.off = flags | (row + (uint32_t)p.xc[0]);
     r1.off = flags | (row + (uint32_t)p.xc[1]);
     ++n_glob;
   }
 }
 
+// wait with a suspend-time hint: a warp that has to wait (the other role is behind) sleeps in the barrier unit instead of
+// spinning through the issue slots the working warps of its scheduler need
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "SLEEPY_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra SLEEPY_DONE;\n\t"
+      "bra SLEEPY_WAIT;\n\t"
+      "SLEEPY_DONE:\n\t"
+      "}" ::"r"(tc::smem_u32(bar)),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-// Persistent, warp-specialised: one CTA per SM walks units u = blockIdx, + stride, ...; the DECODE warps (4) stage unit n + 1
-// (TMA windows + records, two buffers of each) while the TAP warps (8) consume unit n, so the shared-memory pipe -- the
+// Persistent, warp-specialised: one CTA per SM walks units u = blockIdx, + stride, ...; the DECODE warps (8) stage unit n + 1
+// (TMA windows + records, two buffers of each) while the TAP warps (16) consume unit n, so the shared-memory pipe -- the
 // resource that bounds this kernel -- never waits for a decode phase.
 //   win_full[b]  TMA bytes of window buffer b have landed           (decode thread 0 arms it, the copy engine completes it)
 //   rec_full[b]  the records of buffer b are written                (one arrival per decode warp)
@@ -172,9 +203,9 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
     // =========================================================================================== decode warps
     const int dt = tid - TAP_WARPS * 32, lane = tid & 31;
     int n_win = 0, n_glob = 0;                  // (profiling only: points staged / points left to global memory)
-    // KT == 4: a thread decodes the four points of (query, level) pairs -- pair p = dt + 128 i, query = p / L, level = p % L --
+    // KT == 4: a thread decodes the four points of (query, level) pairs -- pair p = dt + 256 i, query = p / L, level = p % L --
     // from registers that were loaded one unit ahead (the global-memory latency hides behind the previous unit's decode)
-    constexpr int NPRE = KT == 4 ? 4 : 1;
+    constexpr int NPRE = KT == 4 ? 2 : 1;
     float4 pre_xy[NPRE][2], pre_w[NPRE];
     auto prefetch = [&](int u) {
       if constexpr (KT == 4) {
@@ -207,7 +238,7 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
       uint8_t *recs = smem + wbase + G.rec_off;
       const float rx = __fdiv_rn(__fadd_rn((float)(tx * G.tw), 0.5f), __fmul_rn(__ldg(vr + 2 * G.lq), (float)G.Wq));
       const float ry = __fdiv_rn(__fadd_rn((float)(ty * G.th), 0.5f), __fmul_rn(__ldg(vr + 2 * G.lq + 1), (float)G.Hq));
-      if (n >= 2) tc::mbar_wait(buf_free + b, ((n >> 1) - 1) & 1);       // the tap warps have finished unit n - 2
+      if (n >= 2) mbar_wait_sleepy(buf_free + b, ((n >> 1) - 1) & 1);       // the tap warps have finished unit n - 2
       if (dt == 0) {
         // where the tile's first reference point lands on every level (deformable_encoder.py:29-40), plus the head's
         // expected offset, minus the radius: the window origin.  Any origin is correct; a good one makes every tap a window tap.
@@ -288,8 +319,8 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
     const ClassGeom &G = P.cls[t.c];
     const int TQ = G.tw * G.th;
     const uint8_t *recs = smem + b * P.stage_bytes + G.rec_off;
-    tc::mbar_wait(rec_full + b, (n >> 1) & 1);
-    tc::mbar_wait(win_full + b, (n >> 1) & 1);
+    mbar_wait_sleepy(rec_full + b, (n >> 1) & 1);
+    mbar_wait_sleepy(win_full + b, (n >> 1) & 1);
     const __half *vb = value + h * 32 + sub * 8;
     for (int ql = grp; ql < TQ; ql += TAP_WARPS * 4) {
       const uint8_t *rq = recs + ql * G.rec_stride + side * 16;
@@ -389,6 +420,9 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
                 int ld_attn, const float *shift, float radius, int max_classes) {
   std::memset(&P, 0, sizeof(P));
   P.L = L, P.K = K, P.H = H, P.S = S, P.xs = xs, P.ld_loc = ld_loc, P.ld_attn = ld_attn, P.radius = radius;
+  P.h_shift = -1;
+  for (int b = 0; b < 5; ++b)
+    if ((1 << b) == H) P.h_shift = b;
   for (int l = 0; l < L; ++l) P.hw[2 * l] = shapes_hw[2 * l], P.hw[2 * l + 1] = shapes_hw[2 * l + 1], P.lsi[l] = level_start[l];
   for (int h = 0; h < H; ++h)
     for (int l = 0; l < L; ++l)
@@ -405,11 +439,12 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
     // as far apart, so the windows of a tile grow with the level), halved while the records of the tile (one per sampling
     // point and x-side) would take more than 40 KB
     G.tw = c == 0 ? 16 : 8, G.th = c <= 1 ? 8 : 4, G.tw_shift = c == 0 ? 4 : 3;
-    while (G.tw * G.th > 32 && (G.tw * G.th * G.rec_stride > 40 * 1024 || (K == 4 && G.tw * G.th * L > 4 * win::DEC_WARPS * 32))) {
+    while (G.tw * G.th > 32 && (G.tw * G.th * G.rec_stride > 40 * 1024 || (K == 4 && G.tw * G.th * L > 2 * win::DEC_WARPS * 32))) {
       if (G.tw > G.th) G.tw >>= 1, --G.tw_shift; else G.th >>= 1;
     }
     if (G.tw * G.th * G.rec_stride > 64 * 1024) break;
     G.tiles_x = ceil_div(G.Wq, G.tw), G.tiles_y = ceil_div(G.Hq, G.th);
+    G.tiles_x_rcp = 1.0f / (float)G.tiles_x;
     const int rec_bytes = G.tw * G.th * G.rec_stride;
     // window extents: footprint of the tile's reference points on the level (+5 % for differing valid ratios) + the radius
     // on both sides + the second bilinear column / row + rounding

@@ -39,7 +39,7 @@ class _Lin:
 
 class FrameEngine:
     def __init__(self, state_dict, cfg, shapes, n_tracks, device="cuda", mode="fp32", tracker=None,
-                 ori_size=(1920, 1080), pos_embed=None):
+                 ori_size=(1920, 1080), pos_embed=None, pad_tracks=False):
         """`n_tracks` is the number of track-query rows (= the capacity of the track table).  `tracker=None`: the
         caller owns the track bookkeeping and every row is live (the reference's model + query-updater path only).
         `tracker=dict(det_score_thresh=, track_score_thresh=, miss_tolerance=, result_score_thresh=)`: the
@@ -48,6 +48,9 @@ class FrameEngine:
         # pos_embed=dict(temperature=20, scale=2*pi): the position maps are rebuilt on the device from the padding masks
         # (PositionEmbeddingSine, models/position_embedding.py:23-49) instead of being an input (None)
         self.pos_cfg = dict(pos_embed) if pos_embed is not None else None
+        # pad_tracks: the caller owns the tracks but uses fewer than n_tracks rows: query_pad (device, uint8 per query, 1 =
+        # unused row) masks them as padded keys, exactly like the device tracker's padding
+        self.use_pad = tracker is not None or bool(pad_tracks)
         assert mode in ("fp32", "bf16")
         self.tracker_cfg, self.ori_size = (dict(tracker) if tracker is not None else None), tuple(ori_size)
         self.cfg, self.mode = dict(cfg), mode
@@ -336,7 +339,7 @@ class FrameEngine:
         P.qs0_b, P.qs1_b = self.query_scale[0].b.data_ptr(), self.query_scale[1].b.data_ptr()
         P.tgt_in, P.ref_in = self.tgt32[0].data_ptr(), self.ref[0].data_ptr()
         P.vr_scale4, P.valid_ratios, P.dim_t = self.vr_scale4.data_ptr(), self.vr.data_ptr(), self.dim_t.data_ptr()
-        P.query_pad = self.query_pad.data_ptr() if self.trk is not None else None
+        P.query_pad = self.query_pad.data_ptr() if self.use_pad else None
         P.kbuf, P.vbuf, P.barrier = self.dec_kbuf.data_ptr(), self.dec_vbuf.data_ptr(), self.dec_barrier.data_ptr()
         for l, (h, w) in enumerate(self.shapes):
             P.shapes[2 * l], P.shapes[2 * l + 1], P.lsi[l] = h, w, self.lsi_host[l]
@@ -719,7 +722,7 @@ class FrameEngine:
             self.lin(self.qk_in, C, sa["qk"], self.qk, 2 * C, n, c_dtype=F32)
             self.lin(out, C, sa["v"], self.v, C, n, c_dtype=F32)
             self.mha(self.qk, 2 * C, self.qk[:, C:], 2 * C, self.v, C, self.d_a, C, n, n,
-                     kpm=self.query_pad if (self.trk is not None and n == nq) else None)
+                     kpm=self.query_pad if (self.use_pad and n == nq) else None)
             self.lin(self.d_a, C, sa["out"], self.d_pre, C, n, c_dtype=F32)
             self.ln(self.d_pre, ly["norm2"], self.t1, n, x2=self.tgt32[lid], y32=self.t1_32, pos=self.query_pos,
                     ypos=self.t1q)
@@ -865,6 +868,24 @@ class FrameEngine:
         self.in_track_ref.copy_(self.st["ref_pts"])
         self.in_track_embed.copy_(self.st["query_embed"])
 
+    def run_clip_two_phase(self, n_frames, feed, group=None):
+        """The exact sharded clip (clip.run_clip_two_phase) on this engine: `feed(i)` puts frame i into the input buffers;
+        phase 1 = encode() per frame of this rank, phase 2 = the recurrent tail on the track memory handed along the
+        ranks.  Eager launches (no graph).  Returns the rank's frame indices."""
+        from . import clip
+
+        def encode(i):
+            feed(i)
+            self.encode()
+            return self.frame_token()
+
+        def decode(i, token):
+            self.load_token(token)
+            self.step_tail()
+
+        out = clip.run_clip_two_phase(n_frames, encode, decode, self.get_track_memory, self.set_track_memory, group=group)
+        return [i for i, _ in out]
+
     def step_tail(self):
         """The recurrent tail of a step: decoder + heads, tracker glue, query updater, feedback."""
         self.decode()
@@ -884,13 +905,25 @@ class FrameEngine:
             self.convert(self.st["query_embed"], F32, self.C, self.in_track_embed, F32, self.C, self.nt, self.C)
         self._mark(4)
 
+    def _recurrent_state(self):
+        """The tensors a step mutates and the next step reads: track table / tracker bookkeeping and the fed-back queries."""
+        ts = [self.in_track_ref, self.in_track_embed, self.query_pad]
+        ts += self.trk.state_tensors() if self.trk is not None else list(self.st.values())
+        return ts
+
     def capture(self, fn=None):
-        """Record `fn` (default: step) into a CUDA graph; replay() then re-issues the whole frame with one launch."""
+        """Record `fn` (default: step) into a CUDA graph; replay() then re-issues the whole frame with one launch.
+        The eager warm-up run that precedes the capture leaves the recurrent state (track table, identities, padding
+        mask, fed-back track queries) exactly as it found it."""
         fn = fn or self.step
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
+            state = self._recurrent_state()
+            saved = [t.clone() for t in state]
             fn()                                            # warm-up outside capture (one-time attribute calls etc.)
+            for t, v in zip(state, saved):
+                t.copy_(v)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.launches = 0
@@ -975,6 +1008,12 @@ class ClipRunner:
             self.host_out["n_active"].copy_(eng.table.n_active, non_blocking=True)
         return self.host_out
 
+    def check(self):
+        """Raise if the device track table overflowed at any point since the last reset (newborn tracks dropped:
+        identities would diverge from the reference).  Synchronises; call it at the end of a clip."""
+        if self.eng.trk is not None:
+            self.eng.trk.check_overflow()
+
     def results(self):
         """Tracker mode, after a synchronize: the frame's result rows (ids, xyxy boxes in pixels, scores) of the kept tracks."""
         ids, boxes, scores, keep = self.eng.trk.split_results(self.host_out["results"])
@@ -992,6 +1031,8 @@ class ClipRunner:
             if i + 1 < len(frames):
                 self.prefetch((i + 1) % 2, *frames[i + 1])
             out = self.run(i % 2)
+        torch.cuda.current_stream(self.eng.dev).synchronize()
+        self.check()
         return out
 
 

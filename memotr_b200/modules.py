@@ -199,6 +199,7 @@ class DeformableTransformer(nn.Module):
         super().__init__()
         assert not two_stage and use_dab, "two-stage / non-DAB variants are outside the hot-path scope"
         self.d_model, self.n_heads, self.two_stage = d_model, n_heads, two_stage
+        self.n_feature_levels, self.n_enc_points, self.n_dec_points = n_feature_levels, n_enc_points, n_dec_points
         self.two_stage_num_proposals, self.use_checkpoint = two_stage_num_proposals, use_checkpoint
         self.checkpoint_level, self.use_dab, self.visualize = checkpoint_level, use_dab, visualize
         enc = DeformableEncoderLayer(d_model, d_ffn, dropout, activation, n_feature_levels, n_heads, n_enc_points, False)
@@ -264,9 +265,10 @@ def build_transformer(config: dict):
 
 
 class QueryUpdater(nn.Module):
-    """update_tracks_embedding of models/query_updater.py:82-166 on plain tensors.  `tracks` items are any objects with
-    the TrackInstances attributes (ref_pts, query_embed, output_embed, last_output, long_memory, logits, boxes); track
-    selection / augmentation (select_active_tracks, :168-255) is host glue and stays with the reference."""
+    """models/query_updater.py:15-255: forward = select_active_tracks + update_tracks_embedding.  `tracks` items are
+    duck-typed: any objects with the TrackInstances attributes (ref_pts, query_embed, output_embed, last_output,
+    long_memory, logits, boxes, ids, iou) and its `cat_tracked_instances` / `__getitem__` -- the reference's own class
+    plugs in unchanged.  Track augmentation (TP_DROP_RATE / FP_INSERT_RATE > 0; 0 in every shipped config) is not built."""
 
     def __init__(self, hidden_dim: int, ffn_dim: int, tp_drop_ratio: float, fp_insert_ratio: float, dropout: float,
                  use_checkpoint: bool, use_dab: bool, update_threshold: float, long_memory_lambda: float,
@@ -288,6 +290,48 @@ class QueryUpdater(nn.Module):
         for p in self.parameters():
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
+
+    def forward(self, previous_tracks, new_tracks, unmatched_dets, no_augment: bool = False):
+        """models/query_updater.py:72-80."""
+        tracks = self.select_active_tracks(previous_tracks, new_tracks, unmatched_dets, no_augment=no_augment)
+        return self.update_tracks_embedding(tracks=tracks)
+
+    def select_active_tracks(self, previous_tracks, new_tracks, unmatched_dets, no_augment: bool = False):
+        """models/query_updater.py:168-254.  Eval (batch 1): newborn tracks get last_output / long_memory from their own
+        output / query embeddings, previous + new are concatenated and the dead ones (ids < 0) dropped.  Training without
+        augmentation: previous + new + unmatched detections, kept where the score passes update_threshold or the id is
+        alive, ids of low-IoU rows cleared; an empty result becomes one fake track (:227-253) so the updater always runs."""
+        out = []
+        if not self.training:
+            assert len(previous_tracks) == 1 and len(new_tracks) == 1, "eval runs batch 1"
+            new = new_tracks[0]
+            new.last_output, new.long_memory = new.output_embed, new.query_embed
+            act = type(new).cat_tracked_instances(previous_tracks[0], new)
+            out.append(act[act.ids >= 0])
+            return out
+        if self.tp_drop_ratio != 0.0 or self.fp_insert_ratio != 0.0:
+            raise NotImplementedError("track augmentation (TP_DROP_RATE / FP_INSERT_RATE > 0) is not part of this build")
+        for b in range(len(new_tracks)):
+            new, um = new_tracks[b], unmatched_dets[b]
+            new.last_output, new.long_memory = new.output_embed, new.query_embed
+            um.last_output, um.long_memory = um.output_embed, um.query_embed
+            cat = type(new).cat_tracked_instances
+            act = cat(cat(previous_tracks[b], new), um)
+            scores = act.logits.sigmoid().max(dim=1).values
+            act = act[(scores > self.update_threshold) | (act.ids >= 0)]
+            act.ids[act.iou < 0.5] = -1
+            if len(act) == 0:
+                dev, C = next(self.query_feat_ffn.parameters()).device, self.hidden_dim
+                fake = type(new)(frame_height=1.0, frame_width=1.0, hidden_dim=C).to(dev)
+                r = lambda *s: torch.randn(s, dtype=torch.float, device=dev)           # noqa: E731
+                fake.query_embed, fake.output_embed, fake.ref_pts, fake.boxes = r(1, C), r(1, C), r(1, 4), r(1, 4)
+                fake.ids = torch.as_tensor([-2], dtype=torch.long, device=dev)
+                fake.matched_idx = torch.as_tensor([-2], dtype=torch.long, device=dev)
+                fake.logits, fake.iou = r(1, act.logits.shape[1]), torch.zeros((1,), dtype=torch.float, device=dev)
+                fake.last_output, fake.long_memory = r(1, C), r(1, C)
+                act = fake
+            out.append(act)
+        return out
 
     def update_tracks_embedding(self, tracks):
         lam = self.long_memory_lambda

@@ -116,6 +116,21 @@ class DeviceTracker:
         self.max_obj_id.fill_(int(max_obj_id))
         self.overflow.zero_()
 
+    def reset_async(self, tracks, max_obj_id=0):
+        """reset(tracks, max_obj_id) without reading anything back from the device (the row count is len(tracks)): usable
+        between the frames of a timed loop."""
+        self.table.load(tracks)
+        n = len(tracks["query_embed"])
+        self.track_pad.fill_(1)
+        self.track_pad[:n] = 0
+        self.max_obj_id.fill_(int(max_obj_id))
+        self.overflow.zero_()
+
+    def state_tensors(self):
+        """Every tensor of the recurrent tracker state (for snapshot / restore around a warm-up step)."""
+        return list(self.table.fields.values()) + [self.table.n_active, self.max_obj_id, self.track_pad, self.overflow,
+                                                   self.src_index]
+
     def update(self, pred_logits, pred_bboxes, outputs, last_ref_pts, aux_queries):
         """One frame.  Every argument is a contiguous fp32 device tensor with n_det + capacity rows (the engine's
         output buffers): detect queries first, then one row per table row."""

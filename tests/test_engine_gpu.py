@@ -427,9 +427,7 @@ def test_clip_runner_host_api_tracker_mode():
     eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 10, DEV, **kw)
     fr0 = frames[0]
     eng.load_frame(fr0["srcs"], fr0["masks"], None, eng.in_track_ref, eng.in_track_embed)
-    eng.capture()
-    eng.trk.reset()
-    eng.in_track_ref.zero_(), eng.in_track_embed.zero_()
+    eng.capture()                               # (the warm-up step inside capture() leaves the recurrent state untouched)
     runner = ClipRunner(eng)
     pin = lambda t: t.contiguous().pin_memory()                                       # noqa: E731
     host = [([pin(t) for t in fr["srcs"]], None, [pin(t.to(torch.uint8)) for t in fr["masks"]]) for fr in frames]
@@ -679,10 +677,7 @@ def test_engine_cuda_graph_replay_equals_eager_and_chains_frames(mode):
     for e in (eager, graph):
         e.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
         e.load_tracks(x["tracks"])
-    graph.capture()
-    # capture() ran the step once eagerly (warm-up) and once while recording; reset the recurrent state
-    graph.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
-    graph.load_tracks(x["tracks"])
+    graph.capture()         # runs the step once eagerly (warm-up) and records it once; the recurrent state is preserved
     for _ in range(3):                      # three chained frames: track queries feed back through the updater
         eager.step()
         graph.replay()
