@@ -176,12 +176,16 @@ MEMOTR_API int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
                            const void *mul, int ldmul, void *C, int ldc, int M, int K1, int Hd, int N2, int c_dtype,
                            int act2, void *stream);
 
-/* memotr_mlp2 with a LayerNorm prologue, fp32 output: C = relu(X W1^T + b1) W2^T + b2 with X = LayerNorm(pre + res) (256
- * columns) computed inside the kernel; out32 (optional) receives X in fp32 -- the pair LayerNorm + FFN of an encoder layer
- * (models/deformable_encoder.py:92-107) without X ever being written to / read from global memory as a GEMM operand. */
-MEMOTR_API int memotr_mlp2_ln(const float *pre, int ldpre, const float *res, int ldres, const float *gamma, const float *beta,
-                              float eps, float *out32, int ld32, const void *W1, const float *b1, const void *W2,
-                              const float *b2, float *C, int ldc, int M, int Hd, void *stream);
+/* The encoder FFN with its LayerNorm in the epilogue (models/deformable_encoder.py:103-107 followed by :128-131):
+ *   y = LayerNorm(res + relu(X W1^T + b1) W2^T + b2) * gamma + beta      (256 columns; the whole row sits in one CTA's TMEM)
+ * written three ways, as the next layer reads it: y (M,256) bf16 ldy; y32 fp32 ld32 (NULL: skip); ypos = y + pos, bf16
+ * (pos / ypos both NULL: skip).  X (M,256) bf16, res (M,256) fp32.  One launch of ceil(M/128) CTAs, one CTA per SM: callers
+ * with more row tiles than SMs pass the first round here and run the remaining rows through memotr_mlp2 (which splits the
+ * hidden dimension of few-tile launches over the idle SMs) + memotr_layernorm. */
+MEMOTR_API int memotr_mlp2_lnout(const void *X, int ldx, const void *W1, const float *b1, const void *W2, const float *b2,
+                                 const float *res, int ldres, const float *gamma, const float *beta, float eps, void *y, int ldy,
+                                 float *y32, int ld32, const void *pos, int ldpos, void *ypos, int ldypos, int M, int Hd,
+                                 void *stream);
 
 /*
  * y = LayerNorm(x [+ x2]) (C == 256, eps as given, affine fp32); optional ypos = y + pos and fp32 copy y32.

@@ -446,7 +446,10 @@ extern "C" int memotr_decoder_forward_cluster(const memotr_dec_params *p, void *
   attr[1].id = cudaLaunchAttributeCooperative;      // all CTAs resident: the grid barrier cannot dead-lock
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  // MEMOTR_NONCOOP=1 (profiling only): plain cluster launch -- ncu cannot replay cooperative cluster launches; with the GPU to
+  // itself (kernels serialised under the profiler, grid <= number of SMs) all CTAs are resident anyway
+  const char *nc = getenv("MEMOTR_NONCOOP");
+  cfg.numAttrs = (nc && nc[0] == '1') ? 1 : 2;
   e = cudaLaunchKernelEx(&cfg, dec::cl::decoder_cluster_kernel, *p);
   if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "decoder_forward_cluster: launch: %s", cudaGetErrorString(e));
   return check_launch("decoder_cluster");

@@ -22,16 +22,16 @@
 //
 // What bounds it (profiles/r01_mlp2_ncu.md): the 128 B/clk shared-memory pipe -- per 128-wide hidden chunk 224 KB of MMA
 // operand reads + 128 KB of TMA writes + 32 KB of epilogue stores = ~3000 clk against 2048 clk of tcgen05 work; a tile
-// costs 6.6 us fixed + 16 x 1.65 us.  One CTA per SM (224 KB), so 175 encoder row tiles on 148 SMs are two rounds: the
-// host launches the tiles beyond the first round separately with the hidden dimension split 4-ways (gridDim.y, TMA
-// reduce-add stores into the zeroed fp32 output): 73 -> 59 us per encoder FFN.  An optional LayerNorm prologue (LnIn)
-// computes X in the kernel; it is correct but slower than the stand-alone LayerNorm kernel and therefore opt-in.
+// costs 6.6 us fixed + 16 x 1.65 us.  One CTA per SM (224 KB), so 175 encoder row tiles on 148 SMs are two rounds: launches
+// with few row tiles split the hidden dimension over gridDim.y (TMA reduce-add stores into the zeroed fp32 output), and the
+// host runs the tiles beyond the first round that way: 73 -> 59 us per encoder FFN.
 //
-// Thread-block clusters (CS = 2 or 4 CTAs on neighbouring SMs, different row tiles; opt-in, measured neutral because the
-// L2 -> SM stream is not the limit): every CTA needs the SAME W1/W2 chunks, so each CTA of a cluster loads 1/CS of every
-// ring slot and TMA-multicasts it into the shared memory of all CS CTAs (cp.async.bulk.tensor ... .multicast::cluster); the slot's
-// `full` mbarrier in every CTA counts the bytes arriving from all issuers, and a slot is re-filled only after the MMA
-// warps of ALL CTAs released it (tcgen05.commit ... multicast::cluster onto every CTA's `empty` barrier, count CS).
+// LayerNorm epilogue (LnOut): for the encoder's `src = norm2(src + ffn(src))` (deformable_encoder.py:103-107,128-131) the
+// final epilogue adds the fp32 residual, normalises the 256-wide row -- the whole row sits in this CTA's TMEM accumulator --
+// and writes the three things the next layer reads: y (bf16, GEMM operand), y fp32 (residual master), y + pos (bf16, the
+// query of the next layer's offset / weight projection).  That removes the stand-alone LayerNorm kernel and the fp32 round
+// trip of the pre-norm sum (19 us + 46 MB per layer).  Variants measured slower in round 1 and removed: LayerNorm in the
+// PROLOGUE, weight multicast in clusters, uniform split-K.
 #include "tc_common.cuh"
 
 namespace memotr {
@@ -54,45 +54,21 @@ constexpr int TOTAL = OFF_BAR + 256 + 1024;
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], "
-      "[%2], %3;" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
-// Optional LayerNorm prologue: X = LayerNorm(pre + res) computed by the (otherwise idle) epilogue warps straight into the
-// shared-memory A tile, instead of a separate LayerNorm kernel writing X to global memory and a TMA load reading it back
-// (deformable_encoder.py:92-95 followed by :97-107).  out32 receives the fp32 result (the residual of the next LayerNorm).
-struct LnIn {
-  const float *pre, *res, *gamma, *beta;   // pre == nullptr: off (X comes from tmX)
-  float *out32;
-  int ldpre, ldres, ld32;
+// LayerNorm epilogue of the final GEMM (res == nullptr: off): out = LayerNorm(acc2 + b2 + res) * gamma + beta
+struct LnOut {
+  const float *res, *gamma, *beta;   // fp32 residual rows, LayerNorm affine
+  float *y32;                        // fp32 copy of the result (may be null)
+  const void *pos;                   // bf16 rows added to the result for the second bf16 output (null: no second output)
+  int ldres, ld32, ldpos;
   float eps;
 };
 
-template <typename TC, int CS>
+template <typename TC>
 __global__ void __launch_bounds__(320, 1)
 mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
-               const float *__restrict__ b1, int M, int Hd, Epilogue ep, int tile0, LnIn ln) {
+               const __grid_constant__ CUtensorMap tmQ, const float *__restrict__ b1, int M, int Hd, Epilogue ep, int tile0,
+               LnOut ln) {
   // tile0: first row tile of this launch (the tail tiles of a GEMM are launched separately with a hidden-dimension split)
   // gridDim.y > 1: split-K over the hidden dimension -- CTA (x, y) handles hidden chunks [y*NC, (y+1)*NC) of row tile x
   // and ADDS its partial product into the (zero-initialised, fp32) output with a TMA reduce-store; bias from split 0.
@@ -109,18 +85,16 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int NC = Hd / HC / (int)gridDim.y;          // hidden chunks of this CTA
   const int c_off = (int)blockIdx.y * NC;           // first hidden chunk of this CTA
   const bool split = gridDim.y > 1;
-  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
-  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    mbar_init(x_full, ln.pre ? 256 : 1);   // LayerNorm prologue: the 8 epilogue warps arrive instead of the TMA
+    mbar_init(x_full, 1);
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, CS);   // released by the MMA warps of all CTAs of the cluster
+      mbar_init(empty + s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc1_full + b, 1);
@@ -137,8 +111,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  if constexpr (CS > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast
-  else __syncthreads();
+  __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_grid_sync();
@@ -149,25 +122,16 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer: X once, then W1(0), [W1(c+1), W2(c)] ... in exactly the order the MMA warp consumes ----
-      if (!ln.pre) {
-        mbar_expect_tx(x_full, X_BYTES);
-        for (int p = 0; p < XP; ++p) tma_load_2d(smem + p * PANEL, &tmX, x_full, p * BK, m_blk * BM);
-      }
+      mbar_expect_tx(x_full, X_BYTES);
+      for (int p = 0; p < XP; ++p) tma_load_2d(smem + p * PANEL, &tmX, x_full, p * BK, m_blk * BM);
       int t = 0;
-      // a ring slot is 256 row-units of 128 B; this CTA loads units [crank*UNITS, (crank+1)*UNITS) and multicasts them
-      constexpr int UNITS = 256 / CS;
       auto load_w1 = [&](int c) {          // slot = [k-block 2*half: 128 rows][k-block 2*half+1: 128 rows]
         for (int half = 0; half < 2; ++half, ++t) {
           const int s = t % NSLOT;
           mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + s, SLOT);
-          if constexpr (CS == 1) {
-            tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, (c_off + c) * HC);
-            tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, (c_off + c) * HC);
-          } else {
-            const int u0 = crank * UNITS, kb = 2 * half + u0 / 128, r0 = u0 % 128;
-            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW1, full + s, kb * BK, (c_off + c) * HC + r0, MC_MASK);
-          }
+          tma_load_2d(ring + s * SLOT, &tmW1, full + s, (2 * half) * BK, (c_off + c) * HC);
+          tma_load_2d(ring + s * SLOT + PANEL, &tmW1, full + s, (2 * half + 1) * BK, (c_off + c) * HC);
         }
       };
       auto load_w2 = [&](int c) {          // slot = 256 output rows x 64 hidden columns
@@ -175,12 +139,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const int s = t % NSLOT;
           mbar_wait(empty + s, ((t / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + s, SLOT);
-          if constexpr (CS == 1) {
-            tma_load_2d(ring + s * SLOT, &tmW2, full + s, (c_off + c) * HC + j * BK, 0);
-          } else {
-            const int u0 = crank * UNITS;
-            tma_load_2d_mc(ring + s * SLOT + u0 * 128, &tmW2, full + s, (c_off + c) * HC + j * BK, u0, MC_MASK);
-          }
+          tma_load_2d(ring + s * SLOT, &tmW2, full + s, (c_off + c) * HC + j * BK, 0);
         }
       };
       load_w1(0);
@@ -213,8 +172,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int k = 0; k < BK / 16; ++k)
               umma_bf16(tmem_base + b * HC, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0);
           }
-          if constexpr (CS > 1) umma_commit_mc(empty + s, MC_MASK);
-          else umma_commit(empty + s);
+          umma_commit(empty + s);
         }
         umma_commit(acc1_full + b);
       };
@@ -230,8 +188,7 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_base + 2 * HC, adesc + 2 * k, bdesc + 2 * k, idesc2, (c | j | k) != 0);
-          if constexpr (CS > 1) umma_commit_mc(empty + s, MC_MASK);
-          else umma_commit(empty + s);
+          umma_commit(empty + s);
         }
         umma_commit(h_empty + b);
       };
@@ -247,61 +204,6 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int quarter = warp & 3, chalf = (warp - 2) >> 2;
     const int r_in = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    if (ln.pre) {
-      // ---- LayerNorm prologue: warp w - 2 normalises rows 16 (w - 2) .. +15 of the tile, four rows in flight; lane = 8
-      //      columns; the bf16 result goes into the 128B-swizzled K-major panels the TMA load would have produced ----
-      const int c0 = lane * 8, wr0 = (warp - 2) * 16;
-      const float4 g0 = ldg_f4(ln.gamma + c0), g1 = ldg_f4(ln.gamma + c0 + 4), be0 = ldg_f4(ln.beta + c0), be1 = ldg_f4(ln.beta + c0 + 4);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
-#pragma unroll 1
-      for (int rb = 0; rb < 16; rb += 4) {
-        float v[4][8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int row = m_blk * BM + wr0 + rb + j;
-          if (row < M) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(ln.pre + (long)row * ln.ldpre + c0);
-            const float4 a1 = *reinterpret_cast<const float4 *>(ln.pre + (long)row * ln.ldpre + c0 + 4);
-            const float4 r0 = *reinterpret_cast<const float4 *>(ln.res + (long)row * ln.ldres + c0);
-            const float4 r1 = *reinterpret_cast<const float4 *>(ln.res + (long)row * ln.ldres + c0 + 4);
-            v[j][0] = a0.x + r0.x, v[j][1] = a0.y + r0.y, v[j][2] = a0.z + r0.z, v[j][3] = a0.w + r0.w;
-            v[j][4] = a1.x + r1.x, v[j][5] = a1.y + r1.y, v[j][6] = a1.z + r1.z, v[j][7] = a1.w + r1.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rt = wr0 + rb + j, row = m_blk * BM + rt;
-          float sum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sum += v[j][i];
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          const float mean = sum * (1.f / 256.f);
-          float q = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float d = v[j][i] - mean;
-            q += d * d;
-          }
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-          const float rstd = rsqrtf(q * (1.f / 256.f) + ln.eps);
-          float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = row < M ? (v[j][i] - mean) * rstd * g[i] + be[i] : 0.f;
-          *reinterpret_cast<uint4 *>(smem + (lane >> 3) * PANEL + rt * 128 + (((lane & 7) ^ (rt & 7)) << 4)) = f32x8_to_bf16(y);
-          if (row < M && blockIdx.y == 0 && ln.out32) {
-            *reinterpret_cast<float4 *>(ln.out32 + (long)row * ln.ld32 + c0) = make_float4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<float4 *>(ln.out32 + (long)row * ln.ld32 + c0 + 4) = make_float4(y[4], y[5], y[6], y[7]);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the UMMA (async proxy)
-      mbar_arrive(x_full);
-    }
     for (int c = 0; c < NC; ++c) {
       const int b = c & 1;
       mbar_wait(acc1_full + b, (c >> 1) & 1);
@@ -342,6 +244,89 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tcgen05_fence_after();
     const int row = m_blk * BM + r_in;
     const bool row_ok = row < M;
+    if (ln.res) {
+      // ---- LayerNorm epilogue: this thread owns columns [chalf*128, +128) of its row; the other half of the row is with
+      //      the warp four above / below, the two partial moments meet in shared memory (the dead H buffer) ----
+      if constexpr (sizeof(TC) == 2) {
+        const float *resp = ln.res + (long)row * ln.ldres;
+        auto chunk = [&](int c0, float (&v)[32]) {            // acc2 + b2 + residual for 32 columns
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(2 * HC + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(ep.bias + c0 + j));
+            const float4 rr = row_ok ? *reinterpret_cast<const float4 *>(resp + c0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = __uint_as_float(r[j]) + bb.x + rr.x, v[j + 1] = __uint_as_float(r[j + 1]) + bb.y + rr.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + bb.z + rr.z, v[j + 3] = __uint_as_float(r[j + 3]) + bb.w + rr.w;
+          }
+        };
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+          float v[32];
+          chunk(c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s1 += v[j], s2 = fmaf(v[j], v[j], s2);
+        }
+        float2 *stat = reinterpret_cast<float2 *>(hbuf);
+        stat[chalf * BM + r_in] = make_float2(s1, s2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float2 o = stat[(1 - chalf) * BM + r_in];
+        const float mean = (s1 + o.x) * (1.f / 256.f);
+        const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.f / 256.f) - mean * mean, 0.f) + ln.eps);
+        const __nv_bfloat16 *posp = (const __nv_bfloat16 *)ln.pos + (long)row * ln.ldpos;
+#pragma unroll 1
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+          float v[32];
+          chunk(c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(ln.gamma + c0 + j));
+            const float4 be = __ldg(reinterpret_cast<const float4 *>(ln.beta + c0 + j));
+            v[j] = (v[j] - mean) * rstd * g.x + be.x, v[j + 1] = (v[j + 1] - mean) * rstd * g.y + be.y;
+            v[j + 2] = (v[j + 2] - mean) * rstd * g.z + be.z, v[j + 3] = (v[j + 3] - mean) * rstd * g.w + be.w;
+          }
+          if (ln.y32 && row_ok) {
+            float4 *yp = reinterpret_cast<float4 *>(ln.y32 + (long)row * ln.ld32 + c0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) yp[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+          // y -> panels 0..3, y + pos -> panels 4..7 (64 bf16 columns per panel, 16-byte chunk k at k ^ (row & 7))
+          const int panel = c0 / 64, kbase = (c0 % 64) / 8;
+          uint8_t *prow = smem + panel * PANEL + r_in * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = v[8 * k + i];
+            *reinterpret_cast<uint4 *>(prow + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t);
+            if (ln.pos) {
+              float pz[8];
+              bf16x8_to_f32(row_ok ? __ldg(reinterpret_cast<const uint4 *>(posp + c0 + 8 * k)) : make_uint4(0, 0, 0, 0), pz);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t[i] += pz[i];
+              *reinterpret_cast<uint4 *>(prow + 4 * PANEL + (((kbase + k) ^ (r_in & 7)) << 4)) = f32x8_to_bf16(t);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+#pragma unroll 1
+          for (int p = 0; p < 4; ++p) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                         "r"(smem_u32(smem + p * PANEL)), "r"(p * 64), "r"(m_blk * BM)
+                         : "memory");
+            if (ln.pos)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQ),
+                           "r"(smem_u32(smem + (4 + p) * PANEL)), "r"(p * 64), "r"(m_blk * BM)
+                           : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+      }
+    } else {
     const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
     constexpr int PANEL_COLS = 128 / (int)sizeof(TC);
     constexpr int N_PANELS = N2 / PANEL_COLS;
@@ -411,29 +396,26 @@ mlp2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    }
   }
   tcgen05_fence_before();
-  if constexpr (CS > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / arrive on it
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
-template <typename TC, int CS>
+template <typename TC>
 static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
                        int Hd, const Epilogue &ep, cudaStream_t st, int nsplit = 1, int tile0 = 0, int ntiles = -1,
-                       const LnIn &ln = LnIn{}, bool zero_first = true) {
+                       const LnOut &ln = LnOut{}, void *Q = nullptr, int ldq = 0) {
   using namespace mlp;
-  CUtensorMap tmX, tmW1, tmW2, tmC;
-  constexpr int W1_BOX = CS == 1 ? HC : (256 / CS < 128 ? 256 / CS : 128), W2_BOX = 256 / CS;
-  // (with the LayerNorm prologue there is no X in global memory; the descriptor is then a placeholder that is never used)
-  if (!make_map(&tmX, X ? X : W1, X ? M : Hd, K1, X ? ldx : K1, BM) || !make_map(&tmW1, W1, Hd, K1, K1, W1_BOX) ||
-      !make_map(&tmW2, W2, N2, Hd, Hd, W2_BOX) ||
-      !make_map(&tmC, C, M, N2, ldc, BM, sizeof(TC) == 4))
+  CUtensorMap tmX, tmW1, tmW2, tmC, tmQ;
+  if (!make_map(&tmX, X, M, K1, ldx, BM) || !make_map(&tmW1, W1, Hd, K1, K1, HC) || !make_map(&tmW2, W2, N2, Hd, Hd, 256) ||
+      !make_map(&tmC, C, M, N2, ldc, BM, sizeof(TC) == 4) || !make_map(&tmQ, Q ? Q : C, M, N2, Q ? ldq : ldc, BM, sizeof(TC) == 4))
     return fail(MEMOTR_ECUDA, "mlp2(tc): cuTensorMapEncodeTiled failed (M=%d Hd=%d)", M, Hd);
-  auto kern = mlp2_tc_kernel<TC, CS>;
+  auto kern = mlp2_tc_kernel<TC>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL);
@@ -441,19 +423,13 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
     attr_set = true;
   }
   const int tiles = ntiles < 0 ? ceil_div(M, BM) - tile0 : ntiles;
-  if constexpr (CS == 1) {
-    if (nsplit > 1 && zero_first) {   // partial products are reduce-added: start from zero (a memset node in a graph)
-      const int r0 = tile0 * BM, nr = (M - r0 < tiles * BM) ? M - r0 : tiles * BM;
-      const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<TC *>(C) + (size_t)r0 * ldc, (size_t)ldc * sizeof(TC), 0,
-                                              (size_t)N2 * sizeof(TC), nr, st);
-      if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
-    }
-    MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, b1, M, Hd, ep, tile0, ln);
-  } else {
-    // CTAs beyond the last tile (grid rounded up to a whole cluster) see zero-filled X and have their stores clipped
-    launch_kernel_cluster(kern, dim3(ceil_div(tiles, CS) * CS), dim3(320), (size_t)TOTAL, st, CS, tmX, tmW1, tmW2, tmC, b1,
-                          M, Hd, ep, 0, LnIn{});
+  if (nsplit > 1) {   // partial products are reduce-added: start from zero (a memset node in a graph)
+    const int r0 = tile0 * BM, nr = (M - r0 < tiles * BM) ? M - r0 : tiles * BM;
+    const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<TC *>(C) + (size_t)r0 * ldc, (size_t)ldc * sizeof(TC), 0,
+                                            (size_t)N2 * sizeof(TC), nr, st);
+    if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
   }
+  MEMOTR_LAUNCH((kern), dim3(tiles, nsplit), 320, TOTAL, st, tmX, tmW1, tmW2, tmC, tmQ, b1, M, Hd, ep, tile0, ln);
   return check_launch("mlp2_tc");
 }
 
@@ -462,42 +438,43 @@ static int launch_mlp2(const void *X, int ldx, const void *W1, const float *b1, 
 
 using namespace memotr;
 
-// fp32-output FFN without activation / multiplier: env-forced uniform split, else the tail split, else one launch
-static int mlp2_f32_balanced(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
-                             int Hd, const Epilogue &ep, cudaStream_t st, const tc::LnIn &ln) {
+static int sm_count() {
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int tiles = ceil_div(M, tc::BM), chunks = Hd / tc::mlp::HC;
-  // Split-K over the hidden dimension (MEMOTR_MLP_SPLIT=2|4|8): CTA (tile, split) handles Hd/nsplit hidden columns and
-  // reduce-adds into the fp32 output.  Measured (tools/time_mlp2.py): 74.8 / 72.7 / 78.8 / 110 us for 1 / 2 / 4 / 8 splits
-  // at the encoder shape -- the ~6.6 us fixed cost per CTA eats the better balance; opt-in only.
-  const char *sp = getenv("MEMOTR_MLP_SPLIT");
-  const int nsplit = sp ? atoi(sp) : 1;
-  if (nsplit > 1 && chunks % nsplit == 0) return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, nsplit, 0, -1, ln);
-  // Tail split (MEMOTR_MLP_TAIL=0 switches it off): with one CTA per SM, 175 row tiles on 148 SMs are two rounds of
-  // 33 us, the second 18 % full.  The first n_sm tiles run as usual; the remaining ones are launched with the hidden
-  // dimension split over as many CTAs as fit on the GPU (27 tiles x 4), so the second round costs 6.6 + 4 x 1.65 us.
+  return n_sm;
+}
+
+// hidden-dimension split for `tiles` row tiles: the largest power of two (<= 8) that still fits one CTA per SM
+static int pick_split(int tiles, int chunks, int n_sm) {
+  int ns = 1;
+  while (ns * 2 <= 8 && tiles * ns * 2 <= n_sm && chunks % (ns * 2) == 0) ns *= 2;
+  return ns;
+}
+
+// fp32-output FFN without activation / multiplier.  One CTA per SM: 175 row tiles on 148 SMs are two rounds of 33 us, the
+// second 18 % full -- so the first n_sm tiles run as usual and the remaining ones (and any launch with few tiles) are
+// launched with the hidden dimension split over as many CTAs as fit on the GPU (27 tiles x 4: 6.6 + 4 x 1.65 us).
+// MEMOTR_MLP_TAIL=0 switches the split off (A/B).
+static int mlp2_f32_balanced(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
+                             int Hd, const Epilogue &ep, cudaStream_t st) {
+  const int n_sm = sm_count(), tiles = ceil_div(M, tc::BM), chunks = Hd / tc::mlp::HC;
   const char *tl = getenv("MEMOTR_MLP_TAIL");
+  if (tl && tl[0] == '0') return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
+  if (tiles * 2 <= n_sm) return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, pick_split(tiles, chunks, n_sm));
   const int tail = tiles - n_sm;
-  if (!(tl && tl[0] == '0') && !sp && tail > 0 && tail * 2 <= n_sm) {
-    int ns = 2;
-    while (ns * 2 <= 8 && tail * ns * 2 <= n_sm && chunks % (ns * 2) == 0) ns *= 2;
-    if (chunks % ns == 0) {
-      // zero the tail rows BEFORE the main launch: the two kernels then follow each other directly (programmatic launch)
-      const int r0 = n_sm * tc::BM;
-      const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<float *>(C) + (size_t)r0 * ldc, (size_t)ldc * sizeof(float), 0,
-                                              (size_t)tc::mlp::N2 * sizeof(float), M - r0, st);
-      if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "mlp2(tc): memset: %s", cudaGetErrorString(e));
-      const int rc = tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, n_sm, ln);
+  if (tail > 0 && tail * 2 <= n_sm) {
+    const int ns = pick_split(tail, chunks, n_sm);
+    if (ns > 1) {
+      const int rc = tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, n_sm);
       if (rc != MEMOTR_OK) return rc;
-      return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail, ln, false);
+      return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, ns, n_sm, tail);
     }
   }
-  return tc::launch_mlp2<float, 1>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, 1, 0, -1, ln);
+  return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
 }
 
 extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *b1, const void *W2, const float *b2,
@@ -516,42 +493,29 @@ extern "C" int memotr_mlp2(const void *X, int ldx, const void *W1, const float *
   if (M == 0) return MEMOTR_OK;
   Epilogue ep{b2, mul, nullptr, nullptr, ldmul, 0, act2};
   cudaStream_t st = (cudaStream_t)stream;
-  // cluster size: enough row tiles to fill the GPU with clusters -> multicast the weights (MEMOTR_MLP_CLUSTER = 1|2|4)
-  const char *cs_str = getenv("MEMOTR_MLP_CLUSTER");
-  const int cs_env = cs_str ? atoi(cs_str) : 0;
-  const int tiles = ceil_div(M, tc::BM);
-  (void)tiles;
-  const int cs = cs_env ? cs_env : 1;   // measured: the kernel is shared-memory-bound, multicast gives nothing (profiles/)
-#define MLP2_GO(TC_, CS_) return tc::launch_mlp2<TC_, CS_>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st)
-  // Split-K over the hidden dimension (MEMOTR_MLP_SPLIT=2|4|8): meant for the case where the row tiles alone leave SMs
-  // idle (one CTA per SM: 175 tiles on 148 SMs are two rounds, the second 18 % full).  CTA (tile, split) handles
-  // Hd/nsplit hidden columns and reduce-adds into the fp32 output.
-  if (c_dtype == MEMOTR_F32 && cs == 1 && act2 == 0 && !mul)
-    return mlp2_f32_balanced(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, tc::LnIn{});
-  if (c_dtype == MEMOTR_F32) {
-    if (cs == 4) MLP2_GO(float, 4);
-    if (cs == 2) MLP2_GO(float, 2);
-    MLP2_GO(float, 1);
-  }
-  if (cs == 4) MLP2_GO(__nv_bfloat16, 4);
-  if (cs == 2) MLP2_GO(__nv_bfloat16, 2);
-  MLP2_GO(__nv_bfloat16, 1);
-#undef MLP2_GO
+  if (c_dtype == MEMOTR_F32 && act2 == 0 && !mul) return mlp2_f32_balanced(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
+  if (c_dtype == MEMOTR_F32) return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
+  return tc::launch_mlp2<__nv_bfloat16>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
 }
 
-extern "C" int memotr_mlp2_ln(const float *pre, int ldpre, const float *res, int ldres, const float *gamma, const float *beta,
-                              float eps, float *out32, int ld32, const void *W1, const float *b1, const void *W2,
-                              const float *b2, float *C, int ldc, int M, int Hd, void *stream) {
-  MEMOTR_REQUIRE(M >= 0 && pre && res && gamma && beta && W1 && b1 && W2 && C, "mlp2_ln: bad arguments");
-  MEMOTR_REQUIRE(Hd > 0 && Hd % 128 == 0, "mlp2_ln: hidden %% 128 != 0 (got %d)", Hd);
-  MEMOTR_REQUIRE(ldpre % 4 == 0 && ldres % 4 == 0 && ldc % 4 == 0 && (!out32 || ld32 % 4 == 0) && aligned16(pre) && aligned16(res) &&
-                     aligned16(gamma) && aligned16(beta) && aligned16(W1) && aligned16(W2) && aligned16(C) && aligned16(b1) &&
-                     (!b2 || aligned16(b2)) && (!out32 || aligned16(out32)),
-                 "mlp2_ln: misaligned buffer");
-  MEMOTR_REQUIRE((const void *)pre != (const void *)C, "mlp2_ln: the output must not alias the LayerNorm input");
-  MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "mlp2_ln: cuTensorMapEncodeTiled unavailable");
+// The encoder FFN with its LayerNorm in the epilogue (deformable_encoder.py:103-107 + :128-131):
+//   y = LayerNorm(res + relu(X W1^T + b1) W2^T + b2) * gamma + beta  ->  y (bf16), y32 (fp32, may be null), ypos = y + pos (bf16;
+//   pos / ypos may be null).  One launch of ceil(M / 128) CTAs (callers with more row tiles than SMs pass the first round here
+//   and run the remaining rows through memotr_mlp2 + memotr_layernorm, whose few tiles split the hidden dimension).
+extern "C" int memotr_mlp2_lnout(const void *X, int ldx, const void *W1, const float *b1, const void *W2, const float *b2,
+                                 const float *res, int ldres, const float *gamma, const float *beta, float eps, void *y, int ldy,
+                                 float *y32, int ld32, const void *pos, int ldpos, void *ypos, int ldypos, int M, int Hd,
+                                 void *stream) {
+  MEMOTR_REQUIRE(M >= 0 && X && W1 && b1 && W2 && b2 && res && gamma && beta && y, "mlp2_lnout: bad arguments");
+  MEMOTR_REQUIRE(Hd > 0 && Hd % tc::mlp::HC == 0, "mlp2_lnout: hidden %% 128 != 0 (got %d)", Hd);
+  MEMOTR_REQUIRE((pos == nullptr) == (ypos == nullptr), "mlp2_lnout: pos and ypos come together");
+  MEMOTR_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldres % 4 == 0 && (!y32 || ld32 % 4 == 0) && (!pos || (ldpos % 8 == 0 && ldypos % 8 == 0)) &&
+                     aligned16(X) && aligned16(W1) && aligned16(W2) && aligned16(y) && aligned16(b1) && aligned16(b2) && aligned16(res) &&
+                     aligned16(gamma) && aligned16(beta) && (!y32 || aligned16(y32)) && (!pos || (aligned16(pos) && aligned16(ypos))),
+                 "mlp2_lnout: misaligned buffer");
+  MEMOTR_REQUIRE(tc::encode_fn() != nullptr, "mlp2_lnout: cuTensorMapEncodeTiled unavailable");
   if (M == 0) return MEMOTR_OK;
   Epilogue ep{b2, nullptr, nullptr, nullptr, 0, 0, ACT_NONE};
-  const tc::LnIn ln{pre, res, gamma, beta, out32, ldpre, ldres, ld32, eps};
-  return mlp2_f32_balanced(nullptr, 0, W1, b1, W2, C, ldc, M, Hd, ep, (cudaStream_t)stream, ln);
+  const tc::LnOut ln{res, gamma, beta, y32, pos, ldres, ld32, ldpos, eps};
+  return tc::launch_mlp2<__nv_bfloat16>(X, ldx, W1, b1, W2, y, ldy, M, Hd, ep, (cudaStream_t)stream, 1, 0, -1, ln, ypos, ldypos);
 }

@@ -77,10 +77,16 @@ struct __align__(8) Rec {
 // window origin of level l for the tile whose first query has the normalised reference point (rx, ry): every thread that
 // needs it evaluates exactly this sequence (explicitly rounded operations: no context-dependent contraction), so the copy
 // the TMA issuer uses and the copies the decoding threads use are the same integers
-__device__ __forceinline__ int2 window_origin(const Params &P, const float *__restrict__ vr, float rx, float ry, int h, int l) {
-  const float px = __fadd_rn(__fmaf_rn(__fmul_rn(rx, __ldg(vr + 2 * l)), (float)P.hw[2 * l + 1], -0.5f), P.shift[(h * MAXL + l) * 2]);
-  const float py = __fadd_rn(__fmaf_rn(__fmul_rn(ry, __ldg(vr + 2 * l + 1)), (float)P.hw[2 * l], -0.5f), P.shift[(h * MAXL + l) * 2 + 1]);
-  return make_int2((int)floorf(__fsub_rn(px, P.radius)), (int)floorf(__fsub_rn(py, P.radius)));
+__device__ __forceinline__ int2 window_origin(const Params &P, const ClassGeom &G, const float *__restrict__ vr, float rx, float ry,
+                                              int h, int l) {
+  const int Hh = P.hw[2 * l], Ww = P.hw[2 * l + 1];
+  const float px = __fadd_rn(__fmaf_rn(__fmul_rn(rx, __ldg(vr + 2 * l)), (float)Ww, -0.5f), P.shift[(h * MAXL + l) * 2]);
+  const float py = __fadd_rn(__fmaf_rn(__fmul_rn(ry, __ldg(vr + 2 * l + 1)), (float)Hh, -0.5f), P.shift[(h * MAXL + l) * 2 + 1]);
+  int ox = (int)floorf(__fsub_rn(px, P.radius)), oy = (int)floorf(__fsub_rn(py, P.radius));
+  // keep the window on the image (one zero column / row of border is all a bilinear footprint can use): border tiles and
+  // levels smaller than their window then stage what can actually be sampled
+  ox = max(-1, min(ox, Ww + 1 - G.ww[l])), oy = max(-1, min(oy, Hh + 1 - G.wh[l]));
+  return make_int2(ox, oy);
 }
 
 struct Unit {
@@ -245,7 +251,7 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
         tc::mbar_expect_tx(win_full + b, (uint32_t)G.win_bytes);
         for (int l = 0; l < L; ++l) {
           if (!G.ww[l]) continue;
-          const int2 org = window_origin(P, vr, rx, ry, h, l);
+          const int2 org = window_origin(P, G, vr, rx, ry, h, l);
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                   tc::smem_u32(smem + wbase + G.off[l])),
@@ -264,7 +270,7 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
 #pragma unroll
           for (int j = 0; j < 4; ++j) r[j][0].off = r[j][1].off = wbase, r[j][0].w = r[j][1].w = __float2half2_rn(0.f);
           if (x < G.Wq && y < G.Hq) {    // (a query outside the level: zero-weight taps on the first bytes of the buffer)
-            const int2 org = window_origin(P, vr, rx, ry, h, l);
+            const int2 org = window_origin(P, G, vr, rx, ry, h, l);
             const float4 a = pre_xy[i][0], bb = pre_xy[i][1], w = pre_w[i];
             make_records(P, G, l, org, wbase, make_float2(a.x, a.y), w.x, r[0][0], r[0][1], n_win, n_glob);
             make_records(P, G, l, org, wbase, make_float2(a.z, a.w), w.y, r[1][0], r[1][1], n_win, n_glob);
@@ -292,7 +298,7 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
             const long q = G.q0 + y * G.Wq + x;
             const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc + q * P.ld_loc) + h * LK + j);
             const float aw = __ldg(attn + q * P.ld_attn + h * LK + j);
-            make_records(P, G, l, window_origin(P, vr, rx, ry, h, l), wbase, xy, aw, r0, r1, n_win, n_glob);
+            make_records(P, G, l, window_origin(P, G, vr, rx, ry, h, l), wbase, xy, aw, r0, r1, n_win, n_glob);
           }
           uint8_t *dst = recs + ql * G.rec_stride + (j >> 1) * 32 + (j & 1) * 8;
           *reinterpret_cast<Rec *>(dst) = r0;

@@ -306,7 +306,10 @@ extern "C" int memotr_updater_forward_cluster(const memotr_upd_params *p, void *
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  // MEMOTR_NONCOOP=1 (profiling only): plain cluster launch -- ncu cannot replay cooperative cluster launches; with the GPU to
+  // itself (kernels serialised under the profiler, grid <= number of SMs) all CTAs are resident anyway
+  const char *nc = getenv("MEMOTR_NONCOOP");
+  cfg.numAttrs = (nc && nc[0] == '1') ? 1 : 2;
   e = cudaLaunchKernelEx(&cfg, dec::upd::updater_cluster_kernel, *p);
   if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "updater_forward_cluster: launch: %s", cudaGetErrorString(e));
   return check_launch("updater_cluster");

@@ -90,12 +90,11 @@ class FrameEngine:
         self.fuse_prep = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_FUSE_PREP", "1") != "0"
                           and cfg["n_levels"] * cfg["n_enc_points"] == 16 and self.H % 2 == 0
                           and 3 * ((self.S + 127) // 128) > n_sm > 0 and self.H * 48 % 128 == 0)
-        # encoder: LayerNorm(norm1) computed inside the FFN kernel's prologue (memotr_mlp2_ln).  Opt-in (MEMOTR_FUSE_LN1=1):
-        # measured 8.7 us per layer SLOWER than the separate LayerNorm kernel -- the prologue (16 rows per warp, four in
-        # flight) sits on the critical path of every CTA (and is repeated by the tail-split CTAs), while the stand-alone
-        # kernel runs at 4.2 TB/s
-        self.fuse_ln1 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN1", "0") == "1" and self.fused_mlp
-                         and self.Fd % 128 == 0 and self.S >= 2048)
+        # encoder: norm2 (+ the fp32 master, + the next layer's query = y + pos) in the EPILOGUE of the fused FFN kernel
+        # (memotr_mlp2_lnout): no LayerNorm launch, no fp32 round trip of the pre-norm sum.  MEMOTR_FUSE_LN2=0: A/B
+        self.fuse_ln2 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN2", "1") != "0" and self.fused_mlp
+                         and self.Fd % 128 == 0 and self.S >= 2048 and n_sm > 0)
+        self.n_sm = n_sm
         # encoder gather from TMA-staged value-map windows in shared memory (csrc/msda_window.cu); MEMOTR_MSDA_WINDOW=0: the
         # global-memory gather (bit-identical results)
         self.msda_window = (self.fuse_prep and self.L <= 5 and self.H <= 16 and cfg["n_enc_points"] % 2 == 0
@@ -269,7 +268,6 @@ class FrameEngine:
         self.attw = f(S, self.H, LK)
         self.att = e(S, C)
         self.pre = f(S, C)                                           # pre-LayerNorm GEMM output, always fp32
-        self.pre2 = f(S, C) if self.fuse_ln1 else None               # FFN output when LayerNorm 1 runs inside the FFN kernel
         self.src1 = e(S, C)
         # fp32 residual stream: in fp32 mode the activation buffers are their own masters
         fp32 = self.mode == "fp32"
@@ -489,14 +487,14 @@ class FrameEngine:
         self._ck(self.lib.memotr_linear(_p(x), ldx, _p(L.w), L.K, _p(L.b), _p(mul), ldmul, _p(add), ldadd, _p(rowzero),
                                         _p(out), ldo, M, L.N, L.K, self.dt, cd, act, path, self._st()), "linear")
 
-    def mlp2(self, x, ldx, L1, L2, out, ldo, M, hid, act2=0, mul=None, ldmul=0, c_dtype=None):
+    def mlp2(self, x, ldx, L1, L2, out, ldo, M, hid, act2=0, mul=None, ldmul=0, c_dtype=None, force=False):
         """out = act2(relu(x L1^T + b1) L2^T + b2) [* mul].  bf16 mode with a 256-wide input/output: ONE tensor-core kernel
         with the hidden activation kept on chip (memotr_mlp2); otherwise two GEMMs through the scratch buffer `hid`."""
         cd = self.dt if c_dtype is None else c_dtype
         # one CTA per 128 rows walks the hidden chunks serially: worth it when there are enough row tiles to fill the
         # GPU (encoder, 175 tiles); on <= 400 decoder rows two GEMMs are as fast or faster (measured 51 vs 30 us for the
         # 2048-wide FFN, 22.5 vs 21.4 us for the 256-wide MLPs; profiles/r01_micro_gemm_v3_fused.json)
-        worth = M >= 2048
+        worth = M >= 2048 or force
         if self.fused_mlp and worth and self.mode == "bf16" and L1.K == 256 and L2.N == 256 and L1.N % 128 == 0 \
                 and L2.K == L1.N:
             self._ck(self.lib.memotr_mlp2(_p(x), ldx, _p(L1.w), _p(L1.b), _p(L2.w), _p(L2.b), _p(mul), ldmul, _p(out), ldo,
@@ -656,23 +654,30 @@ class FrameEngine:
                 self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
                 self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
             self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
-            if self.fuse_ln1:        # norm1 inside the FFN kernel: no LayerNorm launch, no bf16 X round trip
-                g1, b1 = ly["norm1"]
-                self._ck(self.lib.memotr_mlp2_ln(_p(self.pre), C, _p(self.src32), C, _p(g1), _p(b1), 1e-5, _p(self.src1_32),
-                                                 C, _p(ly["lin1"].w), _p(ly["lin1"].b), _p(ly["lin2"].w), _p(ly["lin2"].b),
-                                                 _p(self.pre2), C, S, self.Fd, st()), "mlp2_ln")
-                ffn_out = self.pre2
+            self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
+            tf = self.timer is not None and getattr(self, "time_ffn", False)   # (event nodes cost PDL overlap: opt-in)
+            if tf:
+                _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 5 + 2 * i, st()), "timer_record")
+            if self.fuse_ln2:
+                # first round of row tiles (one CTA per SM): FFN + norm2 in one kernel; the remaining rows: FFN with the hidden
+                # dimension split over the idle SMs, then the stand-alone LayerNorm on those rows only
+                g2, b2 = ly["norm2"]
+                tiles = (S + 127) // 128
+                main = S if tiles <= self.n_sm else self.n_sm * 128
+                l1, l2 = ly["lin1"], ly["lin2"]
+                self._ck(self.lib.memotr_mlp2_lnout(_p(self.src1), C, _p(l1.w), _p(l1.b), _p(l2.w), _p(l2.b), _p(self.src1_32), C,
+                                                    _p(g2), _p(b2), 1e-5, _p(self.src_tok), C, _p(self.src32), C, _p(self.pos_tok), C,
+                                                    _p(self.q_tok), C, main, self.Fd, st()), "mlp2_lnout")
+                if main < S:
+                    self.mlp2(self.src1[main:], C, l1, l2, self.pre[main:], C, S - main, self.hid, c_dtype=F32, force=True)
+                    self.ln(self.pre[main:], ly["norm2"], self.src_tok[main:], S - main, x2=self.src1_32[main:],
+                            y32=self.src32[main:], pos=self.pos_tok[main:], ypos=self.q_tok[main:])
             else:
-                self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
-                tf = self.timer is not None and getattr(self, "time_ffn", False)   # (event nodes cost PDL overlap: opt-in)
-                if tf:
-                    _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 5 + 2 * i, st()), "timer_record")
                 self.mlp2(self.src1, C, ly["lin1"], ly["lin2"], self.pre, C, S, self.hid, c_dtype=F32)
-                if tf:
-                    _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 6 + 2 * i, st()), "timer_record")
-                ffn_out = self.pre
-            self.ln(ffn_out, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
-                    ypos=self.q_tok)
+                self.ln(self.pre, ly["norm2"], self.src_tok, S, x2=self.src1_32, y32=self.src32, pos=self.pos_tok,
+                        ypos=self.q_tok)
+            if tf:
+                _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 6 + 2 * i, st()), "timer_record")
         memory = self.src_tok
         if self.debug_enc is not None:
             self.debug_enc.append(self.src32.float().clone())
@@ -1034,40 +1039,3 @@ class ClipRunner:
         torch.cuda.current_stream(self.eng.dev).synchronize()
         self.check()
         return out
-
-
-def smoke(dev):
-    """Tiny end-to-end engine run against the CPU oracle (called by __graft_entry__.smoke)."""
-    from oracle import frame as oframe          # checker, smoke only
-    from . import synthetic as synth
-    cfg = synth.small_cfg()
-    sd = synth.hot_path_state_dict(cfg, seed=0)
-    x = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 5, seed=1)
-    eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 5, dev, mode="fp32")
-    eng.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
-    eng.forward()
-    torch.cuda.synchronize()
-    with torch.no_grad():
-        want = oframe.frame_forward(sd, x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"],
-                                    x["tracks"]["query_embed"], cfg)
-    got = eng.results()
-    for k in ("pred_logits", "pred_bboxes", "outputs"):
-        err = (got[k].cpu() - want[k]).abs().max() / want[k].abs().max()
-        assert err < 1e-4, (k, float(err))
-    # the whole submit loop with the tracker glue on the device: three frames from an empty table against the oracle
-    from oracle import tracker as otr           # checker, smoke only
-    thr = dict(det_score_thresh=0.66, track_score_thresh=0.6, miss_tolerance=2, result_score_thresh=0.62)
-    sd = synth.hot_path_state_dict(cfg, seed=5)
-    eng = FrameEngine(sd, cfg, synth.SMALL_SHAPES, 10, dev, mode="fp32", tracker=thr)
-    tracks, max_id = otr.empty_tracks(cfg["d_model"], cfg["num_classes"]), 0
-    for t in range(3):
-        fr = synth.frame_inputs(cfg, synth.SMALL_SHAPES, 0, seed=10 + t)
-        eng.load_frame(fr["srcs"], fr["masks"], fr["pos"], eng.in_track_ref, eng.in_track_embed)
-        eng.step()
-        tracks, max_id, _, _ = otr.clip_step(sd, cfg, fr, tracks, max_id, thr["det_score_thresh"],
-                                             thr["track_score_thresh"], thr["miss_tolerance"])
-        got = eng.table.active()
-        assert got["ids"].cpu().tolist() == tracks["ids"].tolist(), (t, got["ids"].tolist(), tracks["ids"].tolist())
-        assert got["disappear_time"].cpu().tolist() == tracks["disappear_time"].tolist(), t
-        err = (got["boxes"].cpu() - tracks["boxes"]).abs().max() / tracks["boxes"].abs().max()
-        assert err < 1e-4, (t, float(err))

@@ -202,18 +202,20 @@ def sine_embed(pts, dim_t, scale4=None, apply_sigmoid=False, out_dtype=torch.flo
     return out
 
 
-def mlp2_ln(pre, res, gamma, beta, w1, b1, w2, b2, eps=1e-5, want_x32=True):
-    """relu(X W1^T + b1) W2^T + b2 with X = LayerNorm(pre + res) computed inside the kernel (fp32 pre / res (M,256), bf16
-    weights).  -> (out fp32 (M,256), X fp32 or None)."""
-    M, Hd = pre.shape[0], w1.shape[0]
-    out = torch.empty((M, 256), dtype=torch.float32, device=pre.device)
-    x32 = torch.empty((M, 256), dtype=torch.float32, device=pre.device) if want_x32 else None
-    with torch.cuda.device(pre.device):
-        rc = _lib.lib().memotr_mlp2_ln(_lib.ptr(pre), _ld(pre), _lib.ptr(res), _ld(res), _lib.ptr(gamma), _lib.ptr(beta),
-                                       float(eps), _lib.ptr(x32), 256, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2),
-                                       _lib.ptr(b2), _lib.ptr(out), 256, M, Hd, _lib.stream_ptr())
-    _lib.check(rc, "memotr_mlp2_ln")
-    return out, x32
+def mlp2_lnout(x, w1, b1, w2, b2, res, gamma, beta, pos=None, eps=1e-5, want_f32=True):
+    """LayerNorm(res + relu(x W1^T + b1) W2^T + b2) in the FFN kernel's epilogue.  x (M,256) bf16, res (M,256) fp32, pos bf16
+    or None.  -> (y bf16, y32 fp32 or None, y + pos bf16 or None)."""
+    M, Hd = x.shape[0], w1.shape[0]
+    y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
+    y32 = torch.empty((M, 256), dtype=torch.float32, device=x.device) if want_f32 else None
+    ypos = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device) if pos is not None else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_mlp2_lnout(_lib.ptr(x), _ld(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                          _lib.ptr(res), _ld(res), _lib.ptr(gamma), _lib.ptr(beta), float(eps), _lib.ptr(y), 256,
+                                          _lib.ptr(y32), 256, _lib.ptr(pos), _ld(pos) if pos is not None else 0, _lib.ptr(ypos),
+                                          256, M, Hd, _lib.stream_ptr())
+    _lib.check(rc, "memotr_mlp2_lnout")
+    return y, y32, ypos
 
 
 def pos_embed_sine(mask, num_pos_feats=128, temperature=20, scale=6.283185307179586):

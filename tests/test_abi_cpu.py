@@ -122,7 +122,7 @@ def test_window_plan_host_logic():
         sizes = [h * w for h, w in shapes]
         assert 1 <= plan["classes"] <= 4 and plan["smem"] <= 224 * 1024
         assert plan["global_q0"] == sum(sizes[:plan["classes"]])
-        assert plan["global_ctas"] == -(-(sum(sizes) - plan["global_q0"]) * 8 * 4 // 384)
+        assert plan["global_ctas"] == -(-(sum(sizes) - plan["global_q0"]) * 8 * 4 // 768)
         units = 0
         for c in plan["cls"]:
             h, w = shapes[c["level"]]

@@ -138,11 +138,9 @@ def test_linear_bf16_tensor_core_epilogues_and_views(M):
     assert rel_err(a, base) < 1e-5
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
 @pytest.mark.parametrize("M,Hd", [(128, 256), (400, 256), (100, 2048), (400, 2048), (22323, 2048), (1000, 1024)])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
-def test_fused_mlp2_tensor_core(M, Hd, out_dtype, cluster, monkeypatch):
-    monkeypatch.setenv("MEMOTR_MLP_CLUSTER", str(cluster))     # 1 = plain, 2/4 = TMA-multicast thread-block clusters
+def test_fused_mlp2_tensor_core(M, Hd, out_dtype):
     """relu(x W1^T + b1) W2^T + b2 with the hidden activation kept on chip; checker: fp64 on the bf16-rounded operands,
     with the hidden activation rounded to bf16 exactly as the kernel does before the second GEMM."""
     g = _g(M + Hd)
@@ -158,14 +156,14 @@ def test_fused_mlp2_tensor_core(M, Hd, out_dtype, cluster, monkeypatch):
     assert rel_err(got, want) < (1e-3 if out_dtype == torch.float32 else 6e-3)
 
 
-@pytest.mark.parametrize("split", [0, 2, 4, 8, 16])
-@pytest.mark.parametrize("M,Hd", [(22323, 2048), (300, 2048), (700, 1024), (128 * 148 + 1, 512), (128 * 221, 256)])
-def test_fused_mlp2_split_hidden(M, Hd, split, monkeypatch):
-    """Split-K over the hidden dimension (CTA (tile, split) reduce-adds its partial product into the zeroed fp32 output
-    with a TMA reduce-store); split = 0 is the automatic choice.  Also into a strided view whose neighbours must stay."""
-    if split:
-        monkeypatch.setenv("MEMOTR_MLP_SPLIT", str(split))
-    g = _g(M + Hd + split)
+@pytest.mark.parametrize("tail", ["1", "0"])
+@pytest.mark.parametrize("M,Hd", [(22323, 2048), (300, 2048), (700, 1024), (128 * 148 + 1, 512), (128 * 221, 256), (3379, 2048)])
+def test_fused_mlp2_split_hidden(M, Hd, tail, monkeypatch):
+    """Hidden-dimension split of launches with few row tiles and of the tiles beyond one round of SMs (CTA (tile, split)
+    reduce-adds its partial product into the zeroed fp32 output with a TMA reduce-store); MEMOTR_MLP_TAIL=0 switches it off.
+    Also into a strided view whose neighbours must stay."""
+    monkeypatch.setenv("MEMOTR_MLP_TAIL", tail)
+    g = _g(M + Hd)
     x = torch.randn(M, 256, generator=g).bfloat16()
     w1 = (torch.randn(Hd, 256, generator=g) / 16).bfloat16()
     w2 = (torch.randn(256, Hd, generator=g) / math.sqrt(Hd)).bfloat16()
@@ -181,26 +179,33 @@ def test_fused_mlp2_split_hidden(M, Hd, split, monkeypatch):
     assert rel_err(again.cpu(), want) < 1e-3
 
 
-@pytest.mark.parametrize("M", [300, 22323, 128 * 148 + 77])
-def test_fused_mlp2_with_layernorm_prologue(M):
-    """memotr_mlp2_ln == memotr_layernorm followed by memotr_mlp2 (the LayerNorm runs in the FFN kernel's prologue, its
-    bf16 result goes straight into the tensor-core operand tile); also against fp64."""
+@pytest.mark.parametrize("M,with_pos", [(300, True), (128 * 148, True), (128 * 148, False), (18000, True), (77, False)])
+def test_fused_mlp2_with_layernorm_epilogue(M, with_pos):
+    """memotr_mlp2_lnout == memotr_mlp2 (fp32 out) followed by memotr_layernorm with residual: y (bf16), fp32 master and
+    y + pos (the three things the next encoder layer reads); also against fp64 on the bf16-rounded operands."""
     g = _g(M)
     Hd = 2048
-    pre, res = torch.randn(M, 256, generator=g), torch.randn(M, 256, generator=g)
+    x = torch.randn(M, 256, generator=g).bfloat16()
+    res = torch.randn(M, 256, generator=g)
+    pos = torch.randn(M, 256, generator=g).bfloat16() if with_pos else None
     gamma, beta = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
     w1 = (torch.randn(Hd, 256, generator=g) / 16).bfloat16()
     w2 = (torch.randn(256, Hd, generator=g) / math.sqrt(Hd)).bfloat16()
     b1, b2 = torch.randn(Hd, generator=g), torch.randn(256, generator=g)
-    d = lambda t: t.to(DEV)                                                                 # noqa: E731
-    out, x32 = K().mlp2_ln(d(pre), d(res), d(gamma), d(beta), d(w1), d(b1), d(w2), d(b2))
-    y, y32 = K().layernorm(d(pre), d(gamma), d(beta), x2=d(res), out_dtype=torch.bfloat16, want_f32=True)
-    two = K().mlp2(y, d(w1), d(b1), d(w2), d(b2), out_dtype=torch.float32)
-    assert torch.equal(x32, y32)                                       # the same LayerNorm arithmetic
-    assert rel_err(out.cpu().numpy(), two.cpu().numpy()) < 2e-6        # same operands, different summation split at most
-    x = F.layer_norm(pre.double() + res.double(), (256,), gamma.double(), beta.double(), 1e-5)
-    h = F.linear(x.float().bfloat16().double(), w1.double(), b1.double()).relu().float().bfloat16().double()
-    assert rel_err(out.cpu().numpy(), F.linear(h, w2.double(), b2.double()).numpy()) < 2e-3
+    d = lambda t: t.to(DEV) if t is not None else None                                      # noqa: E731
+    y, y32, ypos = K().mlp2_lnout(d(x), d(w1), d(b1), d(w2), d(b2), d(res), d(gamma), d(beta), pos=d(pos))
+    two = K().mlp2(d(x), d(w1), d(b1), d(w2), d(b2), out_dtype=torch.float32)
+    ry, ry32 = K().layernorm(two, d(gamma), d(beta), x2=d(res), out_dtype=torch.bfloat16, want_f32=True)
+    assert rel_err(y32.cpu().numpy(), ry32.cpu().numpy()) < 5e-6        # same operands; one-pass vs two-pass moments
+    assert rel_err(y.float().cpu().numpy(), ry.float().cpu().numpy()) < 8e-3   # (a bf16 ulp where the fp32 values straddle a boundary)
+    h = F.linear(x.double(), w1.double(), b1.double()).relu().float().bfloat16().double()
+    want = F.layer_norm(F.linear(h, w2.double(), b2.double()) + res.double(), (256,), gamma.double(), beta.double(), 1e-5)
+    assert rel_err(y32.cpu().numpy(), want.numpy()) < 1e-3
+    assert rel_err(y.float().cpu().numpy(), want.numpy()) < 6e-3
+    if with_pos:
+        assert rel_err(ypos.float().cpu().numpy(), (want + pos.double()).numpy()) < 6e-3
+    else:
+        assert ypos is None
 
 
 def test_fused_mlp2_epilogues_and_views():

@@ -191,7 +191,8 @@ def test_memotr_module_eval_routes_through_the_engine_and_matches_reference(tag,
         assert rel_err(v.cpu().numpy(), g[k]) < tol, (k, rel_err(v.cpu().numpy(), g[k]))
     with torch.no_grad():                       # a second frame reuses the engine (graph replay) and gives the same answer
         res2 = model(frame=frame, tracks=[tr])
-    assert torch.equal(res2["pred_bboxes"], res["pred_bboxes"]) and len(model._engines) == 1
+    # (bit-equal in fp32 mode; the bf16 FFN adds its split-K partial sums with reduce-stores whose order is not fixed)
+    assert rel_err(res2["pred_bboxes"].cpu().numpy(), res["pred_bboxes"].cpu().numpy()) < 1e-3 and len(model._engines) == 1
 
 
 def test_memotr_module_autograd_route_and_query_updater_forward():

@@ -200,7 +200,7 @@ def test_backward_full_encoder_size_vs_c_oracle_and_reference_op():
         assert rel_err(ga, ra.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025])
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])      # the reference list, models/ops/test.py:85-86
 def test_gradcheck_like_reference(channels):
     """models/ops/test.py:63-78 -- torch.autograd.gradcheck in fp64 through MSDeformAttnFunction."""
     from torch.autograd import gradcheck

@@ -246,38 +246,39 @@ MEDIUM_SHAPES = ((64, 104), (32, 52), (16, 26), (8, 13))       # S = 8736: large
 
 
 def _pick_thresholds(cfg, sd, frames, need):
-    """Thresholds in the untrained network's score range with every decision of the 6-frame oracle clip at least `need`
-    (in LOGIT units) away from its threshold: a grid search over the detection threshold."""
+    """Thresholds in the untrained network's score range such that every decision of the oracle clip (births, misses,
+    result filter) is at least `need` LOGITS away from its threshold: the detection threshold is searched over the gaps of
+    the first frame's sorted logits, the track threshold over three offsets below it."""
     import math
+    sig = lambda z: 1.0 / (1.0 + math.exp(-z))                                           # noqa: E731
+    nd = cfg["n_det_queries"]
     with torch.no_grad():
         fr = frames[0]
         out = oframe.frame_forward(sd, fr["srcs"], fr["masks"], fr["pos"], torch.zeros(0, 4), torch.zeros(0, cfg["d_model"]), cfg)
     lg = out["pred_logits"][0, :, 0].sort().values
     best = None
-    for q in torch.linspace(0.55, 0.9, 15).tolist():
-        det_logit = float(lg[int(q * (len(lg) - 1))]) + 1e-3
-        sig = lambda z: 1.0 / (1.0 + math.exp(-z))                                       # noqa: E731
-        thr = dict(det_score_thresh=sig(det_logit), track_score_thresh=sig(det_logit - 0.25), miss_tolerance=2,
-                   result_score_thresh=sig(det_logit - 0.1))
-        tracks, max_id, worst = otr.empty_tracks(cfg["d_model"], cfg["num_classes"]), 0, 1e9
-        clip = []
-        for f in frames:
-            tracks, max_id, o, _ = otr.clip_step(sd, cfg, f, tracks, max_id, thr["det_score_thresh"], thr["track_score_thresh"],
-                                                 thr["miss_tolerance"])
-            nd = cfg["n_det_queries"]
-            z = o["pred_logits"][:, 0]
-            worst = min(worst, float((z[:nd] - det_logit).abs().min()))
-            if len(z) > nd:
-                worst = min(worst, float((z[nd:] - (det_logit - 0.25)).abs().min()))
-            if len(tracks["ids"]):
-                zt = tracks["logits"][:, 0]
-                worst = min(worst, float((zt - (det_logit - 0.1)).abs().min()), float(zt.abs().min()))   # result filter, update_thresh 0.5
-            ids, boxes, _ = otr.frame_results(tracks, thr["result_score_thresh"], 1920, 1080)
-            clip.append(({k: v.clone() for k, v in tracks.items()}, max_id, ids, boxes))
-        n_max = max(len(c[0]["ids"]) for c in clip)
-        if best is None or worst > best[0]:
-            if 2 <= n_max <= 24:
-                best = (worst, thr, clip)
+    for det_logit in [float((lg[i] + lg[i + 1]) / 2) for i in range(len(lg) // 2, len(lg) - 1)]:
+        for dtrk in (0.15, 0.3, 0.5):
+            thr = dict(det_score_thresh=sig(det_logit), track_score_thresh=sig(det_logit - dtrk), miss_tolerance=2,
+                       result_score_thresh=sig(det_logit - dtrk / 2))
+            tracks, max_id, worst, clip, deaths = otr.empty_tracks(cfg["d_model"], cfg["num_classes"]), 0, 1e9, [], False
+            for f in frames:
+                before = set(tracks["ids"].tolist())
+                tracks, max_id, o, _ = otr.clip_step(sd, cfg, f, tracks, max_id, thr["det_score_thresh"],
+                                                     thr["track_score_thresh"], thr["miss_tolerance"])
+                z = o["pred_logits"][:, 0]
+                worst = min(worst, float((z[:nd] - det_logit).abs().min()))
+                if len(z) > nd:
+                    worst = min(worst, float((z[nd:] - (det_logit - dtrk)).abs().min()))
+                if len(tracks["ids"]):
+                    zt = tracks["logits"][:, 0]
+                    worst = min(worst, float((zt - (det_logit - dtrk / 2)).abs().min()), float(zt.abs().min()))
+                deaths |= not before <= set(tracks["ids"].tolist())
+                ids, boxes, _ = otr.frame_results(tracks, thr["result_score_thresh"], 1920, 1080)
+                clip.append(({k: v.clone() for k, v in tracks.items()}, max_id, ids, boxes))
+            n_max = max(len(c[0]["ids"]) for c in clip)
+            if 2 <= n_max <= 28 and (best is None or (deaths, worst) > (best[3], best[0])):
+                best = (worst, thr, clip, deaths)
     assert best is not None and best[0] >= need, f"no threshold with a decision margin >= {need} logits (best {best and best[0]})"
     return best[1], best[2], best[0]
 
@@ -289,14 +290,14 @@ def test_engine_bf16_clip_runner_device_tracker_matches_oracle():
     above the live count (padded rows in every attention): identities, labels, disappear times and result ids BIT-exact
     against the submit loop restated in oracle/, boxes and embeddings within the bf16 bar."""
     from memotr_b200.engine import ClipRunner, FrameEngine
-    cfg = dict(synth.small_cfg(), n_det_queries=40, n_enc_layers=3)
-    sd = synth.reference_init_state_dict(cfg, seed=3)
+    cfg = dict(synth.small_cfg(), n_det_queries=12, n_enc_layers=3)
+    sd = synth.reference_init_state_dict(cfg, seed=5)
     frames = []
     for t in range(6):
         fr = synth.frame_inputs(cfg, MEDIUM_SHAPES, 0, seed=40 + t, padded=True)
         fr["pos"] = [oframe.position_embedding_sine(m) for m in fr["masks"]]
         frames.append(fr)
-    thr, want, margin = _pick_thresholds(cfg, sd, frames, need=0.02)
+    thr, want, margin = _pick_thresholds(cfg, sd, frames, need=0.015)
     print("thresholds", {k: round(v, 5) if isinstance(v, float) else v for k, v in thr.items()}, "margin (logits)", round(margin, 4),
           "live per frame", [len(w[0]["ids"]) for w in want])
     eng = FrameEngine(sd, cfg, MEDIUM_SHAPES, 32, DEV, mode="bf16", tracker=thr, ori_size=(1920, 1080),

@@ -6,7 +6,7 @@ from memotr_b200 import synthetic as synth
 from memotr_b200.engine import FrameEngine
 
 cfg = synth.dancetrack_cfg()
-sd = synth.hot_path_state_dict(cfg, seed=0)
+sd = synth.reference_init_state_dict(cfg, seed=0)
 x = synth.frame_inputs(cfg, synth.DANCETRACK_SHAPES, 100, seed=1)
 eng = FrameEngine(sd, cfg, synth.DANCETRACK_SHAPES, 100, "cuda", mode="bf16")
 eng.load_frame(x["srcs"], x["masks"], x["pos"], x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
