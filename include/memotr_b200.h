@@ -187,6 +187,35 @@ MEMOTR_API int memotr_mlp2_lnout(const void *X, int ldx, const void *W1, const f
                                  float *y32, int ld32, const void *pos, int ldpos, void *ypos, int ldypos, int M, int Hd,
                                  void *stream);
 
+/* The dense half of an encoder layer in ONE kernel per 128-row tile (models/deformable_encoder.py:124-131 with
+ * models/ops/modules/ms_deform_attn.py:129):
+ *   x = LayerNorm1(src32 + att Wout^T + bout)                      front GEMM + LayerNorm, x never leaves the SM as a GEMM operand
+ *   y = LayerNorm2(x + relu(x W1^T + b1) W2^T + b2)                fused FFN + LayerNorm epilogue (memotr_mlp2_lnout)
+ * att (M,256) bf16 = the gather's output rows; src32 (M,256) fp32 residual stream (may alias y32: a tile reads its rows
+ * before it writes them); outputs x32 (fp32 x, residual of norm2), y (bf16), y32 (fp32), ypos = y + pos (bf16); pre (M,256)
+ * fp32 scratch for the row tiles beyond one round of SMs, which run with the hidden dimension split and get LayerNorm2 from
+ * memotr_layernorm.  Replaces output_proj + norm1 + linear1/relu/linear2 + norm2: four launches and ~140 MB of HBM round
+ * trips per layer. */
+MEMOTR_API int memotr_encoder_dense_block(const void *att, int ldatt, const void *Wout, const float *bout, const float *src32,
+                                          int ldsrc, const float *gamma1, const float *beta1, float *x32, int ldx32,
+                                          const void *W1, const float *b1, const void *W2, const float *b2, const float *gamma2,
+                                          const float *beta2, const void *pos, int ldpos, void *y, int ldy, float *y32, int ld32,
+                                          void *ypos, int ldypos, float *pre, int ldpre, int M, int Hd, float eps, void *stream);
+
+/*
+ * y = LayerNorm(res + A W^T + bias) * gamma + beta for a 256 x 256 projection (A, W bf16; res fp32): y bf16, y32 fp32.
+ * `src = norm1(src + output_proj(attn))` of models/deformable_encoder.py:124-126 + models/ops/modules/ms_deform_attn.py:129
+ * as one tcgen05 kernel per 128-row tile (the product never leaves the SM).  Replaces memotr_linear + memotr_layernorm on
+ * that pair.
+ */
+MEMOTR_API int memotr_linear256_layernorm(const void *A, int lda, const void *W, const float *bias, const float *res, int ldres,
+                                          const float *gamma, const float *beta, float eps, void *y, int ldy, float *y32, int ld32,
+                                          int M, void *stream);
+
+/* Profiling hook (tools/micro_dense.py), not part of the reference surface: every later memotr_mlp2* / encoder_dense_block
+ * launch writes 8 clock64 stamps per CTA into `buf` (device int64[8 x CTAs]); null switches it off again. */
+MEMOTR_API int memotr_mlp2_debug_stamps(long long *buf);
+
 /*
  * y = LayerNorm(x [+ x2]) (C == 256, eps as given, affine fp32); optional ypos = y + pos and fp32 copy y32.
  * models/deformable_encoder.py:124-130, models/deformable_decoder.py:251-252,313-318, models/ffn.py:23-24,

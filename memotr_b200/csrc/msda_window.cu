@@ -48,6 +48,7 @@ struct ClassGeom {
   int ww[MAXL], wh[MAXL];       // window extent in pixels per value level (0: no window, the level's taps read global memory)
   int off[MAXL];                // byte offset of the window in dynamic shared memory
   int win_bytes, rec_off, rec_stride;
+  int flag_off;                 // one byte per (query of the tile, level): some point of that level reads global memory
   float tiles_x_rcp;
 };
 
@@ -400,6 +401,276 @@ msda_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Pa
   }
 }
 
+
+// =====================================================================================================================
+// K = 4 points x L = 4 levels (the configuration of every released MeMOTR / Deformable-DETR model): the same pipeline with
+// everything the general kernel decides at run time decided here at compile time.  What the profile of the general kernel
+// showed (profiles/r02_msda_window_v4_ncu.md): 37 M warp instructions per encoder launch of which 7 M spin in mbarrier
+// try-wait loops, the tap warps waiting for records 16 % of their samples -- the DECODE side was the critical path (684
+// instructions per warp and unit, low ILP, two warps per scheduler) -- and 81 instructions per (4 queries, level) in the tap
+// loop against 42 that do work.  Here:
+//   * a decode thread owns ONE level (pair index = thread + 256 i  ->  level = thread % 4): window origin, window bounds as
+//     floats, the level's extents and the record base are per-unit registers; a point inside its window costs ~30
+//     instructions (the window test in floats implies the reference's open-interval test because windows are clamped to
+//     the image plus one zero border; everything else goes through slow_record);
+//   * hand-offs are hardware named barriers in producer / consumer form (bar.arrive by the producers, bar.sync by the
+//     consumers): a waiting warp is parked, not spinning;
+//   * decode publishes one flag byte per (query, level); a tap warp reads the four bytes of a query as one word and, when no
+//     lane of the warp has a global-memory tap (the common case), runs the four levels fully unrolled without a test.
+// Results are bit-identical to the general kernel and to msda_fwd_h16 (tests/test_msda_window_gpu.py).
+// =====================================================================================================================
+__device__ __noinline__ uint4 slow_record(const int *hw, const int *lsi, int l, uint32_t wbase, float2 xy, float aw) {
+  const int Hh = hw[2 * l], Ww = hw[2 * l + 1];
+  const float Hf = (float)Hh, Wf = (float)Ww;
+  const float h_im = __fmaf_rn(xy.y, Hf, -0.5f), w_im = __fmaf_rn(xy.x, Wf, -0.5f);
+  if (!(h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf)) return make_uint4(wbase, 0u, wbase, 0u);   // (.cuh:288; NaN too)
+  const h16::Point p = h16::decode(xy, aw, Hh, Ww);
+  const uint32_t flags = 0x80000000u | (p.yc[1] == p.yc[0] ? 0x40000000u : 0u);
+  const uint32_t row = (uint32_t)(lsi[l] + p.yc[0] * Ww);
+  return make_uint4(flags | (row + (uint32_t)p.xc[0]), *reinterpret_cast<const uint32_t *>(&p.ws[0]), flags | (row + (uint32_t)p.xc[1]),
+                    *reinterpret_cast<const uint32_t *>(&p.ws[1]));
+}
+
+#define MEMOTR_BAR_ARRIVE(id) asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(THREADS) : "memory")
+#define MEMOTR_BAR_SYNC(id) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory")
+
+__global__ void __launch_bounds__(THREADS, 1)
+msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params P, const __half *__restrict__ value,
+                        const float *__restrict__ loc, const float *__restrict__ attn, const float *__restrict__ vr,
+                        unsigned long long *__restrict__ stats, __nv_bfloat16 *__restrict__ out) {
+  constexpr int L = 4, LK = 16;
+  constexpr int REC_FULL = 1, BUF_FREE = 3;       // named barriers REC_FULL + b, BUF_FREE + b (b = buffer 0 / 1)
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t win_full[2];
+  const int tid = threadIdx.x, H = P.H;
+
+  // ------------------------------------------------------------------------------------------- global-memory role
+  if ((int)blockIdx.x < P.n_glob_blocks) {
+    pdl_grid_sync();
+    const int n_qh = (P.S - P.glob_q0) * H;
+    const int qh = (blockIdx.x * THREADS + tid) >> 2, sub = tid & 3;
+    if (qh >= n_qh) return;
+    const int q = P.glob_q0 + qh / H, m = qh % H;
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = 0.f;
+    h16::gather_global<0>(value + m * 32 + sub * 8, h16::ShapesI32{P.hw, P.lsi},
+                           reinterpret_cast<const float2 *>(loc + (long)q * P.ld_loc) + m * LK,
+                           attn + (long)q * P.ld_attn + m * LK, L, 4, P.xs, 0, 1, acc0, acc1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc0[c] += acc1[c];
+    *reinterpret_cast<uint4 *>(out + ((long)q * H + m) * 32 + sub * 8) = f32x8_to_bf16(acc0);
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------------- window role (persistent)
+  const int n_units = P.cls[P.n_cls - 1].unit0 + P.cls[P.n_cls - 1].n_units;
+  const int stride = gridDim.x - P.n_glob_blocks;
+  const int first = blockIdx.x - P.n_glob_blocks;
+  if (tid == 0) {
+    tc::mbar_init(win_full, 1), tc::mbar_init(win_full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_grid_sync();
+
+  if (tid >= TAP_WARPS * 32) {
+    // =========================================================================================== decode warps
+    const int dt = tid - TAP_WARPS * 32, l = dt & 3, qd = dt >> 2;      // this thread: level l of the queries qd, qd + 64
+    const float Hf = (float)P.hw[2 * l], Wf = (float)P.hw[2 * l + 1];
+    int n_win = 0, n_glob = 0;                   // (profiling only)
+    float4 pre_xy[2][2], pre_w[2];
+    auto prefetch = [&](const Unit &t) {        // locations / weights of the unit's points, one unit ahead of their use
+      const ClassGeom &G = P.cls[t.c];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ql = qd + 64 * i;
+        const int x = t.tx * G.tw + (ql & (G.tw - 1)), y = t.ty * G.th + (ql >> G.tw_shift);
+        pre_w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pre_xy[i][0] = pre_xy[i][1] = pre_w[i];
+        if (ql < G.tw * G.th && x < G.Wq && y < G.Hq) {
+          const long q = G.q0 + y * G.Wq + x;
+          const float4 *pl = reinterpret_cast<const float4 *>(loc + q * P.ld_loc + (t.h * LK + l * 4) * 2);
+          pre_xy[i][0] = __ldg(pl), pre_xy[i][1] = __ldg(pl + 1);
+          pre_w[i] = __ldg(reinterpret_cast<const float4 *>(attn + q * P.ld_attn + t.h * LK + l * 4));
+        }
+      }
+    };
+    Unit t = unit_of(P, first < n_units ? first : 0);
+    if (first < n_units) prefetch(t);
+    int n = 0;
+    for (int unit = first; unit < n_units; unit += stride, ++n) {
+      const int b = n & 1;
+      const ClassGeom &G = P.cls[t.c];
+      const int TQ = G.tw * G.th, ww = G.ww[l], wh = G.wh[l];
+      const uint32_t wbase = (uint32_t)(b * P.stage_bytes);
+      // (any origin is correct as long as the copy and the records agree: the fast division is the same instruction sequence
+      //  on the same operands in every thread)
+      const float rx = __fdividef((float)(t.tx * G.tw) + 0.5f, __ldg(vr + 2 * G.lq) * (float)G.Wq);
+      const float ry = __fdividef((float)(t.ty * G.th) + 0.5f, __ldg(vr + 2 * G.lq + 1) * (float)G.Hq);
+      const int2 org = window_origin(P, G, vr, rx, ry, t.h, l);
+      const float oxf = (float)org.x, oyf = (float)org.y;
+      const float xmaxf = ww ? (float)(org.x + ww - 2) : -3e38f, ymaxf = (float)(org.y + wh - 2);
+      const int vbase = (int)wbase + G.off[l] - (org.y * ww + org.x) * 64;      // byte offset of the level's pixel (0, 0)
+      if (n >= 2) MEMOTR_BAR_SYNC(BUF_FREE + b);                               // the tap warps have finished unit n - 2
+      if (dt < L) {
+        if (dt == 0) tc::mbar_expect_tx(win_full + b, (uint32_t)G.win_bytes);
+        __syncwarp(0xfu);
+        if (ww)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                  tc::smem_u32(smem + wbase + G.off[l])),
+              "l"(&maps.m[t.c * MAXL + l]), "r"(tc::smem_u32(win_full + b)), "r"(t.h * 32), "r"(org.x), "r"(org.y)
+              : "memory");
+      }
+      uint8_t *recs = smem + wbase + G.rec_off + l * 64;
+      uint8_t *flags = smem + wbase + G.flag_off + l;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ql = qd + 64 * i;
+        if (ql >= TQ) continue;
+        uint4 r[4];                                 // per point {off side 0, w side 0, off side 1, w side 1}
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = make_uint4(wbase, 0u, wbase, 0u);
+        const int x = t.tx * G.tw + (ql & (G.tw - 1)), y = t.ty * G.th + (ql >> G.tw_shift);
+        if (x < G.Wq && y < G.Hq) {      // (a query outside the level: zero-weight taps on the first bytes of the buffer)
+          const float px[4] = {pre_xy[i][0].x, pre_xy[i][0].z, pre_xy[i][1].x, pre_xy[i][1].z};
+          const float py[4] = {pre_xy[i][0].y, pre_xy[i][0].w, pre_xy[i][1].y, pre_xy[i][1].w};
+          const float pw[4] = {pre_w[i].x, pre_w[i].y, pre_w[i].z, pre_w[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float h_im = __fmaf_rn(py[j], Hf, -0.5f), w_im = __fmaf_rn(px[j], Wf, -0.5f);
+            const float fy = floorf(h_im), fx = floorf(w_im);
+            if (fx >= oxf && fx <= xmaxf && fy >= oyf && fy <= ymaxf) {
+              const float lh = h_im - fy, lw = w_im - fx, hh = 1.f - lh, hw = 1.f - lw, aw = pw[j];
+              const __half2 w0 = __floats2half2_rn(hh * hw * aw, lh * hw * aw), w1 = __floats2half2_rn(hh * lw * aw, lh * lw * aw);
+              const uint32_t off = (uint32_t)(vbase + (__float2int_rz(fy) * ww + __float2int_rz(fx)) * 64);
+              r[j] = make_uint4(off, *reinterpret_cast<const uint32_t *>(&w0), off + 64u, *reinterpret_cast<const uint32_t *>(&w1));
+              ++n_win;
+            } else {
+              r[j] = slow_record(P.hw, P.lsi, l, wbase, make_float2(px[j], py[j]), pw[j]);
+              n_glob += (int)(r[j].x >> 31);
+            }
+          }
+        }
+        // records of a query: per pair of points a 32-byte block [side 0: point 2k, 2k+1 | side 1: point 2k, 2k+1]
+        uint4 *dst = reinterpret_cast<uint4 *>(recs + ql * G.rec_stride);
+        dst[0] = make_uint4(r[0].x, r[0].y, r[1].x, r[1].y);
+        dst[1] = make_uint4(r[0].z, r[0].w, r[1].z, r[1].w);
+        dst[2] = make_uint4(r[2].x, r[2].y, r[3].x, r[3].y);
+        dst[3] = make_uint4(r[2].z, r[2].w, r[3].z, r[3].w);
+        flags[ql * 4] = (uint8_t)((r[0].x | r[1].x | r[2].x | r[3].x) >> 31);
+      }
+      if (unit + stride < n_units) {
+        t = unit_of(P, unit + stride);
+        prefetch(t);
+      }
+      __syncwarp();
+      MEMOTR_BAR_ARRIVE(REC_FULL + b);       // (the record stores above are ordered before the consumers' reads)
+    }
+    if (stats) atomicAdd(stats, (unsigned long long)n_win), atomicAdd(stats + 1, (unsigned long long)n_glob);
+    return;
+  }
+
+  // ============================================================================================= tap warps
+  const int grp = tid >> 3, side = (tid >> 2) & 1, sub = tid & 3;
+  const uint32_t smem0 = tc::smem_u32(smem), lane_base = smem0 + sub * 16;
+  const __half *vb0 = value + sub * 8;
+  const int xs = P.xs;
+  int n = 0;
+  for (int unit = first; unit < n_units; unit += stride, ++n) {
+    const int b = n & 1;
+    const Unit t = unit_of(P, unit);
+    const ClassGeom &G = P.cls[t.c];
+    const int TQ = G.tw * G.th, rec_stride = G.rec_stride;
+    const uint32_t stage = smem0 + (uint32_t)(b * P.stage_bytes);
+    const uint32_t recs = stage + G.rec_off + side * 16, flags = stage + G.flag_off;
+    const uint32_t rowb0 = (uint32_t)G.ww[0] * 64u, rowb1 = (uint32_t)G.ww[1] * 64u, rowb2 = (uint32_t)G.ww[2] * 64u,
+                   rowb3 = (uint32_t)G.ww[3] * 64u;
+    const int x = t.tx * G.tw + (grp & (G.tw - 1)), ystep = 64 >> G.tw_shift;
+    int y = t.ty * G.th + (grp >> G.tw_shift);
+    const bool x_ok = side == 0 && x < G.Wq;
+    __nv_bfloat16 *optr = out + ((long)(G.q0 + y * G.Wq + x) * H + t.h) * 32 + sub * 8;
+    const long ostep = (long)ystep * G.Wq * H * 32;
+    const __half *vb = vb0 + t.h * 32;
+    MEMOTR_BAR_SYNC(REC_FULL + b);
+    mbar_wait_sleepy(win_full + b, (n >> 1) & 1);
+    for (int ql = grp; ql < TQ; ql += TAP_WARPS * 4, y += ystep, optr += ostep) {
+      const uint32_t rq = recs + ql * rec_stride;
+      uint32_t flag;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(flag) : "r"(flags + ql * 4));
+      float acc[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
+      __half2 a[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) a[jj] = __float2half2_rn(0.f);
+      auto lds128 = [](uint32_t addr) {
+        uint4 r;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+        return r;
+      };
+      if (!__any_sync(0xffffffffu, flag != 0u)) {
+        // ---- every tap of these four queries comes from the windows -------------------------------------------------
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const uint32_t rowb = l == 0 ? rowb0 : l == 1 ? rowb1 : l == 2 ? rowb2 : rowb3;
+          const uint4 ra = lds128(rq + l * 64), rb = lds128(rq + l * 64 + 32);
+          const uint32_t a0 = lane_base + ra.x, a1 = lane_base + ra.z, a2 = lane_base + rb.x, a3 = lane_base + rb.z;
+          const uint4 v00 = lds128(a0), v01 = lds128(a0 + rowb), v10 = lds128(a1), v11 = lds128(a1 + rowb);
+          const uint4 v20 = lds128(a2), v21 = lds128(a2 + rowb), v30 = lds128(a3), v31 = lds128(a3 + rowb);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v00, v01);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v10, v11);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.y), v20, v21);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.w), v30, v31);
+          if (l & 1) {                             // end of a level pair: widen into the fp32 sums (msda_h16.cuh)
+            h16::widen_add(acc, a);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) a[jj] = __float2half2_rn(0.f);
+          }
+        }
+      } else {
+        // ---- some lane has a global-memory tap: per-tap choice (same arithmetic) -------------------------------------
+#pragma unroll 1
+        for (int l = 0; l < L; ++l) {
+          const uint32_t rowb = (uint32_t)G.ww[l] * 64u;
+          const int Wl = P.hw[2 * l + 1];
+          auto any_tap = [&](uint32_t off, uint4 &r0, uint4 &r1) {
+            if (off & 0x80000000u) {
+              const __half *p0 = vb + (long)(off & 0x3FFFFFFFu) * xs;
+              const __half *p1 = (off & 0x40000000u) ? p0 : p0 + (long)Wl * xs;
+              r0 = __ldg(reinterpret_cast<const uint4 *>(p0));
+              r1 = __ldg(reinterpret_cast<const uint4 *>(p1));
+            } else {
+              r0 = lds128(lane_base + off), r1 = lds128(lane_base + off + rowb);
+            }
+          };
+          const uint4 ra = lds128(rq + l * 64), rb = lds128(rq + l * 64 + 32);
+          uint4 v[4][2];
+          any_tap(ra.x, v[0][0], v[0][1]);
+          any_tap(ra.z, v[1][0], v[1][1]);
+          any_tap(rb.x, v[2][0], v[2][1]);
+          any_tap(rb.z, v[3][0], v[3][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.y), v[0][0], v[0][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&ra.w), v[1][0], v[1][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.y), v[2][0], v[2][1]);
+          h16::blend(a, *reinterpret_cast<const __half2 *>(&rb.w), v[3][0], v[3][1]);
+          if (l & 1) {
+            h16::widen_add(acc, a);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) a[jj] = __float2half2_rn(0.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], 4);
+      if (x_ok && y < G.Hq) *reinterpret_cast<uint4 *>(optr) = f32x8_to_bf16(acc);
+    }
+    __syncwarp();
+    MEMOTR_BAR_ARRIVE(BUF_FREE + b);
+  }
+}
+
 // 3-D fp16 map of one level of a pixel-major value map: dims (channels, W, H), box (32 channels, ww, wh), no swizzle
 static bool make_level_map(CUtensorMap *map, const void *base, int C, int xs, int Hh, int Ww, int ww, int wh) {
   tc::EncodeTiledFn fn = tc::encode_fn();
@@ -468,7 +739,7 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
         if (big < 0 || G.ww[l] * G.wh[l] > G.ww[big] * G.wh[big]) big = l;
         bytes += (G.ww[l] * G.wh[l] * 64 + 127) / 128 * 128;
       }
-      if (bytes + rec_bytes + 256 <= win::SMEM_BUDGET || big < 0) break;
+      if (bytes + rec_bytes + G.tw * G.th * win::MAXL + 256 <= win::SMEM_BUDGET || big < 0) break;
       G.ww[big] = G.wh[big] = 0;
     }
     int off = 0, any = 0;
@@ -478,6 +749,7 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
     }
     if (!any || off >= (1 << 20)) break;                       // nothing fits: leave this class to the global-memory role
     G.rec_off = off;
+    G.flag_off = off + rec_bytes;
     G.unit0 = units, G.n_units = G.tiles_x * G.tiles_y * H;
     units += G.n_units;
     q_end = G.q0 + G.Hq * G.Wq;
@@ -487,7 +759,7 @@ static int plan(win::Params &P, const int *shapes_hw, const int *level_start, in
   P.n_glob_blocks = ceil_div((S - q_end) * H * 4, win::THREADS);
   P.stage_bytes = 0;
   for (int c = 0; c < P.n_cls; ++c)
-    P.stage_bytes = std::max(P.stage_bytes, (P.cls[c].rec_off + P.cls[c].tw * P.cls[c].th * P.cls[c].rec_stride + 127) / 128 * 128);
+    P.stage_bytes = std::max(P.stage_bytes, (P.cls[c].flag_off + P.cls[c].tw * P.cls[c].th * win::MAXL + 127) / 128 * 128);
   return units;
 }
 
@@ -558,12 +830,15 @@ extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_str
                                           value_pixel_stride, shapes_hw[2 * l], shapes_hw[2 * l + 1], G.ww[l], G.wh[l]))
         return fail(MEMOTR_ECUDA, "msda_forward_window: cuTensorMapEncodeTiled failed (class %d, level %d)", c, l);
   }
-  auto kern = K == 4 ? win::msda_window_kernel<4> : win::msda_window_kernel<0>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[K == 4]) {
+  // K = 4, L = 4: the specialised kernel (MEMOTR_WINDOW_GENERIC=1: the general one, for A/B and its tests)
+  const char *gen = getenv("MEMOTR_WINDOW_GENERIC");
+  const int which = (K == 4 && L == 4 && !(gen && gen[0] == '1')) ? 2 : K == 4 ? 1 : 0;
+  auto kern = which == 2 ? win::msda_window_k4l4_kernel : which == 1 ? win::msda_window_kernel<4> : win::msda_window_kernel<0>;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[which]) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * win::SMEM_BUDGET);
     if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "msda_forward_window: smem attribute: %s", cudaGetErrorString(e));
-    attr_set[K == 4] = true;
+    attr_set[which] = true;
   }
   // persistent window CTAs: one per SM (two stages of shared memory each)
   int dev = 0, n_sm = kNumSMs;

@@ -90,11 +90,19 @@ class FrameEngine:
         self.fuse_prep = (mode == "bf16" and self.value_f16 and os.environ.get("MEMOTR_FUSE_PREP", "1") != "0"
                           and cfg["n_levels"] * cfg["n_enc_points"] == 16 and self.H % 2 == 0
                           and 3 * ((self.S + 127) // 128) > n_sm > 0 and self.H * 48 % 128 == 0)
+        # encoder: output_proj + norm1 as one kernel (memotr_linear256_layernorm; MEMOTR_FUSE_OUTLN=0: GEMM + LayerNorm launches)
+        self.fuse_outln = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_OUTLN", "0") != "0" and self.fused_mlp
+                           and self.C == 256 and self.S >= 2048 and n_sm > 0)
         # encoder: norm2 (+ the fp32 master, + the next layer's query = y + pos) in the EPILOGUE of the fused FFN kernel
-        # (memotr_mlp2_lnout): no LayerNorm launch, no fp32 round trip of the pre-norm sum.  MEMOTR_FUSE_LN2=0: A/B
-        self.fuse_ln2 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN2", "1") != "0" and self.fused_mlp
+        # (memotr_mlp2_lnout): no LayerNorm launch, no fp32 round trip of the pre-norm sum.  Opt-in (MEMOTR_FUSE_LN2=1):
+        # measured 9.5 us per layer SLOWER -- the LayerNorm phase of a tile runs at HBM speed on every SM at once with the
+        # tensor pipes idle, and a one-tile-per-CTA kernel has nothing to overlap it with (tools/micro_dense.py)
+        self.fuse_ln2 = (mode == "bf16" and os.environ.get("MEMOTR_FUSE_LN2", "0") != "0" and self.fused_mlp
                          and self.Fd % 128 == 0 and self.S >= 2048 and n_sm > 0)
         self.n_sm = n_sm
+        # encoder: output_proj + norm1 + FFN + norm2 as ONE kernel per 128-row tile (memotr_encoder_dense_block: the front GEMM
+        # and norm1 run inside the FFN kernel, its input tile never exists in HBM).  MEMOTR_FUSE_BLOCK=0: A/B
+        self.fuse_block = self.fuse_ln2 and os.environ.get("MEMOTR_FUSE_BLOCK", "0") != "0"
         # encoder gather from TMA-staged value-map windows in shared memory (csrc/msda_window.cu); MEMOTR_MSDA_WINDOW=0: the
         # global-memory gather (bit-identical results)
         self.msda_window = (self.fuse_prep and self.L <= 5 and self.H <= 16 and cfg["n_enc_points"] % 2 == 0
@@ -653,8 +661,21 @@ class FrameEngine:
             else:
                 self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
                 self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
-            self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
-            self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
+            if self.fuse_block:
+                (g1, b1n), (g2, b2n), l1, l2 = ly["norm1"], ly["norm2"], ly["lin1"], ly["lin2"]
+                self._ck(self.lib.memotr_encoder_dense_block(
+                    _p(self.att), C, _p(a["out"].w), _p(a["out"].b), _p(self.src32), C, _p(g1), _p(b1n), _p(self.src1_32), C,
+                    _p(l1.w), _p(l1.b), _p(l2.w), _p(l2.b), _p(g2), _p(b2n), _p(self.pos_tok), C, _p(self.src_tok), C,
+                    _p(self.src32), C, _p(self.q_tok), C, _p(self.pre), C, S, self.Fd, 1e-5, st()), "encoder_dense_block")
+                continue
+            if self.fuse_outln:
+                g1, b1n = ly["norm1"]
+                self._ck(self.lib.memotr_linear256_layernorm(_p(self.att), C, _p(a["out"].w), _p(a["out"].b), _p(self.src32), C,
+                                                             _p(g1), _p(b1n), 1e-5, _p(self.src1), C, _p(self.src1_32), C, S, st()),
+                         "linear256_layernorm")
+            else:
+                self.lin(self.att, C, a["out"], self.pre, C, S, c_dtype=F32)
+                self.ln(self.pre, ly["norm1"], self.src1, S, x2=self.src32, y32=self.src1_32)
             tf = self.timer is not None and getattr(self, "time_ffn", False)   # (event nodes cost PDL overlap: opt-in)
             if tf:
                 _lib.check(self.lib.memotr_timer_record(self.timer, 2 * self.n_enc + 5 + 2 * i, st()), "timer_record")

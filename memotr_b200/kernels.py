@@ -218,6 +218,36 @@ def mlp2_lnout(x, w1, b1, w2, b2, res, gamma, beta, pos=None, eps=1e-5, want_f32
     return y, y32, ypos
 
 
+def encoder_dense_block(att, wout, bout, src32, g1, be1, w1, b1, w2, b2, g2, be2, pos, eps=1e-5):
+    """output_proj + norm1 + FFN + norm2 of an encoder layer in one kernel per row tile (memotr_encoder_dense_block).
+    att (M,256) bf16, src32 (M,256) fp32, pos (M,256) bf16 -> (x32 fp32, y bf16, y32 fp32, y + pos bf16)."""
+    M, Hd, dev = att.shape[0], w1.shape[0], att.device
+    x32, y32, pre = (torch.empty((M, 256), dtype=torch.float32, device=dev) for _ in range(3))
+    y, ypos = (torch.empty((M, 256), dtype=torch.bfloat16, device=dev) for _ in range(2))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().memotr_encoder_dense_block(_lib.ptr(att), _ld(att), _lib.ptr(wout), _lib.ptr(bout), _lib.ptr(src32),
+                                                   _ld(src32), _lib.ptr(g1), _lib.ptr(be1), _lib.ptr(x32), 256, _lib.ptr(w1),
+                                                   _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g2), _lib.ptr(be2),
+                                                   _lib.ptr(pos), _ld(pos), _lib.ptr(y), 256, _lib.ptr(y32), 256, _lib.ptr(ypos), 256,
+                                                   _lib.ptr(pre), 256, M, Hd, float(eps), _lib.stream_ptr())
+    _lib.check(rc, "memotr_encoder_dense_block")
+    return x32, y, y32, ypos
+
+
+def linear256_layernorm(a, w, b, res, gamma, beta, eps=1e-5):
+    """LayerNorm(res + a @ w.T + b) for a 256 x 256 projection in one kernel (memotr_linear256_layernorm).
+    a (M,256) bf16, w (256,256) bf16, res (M,256) fp32 -> (y bf16, y32 fp32)."""
+    M = a.shape[0]
+    y = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device)
+    y32 = torch.empty((M, 256), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().memotr_linear256_layernorm(_lib.ptr(a), _ld(a), _lib.ptr(w), _lib.ptr(b), _lib.ptr(res), _ld(res),
+                                                   _lib.ptr(gamma), _lib.ptr(beta), float(eps), _lib.ptr(y), 256, _lib.ptr(y32), 256,
+                                                   M, _lib.stream_ptr())
+    _lib.check(rc, "memotr_linear256_layernorm")
+    return y, y32
+
+
 def pos_embed_sine(mask, num_pos_feats=128, temperature=20, scale=6.283185307179586):
     """PositionEmbeddingSine(normalize=True) of one (H, W) padding mask (bool / uint8, device) -> (2*num_pos_feats, H, W) fp32
     (models/position_embedding.py:23-49)."""

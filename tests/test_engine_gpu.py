@@ -208,6 +208,61 @@ def test_fused_mlp2_with_layernorm_epilogue(M, with_pos):
         assert ypos is None
 
 
+@pytest.mark.parametrize("M", [300, 128 * 148, 22323, 77])
+def test_encoder_dense_block_matches_the_four_ops(M):
+    """memotr_encoder_dense_block (output_proj + norm1 + FFN + norm2 in one kernel per row tile) against the same four ops
+    through the separate kernels, and against fp64 on the bf16-rounded GEMM operands."""
+    g = _g(M + 5)
+    Hd = 2048
+    att = torch.randn(M, 256, generator=g).bfloat16()
+    src = torch.randn(M, 256, generator=g)
+    pos = torch.randn(M, 256, generator=g).bfloat16()
+    wout = (torch.randn(256, 256, generator=g) / 16).bfloat16()
+    w1 = (torch.randn(Hd, 256, generator=g) / 16).bfloat16()
+    w2 = (torch.randn(256, Hd, generator=g) / math.sqrt(Hd)).bfloat16()
+    bout, b1, b2 = torch.randn(256, generator=g), torch.randn(Hd, generator=g), torch.randn(256, generator=g)
+    g1, be1 = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    g2, be2 = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    d = lambda t: t.to(DEV)                                                                 # noqa: E731
+    x32, y, y32, ypos = K().encoder_dense_block(d(att), d(wout), d(bout), d(src), d(g1), d(be1), d(w1), d(b1), d(w2), d(b2),
+                                                d(g2), d(be2), d(pos))
+    # the same through the separate kernels
+    pre = K().linear(d(att), d(wout), d(bout), out_dtype=torch.float32, path="tc")
+    rx, rx32 = K().layernorm(pre, d(g1), d(be1), x2=d(src), out_dtype=torch.bfloat16, want_f32=True)
+    assert rel_err(x32.cpu().numpy(), rx32.cpu().numpy()) < 5e-6
+    ry, ry32, rypos = K().mlp2_lnout(rx, d(w1), d(b1), d(w2), d(b2), rx32, d(g2), d(be2), pos=d(pos))
+    assert rel_err(y32.cpu().numpy(), ry32.cpu().numpy()) < 2e-3       # (x may differ by a bf16 ulp where the fp32 x straddles a boundary)
+    # fp64 on the rounded operands
+    x = F.layer_norm(F.linear(att.double(), wout.double(), bout.double()) + src.double(), (256,), g1.double(), be1.double(), 1e-5)
+    assert rel_err(x32.cpu().numpy(), x.numpy()) < 1e-5
+    xb = x32.cpu().bfloat16().double()                                  # the operand the kernel's FFN saw
+    h = F.linear(xb, w1.double(), b1.double()).relu().float().bfloat16().double()
+    want = F.layer_norm(F.linear(h, w2.double(), b2.double()) + x32.cpu().double(), (256,), g2.double(), be2.double(), 1e-5)
+    assert rel_err(y32.cpu().numpy(), want.numpy()) < 1e-3
+    assert rel_err(y.float().cpu().numpy(), want.numpy()) < 6e-3
+    assert rel_err(ypos.float().cpu().numpy(), (want + pos.double()).numpy()) < 6e-3
+
+
+@pytest.mark.parametrize("M", [1, 77, 128, 300, 22323])
+def test_linear256_layernorm_matches_gemm_plus_layernorm(M):
+    """memotr_linear256_layernorm (output_proj + norm1 in one tcgen05 kernel per row tile) against fp64 on the bf16 operands and
+    against the GEMM + LayerNorm launches it replaces."""
+    g = _g(M + 11)
+    att = torch.randn(M, 256, generator=g).bfloat16()
+    src = torch.randn(M, 256, generator=g)
+    w = (torch.randn(256, 256, generator=g) / 16).bfloat16()
+    b = torch.randn(256, generator=g)
+    g1, be1 = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    d = lambda t: t.to(DEV)                                                                 # noqa: E731
+    y, y32 = K().linear256_layernorm(d(att), d(w), d(b), d(src), d(g1), d(be1))
+    want = F.layer_norm(F.linear(att.double(), w.double(), b.double()) + src.double(), (256,), g1.double(), be1.double(), 1e-5)
+    assert rel_err(y32.cpu().numpy(), want.numpy()) < 1e-5
+    assert torch.equal(y.cpu(), y32.cpu().bfloat16())
+    pre = K().linear(d(att), d(w), d(b), out_dtype=torch.float32, path="tc")
+    ry, ry32 = K().layernorm(pre, d(g1), d(be1), x2=d(src), out_dtype=torch.bfloat16, want_f32=True)
+    assert rel_err(y32.cpu().numpy(), ry32.cpu().numpy()) < 5e-6
+
+
 def test_fused_mlp2_epilogues_and_views():
     g = _g(21)
     M, Hd = 333, 256

@@ -77,9 +77,12 @@ def main():
              ("dancetrack_noise0.5", synth.DANCETRACK_SHAPES, 4, 0.5, None, 0),
              ("dancetrack_noise1.0", synth.DANCETRACK_SHAPES, 4, 1.0, None, 0),
              ("dancetrack_noise1.0_r2.5", synth.DANCETRACK_SHAPES, 4, 1.0, 2.5, 0)]
-    for L, shapes in ((4, synth.BDD_SHAPES), (5, synth.BDD_SHAPES_L5)):
-        for K in (4, 8, 16):
-            cases.append((f"bdd_L{L}K{K}", shapes, K, 0.15, None, 0))
+    if "--quick" in sys.argv:
+        cases = [cases[0], cases[3]]
+    else:
+        for L, shapes in ((4, synth.BDD_SHAPES), (5, synth.BDD_SHAPES_L5)):
+            for K in (4, 8, 16):
+                cases.append((f"bdd_L{L}K{K}", shapes, K, 0.15, None, 0))
     for name, shapes, K, noise, radius, classes in cases:
         c = case(shapes, 8, K, noise, radius, classes)
         stats = torch.zeros(2, dtype=torch.int64, device=DEV)
@@ -89,7 +92,14 @@ def main():
                "plan": kernels.window_plan(shapes, 8, K, c["radius"], classes), "bytes": c["bytes"]}
         nw, ng = (int(v) for v in stats.tolist())
         row["staged_points"], row["global_points_in_staged_units"] = nw, ng
-        for tag, fn in (("window", lambda: run_window(c)), ("global", lambda: run_global(c))):
+        def run_generic():
+            os.environ["MEMOTR_WINDOW_GENERIC"] = "1"      # (the library reads it at every launch)
+            try:
+                return run_window(c)
+            finally:
+                os.environ.pop("MEMOTR_WINDOW_GENERIC")
+        row["generic_bit_equal"] = bool(torch.equal(run_generic(), b))
+        for tag, fn in (("window", lambda: run_window(c)), ("window_generic", run_generic), ("global", lambda: run_global(c))):
             t, tmin = timeit(fn, flush=flush)
             row[f"{tag}_us"], row[f"{tag}_min_us"] = t, tmin
             row[f"{tag}_gbs"] = c["bytes"] / t / 1e3
