@@ -215,6 +215,8 @@ MEMOTR_API int memotr_linear256_layernorm(const void *A, int lda, const void *W,
 /* Profiling hook (tools/micro_dense.py), not part of the reference surface: every later memotr_mlp2* / encoder_dense_block
  * launch writes 8 clock64 stamps per CTA into `buf` (device int64[8 x CTAs]); null switches it off again. */
 MEMOTR_API int memotr_mlp2_debug_stamps(long long *buf);
+/* same for the persistent tcgen05 GEMM (memotr_linear with more tiles than SMs, memotr_linear_msda_prep): 20 stamps per CTA */
+MEMOTR_API int memotr_gemm_debug_stamps(long long *buf);
 
 /*
  * y = LayerNorm(x [+ x2]) (C == 256, eps as given, affine fp32); optional ypos = y + pos and fp32 copy y32.

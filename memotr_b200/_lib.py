@@ -90,6 +90,7 @@ _SIGNATURES = {
     "memotr_encoder_dense_block": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i,
                                     _vp, _i, _vp, _i, _i, _i, _f, _vp], _i),
     "memotr_mlp2_debug_stamps": ([_vp], _i),
+    "memotr_gemm_debug_stamps": ([_vp], _i),
     "memotr_linear256_layernorm": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _i, _i, _vp], _i),
     "memotr_layernorm": ([_vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp], _i),
     "memotr_mha": ([_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i] + [_i] * 6 + [_vp], _i),

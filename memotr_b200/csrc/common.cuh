@@ -164,6 +164,7 @@ struct Epilogue {
   int prep, prep_L, prep_K, prep_nh;
   int prep_hw[16], prep_lsi[8];   // (H_l, W_l) and first row of every level
   const float *prep_vr;           // device (L, 2) valid ratios
+  long long *stamps;              // profiling (tools/micro_gemm.py): 20 clock64 stamps per CTA of the persistent GEMM, else null
 };
 
 }  // namespace memotr

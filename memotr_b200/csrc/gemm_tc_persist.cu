@@ -17,12 +17,21 @@ namespace memotr {
 namespace tc {
 namespace persist {
 
-constexpr int NST = 4, BN = 128;
+constexpr int BN = 128;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
-constexpr int OFF_OUT = NST * STAGE_BYTES;                                                   // 128 KB
-constexpr int OUT_BYTES = 4 * BM * 128;                                                      // up to 4 panels (fp32)
-constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
-constexpr int TOTAL = OFF_BAR + 256 + 1024;
+// Shared-memory plan per output type.  The staging tile is DOUBLE-BUFFERED: the in-kernel stamps (tools/gemm_phases.py)
+// showed the epilogue of tile i + 1 waiting 1.2 us for the TMA store of tile i to finish reading a single staging buffer
+// (64 KB of fp32 per tile) -- as long as the epilogue itself.  fp32 output: 3 ring stages + 2 x 64 KB; 16-bit output: 4 ring
+// stages + 2 x 32 KB.
+template <typename TC>
+struct Plan {
+  static constexpr int NST = sizeof(TC) == 4 ? 3 : 4;
+  static constexpr int OUT_BYTES = (BN * (int)sizeof(TC) / 128) * BM * 128;                   // 4 (fp32) or 2 panels of 16 KB
+  static constexpr int OFF_OUT = NST * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_OUT + 2 * OUT_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static_assert(TOTAL <= 227 * 1024, "shared memory plan");
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -33,11 +42,11 @@ __global__ void __launch_bounds__(320, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int NST = Plan<TC>::NST, OFF_OUT = Plan<TC>::OFF_OUT, OUT_BYTES = Plan<TC>::OUT_BYTES, OFF_BAR = Plan<TC>::OFF_BAR;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + OFF_BAR), *empty = full + NST, *acc_full = empty + NST,
            *acc_empty = acc_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  uint8_t *stage_out = smem + OFF_OUT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = K / BK, n_nblk = N / BN, n_tiles = n_nblk * ceil_div(M, BM);
@@ -103,19 +112,25 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ---- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 (the epilogue is the pace-maker
     //      of this kernel: with four warps the tile rate was bound by 128 threads x 128 values each) ----
     const int chalf = (warp - 2) >> 2;
+    long long *stamps = (ep.stamps && warp == 2 && lane == 0) ? ep.stamps + 20 * blockIdx.x : nullptr;
+    if (stamps) stamps[0] = clock64();
     int i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int m_blk = t / n_nblk, n_blk = t % n_nblk, buf = i & 1;
-      // the previous tile's TMA store must have finished READING the staging panels before they are overwritten
-      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // staging buffer (i & 1): the TMA store of tile i - 2 must have finished READING it (the store of tile i - 1 may still run)
+      uint8_t *stage_out = smem + OFF_OUT + (i & 1) * OUT_BYTES;
+      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (stamps && i < 6) stamps[1 + 3 * i] = clock64();        // staging free (previous store has read it)
       mbar_wait(acc_full + buf, (i >> 1) & 1);
       tcgen05_fence_after();
+      if (stamps && i < 6) stamps[2 + 3 * i] = clock64();        // accumulator ready
         const int quarter = warp & 3;
         const int r_in = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const int row = m_blk * BM + r_in;
         const bool row_ok = row < M;
         float prep_bx = 0.f, prep_by = 0.f;         // encoder reference point of this row (pixel centre / valid extent)
+        float lvl_sx[4], lvl_sy[4], lvl_rw[4], lvl_rh[4];   // K = 4 fast path: per value level, reference * valid ratio and 1 / extent
         if (ep.prep) {
           const int rr = row_ok ? row : 0;
           int lq = 0;
@@ -125,6 +140,13 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int yy = (int)(((float)pp + 0.5f) * __frcp_rn((float)Wq)), xx = pp - yy * Wq;
           prep_bx = ((float)xx + 0.5f) * __frcp_rn(__ldg(ep.prep_vr + 2 * lq) * (float)Wq);
           prep_by = ((float)yy + 0.5f) * __frcp_rn(__ldg(ep.prep_vr + 2 * lq + 1) * (float)Hq);
+          if (ep.prep_K == 4) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+              lvl_sx[l] = prep_bx * __ldg(ep.prep_vr + 2 * l), lvl_sy[l] = prep_by * __ldg(ep.prep_vr + 2 * l + 1);
+              lvl_rw[l] = __frcp_rn((float)ep.prep_hw[2 * l + 1]), lvl_rh[l] = __frcp_rn((float)ep.prep_hw[2 * l]);
+            }
+          }
         }
         const bool zero_row = row_ok && ep.rowzero && ep.rowzero[row];
         const __nv_bfloat16 *mulp = (const __nv_bfloat16 *)ep.mul + (long)row * ep.ldmul;
@@ -151,7 +173,13 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
           if (ep.prep) {
-            if (col0 < ep.prep_nh * 32) {             // 16 (x, y) offsets of one head -> sampling locations
+            if (col0 < ep.prep_nh * 32 && ep.prep_K == 4) {   // 16 (x, y) offsets of one head -> sampling locations
+#pragma unroll
+              for (int i2 = 0; i2 < 16; ++i2) {              // (same products and sums as the general branch below, the
+                v[2 * i2] = lvl_sx[i2 >> 2] + v[2 * i2] * lvl_rw[i2 >> 2];          //  per-level factors hoisted out of the loop)
+                v[2 * i2 + 1] = lvl_sy[i2 >> 2] + v[2 * i2 + 1] * lvl_rh[i2 >> 2];
+              }
+            } else if (col0 < ep.prep_nh * 32) {
 #pragma unroll
               for (int i2 = 0; i2 < 16; ++i2) {
                 const int l = i2 / ep.prep_K;
@@ -224,6 +252,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (stamps && i < 6) stamps[3 + 3 * i] = clock64();        // tile staged
       if (warp == 2 && lane == 0) {
 #pragma unroll 1
         for (int p = 0; p < N_PANELS; ++p)
@@ -234,6 +263,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
     if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete
+    if (stamps) stamps[19] = clock64();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -242,6 +272,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
+
+static long long *g_stamps = nullptr;   // memotr_gemm_debug_stamps
 
 template <typename TC>
 static int launch(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
@@ -253,12 +285,14 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
   auto kern = gemm_tc_persist_kernel<TC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<TC>::TOTAL);
     if (e != cudaSuccess) return fail(MEMOTR_ECUDA, "linear(tc, persistent): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = (N / BN) * ceil_div(M, BM);
-  MEMOTR_LAUNCH((kern), tiles < n_sm ? tiles : n_sm, 320, TOTAL, st, tmA, tmW, tmC, M, N, K, ep);
+  Epilogue eps = ep;
+  eps.stamps = g_stamps;
+  MEMOTR_LAUNCH((kern), tiles < n_sm ? tiles : n_sm, 320, Plan<TC>::TOTAL, st, tmA, tmW, tmC, M, N, K, eps);
   return check_launch("gemm_tc_persist");
 }
 
@@ -289,6 +323,13 @@ int linear_tc_persist_bf16(const void *A, int lda, const void *W, int ldw, void 
 }  // namespace memotr
 
 using namespace memotr;
+
+// Profiling hook (tools/micro_gemm.py): every later persistent-GEMM launch writes 20 clock64 stamps per CTA into `buf` (device
+// int64[20 x CTAs]; null: off): 0 start; per tile i < 6: 1+3i staging free, 2+3i accumulator ready, 3+3i tile staged; 19 end.
+extern "C" int memotr_gemm_debug_stamps(long long *buf) {
+  tc::persist::g_stamps = buf;
+  return MEMOTR_OK;
+}
 
 extern "C" int memotr_linear_msda_prep(const void *A, int lda, const void *W, int ldw, const float *bias, float *out, int ldo,
                                        int M, int K, int n_heads, int n_levels, int n_points, const int *shapes_hw,
