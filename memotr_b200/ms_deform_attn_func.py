@@ -63,7 +63,12 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
 
 
 class MSDeformAttnFunction(Function):
+    # Under torch.autocast the linear layers around the op hand it bf16 / fp16 tensors.  The reference's op has no half
+    # instantiation at all (AT_DISPATCH_FLOATING_TYPES, src/cuda/ms_deform_attn_cuda.cu:64) -- its training runs in fp32 -- so
+    # a mixed-precision step (BASELINE.json config 3) keeps the sampling core in fp32: inputs are cast up on entry and
+    # autocast is off inside, exactly what custom_fwd(cast_inputs=float32) is for.  Outside autocast nothing changes.
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
                 im2col_step):
         ctx.im2col_step = im2col_step
@@ -75,6 +80,7 @@ class MSDeformAttnFunction(Function):
 
     @staticmethod
     @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_output):
         value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
         grad_value, grad_sampling_loc, grad_attn_weight = ms_deform_attn_backward(
