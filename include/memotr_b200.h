@@ -261,6 +261,13 @@ MEMOTR_API int memotr_tokens_from_nchw_emb(const float *src, const float *emb, c
                                            void *src_tok, void *pos_tok, void *q_tok, float *src_tok32, int C, int HW,
                                            int row0, int ld, int dtype, void *stream);
 
+/* memotr_tokens_from_nchw_emb for all levels in ONE launch (C % 64 == 0): srcs = host array of the levels' (C, H_l W_l) fp32
+ * device pointers, level_embed (L, C); two channels (a sin / cos pair) per thread, 4-byte paired stores. */
+MEMOTR_API int memotr_tokens_from_nchw_levels(const float *const *srcs, const float *emb, const float *dim_i, const float *level_embed,
+                                              void *src_tok, void *pos_tok, void *q_tok, float *src_tok32, int C,
+                                              const int *shapes_hw, const int *level_start, int n_levels, int ld, int dtype,
+                                              void *stream);
+
 /* valid ratio (w,h) of one level's (H,W) uint8 padding mask -- models/deformable_transformer.py:175-190 */
 MEMOTR_API int memotr_valid_ratio(const unsigned char *mask, int H, int W, float *out2, void *stream);
 

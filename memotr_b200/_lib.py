@@ -98,6 +98,7 @@ _SIGNATURES = {
     "memotr_tokens_from_nchw_pe": ([_vp, _vp, _i, _i, _vp, _f, _vp] + [_vp] * 5 + [_i] * 4 + [_vp], _i),
     "memotr_pos_cumsum_levels": ([_vp, _vp, _vp, _i, _f, _vp, _vp, _vp], _i),
     "memotr_tokens_from_nchw_emb": ([_vp] * 8 + [_i] * 5 + [_vp], _i),
+    "memotr_tokens_from_nchw_levels": ([_vp] * 8 + [_i, _vp, _vp, _i, _i, _i, _vp], _i),
     "memotr_valid_ratio": ([_vp, _i, _i, _vp, _vp], _i),
     "memotr_pos_embed_sine": ([_vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp], _i),
     "memotr_sine_embed": ([_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp], _i),

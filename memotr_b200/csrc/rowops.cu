@@ -251,6 +251,55 @@ tokens_kernel(const float *__restrict__ src, const float *__restrict__ pos, cons
   }
 }
 
+// All levels in one launch, position map evaluated in place (the `emb` mode of tokens_kernel), two adjacent channels per
+// thread: a sin / cos pair of PositionEmbeddingSine shares its argument (one division and one sincosf instead of two of each)
+// and every store is a 4-byte bf16 pair -- 128 contiguous bytes per warp and array instead of 64.  Tile = 32 pixels x 64
+// channels; blockIdx.x walks the pixel tiles of all levels (TokLevels::tile0 = prefix sums).
+struct TokLevels {
+  int n, hw[8], off[8], tile0[9];   // pixels, first token row and first pixel tile of every level
+  const float *src[8];              // (C, H_l * W_l) fp32 feature map of every level
+};
+
+__device__ __forceinline__ void store2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(__nv_bfloat16 *p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tokens_levels_kernel(const TokLevels lv, const float *__restrict__ emb, const float *__restrict__ dim_i,
+                     const float *__restrict__ lvl_embed, T *__restrict__ src_tok, T *__restrict__ pos_tok, T *__restrict__ q_tok,
+                     float *__restrict__ src_tok32, int C, int ld) {
+  pdl_grid_sync();
+  __shared__ float ts[32][65];                       // [pixel][channel], odd pitch: the transposing store is conflict-free
+  int l = 0;
+  while (l + 1 < lv.n && (int)blockIdx.x >= lv.tile0[l + 1]) ++l;
+  const int HW = lv.hw[l], p0 = ((int)blockIdx.x - lv.tile0[l]) * 32, c0 = blockIdx.y * 64;
+  const float *__restrict__ src = lv.src[l];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 64; i += 8) {
+    const int p = p0 + tx;
+    ts[tx][i] = p < HW ? src[(long)(c0 + i) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  const int c = c0 + 2 * tx, npf = C >> 1, half = c >= npf, j = half ? c - npf : c;     // (c even: j even, the sin channel)
+  const float dj = __ldg(dim_i + j), le0 = lvl_embed[l * C + c], le1 = lvl_embed[l * C + c + 1];
+  const float *__restrict__ ecnt = emb + 2 * (long)lv.off[l] + (long)half * HW;
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i;
+    if (p >= HW) break;
+    const float s0 = ts[i][2 * tx], s1 = ts[i][2 * tx + 1];
+    float sn, cs;
+    sincosf(__fdiv_rn(ecnt[p], dj), &sn, &cs);
+    const float pe0 = sn + le0, pe1 = cs + le1;
+    const long o = (long)(lv.off[l] + p) * ld + c;
+    store2(src_tok + o, s0, s1);
+    if (src_tok32) store2(src_tok32 + o, s0, s1);
+    store2(pos_tok + o, pe0, pe1);
+    store2(q_tok + o, s0 + pe0, s1 + pe1);
+  }
+}
+
 // valid ratio of one level's padding mask (deformable_transformer.py:175-190): (#valid in row 0)/W, (#valid in col 0)/H
 __global__ void valid_ratio_kernel(const unsigned char *__restrict__ mask, int Hh, int Ww, float *__restrict__ out2) {
   pdl_grid_sync();
@@ -571,6 +620,34 @@ extern "C" int memotr_pos_cumsum_levels(const unsigned char *mask, const int *sh
   MEMOTR_REQUIRE(mx <= 48 * 1024, "pos_cumsum_levels: level larger than 48K pixels");
   MEMOTR_LAUNCH((pos_cumsum_levels_kernel), n_levels, 1024, (size_t)mx, (cudaStream_t)stream, mask, lv, scale, emb, valid_ratios);
   return check_launch("pos_cumsum_levels");
+}
+
+// memotr_tokens_from_nchw_emb for ALL levels in one launch (C % 64 == 0, token rows 4-byte aligned pairs): `srcs` = host array
+// of the levels' (C, H_l W_l) fp32 device pointers, `emb` = the planes memotr_pos_cumsum_levels wrote, level_embed (L, C).
+extern "C" int memotr_tokens_from_nchw_levels(const float *const *srcs, const float *emb, const float *dim_i, const float *level_embed,
+                                              void *src_tok, void *pos_tok, void *q_tok, float *src_tok32, int C,
+                                              const int *shapes_hw, const int *level_start, int n_levels, int ld, int dtype,
+                                              void *stream) {
+  MEMOTR_REQUIRE(srcs && emb && dim_i && level_embed && src_tok && pos_tok && q_tok && shapes_hw && level_start && n_levels >= 1 &&
+                     n_levels <= 8 && C > 0 && C % 64 == 0 && ld >= C && ld % 2 == 0,
+                 "tokens_from_nchw_levels: bad arguments (needs C %% 64 == 0, <= 8 levels)");
+  MEMOTR_DTYPE_AB(dtype);
+  TokLevels lv;
+  lv.n = n_levels, lv.tile0[0] = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    MEMOTR_REQUIRE(srcs[l] && shapes_hw[2 * l] > 0 && shapes_hw[2 * l + 1] > 0, "tokens_from_nchw_levels: bad level %d", l);
+    lv.hw[l] = shapes_hw[2 * l] * shapes_hw[2 * l + 1], lv.off[l] = level_start[l], lv.src[l] = srcs[l];
+    lv.tile0[l + 1] = lv.tile0[l] + ceil_div(lv.hw[l], 32);
+  }
+  dim3 grid(lv.tile0[n_levels], C / 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MEMOTR_F32)
+    MEMOTR_LAUNCH((tokens_levels_kernel<float>), grid, 256, 0, st, lv, emb, dim_i, level_embed, (float *)src_tok, (float *)pos_tok,
+                  (float *)q_tok, src_tok32, C, ld);
+  else
+    MEMOTR_LAUNCH((tokens_levels_kernel<__nv_bfloat16>), grid, 256, 0, st, lv, emb, dim_i, level_embed, (__nv_bfloat16 *)src_tok,
+                  (__nv_bfloat16 *)pos_tok, (__nv_bfloat16 *)q_tok, src_tok32, C, ld);
+  return check_launch("tokens_from_nchw_levels");
 }
 
 extern "C" int memotr_tokens_from_nchw_emb(const float *src, const float *emb, const float *dim_i, const float *level_embed,

@@ -72,6 +72,7 @@ class FrameEngine:
         self.launches = 0
         import os
         self.fused_mlp = os.environ.get("MEMOTR_FUSED_MLP", "1") != "0"   # A/B switch for the on-chip FFN/MLP kernel
+        self.tokens_levels = os.environ.get("MEMOTR_TOKENS_LEVELS", "1") != "0"   # all levels' tokens in one launch
         # value maps in fp16 (bf16 mode): more mantissa than bf16 for this read-only intermediate, and the gather can
         # blend corners with packed HFMA2 instead of widening every bf16 element on the (binding) ALU pipe; A/B switch
         self.value_f16 = mode == "bf16" and os.environ.get("MEMOTR_VALUE_F16", "1") != "0"
@@ -626,6 +627,7 @@ class FrameEngine:
         st = self._st
         self._mark(0)
         # -- level flattening, level embedding, valid ratios (deformable_transformer.py:196-220)
+        tokens_levels = self.tokens_levels and self.pos_cfg is not None and C % 64 == 0 and self.L <= 8
         for l, (h, w) in enumerate(self.shapes):
             if self.pos_cfg is not None:      # position map of this level evaluated inside the token kernel
                 if l == 0:                    # normalised cumulative counts of all levels: one launch
@@ -637,6 +639,15 @@ class FrameEngine:
                                                                float(self.pos_cfg.get("scale", 2 * math.pi)),
                                                                _p(self.pos_scratch), _p(self.vr), st()),
                              "pos_cumsum_levels")                      # (also writes the valid ratios of all levels)
+                    if tokens_levels:         # every level's tokens in one launch (MEMOTR_TOKENS_LEVELS=0: one launch per level)
+                        if not hasattr(self, "_src_ptrs"):
+                            self._src_ptrs = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in self.in_src])
+                        self._ck(self.lib.memotr_tokens_from_nchw_levels(
+                            self._src_ptrs, _p(self.pos_scratch), _p(self.pos_dim_i), _p(self.level_embed), _p(self.src_tok),
+                            _p(self.pos_tok), _p(self.q_tok), _p(None if self.mode == "fp32" else self.src32), C, self._pos_hw,
+                            self._pos_lsi, self.L, C, dt, st()), "tokens_levels")
+                if tokens_levels:
+                    continue
                 self._ck(self.lib.memotr_tokens_from_nchw_emb(
                     _p(self.in_src[l]), _p(self.pos_scratch[2 * self.lsi_host[l]:]), _p(self.pos_dim_i),
                     _p(self.level_embed[l]), _p(self.src_tok), _p(self.pos_tok), _p(self.q_tok),

@@ -40,6 +40,8 @@ def phases(fn, n_cta=148):
     tiles = []
     for i in range(6):
         ok = s[:, 3 + 3 * i] > 0
+        if i >= 4 and "tiles_5plus" not in out:
+            out["tiles_5plus"] = "stamps cover the first 6 tiles of a CTA only"
         if ok.sum() == 0:
             break
         a = s[ok]
@@ -57,7 +59,8 @@ def main():
     g = torch.Generator().manual_seed(0)
     x = torch.randn(S, 256, generator=g).bfloat16().to(DEV)
     res = {}
-    for name, N, odt in (("value_proj_f16", 256, torch.float16), ("out_proj_f32", 256, torch.float32), ("n384_f32_plain", 384, torch.float32)):
+    for name, N, odt in (("value_proj_f16", 256, torch.float16), ("out_proj_f32", 256, torch.float32), ("n384_f32_plain", 384, torch.float32),
+                         ("dec_value_all_f16", 1536, torch.float16)):
         w = (torch.randn(N, 256, generator=g) / 16).bfloat16().to(DEV)
         b = torch.randn(N, generator=g).to(DEV)
         out = torch.empty(S, N, dtype=odt, device=DEV)
