@@ -973,6 +973,88 @@ class FrameEngine:
     def replay(self):
         self.graph.replay()
 
+    # ------------------------------------------------------------------------------------------------ frame pipelining
+    # The recurrent tail of a frame (decoder + heads, tracker glue, query updater) is a latency chain on ~100 of the 148 SMs
+    # (profiles/r02_decoder_cluster_ncu.md: issue slots 15 %), and the encoder of the NEXT frame depends on nothing it
+    # produces.  For a clip whose frames are at hand (the submit loop reads a video) the two run concurrently: tail(k) on
+    # the capture stream, encode(k + 1) on a second stream, one CUDA graph with a fork and a join per frame.  encode() hands
+    # decode() two things -- the stacked decoder value maps and the valid ratios -- so those exist twice (`use_set`), and
+    # there is one graph per parity.  Same kernels, same per-frame order, same results as step() (tests/test_engine_gpu.py).
+    def enable_pipeline(self):
+        import ctypes
+        if getattr(self, "_sets", None) is not None:
+            return
+        if not self.dec_cluster:
+            raise RuntimeError("FrameEngine.enable_pipeline: needs the fused decoder (bf16 mode)")
+        C = self.C
+        sets = [dict(value_all=self.value_all, vr=self.vr, dec=self.dec_params_cl)]
+        v2, vr2 = torch.empty_like(self.value_all), torch.empty_like(self.vr)
+        P = _lib.DecParams()
+        ctypes.memmove(ctypes.byref(P), ctypes.byref(self.dec_params_cl), ctypes.sizeof(P))
+        P.valid_ratios = vr2.data_ptr()
+        for lid in range(self.n_dec):
+            P.layers[lid].value = v2.data_ptr() + lid * C * 2
+        sets.append(dict(value_all=v2, vr=vr2, dec=P))
+        self._sets = sets
+
+    def use_set(self, i):
+        """Which copy of (value_all, vr) the following encode() writes / decode() reads (enqueue-time pointers)."""
+        d = self._sets[i]
+        self.value_all, self.vr, self.dec_params_cl = d["value_all"], d["vr"], d["dec"]
+
+    def capture_pipeline(self):
+        """Five graphs: encode-only into set 0 (clip prologue), [tail(set c) || encode(set 1 - c)] for c = 0, 1, tail-only for
+        c = 0, 1 (clip epilogue).  Call after capture() (which did the one-time warm-up of every kernel)."""
+        if self.graph is None:
+            raise RuntimeError("FrameEngine.capture_pipeline: call capture() first")
+        self.enable_pipeline()
+        timer, self.timer = self.timer, None                   # (event nodes only in the sequential instrumented graph)
+        main = torch.cuda.Stream(self.dev, priority=-1)        # the tail: fewer, longer CTAs -- scheduled first
+        side = torch.cuda.Stream(self.dev)
+        torch.cuda.synchronize(self.dev)
+
+        def graph_of(body):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=main):
+                body()
+            return g
+
+        def pair(c):
+            def body():
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self.use_set(1 - c)
+                    self.encode()
+                self.use_set(c)
+                self.step_tail()
+                main.wait_stream(side)
+            return body
+
+        def only(fn, c):
+            def body():
+                self.use_set(c)
+                fn()
+            return body
+        try:
+            self.g_first = graph_of(only(self.encode, 0))
+            self.g_pipe = [graph_of(pair(0)), graph_of(pair(1))]
+            self.g_last = [graph_of(only(self.step_tail, 0)), graph_of(only(self.step_tail, 1))]
+        finally:
+            self.use_set(0)
+            self.timer = timer
+
+    def run_clip_pipelined(self, n_frames, feed):
+        """Frames 0 .. n_frames - 1 of a clip with frame pipelining; feed(j) loads frame j's inputs into the static input buffers
+        (stream-ordered, e.g. device-to-device copies).  After it returns the recurrent state is that of the sequential clip."""
+        if n_frames <= 0:
+            return
+        feed(0)
+        self.g_first.replay()
+        for j in range(n_frames - 1):
+            feed(j + 1)                                        # (encode(j) has finished with the input buffers: graph order)
+            self.g_pipe[j & 1].replay()
+        self.g_last[(n_frames - 1) & 1].replay()
+
 
 class ClipRunner:
     """Public host-buffer API for a clip: frames arrive as pinned HOST tensors, results go back to pinned host tensors.
@@ -1054,6 +1136,64 @@ class ClipRunner:
     def results(self):
         """Tracker mode, after a synchronize: the frame's result rows (ids, xyxy boxes in pixels, scores) of the kept tracks."""
         ids, boxes, scores, keep = self.eng.trk.split_results(self.host_out["results"])
+        k = keep.bool()
+        return ids[k], boxes[k], scores[k]
+
+    def run_clip_pipelined(self, frames, sync=True):
+        """run_clip with frame pipelining (FrameEngine.run_clip_pipelined): while the recurrent tail of frame k runs, the
+        encoder of frame k + 1 runs on a second stream and frame k + 2 crosses PCIe.  frames: list of (srcs, pos, masks) pinned
+        host tensors.  Tracker mode returns the per-frame result buffers, one row per frame (pinned; `frame_results(i)`
+        decodes row i); raw mode returns the last frame's outputs.  Same results as run_clip."""
+        eng = self.eng
+        frames = list(frames)
+        n = len(frames)
+        if n == 0:
+            return None
+        if getattr(eng, "g_pipe", None) is None:
+            eng.capture_pipeline()
+        if not self.raw_outputs and (getattr(self, "clip_results", None) is None or self.clip_results.shape[0] < n):
+            self.clip_results = torch.empty(n, eng.trk.res_flat.numel(), dtype=torch.uint8).pin_memory()
+            self.clip_n_active = torch.empty(n, dtype=torch.int32).pin_memory()
+        cur = torch.cuda.current_stream(eng.dev)
+
+        def hand_over(j):                      # staged frame j -> the static input buffers (one device-to-device copy)
+            slot = j % 2
+            cur.wait_event(self.ready[slot])
+            eng.in_flat.copy_(self.stage[slot]["flat"], non_blocking=True)
+            self.free[slot].record(cur)
+
+        def read_back(j):
+            if self.raw_outputs:
+                k = eng.n_dec
+                self.host_out["pred_logits"].copy_(eng.pred_logit[k - 1], non_blocking=True)
+                self.host_out["pred_bboxes"].copy_(eng.pred_box[k - 1], non_blocking=True)
+                self.host_out["track_query_embed"].copy_(eng.st["query_embed"], non_blocking=True)
+                self.host_out["track_ref_pts"].copy_(eng.st["ref_pts"], non_blocking=True)
+            else:
+                self.clip_results[j].copy_(eng.trk.res_flat, non_blocking=True)
+                self.clip_n_active[j:j + 1].copy_(eng.table.n_active, non_blocking=True)
+
+        self.prefetch(0, *frames[0])
+        if n > 1:
+            self.prefetch(1, *frames[1])
+        hand_over(0)
+        eng.g_first.replay()
+        for j in range(n - 1):
+            hand_over(j + 1)                   # (encode(j) is done with the input buffers: graph order on this stream)
+            if j + 2 < n:
+                self.prefetch(j % 2, *frames[j + 2])
+            eng.g_pipe[j & 1].replay()
+            read_back(j)
+        eng.g_last[(n - 1) & 1].replay()
+        read_back(n - 1)
+        if sync:
+            cur.synchronize()
+            self.check()
+        return self.host_out if self.raw_outputs else self.clip_results[:n]
+
+    def frame_results(self, i):
+        """After run_clip_pipelined (tracker mode, synchronised): frame i's result rows (ids, xyxy boxes in pixels, scores)."""
+        ids, boxes, scores, keep = self.eng.trk.split_results(self.clip_results[i])
         k = keep.bool()
         return ids[k], boxes[k], scores[k]
 

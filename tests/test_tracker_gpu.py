@@ -327,3 +327,82 @@ def test_engine_bf16_clip_runner_device_tracker_matches_oracle():
             if len(w["ids"]):
                 assert rel_err(got[k].cpu().numpy(), w[k].numpy()) <= 2e-2, (t, k)
     runner.check()
+
+
+def test_pipelined_clip_equals_sequential_clip():
+    """FrameEngine.run_clip_pipelined (tail of frame k and encoder of frame k + 1 on two streams, one forked CUDA graph per
+    frame, the encode -> decode hand-off double-buffered) against the same clip replayed frame by frame: identities, labels,
+    disappear times, id counter and the last frame's result rows bit-exact, float state to the split-K reduction order."""
+    from memotr_b200.engine import FrameEngine
+    cfg = dict(synth.small_cfg(), n_det_queries=12, n_enc_layers=3)
+    sd = synth.reference_init_state_dict(cfg, seed=5)
+    frames = [synth.frame_inputs(cfg, MEDIUM_SHAPES, 0, seed=40 + t, padded=True) for t in range(7)]
+    thr = dict(det_score_thresh=0.02, track_score_thresh=0.018, miss_tolerance=2, result_score_thresh=0.019)
+    engs = []
+    for _ in range(2):
+        eng = FrameEngine(sd, cfg, MEDIUM_SHAPES, 32, DEV, mode="bf16", tracker=thr, ori_size=(1920, 1080),
+                          pos_embed=dict(temperature=20))
+        fr = frames[0]
+        eng.load_frame(fr["srcs"], fr["masks"], None, eng.in_track_ref, eng.in_track_embed)
+        eng.capture()
+        engs.append(eng)
+    seq, pipe = engs
+    pipe.capture_pipeline()
+
+    def feeder(eng):
+        def feed(j):
+            fr = frames[j]
+            eng.load_frame(fr["srcs"], fr["masks"], None, eng.in_track_ref, eng.in_track_embed)
+        return feed
+    for clip in range(2):                                   # two clips back to back: the parity bookkeeping survives a clip
+        n = 7 if clip == 0 else 4
+        for j in range(n):
+            feeder(seq)(j)
+            seq.replay()
+        pipe.run_clip_pipelined(n, feeder(pipe))
+        torch.cuda.synchronize()
+        a, b = seq.table.active(), pipe.table.active()
+        assert len(a["ids"]) > 0
+        for k in ("ids", "labels", "disappear_time"):
+            assert a[k].cpu().tolist() == b[k].cpu().tolist(), (clip, k)
+        assert int(seq.trk.max_obj_id.item()) == int(pipe.trk.max_obj_id.item())
+        for k in ("boxes", "ref_pts", "query_embed", "output_embed", "long_memory", "last_output", "logits"):
+            assert rel_err(b[k].cpu().numpy(), a[k].cpu().numpy()) < 2e-3, (clip, k)
+        assert seq.trk.res_keep.cpu().tolist() == pipe.trk.res_keep.cpu().tolist(), clip
+        keep = seq.trk.res_keep.bool()
+        assert seq.trk.res_ids[keep].cpu().tolist() == pipe.trk.res_ids[keep].cpu().tolist(), clip
+
+
+def test_clip_runner_pipelined_matches_frame_by_frame_results():
+    """ClipRunner.run_clip_pipelined (host frames in, per-frame result rows out, H2D / encoder / tail of three consecutive
+    frames in flight) returns for EVERY frame the ids the frame-by-frame runner returns."""
+    from memotr_b200.engine import ClipRunner, FrameEngine
+    cfg = dict(synth.small_cfg(), n_det_queries=12, n_enc_layers=3)
+    sd = synth.reference_init_state_dict(cfg, seed=5)
+    frames = [synth.frame_inputs(cfg, MEDIUM_SHAPES, 0, seed=40 + t, padded=True) for t in range(6)]
+    thr = dict(det_score_thresh=0.02, track_score_thresh=0.018, miss_tolerance=2, result_score_thresh=0.019)
+    pin = lambda t: t.contiguous().pin_memory()                                       # noqa: E731
+    host = [([pin(t) for t in fr["srcs"]], None, [pin(t.to(torch.uint8)) for t in fr["masks"]]) for fr in frames]
+    runners = []
+    for _ in range(2):
+        eng = FrameEngine(sd, cfg, MEDIUM_SHAPES, 32, DEV, mode="bf16", tracker=thr, ori_size=(1920, 1080),
+                          pos_embed=dict(temperature=20))
+        runners.append(ClipRunner(eng))
+    seq, pipe = runners
+    want = []
+    seq.prefetch(0, *host[0])
+    for t in range(6):
+        if t + 1 < 6:
+            seq.prefetch((t + 1) % 2, *host[t + 1])
+        seq.run(t % 2)
+        torch.cuda.synchronize()
+        ids, boxes, _ = seq.results()
+        want.append((ids.tolist(), boxes.clone()))
+    pipe.run_clip_pipelined(host)
+    assert sum(len(w[0]) for w in want) > 0
+    for t in range(6):
+        ids, boxes, _ = pipe.frame_results(t)
+        assert ids.tolist() == want[t][0], t
+        if len(ids):
+            assert rel_err(boxes.numpy(), want[t][1].numpy()) < 2e-3, t
+    assert pipe.eng.table.active()["ids"].cpu().tolist() == seq.eng.table.active()["ids"].cpu().tolist()
