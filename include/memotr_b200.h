@@ -387,7 +387,7 @@ typedef struct memotr_dec_params {
   unsigned int *barrier;                        /* scratch: one counter */
   long long *prof;                              /* NULL, or (blocks, n_layers, 16) clock64 phase stamps (measurement) */
   float *init_ref_out, *last_ref_out;           /* NULL or (nq,4): inverse_sigmoid of the references entering the first /
-                                                   the last layer (memotr.py:183-187); cluster kernel only */
+                                                   the last layer (memotr.py:183-187) */
   int shapes[16], lsi[8];                       /* (H, W) and first pixel of every level */
   memotr_dec_layer layers[MEMOTR_DEC_MAX_LAYERS];
 } memotr_dec_params;
@@ -401,6 +401,22 @@ typedef struct memotr_dec_params {
  * (K padded to a multiple of 256), bbox_embed.0 / .1 rows.  Requires n_levels * n_points == 16.
  */
 MEMOTR_API int memotr_decoder_forward_cluster(const memotr_dec_params *params, void *stream);
+
+/*
+ * The same decoder with ONE CTA per 16-row block (csrc/decoder_fused.cu): 25 CTAs at the DanceTrack size, ~600 us instead of
+ * ~380 us, but 15 k instead of 38 k SM-microseconds -- the variant the frame-pipelined clip uses, where the decoder of frame k
+ * shares the GPU with the encoder of frame k+1 and its latency hides behind it (FrameEngine.run_clip_pipelined).  `prog` is ONE
+ * program in layer order: rph0, rph1, [qs0, qs1 if layer > 0], qk, v, sa_out, ol, ca_out, ffn1 / ffn2 (in two halves of the
+ * hidden dimension when d_ffn > 1024), bb0, bb1; slot images as memotr_dec_gemm describes.
+ */
+MEMOTR_API int memotr_decoder_forward(const memotr_dec_params *params, void *stream);
+
+/*
+ * Cap the number of SMs the persistent kernels of LATER launches size their grids for (persistent tcgen05 GEMM, fused FFN,
+ * windowed gather); 0 = all SMs.  Host-side state read at launch time (grids are baked into a captured graph): the
+ * frame-pipelined clip launches the first encoder layers of frame k+1 with the SMs the decoder of frame k occupies left free.
+ */
+MEMOTR_API int memotr_set_sm_budget(int n_sm);
 
 /*
  * QueryUpdater.update_tracks_embedding (models/query_updater.py:82-166, DAB branch) on a device-resident track table as one

@@ -6,6 +6,17 @@ using memotr::fail;
 extern "C" int memotr_abi_version(void) { return MEMOTR_ABI_VERSION; }
 extern "C" const char *memotr_last_error(void) { return memotr::err_buf(); }
 
+// ---- SM budget of the persistent kernels (include/memotr_b200.h: memotr_set_sm_budget) ---------------------------------
+static int g_sm_budget = 0;
+extern "C" int memotr_set_sm_budget(int n_sm) {
+  MEMOTR_REQUIRE(n_sm >= 0, "set_sm_budget: negative budget");
+  g_sm_budget = n_sm;
+  return MEMOTR_OK;
+}
+namespace memotr {
+int sm_limit(int n_sm) { return (g_sm_budget > 0 && g_sm_budget < n_sm) ? g_sm_budget : n_sm; }
+}  // namespace memotr
+
 // ---- device-side interval timer usable inside CUDA graphs ------------------------------------------------------------
 // bench.py measures the dominant kernel's duration live, inside the timed region, on the launching stream.  Events
 // recorded with cudaEventRecordExternal become event-record nodes when the stream is being captured, and -- unlike

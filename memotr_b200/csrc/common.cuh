@@ -152,6 +152,9 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { retu
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
+// SM budget of the persistent kernels (memotr_set_sm_budget, capi.cu): min(n_sm, budget) when a budget is set
+int sm_limit(int n_sm);
+
 struct Epilogue {
   const float *bias;             // (N) or null
   const void *mul;               // (M,N) activation dtype or null: result *= mul

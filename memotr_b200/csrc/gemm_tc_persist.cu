@@ -292,7 +292,8 @@ static int launch(const void *A, int lda, const void *W, int ldw, void *C, int l
   const int tiles = (N / BN) * ceil_div(M, BM);
   Epilogue eps = ep;
   eps.stamps = g_stamps;
-  MEMOTR_LAUNCH((kern), tiles < n_sm ? tiles : n_sm, 320, Plan<TC>::TOTAL, st, tmA, tmW, tmC, M, N, K, eps);
+  const int ctas = sm_limit(n_sm);      // (memotr_set_sm_budget: leave SMs to a concurrent kernel)
+  MEMOTR_LAUNCH((kern), tiles < ctas ? tiles : ctas, 320, Plan<TC>::TOTAL, st, tmA, tmW, tmC, M, N, K, eps);
   return check_launch("gemm_tc_persist");
 }
 

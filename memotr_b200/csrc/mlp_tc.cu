@@ -614,12 +614,12 @@ static int pick_split(int tiles, int chunks, int n_sm) {
 // MEMOTR_MLP_TAIL=0 switches the split off (A/B).
 static int mlp2_f32_balanced(const void *X, int ldx, const void *W1, const float *b1, const void *W2, void *C, int ldc, int M,
                              int Hd, const Epilogue &ep, cudaStream_t st) {
-  const int n_sm = sm_count(), tiles = ceil_div(M, tc::BM), chunks = Hd / tc::mlp::HC;
+  const int n_sm = sm_limit(sm_count()), tiles = ceil_div(M, tc::BM), chunks = Hd / tc::mlp::HC;
   const char *tl = getenv("MEMOTR_MLP_TAIL");
   if (tl && tl[0] == '0') return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st);
   if (tiles * 2 <= n_sm) return tc::launch_mlp2<float>(X, ldx, W1, b1, W2, C, ldc, M, Hd, ep, st, pick_split(tiles, chunks, n_sm));
   const int tail = tiles - n_sm;
-  if (tail > 0 && tail * 2 <= n_sm) {
+  if (tail > 0 && tail <= n_sm) {
     const int ns = pick_split(tail, chunks, n_sm);
     if (ns > 1) {   // the first round clears the rows the split round adds into (no memset node between the two launches)
       tc::Front z{};

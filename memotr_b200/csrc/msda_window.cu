@@ -844,7 +844,7 @@ extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_str
   int dev = 0, n_sm = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const int win_ctas = std::min(units, n_sm);
+  const int win_ctas = std::min(units, sm_limit(n_sm));
   MEMOTR_LAUNCH((kern), P.n_glob_blocks + win_ctas, win::THREADS, smem, st, M, P, (const __half *)value, sampling_loc,
                 attn_weight, valid_ratios, stats, (__nv_bfloat16 *)output);
   return check_launch("msda_window");

@@ -115,6 +115,13 @@ class FrameEngine:
         if self.dec_fused:
             self._build_decoder_program()
             self._build_decoder_program_cluster()
+        # the one-CTA-per-row-block decoder (csrc/decoder_fused.cu) for frame-pipelined clips; MEMOTR_DEC_SINGLE=0: never
+        F_ = cfg["d_ffn"]
+        self.dec_single_ok = (self.dec_fused and os.environ.get("MEMOTR_DEC_SINGLE", "1") != "0"
+                              and (F_ % 512 == 0 if F_ > 1024 else F_ % 256 == 0))
+        self.dec_use_single = False
+        if self.dec_single_ok:
+            self._build_decoder_program_single()
         # the query updater as one persistent cluster kernel (csrc/updater_cluster.cu); A/B switch MEMOTR_UPD_FUSED=0
         self.upd_fused = (self.dec_cluster and os.environ.get("MEMOTR_UPD_FUSED", "1") != "0"
                           and 1 <= self.nt and (self.nt + 15) // 16 * 4 <= 132)
@@ -414,6 +421,49 @@ class FrameEngine:
         P.init_ref_out, P.last_ref_out = self.init_ref_pts.data_ptr(), self.last_ref_pts.data_ptr()
         self.dec_params_cl = P
 
+    def _build_decoder_program_single(self):
+        """Weight program of memotr_decoder_forward (one CTA per row block, csrc/decoder_fused.cu): the variant the pipelined clip
+        runs next to the encoder of the following frame."""
+        import ctypes
+        dev, F = self.dev, self.Fd
+        prog, self.dec_packed = [], []
+
+        def g(L, row0=0, rows=None, col0=0, K=None):
+            """Pack W[row0:row0+rows, col0:col0+K] as slot images (see memotr_dec_gemm in include/memotr_b200.h)."""
+            rows, K = (L.N if rows is None else rows), (L.K if K is None else K)
+            assert rows % 64 == 0 and K % 256 == 0 and L.w.dtype == torch.bfloat16
+            w = L.w[row0:row0 + rows, col0:col0 + K].reshape(rows // 64, 64, K // 256, 256)
+            if K == 256:
+                img = torch.zeros(rows // 64, 1, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = w.permute(0, 2, 1, 3)
+            else:                                   # k-slice-major; the kernel keeps all four n-blocks' accumulators live
+                assert rows == 256
+                img = torch.zeros(K // 256, rows // 64, 64, 264, dtype=torch.bfloat16, device=dev)
+                img[..., :256] = w.permute(2, 0, 1, 3)
+            self.dec_packed.append(img)
+            prog.append((img.data_ptr(), 264, rows, K))
+
+        for lid, ly in enumerate(self.dec):
+            g(self.ref_point_head[0]), g(self.ref_point_head[1])
+            if lid > 0:
+                g(self.query_scale[0]), g(self.query_scale[1])
+            g(ly["self"]["qk"]), g(ly["self"]["v"]), g(ly["self"]["out"]), g(ly["attn"]["ol"]), g(ly["attn"]["out"])
+            nh = 2 if F > 1024 else 1
+            for half in range(nh):
+                g(ly["lin1"], row0=half * F // nh, rows=F // nh)
+                g(ly["lin2"], col0=half * F // nh, K=F // nh)
+            g(ly["bbox"][0]), g(ly["bbox"][1])
+        arr = (_lib.DecGemm * len(prog))(*[_lib.DecGemm(w, ldw, n, k, 0) for (w, ldw, n, k) in prog])
+        self.dec_prog = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.dec_kbuf1 = torch.zeros_like(self.dec_kbuf)
+        self.dec_vbuf1 = torch.zeros_like(self.dec_vbuf)
+        self.dec_barrier1 = torch.zeros_like(self.dec_barrier)
+        P = _lib.DecParams()
+        ctypes.memmove(ctypes.byref(P), ctypes.byref(self.dec_params_cl), ctypes.sizeof(P))
+        P.prog, P.n_prog = self.dec_prog.data_ptr(), len(prog)
+        P.kbuf, P.vbuf, P.barrier = self.dec_kbuf1.data_ptr(), self.dec_vbuf1.data_ptr(), self.dec_barrier1.data_ptr()
+        self.dec_params_single = P
+
     def _build_updater_program(self):
         """Per-rank weight programs + parameter block of memotr_updater_forward_cluster (include/memotr_b200.h)."""
         dev, F, C, nt, u, CS = self.dev, self.Fd, self.C, self.nt, self.upd, 4
@@ -478,8 +528,11 @@ class FrameEngine:
 
     def _decoder_fused(self):
         import ctypes
-        self._ck(self.lib.memotr_decoder_forward_cluster(ctypes.byref(self.dec_params_cl), self._st()),
-                 "decoder_forward_cluster")
+        if self.dec_use_single:      # one CTA per row block: slower, but a third of the SM-time (pipelined clips)
+            self._ck(self.lib.memotr_decoder_forward(ctypes.byref(self.dec_params_single), self._st()), "decoder_forward")
+        else:
+            self._ck(self.lib.memotr_decoder_forward_cluster(ctypes.byref(self.dec_params_cl), self._st()),
+                     "decoder_forward_cluster")
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------------ launch helpers
@@ -620,9 +673,22 @@ class FrameEngine:
         self.encode()
         self.decode()
 
-    def encode(self):
+    def encode(self, sm_plan=None):
         """Everything that depends on the frame alone (phase 1 of an exact sharded clip, memotr_b200/clip.py): level
-        flattening, the encoder, and the stacked value projection of all decoder layers."""
+        flattening, the encoder, and the stacked value projection of all decoder layers.
+        sm_plan = (budget, n_layers): the persistent kernels of the first n_layers encoder layers size their grids for `budget`
+        SMs (a concurrent kernel holds the others: capture_pipeline)."""
+        C, S, H, L, dt = self.C, self.S, self.H, self.L, self.dt
+        st = self._st
+        if sm_plan is not None:
+            _lib.check(self.lib.memotr_set_sm_budget(int(sm_plan[0])), "set_sm_budget")
+        try:
+            self._encode(sm_plan)
+        finally:
+            if sm_plan is not None:
+                _lib.check(self.lib.memotr_set_sm_budget(0), "set_sm_budget")
+
+    def _encode(self, sm_plan):
         C, S, H, L, dt = self.C, self.S, self.H, self.L, self.dt
         st = self._st
         self._mark(0)
@@ -664,6 +730,8 @@ class FrameEngine:
         Ke = self.cfg["n_enc_points"]
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
+            if sm_plan is not None and i == sm_plan[1]:
+                _lib.check(self.lib.memotr_set_sm_budget(0), "set_sm_budget")
             if self.debug_enc is not None:
                 self.debug_enc.append(self.src32.float().clone())
             self.lin(self.src_tok, C, a["value"], self.value, C, S, rowzero=self.mask_flat, c_dtype=self.vdt)
@@ -987,27 +1055,56 @@ class FrameEngine:
         if not self.dec_cluster:
             raise RuntimeError("FrameEngine.enable_pipeline: needs the fused decoder (bf16 mode)")
         C = self.C
-        sets = [dict(value_all=self.value_all, vr=self.vr, dec=self.dec_params_cl)]
+        single = self.dec_params_single if self.dec_single_ok else None
+        sets = [dict(value_all=self.value_all, vr=self.vr, dec=self.dec_params_cl, dec1=single)]
         v2, vr2 = torch.empty_like(self.value_all), torch.empty_like(self.vr)
-        P = _lib.DecParams()
-        ctypes.memmove(ctypes.byref(P), ctypes.byref(self.dec_params_cl), ctypes.sizeof(P))
-        P.valid_ratios = vr2.data_ptr()
-        for lid in range(self.n_dec):
-            P.layers[lid].value = v2.data_ptr() + lid * C * 2
-        sets.append(dict(value_all=v2, vr=vr2, dec=P))
+
+        def second(src):
+            if src is None:
+                return None
+            P = _lib.DecParams()
+            ctypes.memmove(ctypes.byref(P), ctypes.byref(src), ctypes.sizeof(P))
+            P.valid_ratios = vr2.data_ptr()
+            for lid in range(self.n_dec):
+                P.layers[lid].value = v2.data_ptr() + lid * C * 2
+            return P
+        sets.append(dict(value_all=v2, vr=vr2, dec=second(self.dec_params_cl), dec1=second(single)))
         self._sets = sets
 
     def use_set(self, i):
         """Which copy of (value_all, vr) the following encode() writes / decode() reads (enqueue-time pointers)."""
         d = self._sets[i]
-        self.value_all, self.vr, self.dec_params_cl = d["value_all"], d["vr"], d["dec"]
+        self.value_all, self.vr, self.dec_params_cl, self.dec_params_single = d["value_all"], d["vr"], d["dec"], d["dec1"]
 
-    def capture_pipeline(self):
+    def capture_pipeline(self, single=None, split=None):
         """Five graphs: encode-only into set 0 (clip prologue), [tail(set c) || encode(set 1 - c)] for c = 0, 1, tail-only for
-        c = 0, 1 (clip epilogue).  Call after capture() (which did the one-time warm-up of every kernel)."""
+        c = 0, 1 (clip epilogue).  Call after capture() (which did the one-time warm-up of every kernel).
+        In the forked graphs the decoder is the one-CTA-per-row-block kernel (`single`, default on when available): ~600 us on 25
+        SMs instead of ~380 us on 100 -- its latency hides behind the encoder, its SM-time is what the encoder loses -- and the
+        first `split` encoder layers (default: two thirds) size their persistent grids for the SMs that leaves free
+        (memotr_set_sm_budget); by the time the later layers launch, the tail is done.  Measured at the DanceTrack size
+        (frames/s): cluster decoder 666; single-CTA decoder with split 0 / 2 / 3 / 4 / 5 / 6: 652 / 681 / 714 / 726 / 717 / 702.
+        MEMOTR_PIPE_SINGLE / MEMOTR_PIPE_SPLIT / MEMOTR_PIPE_RESERVE override."""
+        import os
         if self.graph is None:
             raise RuntimeError("FrameEngine.capture_pipeline: call capture() first")
         self.enable_pipeline()
+        if single is None:
+            single = os.environ.get("MEMOTR_PIPE_SINGLE", "1") != "0"
+        single = bool(single) and self.dec_single_ok
+        if split is None:
+            split = int(os.environ.get("MEMOTR_PIPE_SPLIT", str((2 * self.n_enc + 2) // 3)))
+        reserve = int(os.environ.get("MEMOTR_PIPE_RESERVE", str((self.nq + 15) // 16)))     # SMs left to the tail
+        budget = self.n_sm - reserve if single else 0
+        if single:           # one-time attribute calls of the kernel outside capture (a warm-up launch; state restored)
+            state = self._recurrent_state()
+            saved = [t.clone() for t in state]
+            self.dec_use_single = True
+            self.step_tail()
+            self.dec_use_single = False
+            for t, v in zip(state, saved):
+                t.copy_(v)
+            torch.cuda.synchronize(self.dev)
         timer, self.timer = self.timer, None                   # (event nodes only in the sequential instrumented graph)
         main = torch.cuda.Stream(self.dev, priority=-1)        # the tail: fewer, longer CTAs -- scheduled first
         side = torch.cuda.Stream(self.dev)
@@ -1024,9 +1121,13 @@ class FrameEngine:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     self.use_set(1 - c)
-                    self.encode()
+                    self.encode(sm_plan=(budget, split) if budget > 0 else None)
                 self.use_set(c)
-                self.step_tail()
+                self.dec_use_single = single
+                try:
+                    self.step_tail()
+                finally:
+                    self.dec_use_single = False
                 main.wait_stream(side)
             return body
 

@@ -138,14 +138,28 @@ def inverse_sigmoid(x, eps=1e-5):
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
+def _r32(x, like):
+    """A float64 intermediate rounded the way a float32 evaluation rounds it (identity for float64 inputs)."""
+    return x.float().double() if like.dtype != torch.float64 else x
+
+
+def _dim_table(num_pos_feats, temperature, like):
+    i = torch.arange(num_pos_feats, dtype=torch.float64, device=like.device)
+    e32 = _r32(2 * torch.div(i, 2, rounding_mode="trunc") / num_pos_feats, like)
+    return _r32(torch.as_tensor(float(temperature), dtype=torch.float64, device=like.device) ** e32, like)
+
+
 def pos_to_pos_embed(pos, num_pos_feats=64, temperature=10000, scale=2 * math.pi):
-    """models/utils.py:78-85: interleaved sin/cos, coordinate-major."""
-    pos = pos * scale
-    i = torch.arange(num_pos_feats, dtype=torch.float32, device=pos.device)
-    dim_i = temperature ** (2 * torch.div(i, 2, rounding_mode="trunc") / num_pos_feats)
-    e = pos[..., None] / dim_i
+    """models/utils.py:78-85: interleaved sin/cos, coordinate-major.
+    Evaluated as the correctly rounded float32 sequence of the reference (every step in float64, rounded to float32 where the
+    reference holds a float32): the result does not depend on which vectorised float32 pow / sin / cos the host's torch build
+    dispatches to (a GPU-box host type was seen to deviate by 1.5e-4 here, enough to fail 1e-5 kernel tests)."""
+    like = pos
+    s32 = float(torch.tensor(scale, dtype=torch.float32)) if pos.dtype != torch.float64 else scale
+    p = _r32(pos.double() * s32, like)
+    e = _r32(p[..., None] / _dim_table(num_pos_feats, temperature, like), like)
     e = torch.stack((e[..., 0::2].sin(), e[..., 1::2].cos()), dim=-1)
-    return torch.flatten(e, start_dim=-3)
+    return torch.flatten(e, start_dim=-3).to(like.dtype)
 
 
 def mha(sd, key, q, k, v, n_heads, key_padding_mask=None):

@@ -392,14 +392,22 @@ def test_sine_embed_and_box_refine():
     i = torch.arange(128, dtype=torch.float32)
     dim_t = 10000 ** (2 * torch.div(i, 2, rounding_mode="trunc") / 128)
     pts = torch.rand(50, 4, generator=g)
-    want = oframe.pos_to_pos_embed(pts, num_pos_feats=128)
+
+    def truth(p):
+        """models/utils.py:78-85 in float64 on the very dim_t the kernel is given: independent of the host's float32 pow / sin
+        (the float32 CPU oracle was seen 1.5e-4 off on one GPU-box host type; that is reported below, not asserted)."""
+        e = (p.double() * float(torch.tensor(2 * math.pi, dtype=torch.float32)))[..., None] / dim_t.double()
+        return torch.stack((e[..., 0::2].sin(), e[..., 1::2].cos()), dim=-1).flatten(-3)
     got = K().sine_embed(pts.to(DEV), dim_t.to(DEV)).cpu()
-    assert rel_err(got, want) < 1e-5
+    assert rel_err(got, truth(pts)) < 2e-6
+    host = rel_err(oframe.pos_to_pos_embed(pts, num_pos_feats=128), truth(pts))
+    if host > 1e-5:
+        import warnings
+        warnings.warn(f"this host's float32 CPU path deviates {host:.1e} from float64 in pos_to_pos_embed")
     raw = torch.randn(50, 4, generator=g)
     scale = torch.tensor([0.9, 0.8, 0.9, 0.8])
-    want = oframe.pos_to_pos_embed(raw.sigmoid() * scale, num_pos_feats=128)
     got = K().sine_embed(raw.to(DEV), dim_t.to(DEV), scale4=scale.to(DEV), apply_sigmoid=True).cpu()
-    assert rel_err(got, want) < 1e-5
+    assert rel_err(got, truth((raw.sigmoid() * scale))) < 2e-6
     delta, ref = torch.randn(50, 4, generator=g), torch.rand(50, 4, generator=g)
     ref[0, 0], ref[1, 1] = 0.0, 1.0                       # inverse_sigmoid clamps (utils/utils.py:71-73)
     want = (delta + oframe.inverse_sigmoid(ref)).sigmoid()
@@ -443,7 +451,22 @@ def test_pos_embed_sine_matches_oracle_and_reference_golden(h, w, vh, vw):
     m[:, :vh, :vw] = False
     want = oframe.position_embedding_sine(m)[0]
     got = K().pos_embed_sine(m[0].to(DEV)).cpu()
-    assert got.shape == want.shape and (got - want).abs().max() <= 2e-6
+    # float64 restatement of models/position_embedding.py:23-43 (host-independent yardstick; the float32 oracle is reported)
+    nm = (~m).double()
+    y, x = nm.cumsum(1), nm.cumsum(2)
+    y, x = (y - 0.5) / (y[:, -1:, :] + 1e-6) * 2 * math.pi, (x - 0.5) / (x[:, :, -1:] + 1e-6) * 2 * math.pi
+    di = 20.0 ** (2 * torch.div(torch.arange(128, dtype=torch.float64), 2, rounding_mode="trunc") / 128)
+    px, py = x[:, :, :, None] / di, y[:, :, :, None] / di
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
+    t64 = torch.cat((py, px), dim=3).permute(0, 3, 1, 2)[0]
+    valid = ~m[0]            # (fully padded rows / columns have arguments ~ -3e6: chaotic in float32, compared through the golden)
+    assert got.shape == want.shape and (got.double() - t64)[:, valid].abs().max() <= 5e-6
+    if (want.double() - t64)[:, valid].abs().max() > 5e-6 or (got - want).abs().max() > 2e-6:
+        import warnings
+        warnings.warn(f"this host's float32 CPU path deviates from the kernel / float64 in position_embedding_sine: "
+                      f"{float((want.double() - t64)[:, valid].abs().max()):.1e} on valid pixels, "
+                      f"{float((got - want).abs().max()):.1e} overall")
     g = np.load(os.path.join(GOLDEN, "pos_embed.npz"))            # outputs of the reference's own class
     for i in (0, 1):
         got = K().pos_embed_sine(torch.from_numpy(g[f"mask{i}"][0]).to(DEV)).cpu().numpy()
@@ -747,3 +770,25 @@ def test_engine_cuda_graph_replay_equals_eager_and_chains_frames(mode):
     for k in UPD_KEYS:
         assert torch.equal(eager.st[k], graph.st[k]), k
     assert graph.graph_launches > 20
+
+
+def test_single_cta_decoder_matches_cluster_decoder():
+    """memotr_decoder_forward (one CTA per row block, the pipelined clip's decoder) against memotr_decoder_forward_cluster on
+    the same frame: same arithmetic, different work split -- every output within fp32 re-association noise of bf16 GEMMs."""
+    from memotr_b200.engine import FrameEngine
+    shapes = ((64, 104), (32, 52), (16, 26), (8, 13))
+    cfg = dict(synth.small_cfg(), n_det_queries=40)
+    sd = synth.reference_init_state_dict(cfg, seed=3)
+    x = synth.frame_inputs(cfg, shapes, 8, seed=2, padded=True)
+    eng = FrameEngine(sd, cfg, shapes, 8, DEV, mode="bf16", pos_embed=dict(temperature=20), pad_tracks=16)
+    assert eng.dec_cluster and eng.dec_single_ok
+    eng.load_frame(x["srcs"], x["masks"], None, x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
+    out = []
+    for single in (False, True):
+        eng.dec_use_single = single
+        eng.forward()
+        torch.cuda.synchronize()
+        out.append({k: v.clone() for k, v in eng.results().items()})
+    eng.dec_use_single = False
+    for k in ("pred_logits", "pred_bboxes", "outputs", "aux_logits", "aux_bboxes", "aux_queries", "last_ref_pts", "init_ref_pts"):
+        assert rel_err(out[1][k].float().cpu().numpy(), out[0][k].float().cpu().numpy()) < 2e-3, k

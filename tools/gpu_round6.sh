@@ -1,7 +1,7 @@
 #!/bin/bash
 # full GPU suite, smoke, default bench, reference arm, launch list of one eager step (no kernel-name filter)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/ -m gpu -q --tb=short -x > gpurun_out/pytest_gpu_full.log 2>&1
+timeout 1500 python -m pytest tests/ -m gpu -q --tb=short > gpurun_out/pytest_gpu_full.log 2>&1
 echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu_full.log | tail -8
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
