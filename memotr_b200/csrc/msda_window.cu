@@ -37,7 +37,8 @@ namespace win {
 
 constexpr int MAXL = 5, MAXC = 4, MAXH = 16;
 constexpr int TAP_WARPS = 16, DEC_WARPS = 8, THREADS = (TAP_WARPS + DEC_WARPS) * 32;
-constexpr int SMEM_BUDGET = 112 * 1024;      // per stage (windows + records of one unit); a CTA holds two stages (227 KB per SM)
+constexpr int SMEM_BUDGET = 110 * 1024;      // per stage (windows + records of one unit); a CTA holds two stages + ~5 KB of static
+                                             // shared memory (unit descriptors, barriers) in the 227 KB of an SM
 
 struct ClassGeom {
   int lq;                       // the level this class's queries live on
@@ -59,6 +60,8 @@ struct Params {
   int L, K, H, S, xs, ld_loc, ld_attn;
   int stage_bytes;                     // bytes of one stage (windows + records); the CTA double-buffers stages
   int h_shift;                         // log2(H) when H is a power of two, else -1
+  int debug;                           // MEMOTR_WINDOW_DEBUG (timing experiments, wrong results): 1 = the decode warps build records
+                                       // for their first two units only (tap-bound time), 2 = the tap warps skip the taps (decode-bound)
   float radius;
   float shift[MAXH * MAXL * 2];        // per (head, level): expected sampling offset (x, y) in pixels of that level
 };
@@ -431,6 +434,41 @@ __device__ __noinline__ uint4 slow_record(const int *hw, const int *lsi, int l, 
                     *reinterpret_cast<const uint32_t *>(&p.ws[1]));
 }
 
+// Per-unit descriptor, computed ONCE per CTA for all of its units before the pipeline starts (one thread per unit; the tap
+// warps have nothing to do during the pipeline fill anyway).  The decode-only experiment (MEMOTR_WINDOW_DEBUG=2) showed the
+// decode warps alone need 42 of the kernel's 58 us -- 2.8 us per unit, a third of it the serial head of every unit: unit
+// index -> (class, head, tile), the fast division for the tile's reference point, the window origin, indexed constant loads.
+struct __align__(16) UnitLevel {
+  int ox, oy;            // window origin
+  float oxf, oyf, xmaxf, ymaxf;   // in-window test on the floored sample position (xmaxf = -3e38: no window for this level)
+  int vrel, ww;          // window base - (oy * ww + ox) * 64 relative to the stage; window width in pixels
+};
+struct __align__(16) UnitDesc {
+  int c, h, tx, ty;
+  UnitLevel lv[4];
+};
+constexpr int MAX_CTA_UNITS = 32;      // units per CTA covered by descriptors (more: computed on the fly, as before)
+
+__device__ __forceinline__ UnitDesc describe_unit(const Params &P, const float *__restrict__ vr, int u) {
+  UnitDesc d;
+  const Unit t = unit_of(P, u);
+  const ClassGeom &G = P.cls[t.c];
+  d.c = t.c, d.h = t.h, d.tx = t.tx, d.ty = t.ty;
+  // (any origin is correct as long as the copy and the records agree: both read this descriptor)
+  const float rx = __fdividef((float)(t.tx * G.tw) + 0.5f, __ldg(vr + 2 * G.lq) * (float)G.Wq);
+  const float ry = __fdividef((float)(t.ty * G.th) + 0.5f, __ldg(vr + 2 * G.lq + 1) * (float)G.Hq);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int2 org = window_origin(P, G, vr, rx, ry, t.h, l);
+    const int ww = G.ww[l], wh = G.wh[l];
+    UnitLevel &L = d.lv[l];
+    L.ox = org.x, L.oy = org.y, L.oxf = (float)org.x, L.oyf = (float)org.y;
+    L.xmaxf = ww ? (float)(org.x + ww - 2) : -3e38f, L.ymaxf = (float)(org.y + wh - 2);
+    L.vrel = G.off[l] - (org.y * ww + org.x) * 64, L.ww = ww;
+  }
+  return d;
+}
+
 #define MEMOTR_BAR_ARRIVE(id) asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(THREADS) : "memory")
 #define MEMOTR_BAR_SYNC(id) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory")
 
@@ -467,12 +505,14 @@ msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant
   const int n_units = P.cls[P.n_cls - 1].unit0 + P.cls[P.n_cls - 1].n_units;
   const int stride = gridDim.x - P.n_glob_blocks;
   const int first = blockIdx.x - P.n_glob_blocks;
+  __shared__ UnitDesc udesc[MAX_CTA_UNITS];
   if (tid == 0) {
     tc::mbar_init(win_full, 1), tc::mbar_init(win_full + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
   pdl_grid_sync();
+  if (tid < MAX_CTA_UNITS && first + tid * stride < n_units) udesc[tid] = describe_unit(P, vr, first + tid * stride);
+  __syncthreads();
 
   if (tid >= TAP_WARPS * 32) {
     // =========================================================================================== decode warps
@@ -496,22 +536,33 @@ msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant
         }
       }
     };
-    Unit t = unit_of(P, first < n_units ? first : 0);
+    auto unit_at = [&](int n, int unit) {        // the n-th unit of this CTA: from its descriptor when there is one
+      if (n < MAX_CTA_UNITS) {
+        const int4 v = *reinterpret_cast<const int4 *>(&udesc[n]);
+        Unit t;
+        t.c = v.x, t.h = v.y, t.tx = v.z, t.ty = v.w;
+        return t;
+      }
+      return unit_of(P, unit);
+    };
+    Unit t = unit_at(0, first < n_units ? first : 0);
     if (first < n_units) prefetch(t);
     int n = 0;
     for (int unit = first; unit < n_units; unit += stride, ++n) {
       const int b = n & 1;
       const ClassGeom &G = P.cls[t.c];
-      const int TQ = G.tw * G.th, ww = G.ww[l], wh = G.wh[l];
+      const int TQ = G.tw * G.th;
       const uint32_t wbase = (uint32_t)(b * P.stage_bytes);
-      // (any origin is correct as long as the copy and the records agree: the fast division is the same instruction sequence
-      //  on the same operands in every thread)
-      const float rx = __fdividef((float)(t.tx * G.tw) + 0.5f, __ldg(vr + 2 * G.lq) * (float)G.Wq);
-      const float ry = __fdividef((float)(t.ty * G.th) + 0.5f, __ldg(vr + 2 * G.lq + 1) * (float)G.Hq);
-      const int2 org = window_origin(P, G, vr, rx, ry, t.h, l);
-      const float oxf = (float)org.x, oyf = (float)org.y;
-      const float xmaxf = ww ? (float)(org.x + ww - 2) : -3e38f, ymaxf = (float)(org.y + wh - 2);
-      const int vbase = (int)wbase + G.off[l] - (org.y * ww + org.x) * 64;      // byte offset of the level's pixel (0, 0)
+      UnitLevel UL;
+      if (n < MAX_CTA_UNITS) {
+        UL = udesc[n].lv[l];
+      } else {
+        UL = describe_unit(P, vr, unit).lv[l];
+      }
+      const int ww = UL.ww;
+      const int2 org = make_int2(UL.ox, UL.oy);
+      const float oxf = UL.oxf, oyf = UL.oyf, xmaxf = UL.xmaxf, ymaxf = UL.ymaxf;
+      const int vbase = (int)wbase + UL.vrel;                                   // byte offset of the level's pixel (0, 0)
       if (n >= 2) MEMOTR_BAR_SYNC(BUF_FREE + b);                               // the tap warps have finished unit n - 2
       if (dt < L) {
         if (dt == 0) tc::mbar_expect_tx(win_full + b, (uint32_t)G.win_bytes);
@@ -528,7 +579,7 @@ msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int ql = qd + 64 * i;
-        if (ql >= TQ) continue;
+        if (ql >= TQ || (P.debug == 1 && n >= 2)) continue;
         uint4 r[4];                                 // per point {off side 0, w side 0, off side 1, w side 1}
 #pragma unroll
         for (int j = 0; j < 4; ++j) r[j] = make_uint4(wbase, 0u, wbase, 0u);
@@ -562,7 +613,7 @@ msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant
         flags[ql * 4] = (uint8_t)((r[0].x | r[1].x | r[2].x | r[3].x) >> 31);
       }
       if (unit + stride < n_units) {
-        t = unit_of(P, unit + stride);
+        t = unit_at(n + 1, unit + stride);
         prefetch(t);
       }
       __syncwarp();
@@ -580,7 +631,13 @@ msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant
   int n = 0;
   for (int unit = first; unit < n_units; unit += stride, ++n) {
     const int b = n & 1;
-    const Unit t = unit_of(P, unit);
+    Unit t;
+    if (n < MAX_CTA_UNITS) {
+      const int4 v = *reinterpret_cast<const int4 *>(&udesc[n]);
+      t.c = v.x, t.h = v.y, t.tx = v.z, t.ty = v.w;
+    } else {
+      t = unit_of(P, unit);
+    }
     const ClassGeom &G = P.cls[t.c];
     const int TQ = G.tw * G.th, rec_stride = G.rec_stride;
     const uint32_t stage = smem0 + (uint32_t)(b * P.stage_bytes);
@@ -596,6 +653,7 @@ msda_window_k4l4_kernel(const __grid_constant__ Maps maps, const __grid_constant
     MEMOTR_BAR_SYNC(REC_FULL + b);
     mbar_wait_sleepy(win_full + b, (n >> 1) & 1);
     for (int ql = grp; ql < TQ; ql += TAP_WARPS * 4, y += ystep, optr += ostep) {
+      if (P.debug == 2) continue;
       const uint32_t rq = recs + ql * rec_stride;
       uint32_t flag;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(flag) : "r"(flags + ql * 4));
@@ -845,6 +903,8 @@ extern "C" int memotr_msda_forward_window(const void *value, int value_pixel_str
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int win_ctas = std::min(units, sm_limit(n_sm));
+  const char *dbg = getenv("MEMOTR_WINDOW_DEBUG");
+  P.debug = dbg ? atoi(dbg) : 0;
   MEMOTR_LAUNCH((kern), P.n_glob_blocks + win_ctas, win::THREADS, smem, st, M, P, (const __half *)value, sampling_loc,
                 attn_weight, valid_ratios, stats, (__nv_bfloat16 *)output);
   return check_launch("msda_window");

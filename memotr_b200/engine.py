@@ -730,7 +730,7 @@ class FrameEngine:
         Ke = self.cfg["n_enc_points"]
         for i, ly in enumerate(self.enc):
             a = ly["attn"]
-            if sm_plan is not None and i == sm_plan[1]:
+            if sm_plan is not None and i == sm_plan[1]:            # (sm_plan[1] = k: full budget from layer k on;
                 _lib.check(self.lib.memotr_set_sm_budget(0), "set_sm_budget")
             if self.debug_enc is not None:
                 self.debug_enc.append(self.src32.float().clone())
@@ -740,6 +740,8 @@ class FrameEngine:
             else:
                 self.lin(self.q_tok, C, a["ol"], self.ol, a["ol"].N, S, c_dtype=F32)
                 self.msda(self.value, C, self.ol, a["ol"].N, 0, None, self.att, S, Ke)
+            if sm_plan is not None and i + 0.5 == sm_plan[1]:      #  k + 0.5: from the dense half of layer k on)
+                _lib.check(self.lib.memotr_set_sm_budget(0), "set_sm_budget")
             if self.fuse_block:
                 (g1, b1n), (g2, b2n), l1, l2 = ly["norm1"], ly["norm2"], ly["lin1"], ly["lin2"]
                 self._ck(self.lib.memotr_encoder_dense_block(
@@ -1083,7 +1085,8 @@ class FrameEngine:
         SMs instead of ~380 us on 100 -- its latency hides behind the encoder, its SM-time is what the encoder loses -- and the
         first `split` encoder layers (default: two thirds) size their persistent grids for the SMs that leaves free
         (memotr_set_sm_budget); by the time the later layers launch, the tail is done.  Measured at the DanceTrack size
-        (frames/s): cluster decoder 666; single-CTA decoder with split 0 / 2 / 3 / 4 / 5 / 6: 652 / 681 / 714 / 726 / 717 / 702.
+        (frames/s): cluster decoder 666; single-CTA decoder with split 0 / 2 / 3 / 4 / 5 / 6: 652 / 681 / 714 / 726 / 717 / 702
+        (25 SMs reserved); k + 0.5 = budget until after the gather of layer k; 4.5 with 28 reserved: 733 (the plateau is flat).
         MEMOTR_PIPE_SINGLE / MEMOTR_PIPE_SPLIT / MEMOTR_PIPE_RESERVE override."""
         import os
         if self.graph is None:
@@ -1093,8 +1096,9 @@ class FrameEngine:
             single = os.environ.get("MEMOTR_PIPE_SINGLE", "1") != "0"
         single = bool(single) and self.dec_single_ok
         if split is None:
-            split = int(os.environ.get("MEMOTR_PIPE_SPLIT", str((2 * self.n_enc + 2) // 3)))
-        reserve = int(os.environ.get("MEMOTR_PIPE_RESERVE", str((self.nq + 15) // 16)))     # SMs left to the tail
+            split = float(os.environ.get("MEMOTR_PIPE_SPLIT", str((2 * self.n_enc + 2) // 3 + 0.5)))
+        # SMs left to the tail: the decoder's CTAs (one per 16 query rows) or the updater's (a 4-CTA cluster per 16 track rows)
+        reserve = int(os.environ.get("MEMOTR_PIPE_RESERVE", str(max((self.nq + 15) // 16, 4 * ((self.nt + 15) // 16)))))
         budget = self.n_sm - reserve if single else 0
         if single:           # one-time attribute calls of the kernel outside capture (a warm-up launch; state restored)
             state = self._recurrent_state()
