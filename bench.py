@@ -344,7 +344,8 @@ def main():
     # Two captured graphs of the same step(): forward + tracker + updater + feedback.  The plain one is what a user replays.
     # The instrumented one carries 17 event-record nodes (gather launches, section marks); every such node breaks a
     # programmatic-dependent-launch edge, so it is replayed for the LAST frame of every clip only: those frames are inside the
-    # timed region and are where `roofline` and `sections_us` are sampled.
+    # timed region and are where `roofline` and `sections_us` are sampled (since the pipelined clip: the last frame of the LAST
+    # clip of the timed region only).
     eng.capture()
     g_plain, plain_launches = eng.graph, eng.graph_launches
     eng.enable_msda_timer()
@@ -388,32 +389,37 @@ def main():
             else:
                 gathered["last"] = clip_mod.gather_track_memory(eng.st)
 
-    def run_clip_resident():
+    def run_clip_resident(instr):
+        """One clip.  instr: the clip's last frame runs sequentially through the instrumented graph (the LAST clip of the timed
+        region and of the warm-up: where `roofline` / `sections_us` are sampled; one frame per timed region, not per clip, so
+        that short sub-clips at large N do not pay for it every time)."""
         reset_clip()
         idx = list(my_frames)
-        if pipelined:      # frames 0 .. n-2 pipelined (FrameEngine.run_clip_pipelined), the last one through the instrumented graph
-            eng.run_clip_pipelined(len(idx) - 1, lambda j: feed_resident(idx[j]))
-            feed_resident(idx[-1])
-            g_instr.replay()
+        if pipelined:
+            n_pipe = len(idx) - 1 if instr else len(idx)
+            eng.run_clip_pipelined(n_pipe, lambda j: feed_resident(idx[j]))
+            if instr:
+                feed_resident(idx[-1])
+                g_instr.replay()
         else:
             for j, i in enumerate(idx):
                 feed_resident(i)
-                (g_instr if j == len(idx) - 1 else g_plain).replay()
+                (g_instr if instr and j == len(idx) - 1 else g_plain).replay()
         clip_exchange()
 
     # ---- resident-input throughput ("value") -----------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(W):
-        run_clip_resident()
+    for k in range(W):
+        run_clip_resident(k == W - 1)
     barrier()
     sampler.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     host_t0 = time.perf_counter()
-    for _ in range(K):
-        run_clip_resident()
+    for k in range(K):
+        run_clip_resident(k == K - 1)
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / (K * max(len(my_frames), 1))
     t1.record()
     barrier()
@@ -548,8 +554,8 @@ def main():
                    "frame_pipelining": ("on: the recurrent tail of frame k (decoder + heads, tracker glue, query updater -- a latency chain "
                                         "on ~100 SMs) runs concurrently with the encoder of frame k+1 on a second stream, one forked CUDA "
                                         "graph per frame (FrameEngine.run_clip_pipelined; results identical to the sequential clip, "
-                                        "tests/test_tracker_gpu.py); the last frame of every clip runs sequentially through the "
-                                        "instrumented graph" if pipelined else "off (--no-pipeline / fp32 / sub-clip shorter than 3 frames)"),
+                                        "tests/test_tracker_gpu.py); the last frame of the last timed clip runs sequentially through "
+                                        "the instrumented graph" if pipelined else "off (--no-pipeline / fp32 / sub-clip shorter than 3 frames)"),
                    "weights": "reference initialisation distributions (synthetic.reference_init_state_dict), random-init, no checkpoint",
                    "l2": f"inputs larger than L2: {N_ROT} resident frames x {h2d / 1e6:.1f} MB rotate through the input buffers and a "
                          "step touches ~0.5 GB of workspace (L2 = 126 MB)",
@@ -574,8 +580,8 @@ def main():
                      "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "duration_us": dur,
                      "samples": f"{len(msda_us)} launches (the encoder layers of the last frame of the last timed clip), CUDA "
-                                "events recorded inside the captured graph; the other frames of a clip replay the same step "
-                                "without event nodes",
+                                "events recorded inside the captured graph; all other frames replay the same step without "
+                                "event nodes",
                      "on_chip_floor_us": 19.6,
                      "ceiling_note": "the gather reads S*H*L*K*4 corners*64 B = 731 MB of taps per launch through the SMs' shared-memory "
                                      "pipes (128 B/clk/SM): 19.6 us, i.e. at most 0.44 of the HBM roofline by on-chip bandwidth alone; see DESIGN.md"},
