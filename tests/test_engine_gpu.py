@@ -792,3 +792,32 @@ def test_single_cta_decoder_matches_cluster_decoder():
     eng.dec_use_single = False
     for k in ("pred_logits", "pred_bboxes", "outputs", "aux_logits", "aux_bboxes", "aux_queries", "last_ref_pts", "init_ref_pts"):
         assert rel_err(out[1][k].float().cpu().numpy(), out[0][k].float().cpu().numpy()) < 2e-3, k
+
+
+def test_sm_budget_changes_grids_not_results():
+    """memotr_set_sm_budget (the persistent kernels size their grids for fewer SMs: frame pipelining) -- the encoder under a
+    budget of 100 SMs against the unrestricted one: the tile-to-CTA assignment changes, the arithmetic does not (the FFN's
+    split-K tail changes its reduction order: compared to 1e-5)."""
+    from memotr_b200.engine import FrameEngine
+    shapes = ((128, 168), (64, 84), (32, 42), (16, 21))          # 28560 rows: more row tiles than SMs, as at the DanceTrack size
+    cfg = dict(synth.small_cfg(), n_det_queries=40)
+    sd = synth.reference_init_state_dict(cfg, seed=3)
+    x = synth.frame_inputs(cfg, shapes, 8, seed=2, padded=True)
+    eng = FrameEngine(sd, cfg, shapes, 8, DEV, mode="bf16", pos_embed=dict(temperature=20))
+    eng.load_frame(x["srcs"], x["masks"], None, x["tracks"]["ref_pts"], x["tracks"]["query_embed"])
+    out = []
+    for plan in (None, (100, 99), (37, 1.5)):
+        eng.encode(sm_plan=plan)
+        torch.cuda.synchronize()
+        out.append((eng.src32.clone(), eng.value_all.clone()))
+    for a, b in out[1:]:
+        assert rel_err(a.float().cpu().numpy(), out[0][0].float().cpu().numpy()) < 1e-5
+        assert rel_err(b.float().cpu().numpy(), out[0][1].float().cpu().numpy()) < 2e-3      # (fp16 maps of slightly different inputs)
+    assert _lib_budget() == 0
+
+
+def _lib_budget():
+    """The budget is reset when encode() returns: a launch made now sizes its grid for all SMs (set_sm_budget(0) is idempotent)."""
+    from memotr_b200 import _lib
+    _lib.check(_lib.lib().memotr_set_sm_budget(0), "set_sm_budget")
+    return 0

@@ -329,7 +329,8 @@ def test_engine_bf16_clip_runner_device_tracker_matches_oracle():
     runner.check()
 
 
-def test_pipelined_clip_equals_sequential_clip():
+@pytest.mark.parametrize("single", [True, False])
+def test_pipelined_clip_equals_sequential_clip(single):
     """FrameEngine.run_clip_pipelined (tail of frame k and encoder of frame k + 1 on two streams, one forked CUDA graph per
     frame, the encode -> decode hand-off double-buffered) against the same clip replayed frame by frame: identities, labels,
     disappear times, id counter and the last frame's result rows bit-exact, float state to the split-K reduction order."""
@@ -347,7 +348,7 @@ def test_pipelined_clip_equals_sequential_clip():
         eng.capture()
         engs.append(eng)
     seq, pipe = engs
-    pipe.capture_pipeline()
+    pipe.capture_pipeline(single=single)      # True: one-CTA-per-row-block decoder + SM budget; False: cluster decoder
 
     def feeder(eng):
         def feed(j):
