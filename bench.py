@@ -378,10 +378,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    align = torch.zeros(1, device=dev)
+
+    def device_align():
+        """Start of a timed region, N > 1: dist.barrier() aligns the HOSTS to within their scheduling jitter (milliseconds, measured
+        3.3 ms at N = 4 -- 3.6 % of a 4-clip region, paid by every rank at the first all-gather); one tiny all-reduce enqueued right
+        before the start event aligns the DEVICES: every rank's timed region begins when the collective completes."""
+        if world > 1:
+            dist.all_reduce(align)
+
     gathered = {}
+    xev = []          # MEMOTR_BENCH_TIME_EXCHANGE=1: (before, after) event pairs around the per-clip exchange (diagnostic)
+    time_x = os.environ.get("MEMOTR_BENCH_TIME_EXCHANGE", "0") == "1"
 
     def clip_exchange():
         """One NCCL all-gather of the complete track memory per clip (memotr_b200/clip.py)."""
+        if world > 1 and time_x:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            _clip_exchange()
+            ev[1].record()
+            xev.append(ev)
+        else:
+            _clip_exchange()
+
+    def _clip_exchange():
         if world > 1:
             if eng.trk is not None:
                 gathered["last"] = clip_mod.gather_track_memory({k: eng.table[k] for k in clip_mod.FLOAT_FIELDS + clip_mod.INT_FIELDS},
@@ -416,6 +437,7 @@ def main():
     barrier()
     sampler.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    device_align()
     t0.record()
     host_t0 = time.perf_counter()
     for k in range(K):
@@ -486,6 +508,7 @@ def main():
     e2e_clip()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    device_align()
     e0.record()
     for _ in range(K):
         e2e_clip()
@@ -572,6 +595,7 @@ def main():
                 "h2d_bytes_per_frame": h2d, "d2h_bytes_per_frame": d2h},
         "gpu_launches": eng.graph_launches * K * len(my_frames) * world,
         "frames_per_step": CLIP, "ms_per_frame": ms_total / (K * max(len(my_frames), 1)), "rank_ms": ms_all,
+        **({"exchange_us": [round(a.elapsed_time(b) * 1e3, 1) for a, b in xev[-8:]]} if xev else {}),
         "sections_us": {k: round(v, 1) for k, v in sections.items()},
         "host_enqueue_ms_per_frame": round(host_enqueue_ms, 3),
         "host_graph_launch_ms": round(host_launch_ms, 3),
