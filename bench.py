@@ -428,20 +428,40 @@ def main():
                 (g_instr if instr and j == len(idx) - 1 else g_plain).replay()
         clip_exchange()
 
+    def run_clips_resident(n_clips):
+        """n_clips clips back to back.  Pipelined: ONE stream of clips (FrameEngine.run_clips_pipelined) -- the tail of a clip's last
+        frame overlaps the encoder of the next clip's first frame, the all-gather and the track reset sit between the two in stream
+        order; the last frame of the last clip runs sequentially through the instrumented graph."""
+        if not pipelined:
+            for k in range(n_clips):
+                run_clip_resident(k == n_clips - 1)
+            return
+        idx = list(my_frames)
+        lens = [len(idx)] * (n_clips - 1) + [len(idx) - 1]
+
+        def between(c):
+            if c == n_clips - 1:
+                feed_resident(idx[-1])
+                g_instr.replay()
+                clip_exchange()
+            else:
+                clip_exchange()
+                reset_clip()
+        reset_clip()
+        eng.run_clips_pipelined(lens, lambda c, j: feed_resident(idx[j]), between)
+
     # ---- resident-input throughput ("value") -----------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for k in range(W):
-        run_clip_resident(k == W - 1)
+    run_clips_resident(W)
     barrier()
     sampler.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     device_align()
     t0.record()
     host_t0 = time.perf_counter()
-    for k in range(K):
-        run_clip_resident(k == K - 1)
+    run_clips_resident(K)
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / (K * max(len(my_frames), 1))
     t1.record()
     barrier()
@@ -577,8 +597,9 @@ def main():
                    "frame_pipelining": ("on: the recurrent tail of frame k (decoder + heads, tracker glue, query updater -- a latency chain "
                                         "on ~100 SMs) runs concurrently with the encoder of frame k+1 on a second stream, one forked CUDA "
                                         "graph per frame (FrameEngine.run_clip_pipelined; results identical to the sequential clip, "
-                                        "tests/test_tracker_gpu.py); the last frame of the last timed clip runs sequentially through "
-                                        "the instrumented graph" if pipelined else "off (--no-pipeline / fp32 / sub-clip shorter than 3 frames)"),
+                                        "tests/test_tracker_gpu.py); the K clips of the timed region are one stream (the last tail of a "
+                                        "clip overlaps the first encoder of the next; all-gather and track reset in between); the last "
+                                        "frame of the last timed clip runs sequentially through the instrumented graph" if pipelined else "off (--no-pipeline / fp32 / sub-clip shorter than 3 frames)"),
                    "weights": "reference initialisation distributions (synthetic.reference_init_state_dict), random-init, no checkpoint",
                    "l2": f"inputs larger than L2: {N_ROT} resident frames x {h2d / 1e6:.1f} MB rotate through the input buffers and a "
                          "step touches ~0.5 GB of workspace (L2 = 126 MB)",

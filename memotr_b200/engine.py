@@ -1160,6 +1160,33 @@ class FrameEngine:
             self.g_pipe[j & 1].replay()
         self.g_last[(n_frames - 1) & 1].replay()
 
+    def run_clips_pipelined(self, frames_per_clip, feed, between=None):
+        """A STREAM of clips as one pipeline: like run_clip_pipelined per clip, except that the tail of a clip's last frame runs
+        concurrently with the encoder of the NEXT clip's first frame (which depends on no track state), so only the stream's very
+        first encoder and very last tail run alone -- what a rank with 8-frame sub-clips pays per clip otherwise is 4 % of it.
+        frames_per_clip: list of frame counts; feed(c, j) loads frame j of clip c; between(c) is called when every frame of clip c
+        has been enqueued (its track state is final in stream order): exchange it, then reset the tracks for clip c + 1 there."""
+        clips = [(c, n) for c, n in enumerate(frames_per_clip) if n > 0]
+        if not clips:
+            return
+        p = 0                                                   # the set that holds the encoded, not yet decoded frame
+        feed(clips[0][0], 0)
+        self.g_first.replay()
+        for i, (c, n) in enumerate(clips):
+            for j in range(n):
+                if j + 1 < n:
+                    nxt = (c, j + 1)
+                else:
+                    nxt = (clips[i + 1][0], 0) if i + 1 < len(clips) else None
+                if nxt is None:
+                    self.g_last[p].replay()
+                else:
+                    feed(*nxt)
+                    self.g_pipe[p].replay()                     # tail(c, j) from set p || encode(nxt) into set 1 - p
+                    p ^= 1
+            if between is not None:
+                between(c)
+
 
 class ClipRunner:
     """Public host-buffer API for a clip: frames arrive as pinned HOST tensors, results go back to pinned host tensors.

@@ -1,5 +1,6 @@
 #!/bin/bash
-# sub-clip lengths a rank sees at N = 8 / 16 / 32 / 64 on a 64-frame clip, run on one GPU (same code path minus NCCL)
+# sub-clip lengths a rank sees at N = 1 / 8 / 21 on a 64-frame clip, run on one GPU (same code path minus NCCL)
+timeout 600 python -m pytest tests/test_tracker_gpu.py -m gpu -q --tb=short -x -k "pipelined" 2>&1 | tail -3
 for cf in 64 8 3; do
 timeout 600 python bench.py --steps 4 --warmup 3 --no-baselines --clip-frames $cf > gpurun_out/bench_cf.json 2> gpurun_out/bench_cf.err; echo "clip-frames $cf rc=$?"
 python - <<'PY'
