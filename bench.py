@@ -167,6 +167,35 @@ def cpu_reference_fps(steps, warmup):
     return len(times) / sum(times), threads
 
 
+def fp32_modes_fps(dev, sd, cfg, tracker, frames, n_frames=12):
+    """The engine's fp32-accurate modes on the same workload (frame after frame, one CUDA graph per frame): "fp32tc" (large GEMMs on
+    the tensor cores at fp32 accuracy, parity <= 1e-4) and "fp32" (everything on CUDA cores).  Extras: the headline is the bf16 mode."""
+    from memotr_b200.engine import FrameEngine
+    out = {}
+    for mode in ("fp32tc", "fp32"):
+        eng = FrameEngine(sd, cfg, synth.DANCETRACK_SHAPES, N_TRACKS, dev, mode=mode, tracker=tracker, ori_size=(1920, 1080),
+                          pos_embed=dict(temperature=20))
+        x0 = frames[0]
+        eng.load_frame(x0["srcs"], x0["masks"], None, x0["tracks"]["ref_pts"], x0["tracks"]["query_embed"])
+        eng.load_tracks(x0["tracks"])
+        if eng.trk is not None:
+            eng.trk.reset(x0["tracks"])
+        eng.capture()
+        for _ in range(3):
+            eng.replay()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n_frames):
+            eng.replay()
+        e.record()
+        torch.cuda.synchronize(dev)
+        out[mode] = round(n_frames / (s.elapsed_time(e) * 1e-3), 1)
+        del eng
+        torch.cuda.empty_cache()
+    return out
+
+
 def gpu_reference_fps(dev, steps, warmup):
     """The reference GPU path restated: stock PyTorch fp32 ops (TF32 off, main.py:96-97) + the reference's own CUDA op
     compiled into oracle/_ref.  Reported beside our numbers; None when the .so did not travel."""
@@ -268,7 +297,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)      # clips; 8 x 64 frames ~ 1 s timed at N = 1
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "fp32tc"],
+                    help="fp32: CUDA-core fp32 GEMMs; fp32tc: the fp32 engine with its large GEMMs on the tensor cores at fp32 accuracy")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clip-frames", type=int, default=64)
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / gpu_reference / extras legs")
@@ -610,7 +640,10 @@ def main():
                    if eng.trk is not None else "off (--no-tracker)",
                    "arithmetic": "bf16 GEMM operands + fp16 value maps + fp32 accumulate/residual/LayerNorm/geometry; parity vs the "
                                  "reference modules <= 1e-2 on every output (tests/test_engine_gpu.py, frame_full_refinit)"
-                   if args.mode == "bf16" else "fp32 everywhere (TF32 off, as the reference)"},
+                   if args.mode == "bf16" else
+                   ("fp32 everywhere (TF32 off, as the reference); the large-M GEMMs on the tensor cores at fp32 accuracy: two-term "
+                    "fp16 operand splits, three products, fp32 accumulation (memotr_linear_f32x3); parity <= 1e-4 (measured 1.3e-5) on "
+                    "frame_full_refinit" if args.mode == "fp32tc" else "fp32 everywhere on CUDA cores (TF32 off, as the reference)")},
         "clocks": clocks,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d * CLIP, "d2h_bytes_per_step": d2h * CLIP,
                 "h2d_bytes_per_frame": h2d, "d2h_bytes_per_frame": d2h},
@@ -654,6 +687,14 @@ def main():
         out["gpu_reference"] = {"value": g, "unit": "frames/s",
                                 "what": "reference models/ops CUDA op (oracle/_ref, compiled from /root/reference) + stock "
                                         "PyTorch fp32 eager modules (TF32 off) on the same GPU and inputs"} if g else None
+        try:
+            fm = fp32_modes_fps(dev, sd, cfg, tracker, frames)
+            out["fp32_modes"] = {"unit": "frames/s", **fm,
+                                 "what": "the engine's fp32-accurate modes on the same frames, sequential CUDA-graph replays: fp32tc = "
+                                         "large-M GEMMs on the tensor cores with two-term fp16 operand splits (parity <= 1e-4 on "
+                                         "frame_full_refinit, measured 1.3e-5), fp32 = every GEMM on CUDA cores"}
+        except Exception as e:                                              # noqa: BLE001
+            out["fp32_modes"] = {"error": repr(e)}
         try:
             sweep, bwd = msda_extras(dev, peak)
             out["msda_sweep"] = {"what": "BASELINE.json configs[4]: 1280x720 pyramid, 8 heads, encoder-shaped (windowed kernel, ring + "

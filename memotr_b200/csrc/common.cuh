@@ -168,6 +168,8 @@ struct Epilogue {
   int prep_hw[16], prep_lsi[8];   // (H_l, W_l) and first row of every level
   const float *prep_vr;           // device (L, 2) valid ratios
   long long *stamps;              // profiling (tools/micro_gemm.py): 20 clock64 stamps per CTA of the persistent GEMM, else null
+  int in_f16;                     // persistent tcgen05 GEMM: the 16-bit operands are fp16, not bf16 (memotr_linear_f32x3)
+  float out_scale;                // != 0: the accumulator is multiplied by it before the bias (exact power of two of the split weights)
 };
 
 }  // namespace memotr

