@@ -111,7 +111,10 @@ def _worker(rank, world, port, q, n_frames):
 def _spawn(world, n_frames):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
+    import socket
+    with socket.socket() as sk:                    # a free port chosen by the kernel (a pid-derived one collided once)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, n_frames)) for r in range(world)]
     for p in procs:
         p.start()
