@@ -170,6 +170,7 @@ def cpu_reference_fps(steps, warmup):
 def fp32_modes_fps(dev, sd, cfg, tracker, frames, n_frames=12):
     """The engine's fp32-accurate modes on the same workload (frame after frame, one CUDA graph per frame): "fp32tc" (large GEMMs on
     the tensor cores at fp32 accuracy, parity <= 1e-4) and "fp32" (everything on CUDA cores).  Extras: the headline is the bf16 mode."""
+    from memotr_b200 import synthetic as synth
     from memotr_b200.engine import FrameEngine
     out = {}
     for mode in ("fp32tc", "fp32"):
