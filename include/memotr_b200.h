@@ -217,10 +217,13 @@ MEMOTR_API int memotr_linear256_layernorm(const void *A, int lda, const void *W,
  * two fp16 terms and the three significant products are summed in fp32 (one fp16 GEMM with 3K; error ~2^-22 per product).
  * W3 (N, 3K) fp16 = [hi | lo | hi] of (2^s W) packed once by the host, w_scale_inv = 2^-s; scratch_a3: M x 3K fp16.
  * The nn.Linear call sites of the encoder in the engine's "fp32tc" mode (the reference runs them in fp32 with TF32 off,
- * main.py:96-97).  Needs N % 128 == 0, K % 64 == 0 and more 128 x 128 tiles than SMs.
+ * main.py:96-97).  Needs N % 64 == 0 and K % 64 == 0.
  */
-MEMOTR_API int memotr_linear_f32x3(const float *A, int lda, const void *W3, const float *bias, const unsigned char *rowzero, float *C,
-                                   int ldc, int M, int N, int K, int act, float w_scale_inv, void *scratch_a3, void *stream);
+MEMOTR_API int memotr_linear_f32x3(const float *A /* NULL: scratch_a3 already holds the split operand */, int lda, const void *W3,
+                                   const float *bias, const unsigned char *rowzero, float *C, int ldc, int M, int N, int K, int act,
+                                   float w_scale_inv, void *scratch_a3,
+                                   void *split_out /* NULL, or (M, 3N) fp16: the result as the split operand of the next call */,
+                                   void *stream);
 
 /* Profiling hook (tools/micro_dense.py), not part of the reference surface: every later memotr_mlp2* / encoder_dense_block
  * launch writes 8 clock64 stamps per CTA into `buf` (device int64[8 x CTAs]); null switches it off again. */

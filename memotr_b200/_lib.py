@@ -113,7 +113,7 @@ _SIGNATURES = {
     "memotr_decoder_forward_cluster": ([_vp, _vp], _i),
     "memotr_decoder_forward": ([_vp, _vp], _i),
     "memotr_set_sm_budget": ([_i], _i),
-    "memotr_linear_f32x3": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp], _i),
+    "memotr_linear_f32x3": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
     "memotr_updater_forward_cluster": ([_vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),
     "memotr_timer_destroy": ([_vp], None),

@@ -170,6 +170,8 @@ struct Epilogue {
   long long *stamps;              // profiling (tools/micro_gemm.py): 20 clock64 stamps per CTA of the persistent GEMM, else null
   int in_f16;                     // persistent tcgen05 GEMM: the 16-bit operands are fp16, not bf16 (memotr_linear_f32x3)
   float out_scale;                // != 0: the accumulator is multiplied by it before the bias (exact power of two of the split weights)
+  int split3_n;                   // persistent GEMM, fp32 instantiation: != 0 = N of this GEMM; the result is written as the split fp16
+                                  // A operand [hi | hi | lo] (M, 3N) of the NEXT memotr_linear_f32x3 instead of as fp32
 };
 
 }  // namespace memotr

@@ -89,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BN);
+      const uint32_t idesc = ep.in_f16 ? umma_idesc_f16(BN) : umma_idesc(BN);
       for (int kb = 0; kb < num_k; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -126,6 +126,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.out_scale != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= ep.out_scale;
+      }
       if (ep.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {

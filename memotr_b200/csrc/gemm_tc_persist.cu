@@ -238,6 +238,25 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int panel = c0 / PANEL_COLS;
           uint8_t *prow = stage_out + panel * (BM * 128) + r_in * 128;
           if constexpr (sizeof(TC) == 4) {
+            if (ep.split3_n) {
+              // split output: panels 0, 1 = fp16 hi of columns [0, 64), [64, 128) of the tile; panels 2, 3 = the lo terms
+              uint8_t *ph = stage_out + (c0 / 64) * (BM * 128) + r_in * 128, *pl = ph + 2 * (BM * 128);
+              const int kb = (c0 % 64) / 8;
+    #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint32_t hw[4], lw[4];
+    #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __half2 h = __floats2half2_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                  const float2 f = __half22float2(h);
+                  const __half2 l = __floats2half2_rn(v[8 * k + 2 * i] - f.x, v[8 * k + 2 * i + 1] - f.y);
+                  hw[i] = *reinterpret_cast<const uint32_t *>(&h), lw[i] = *reinterpret_cast<const uint32_t *>(&l);
+                }
+                *reinterpret_cast<uint4 *>(ph + (((kb + k) ^ (r_in & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(pl + (((kb + k) ^ (r_in & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+              continue;
+            }
     #pragma unroll
             for (int k = 0; k < 8; ++k)
               *reinterpret_cast<float4 *>(prow + ((k ^ (r_in & 7)) << 4)) =
@@ -258,11 +277,21 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (stamps && i < 6) stamps[3 + 3 * i] = clock64();        // tile staged
       if (warp == 2 && lane == 0) {
+        if (sizeof(TC) == 4 && ep.split3_n) {       // (tmC: the (M, 3N) fp16 tensor; hi to columns n and N + n, lo to 2N + n)
+#pragma unroll 1
+          for (int p = 0; p < 6; ++p) {
+            const int src = p < 4 ? (p & 1) : 2 + (p & 1), col = (p >> 1) * ep.split3_n + n_blk * BN + (p & 1) * 64;
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                         "r"(smem_u32(stage_out + src * (BM * 128))), "r"(col), "r"(m_blk * BM)
+                         : "memory");
+          }
+        } else {
 #pragma unroll 1
         for (int p = 0; p < N_PANELS; ++p)
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
                        "r"(smem_u32(stage_out + p * (BM * 128))), "r"(n_blk * BN + p * PANEL_COLS), "r"(m_blk * BM)
                        : "memory");
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
@@ -283,8 +312,10 @@ template <typename TC>
 static int launch(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int M, int N, int K,
                   const Epilogue &ep, int n_sm, cudaStream_t st) {
   CUtensorMap tmA, tmW, tmC;
+  const bool split3 = sizeof(TC) == 4 && ep.split3_n != 0;    // the output tensor is then (M, 3N) fp16, 64-column panels
   if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, W, N, K, ldw, BN) ||
-      !make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4, std::is_same<TC, __half>::value))
+      !(split3 ? make_map(&tmC, C, M, 3 * N, ldc, BM, false, true)
+               : make_map(&tmC, C, M, N, ldc, BM, sizeof(TC) == 4, std::is_same<TC, __half>::value)))
     return fail(MEMOTR_ECUDA, "linear(tc, persistent): cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   auto kern = gemm_tc_persist_kernel<TC>;
   static bool attr_set = false;
@@ -363,23 +394,40 @@ split3_kernel(const float *__restrict__ x, int ldx, __half *__restrict__ a3, int
   *reinterpret_cast<uint2 *>(row + 2 * K) = lo;
 }
 
+namespace memotr {
+int linear_tc_bf16(const void *A, int lda, const void *W, int ldw, void *C, int ldc, int c_dtype, int M, int N, int K,
+                   const Epilogue &ep, cudaStream_t st);
+}
+
 extern "C" int memotr_linear_f32x3(const float *A, int lda, const void *W3, const float *bias, const unsigned char *rowzero, float *C,
-                                   int ldc, int M, int N, int K, int act, float w_scale_inv, void *scratch_a3, void *stream) {
-  MEMOTR_REQUIRE(A && W3 && C && scratch_a3 && M > 0 && N > 0 && K > 0, "linear_f32x3: bad arguments");
-  MEMOTR_REQUIRE(K % 64 == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(W3) && aligned16(C) && aligned16(scratch_a3) &&
-                     (!bias || aligned16(bias)) && act >= 0 && act <= 2 && tc::encode_fn() != nullptr,
+                                   int ldc, int M, int N, int K, int act, float w_scale_inv, void *scratch_a3, void *split_out,
+                                   void *stream) {
+  // A == NULL: scratch_a3 already holds the split operand [hi | hi | lo] (M, 3K) -- the split_out of a previous call.
+  // split_out != NULL (C may be NULL): the result is written as the split fp16 operand (M, 3N) of the next call instead of as
+  // fp32 (the FFN: linear1 -> relu -> linear2 without the fp32 hidden activation in HBM).
+  MEMOTR_REQUIRE(W3 && (C || split_out) && scratch_a3 && M > 0 && N > 0 && K > 0, "linear_f32x3: bad arguments");
+  MEMOTR_REQUIRE(K % 64 == 0 && (!A || (lda % 4 == 0 && aligned16(A))) && aligned16(W3) && aligned16(scratch_a3) &&
+                     (!C || (ldc % 4 == 0 && aligned16(C))) && (!split_out || aligned16(split_out)) && (!bias || aligned16(bias)) &&
+                     act >= 0 && act <= 2 && tc::encode_fn() != nullptr,
                  "linear_f32x3: needs K %% 64 == 0 and 16-byte aligned buffers");
-  int n_sm = 0;
-  MEMOTR_REQUIRE(linear_tc_persist_wanted(M, N, &n_sm), "linear_f32x3: needs N %% 128 == 0 and more 128 x 128 tiles than SMs (M = %d, N = %d)",
-                 M, N);
+  MEMOTR_REQUIRE(N % 64 == 0, "linear_f32x3: needs N %% 64 == 0 (N = %d)", N);
   cudaStream_t st = (cudaStream_t)stream;
-  const long n4 = (long)M * (K / 4);
-  MEMOTR_LAUNCH((split3_kernel), (int)((n4 + 255) / 256), 256, 0, st, A, lda, (__half *)scratch_a3, M, K);
-  int rc = check_launch("split3");
-  if (rc != MEMOTR_OK) return rc;
+  if (A) {
+    const long n4 = (long)M * (K / 4);
+    MEMOTR_LAUNCH((split3_kernel), (int)((n4 + 255) / 256), 256, 0, st, A, lda, (__half *)scratch_a3, M, K);
+    const int rc = check_launch("split3");
+    if (rc != MEMOTR_OK) return rc;
+  }
   Epilogue ep{bias, nullptr, nullptr, rowzero, 0, 0, act};
   ep.in_f16 = 1, ep.out_scale = w_scale_inv;
-  return linear_tc_persist_bf16(scratch_a3, 3 * K, W3, 3 * K, C, ldc, MEMOTR_F32, M, N, 3 * K, ep, n_sm, st);
+  if (split_out) {
+    int n_sm = 0;
+    MEMOTR_REQUIRE(N % 128 == 0 && linear_tc_persist_wanted(M, N, &n_sm),
+                   "linear_f32x3: split output needs N %% 128 == 0 and more 128 x 128 tiles than SMs (M = %d, N = %d)", M, N);
+    ep.split3_n = N;
+    return linear_tc_persist_bf16(scratch_a3, 3 * K, W3, 3 * K, split_out, 3 * N, MEMOTR_F32, M, N, 3 * K, ep, n_sm, st);
+  }
+  return linear_tc_bf16(scratch_a3, 3 * K, W3, 3 * K, C, ldc, MEMOTR_F32, M, N, 3 * K, ep, st);   // persistent when tiles > SMs
 }
 
 extern "C" int memotr_linear_msda_prep(const void *A, int lda, const void *W, int ldw, const float *bias, float *out, int ldo,

@@ -263,8 +263,9 @@ class FrameEngine:
         LK = self.L * max(self.cfg["n_enc_points"], self.cfg["n_dec_points"])
         self.shapes_t = torch.as_tensor(self.shapes, dtype=torch.long, device=dev)
         # fp32tc: scratch for the split A operand [hi | hi | lo] of the widest large-M GEMM (linear2: K = d_ffn)
-        self.a3 = (torch.empty(S * 3 * max(self.Fd, C), dtype=torch.float16, device=dev) if getattr(self, "tc3", False)
-                   else torch.empty(0, dtype=torch.float16, device=dev))
+        tc3 = getattr(self, "tc3", False)
+        self.a3 = torch.empty(S * 3 * max(self.Fd, C) if tc3 else 0, dtype=torch.float16, device=dev)
+        self.a3h = torch.empty(S * 3 * self.Fd if tc3 else 0, dtype=torch.float16, device=dev)     # linear1's split output
         sizes = [h * w for h, w in self.shapes]
         self.lsi_host = [sum(sizes[:i]) for i in range(self.L)]
         self.lsi_t = torch.as_tensor(self.lsi_host, dtype=torch.long, device=dev)
@@ -554,13 +555,13 @@ class FrameEngine:
     def lin(self, x, ldx, L, out, ldo, M, act=0, mul=None, ldmul=0, add=None, ldadd=0, rowzero=None, c_dtype=None,
             path=0):
         cd = self.dt if c_dtype is None else c_dtype
-        if (self.tc3 and mul is None and add is None and cd == F32 and L.N % 128 == 0 and L.K % 64 == 0
-                and (L.N // 128) * ((M + 127) // 128) > self.n_sm > 0 and M * 3 * L.K <= self.a3.numel()):
+        if (self.tc3 and mul is None and add is None and cd == F32 and L.N % 64 == 0 and L.K % 64 == 0 and ldx % 4 == 0
+                and ldo % 4 == 0 and M >= 64 and M * 3 * L.K <= self.a3.numel() and L.w.dtype == torch.float32):
             if getattr(L, "w3", None) is None:
                 from .kernels import pack_w3
                 L.w3 = pack_w3(L.w)
             self._ck(self.lib.memotr_linear_f32x3(_p(x), ldx, _p(L.w3), _p(L.b), _p(rowzero), _p(out), ldo, M, L.N, L.K, act,
-                                                  2.0 ** -6, _p(self.a3), self._st()), "linear_f32x3")
+                                                  2.0 ** -6, _p(self.a3), None, self._st()), "linear_f32x3")
             self.launches += 1
             return
         self._ck(self.lib.memotr_linear(_p(x), ldx, _p(L.w), L.K, _p(L.b), _p(mul), ldmul, _p(add), ldadd, _p(rowzero),
@@ -578,6 +579,20 @@ class FrameEngine:
                 and L2.K == L1.N:
             self._ck(self.lib.memotr_mlp2(_p(x), ldx, _p(L1.w), _p(L1.b), _p(L2.w), _p(L2.b), _p(mul), ldmul, _p(out), ldo,
                                           M, L1.K, L1.N, L2.N, cd, act2, self._st()), "mlp2")
+            return
+        if (self.tc3 and mul is None and cd == F32 and act2 == 0 and L1.N % 128 == 0 and L1.K % 64 == 0 and L2.N % 64 == 0
+                and (L1.N // 128) * ((M + 127) // 128) > self.n_sm > 0 and M * 3 * L1.N <= self.a3h.numel()
+                and M * 3 * L1.K <= self.a3.numel() and L1.w.dtype == torch.float32 and ldx % 4 == 0 and ldo % 4 == 0):
+            # fp32tc FFN: linear1 writes relu(.) straight as the split fp16 operand of linear2 (no fp32 hidden tensor in HBM)
+            from .kernels import pack_w3
+            for L in (L1, L2):
+                if getattr(L, "w3", None) is None:
+                    L.w3 = pack_w3(L.w)
+            self._ck(self.lib.memotr_linear_f32x3(_p(x), ldx, _p(L1.w3), _p(L1.b), None, None, 0, M, L1.N, L1.K, 1, 2.0 ** -6,
+                                                  _p(self.a3), _p(self.a3h), self._st()), "linear_f32x3(split out)")
+            self._ck(self.lib.memotr_linear_f32x3(None, 0, _p(L2.w3), _p(L2.b), None, _p(out), ldo, M, L2.N, L2.K, 0, 2.0 ** -6,
+                                                  _p(self.a3h), None, self._st()), "linear_f32x3(split in)")
+            self.launches += 1
             return
         self.lin(x, ldx, L1, hid, L1.N, M, act=1)
         self.lin(hid, L1.N, L2, out, ldo, M, act=act2, mul=mul, ldmul=ldmul, c_dtype=cd)

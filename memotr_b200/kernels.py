@@ -245,21 +245,27 @@ def pack_w3(w):
     return torch.cat((hi, lo, hi), dim=1).contiguous()
 
 
-def linear_f32x3(x, w3, bias=None, act=None, rowzero=None, out=None, scratch=None):
-    """act(x @ w.T + bias) for fp32 x with fp32-accurate products on the tensor cores (memotr_linear_f32x3); w3 = pack_w3(w)."""
-    M, K = x.shape
+def linear_f32x3(x, w3, bias=None, act=None, rowzero=None, out=None, scratch=None, split_out=False):
+    """act(x @ w.T + bias) for fp32 x with fp32-accurate products on the tensor cores (memotr_linear_f32x3); w3 = pack_w3(w).
+    x may already be a split operand (fp16, (M, 3K): the split_out=True result of a previous call); split_out=True returns the
+    result as such an operand (M, 3N) instead of fp32."""
+    pre = x.dtype == torch.float16
+    M, K = x.shape[0], (x.shape[1] // 3 if pre else x.shape[1])
     N = w3.shape[0]
-    assert w3.shape[1] == 3 * K and x.dtype == torch.float32 and w3.dtype == torch.float16
-    if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    assert w3.shape[1] == 3 * K and w3.dtype == torch.float16 and (pre or x.dtype == torch.float32)
+    if split_out:
+        res = torch.empty((M, 3 * N), dtype=torch.float16, device=x.device)
+    else:
+        res = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x.device)
     if scratch is None:
-        scratch = torch.empty((M, 3 * K), dtype=torch.float16, device=x.device)
+        scratch = x if pre else torch.empty((M, 3 * K), dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
-        rc = _lib.lib().memotr_linear_f32x3(_lib.ptr(x), _ld(x), _lib.ptr(w3), _lib.ptr(bias), _lib.ptr(rowzero), _lib.ptr(out),
-                                            _ld(out), M, N, K, _ACT[act], float(2.0 ** -W3_SHIFT), _lib.ptr(scratch),
-                                            _lib.stream_ptr())
+        rc = _lib.lib().memotr_linear_f32x3(None if pre else _lib.ptr(x), 0 if pre else _ld(x), _lib.ptr(w3), _lib.ptr(bias),
+                                            _lib.ptr(rowzero), None if split_out else _lib.ptr(res), 0 if split_out else _ld(res),
+                                            M, N, K, _ACT[act], float(2.0 ** -W3_SHIFT), _lib.ptr(scratch),
+                                            _lib.ptr(res) if split_out else None, _lib.stream_ptr())
     _lib.check(rc, "memotr_linear_f32x3")
-    return out
+    return res
 
 
 def linear256_layernorm(a, w, b, res, gamma, beta, eps=1e-5):

@@ -823,7 +823,8 @@ def _lib_budget():
     return 0
 
 
-@pytest.mark.parametrize("M,N,K,act", [(22323, 256, 256, None), (20000, 384, 256, None), (19000, 2048, 256, "relu"), (19000, 256, 2048, None)])
+@pytest.mark.parametrize("M,N,K,act", [(22323, 256, 256, None), (20000, 384, 256, None), (19000, 2048, 256, "relu"), (19000, 256, 2048, None),
+                                       (400, 256, 512, "relu"), (100, 192, 256, None)])
 def test_linear_f32x3_is_fp32_accurate(M, N, K, act):
     """memotr_linear_f32x3 (two-term fp16 operand splits, three products, fp32 accumulation on the tensor cores) against fp64:
     as accurate as an fp32 GEMM (the reference's contract: TF32 off), three orders below the bf16 path."""
@@ -867,3 +868,23 @@ def test_engine_fp32tc_matches_reference_modules_full_size():
     # accumulation (1.3e-5 on the 2048-long dot products of linear2, against 6e-7 for an IEEE fp32 chain) shows as 1.4e-3 here,
     # where the CUDA-core fp32 engine stays below 1e-4.  Asserted so that a regression is seen, not as a parity claim.
     assert worst["full"] < 5e-3
+
+
+def test_linear_f32x3_split_output_chains_into_the_next_gemm():
+    """linear1 -> relu -> linear2 with linear1's epilogue writing the split fp16 operand [hi | hi | lo] of linear2 directly (the
+    fp32tc FFN: no fp32 hidden tensor in HBM) against fp64 and against the two-step path through an fp32 hidden tensor."""
+    g = _g(77)
+    M, C, Hd = 20000, 256, 1024
+    x = torch.randn(M, C, generator=g)
+    w1, b1 = torch.randn(Hd, C, generator=g) / 16, torch.randn(Hd, generator=g)
+    w2, b2 = torch.randn(C, Hd, generator=g) / 32, torch.randn(C, generator=g)
+    d = lambda t: t.to(DEV)                                                                 # noqa: E731
+    w31, w32 = K().pack_w3(d(w1)), K().pack_w3(d(w2))
+    h3 = K().linear_f32x3(d(x), w31, d(b1), act="relu", split_out=True)
+    assert h3.dtype == torch.float16 and tuple(h3.shape) == (M, 3 * Hd)
+    assert torch.equal(h3[:, :Hd], h3[:, Hd:2 * Hd])
+    got = K().linear_f32x3(h3, w32, d(b2)).cpu()
+    two = K().linear_f32x3(K().linear_f32x3(d(x), w31, d(b1), act="relu"), w32, d(b2)).cpu()
+    want = F.linear(F.linear(x.double(), w1.double(), b1.double()).relu(), w2.double(), b2.double())
+    assert rel_err(got.numpy(), want.numpy()) < 1e-5
+    assert rel_err(got.numpy(), two.numpy()) < 2e-6
