@@ -692,8 +692,9 @@ def main():
             fm = fp32_modes_fps(dev, sd, cfg, tracker, frames)
             out["fp32_modes"] = {"unit": "frames/s", **fm,
                                  "what": "the engine's fp32-accurate modes on the same frames, sequential CUDA-graph replays: fp32tc = "
-                                         "large-M GEMMs on the tensor cores with two-term fp16 operand splits (parity <= 1e-4 on "
-                                         "frame_full_refinit, measured 1.3e-5), fp32 = every GEMM on CUDA cores"}
+                                         "every nn.Linear on the tensor cores at fp32 accuracy (two-term fp16 operand splits, three "
+                                         "products, fp32 accumulation: memotr_linear_f32x3; parity <= 1e-4 on frame_full_refinit, "
+                                         "measured 1.3e-5), fp32 = every GEMM on CUDA cores"}
         except Exception as e:                                              # noqa: BLE001
             out["fp32_modes"] = {"error": repr(e)}
         try:
