@@ -463,6 +463,8 @@ def main():
         """n_clips clips back to back.  Pipelined: ONE stream of clips (FrameEngine.run_clips_pipelined) -- the tail of a clip's last
         frame overlaps the encoder of the next clip's first frame, the all-gather and the track reset sit between the two in stream
         order; the last frame of the last clip runs sequentially through the instrumented graph."""
+        if n_clips <= 0:
+            return
         if not pipelined:
             for k in range(n_clips):
                 run_clip_resident(k == n_clips - 1)
