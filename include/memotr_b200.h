@@ -225,6 +225,17 @@ MEMOTR_API int memotr_linear_f32x3(const float *A /* NULL: scratch_a3 already ho
                                    void *split_out /* NULL, or (M, 3N) fp16: the result as the split operand of the next call */,
                                    void *stream);
 
+/*
+ * Input projections in front of the transformer (models/memotr.py:66-78,107-123), batch 1, fp32, channel-major maps (C, H*W):
+ *   memotr_conv_gemm     Y (M, N) = W (M, K) X (K, N) + bias[m]: a 1x1 convolution (M = C_out, K = C_in, N = pixels), or the
+ *                        3x3 / stride 2 convolution over the im2col buffer (K = 9 C_in)
+ *   memotr_im2col_3x3s2  col (9 C, Ho Wo) of x (C, H, W) for kernel 3, stride 2, padding 1; Ho = (H - 1) / 2 + 1
+ *   memotr_groupnorm_cm  GroupNorm(groups, C) in place on a channel-major (C, P) map (biased variance, eps as given)
+ */
+MEMOTR_API int memotr_conv_gemm(const float *W, const float *X, const float *bias, float *Y, int M, int N, int K, void *stream);
+MEMOTR_API int memotr_im2col_3x3s2(const float *x, int C, int H, int W, float *col, void *stream);
+MEMOTR_API int memotr_groupnorm_cm(float *x, const float *gamma, const float *beta, int groups, int C, int P, float eps, void *stream);
+
 /* Profiling hook (tools/micro_dense.py), not part of the reference surface: every later memotr_mlp2* / encoder_dense_block
  * launch writes 8 clock64 stamps per CTA into `buf` (device int64[8 x CTAs]); null switches it off again. */
 MEMOTR_API int memotr_mlp2_debug_stamps(long long *buf);

@@ -113,6 +113,9 @@ _SIGNATURES = {
     "memotr_decoder_forward_cluster": ([_vp, _vp], _i),
     "memotr_decoder_forward": ([_vp, _vp], _i),
     "memotr_set_sm_budget": ([_i], _i),
+    "memotr_conv_gemm": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "memotr_im2col_3x3s2": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "memotr_groupnorm_cm": ([_vp, _vp, _vp, _i, _i, _i, _f, _vp], _i),
     "memotr_linear_f32x3": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp], _i),
     "memotr_updater_forward_cluster": ([_vp, _vp], _i),
     "memotr_timer_create": ([_i], _vp),
