@@ -77,12 +77,24 @@ class MeMOTR(nn.Module):
         features, pos = self.backbone(frame)
         pos = list(pos)
         srcs, masks = [], []
-        for layer, feat in enumerate(features):
-            src, mask = feat.decompose()
-            srcs.append(self.feature_projs[layer](src))
+        maps = [feat.decompose() for feat in features]
+        # inference on one CUDA frame: the projections on our kernels (memotr_b200/input_proj.py); otherwise the nn.Modules
+        proj = None
+        standard = all(isinstance(p, nn.Sequential) and len(p) == 2 and isinstance(p[0], nn.Conv2d) and isinstance(p[1], nn.GroupNorm)
+                       for p in self.feature_projs)
+        if (standard and not self.training and not torch.is_grad_enabled()
+                and all(m[0].is_cuda and m[0].shape[0] == 1 and m[0].dtype == torch.float32 for m in maps)):
+            if getattr(self, "_input_proj", None) is None:
+                from .input_proj import InputProj
+                self._input_proj = InputProj({k: v for k, v in self.state_dict().items() if k.startswith("feature_projs.")},
+                                             maps[0][0].device)
+            proj = self._input_proj([m[0] for m in maps])
+        for layer, (src, mask) in enumerate(maps):
+            srcs.append(proj[layer] if proj is not None else self.feature_projs[layer](src))
             masks.append(mask)
         for layer in range(len(srcs), self.n_feature_levels):
-            src = self.feature_projs[layer](features[-1].tensors if layer == len(features) else srcs[-1])
+            src = proj[layer] if proj is not None else self.feature_projs[layer](
+                features[-1].tensors if layer == len(features) else srcs[-1])
             mask = F.interpolate(frame.masks[None].float(), size=src.shape[-2:])[0].to(torch.bool)
             pos.append(self.backbone.position_embedding(_Nested(src, mask)).to(src.device))
             srcs.append(src)
@@ -136,7 +148,7 @@ class MeMOTR(nn.Module):
     def _engine_eligible(self, srcs, tracks):
         t = self.transformer
         return (not self.training and not torch.is_grad_enabled() and len(tracks) == 1 and srcs[0].is_cuda
-                and srcs[0].shape[0] == 1 and self.engine_mode in ("fp32", "bf16") and self.hidden_dim == 256
+                and srcs[0].shape[0] == 1 and self.engine_mode in ("fp32", "bf16", "fp32tc") and self.hidden_dim == 256
                 and t.n_heads == 8 and len(srcs) == t.n_feature_levels)
 
     def hot_path_config(self):
@@ -150,6 +162,7 @@ class MeMOTR(nn.Module):
     def reset_engines(self):
         """Drop the cached engines (call after changing the weights: an engine packs them once)."""
         self._engines = {}
+        self._input_proj = None
 
     def _engine(self, shapes, n_tracks, device):
         from .engine import FrameEngine

@@ -224,3 +224,30 @@ def test_memotr_module_autograd_route_and_query_updater_forward():
     want = oframe.update_tracks({k: v.cpu() for k, v in model.state_dict().items()}, {k: v.cpu() for k, v in want_in.items()}, cfg)
     for k in ("ref_pts", "query_embed", "long_memory", "last_output"):
         assert rel_err(getattr(out[0], k).cpu().numpy(), want[k].numpy()) < 1e-4, k
+
+
+def test_memotr_module_input_projections_run_on_our_kernels_in_eval():
+    """MeMOTR._pyramid: with the reference's own feature_projs (Conv2d + GroupNorm) the eval / no-grad / batch-1 route computes
+    the projections with memotr_b200.input_proj (csrc/input_proj.cu); same pyramid as the nn.Module route."""
+    from memotr_b200 import memotr as mm
+    torch.backends.cuda.matmul.allow_tf32 = False          # the reference's precision contract (main.py:96-97); cuDNN's
+    torch.backends.cudnn.allow_tf32 = False                # default would run the yardstick convolutions in TF32
+    cfg = synth.small_cfg()
+    rc = dict(oframe.to_reference_config(cfg), DATASET="DanceTrack", ENGINE_MODE="fp32")
+    g = torch.Generator().manual_seed(4)
+    shapes = [(24, 40), (12, 20), (6, 10)]
+    feats = [torch.randn(1, 8, h, w, generator=g).to(DEV) for h, w in shapes]
+    masks = [torch.zeros(1, h, w, dtype=torch.bool, device=DEV) for h, w in shapes]
+    pos = [torch.randn(1, 256, h, w, generator=g).to(DEV) for h, w in shapes] + [torch.randn(1, 256, 3, 5, generator=g).to(DEV)]
+    model = mm.build(rc, _FakeBackbone(feats, masks, pos)).to(DEV)
+    assert isinstance(model.feature_projs[0][0], nn.Conv2d) and len(model.feature_projs) == 4
+    frame = _NT(torch.zeros(1, 3, 24 * 8, 40 * 8, device=DEV), torch.zeros(1, 24 * 8, 40 * 8, dtype=torch.bool, device=DEV))
+    model.train()
+    want, _, _ = model._pyramid(frame)                              # nn.Conv2d + nn.GroupNorm
+    assert getattr(model, "_input_proj", None) is None
+    model.eval()
+    with torch.no_grad():
+        got, _, _ = model._pyramid(frame)
+    assert model._input_proj is not None and len(got) == 4
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel_err(a.cpu().numpy(), b.detach().cpu().numpy()) < 1e-5
