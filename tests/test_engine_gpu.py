@@ -407,10 +407,10 @@ def test_sine_embed_and_box_refine():
     raw = torch.randn(50, 4, generator=g)
     scale = torch.tensor([0.9, 0.8, 0.9, 0.8])
     got = K().sine_embed(raw.to(DEV), dim_t.to(DEV), scale4=scale.to(DEV), apply_sigmoid=True).cpu()
-    assert rel_err(got, truth((raw.sigmoid() * scale))) < 2e-6
+    assert rel_err(got, truth(raw.double().sigmoid() * scale.double())) < 2e-6
     delta, ref = torch.randn(50, 4, generator=g), torch.rand(50, 4, generator=g)
     ref[0, 0], ref[1, 1] = 0.0, 1.0                       # inverse_sigmoid clamps (utils/utils.py:71-73)
-    want = (delta + oframe.inverse_sigmoid(ref)).sigmoid()
+    want = (delta.double() + oframe.inverse_sigmoid(ref.double())).sigmoid()      # float64 yardstick (host-independent)
     new, nxt = K().box_refine(delta.to(DEV), ref.to(DEV), 30)
     assert rel_err(new.cpu(), want) < 1e-6
     assert torch.equal(nxt[:30].cpu(), new[:30].cpu()) and torch.equal(nxt[30:].cpu(), ref[30:])
