@@ -83,3 +83,23 @@ def test_pack_w3_reconstructs_the_scaled_weight_to_22_bits():
     rel = ((rec - w.double()).abs() / w.double().abs().clamp_min(1e-3)).max()
     assert rel < 2.0 ** -20
     assert (lo.float().abs() > 0).float().mean() > 0.9 and lo.float().abs().max() < 2.0 ** -9 * hi.float().abs().max() * 4
+
+
+def test_split_operand_layout_reproduces_the_oracle_fp16x3_model():
+    """The data layout memotr_linear_f32x3 multiplies -- A3 = [x_hi | x_hi | x_lo], W3 = pack_w3(w) = [w_hi | w_lo | w_hi] of 2^6 w,
+    one GEMM over 3K, the scale taken out of the result -- is the "fp16x3" rounding model of oracle/frame.py (the model the
+    full-size parity estimate of DESIGN.md section 6 was made with), and both are fp32-accurate."""
+    from memotr_b200.kernels import W3_SHIFT, pack_w3
+    from oracle import frame as oframe
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(64, 256, generator=g) * 2
+    w = torch.randn(128, 256, generator=g) / 16
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    a3 = torch.cat((hi, hi, lo), dim=1).double()
+    got = (a3 @ pack_w3(w).double().T) / 2 ** W3_SHIFT
+    model = oframe._rounded_matmul(x, w, "fp16x3").double()
+    exact = x.double() @ w.double().T
+    scale = exact.abs().max()
+    assert (got - model).abs().max() / scale < 2e-6          # the same three products; the model sums them in fp32
+    assert (got - exact).abs().max() / scale < 5e-7          # the dropped lo x lo term and the fp16 rounding of the lo halves
