@@ -28,7 +28,9 @@
 extern "C" {
 #endif
 
-#define MEMOTR_ABI_VERSION 1
+/* 2: round 2 -- memotr_msda_forward_strided lost its layout flag, the pair / head-major / prologue-LN entry points are gone,
+ * the windowed gather, the fused-LayerNorm variants, the pipelining / fp32x3 / input-projection entry points were added */
+#define MEMOTR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MEMOTR_API __attribute__((visibility("default")))
