@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmemotr_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, F64, BF16, F16 = 0, 1, 2, 3
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
